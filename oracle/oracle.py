@@ -1,0 +1,178 @@
+"""ctypes front-end for the CPU oracle (oracle/rcv_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see the header of rcv_oracle.c.  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs may import this module; the product package
+``rcvpose_b200`` never does.
+
+The functions mirror the reference's call surface for the voting path:
+  rgbd_to_point_cloud   AccumulatorSpace.py:77-85
+  Accumulator_3D        AccumulatorSpace.py:373-419   (prelude :373-401, fast_for :325-341, peak :406-419)
+  lmshorn               util/horn.py:75-181
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+POLICY_LM = 0      # AccumulatorSpace.py:373-419
+POLICY_YCBGEN = 1  # 3DRadius_ycb.py:113-161
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "librcv_oracle.so")
+    src = os.path.join(_HERE, "rcv_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+        L.orc_pairwise_sum.restype = C.c_double
+        L.orc_pairwise_sum.argtypes = [vp, C.c_long, C.c_long]
+        L.orc_backproject.restype = C.c_long
+        L.orc_backproject.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        L.orc_prelude.restype = C.c_int
+        L.orc_prelude.argtypes = [vp, C.c_long, vp, C.c_int, C.c_double, C.c_double, C.c_int, vp, vp, vp, ip, ip, dp]
+        L.orc_fast_for.restype = None
+        L.orc_fast_for.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_int]
+        L.orc_fast_for_literal.restype = None
+        L.orc_fast_for_literal.argtypes = [vp, vp, C.c_long, C.c_int, vp]
+        L.orc_scatter.restype = None
+        L.orc_scatter.argtypes = [vp, vp, C.c_long, C.c_int, vp]
+        L.orc_peak.restype = C.c_long
+        L.orc_peak.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_int32)]
+        L.orc_center_mm.restype = None
+        L.orc_center_mm.argtypes = [vp, C.c_int, vp, C.c_double, C.c_int, vp]
+        L.orc_lmshorn.restype = None
+        L.orc_lmshorn.argtypes = [vp, vp, C.c_int, vp]
+        L.orc_accumulator_3d.restype = C.c_int
+        L.orc_accumulator_3d.argtypes = [vp, C.c_long, vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                         vp, ip, ip, C.POINTER(C.c_int32), C.POINTER(C.c_longlong), vp]
+        L.orc_num_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def pairwise_sum(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return lib().orc_pairwise_sum(_p(a), a.size, 1)
+
+
+def rgbd_to_point_cloud(K, depth, swap_xy=False):
+    """AccumulatorSpace.py:77-85 -> (N,3) float64 in depth units."""
+    K = np.ascontiguousarray(K, dtype=np.float64)
+    d = np.ascontiguousarray(depth, dtype=np.float64)
+    H, W = d.shape
+    n = lib().orc_backproject(_p(K), _p(d), H, W, int(swap_xy), None)
+    out = np.empty((n, 3), dtype=np.float64)
+    lib().orc_backproject(_p(K), _p(d), H, W, int(swap_xy), _p(out))
+    return out
+
+
+def _radii(radial_list):
+    r = np.asarray(radial_list)
+    if r.dtype == np.float32:
+        return np.ascontiguousarray(r), 1
+    return np.ascontiguousarray(r, dtype=np.float64), 0
+
+
+def prelude(xyz, radial_list, acc_unit=5.0, radius_scale=100.0, policy=POLICY_LM):
+    """AccumulatorSpace.py:373-401 -> dict(p (n,3) f64, R (n,) i32, mean (3,), zb, D, rmax)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    n = xyz.shape[0]
+    if n == 0:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    r, is32 = _radii(radial_list)
+    p = np.empty((n, 3), dtype=np.float64)
+    R = np.empty(n, dtype=np.int32)
+    mean = np.empty(3, dtype=np.float64)
+    zb, D, rmax = C.c_int(), C.c_int(), C.c_double()
+    lib().orc_prelude(_p(xyz), n, _p(r), is32, acc_unit, radius_scale, policy, _p(p), _p(R), _p(mean),
+                      C.byref(zb), C.byref(D), C.byref(rmax))
+    return dict(p=p, R=R, mean=mean, zb=zb.value, D=D.value, rmax=rmax.value)
+
+
+def fast_for(p, R, D, threads=0, method="brute"):
+    """AccumulatorSpace.py:325-341 on voxel-unit points with integer radii -> int32 (D,D,D)."""
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    R = np.ascontiguousarray(R, dtype=np.int32)
+    vol = np.zeros((D, D, D), dtype=np.int32)
+    if method == "brute":
+        lib().orc_fast_for(_p(p), _p(R), p.shape[0], D, _p(vol), threads)
+    elif method == "literal":
+        lib().orc_fast_for_literal(_p(p), _p(R), p.shape[0], D, _p(vol))
+    elif method == "scatter":
+        lib().orc_scatter(_p(p), _p(R), p.shape[0], D, _p(vol))
+    else:
+        raise ValueError(method)
+    return vol
+
+
+def peak(vol):
+    """AccumulatorSpace.py:406 -> (first argmax (i,j,k) in C order, max count, number of ties)."""
+    vol = np.ascontiguousarray(vol, dtype=np.int32)
+    idx = np.empty(3, dtype=np.int32)
+    mx = C.c_int32()
+    ties = lib().orc_peak(_p(vol), vol.shape[0], _p(idx), C.byref(mx))
+    return idx, mx.value, ties
+
+
+def center_mm(idx, zb, mean, acc_unit=5.0, policy=POLICY_LM):
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    mean = np.ascontiguousarray(mean, dtype=np.float64)
+    out = np.empty(3, dtype=np.float64)
+    lib().orc_center_mm(_p(idx), zb, _p(mean), acc_unit, policy, _p(out))
+    return out
+
+
+def Accumulator_3D(xyz, radial_list, acc_unit=5.0, radius_scale=100.0, policy=POLICY_LM, method="brute", threads=0,
+                   return_info=False, return_volume=False):
+    """AccumulatorSpace.py:373-419.  Returns (1,3) float64 mm (row 0 of the reference's result)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    n = xyz.shape[0]
+    if n == 0:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    r, is32 = _radii(radial_list)
+    c = np.empty(3, dtype=np.float64)
+    D, zb, pk, votes = C.c_int(), C.c_int(), C.c_int32(), C.c_longlong()
+    vol = None
+    if return_volume:
+        pre = prelude(xyz, r, acc_unit, radius_scale, policy)
+        vol = np.zeros((pre["D"],) * 3, dtype=np.int32)
+    rc = lib().orc_accumulator_3d(_p(xyz), n, _p(r), is32, acc_unit, radius_scale, policy, int(method == "brute"), threads,
+                                  _p(c), C.byref(D), C.byref(zb), C.byref(pk), C.byref(votes),
+                                  _p(vol) if vol is not None else None)
+    if rc == 2:
+        raise ValueError("negative dimensions are not allowed")
+    out = c.reshape(1, 3)
+    if return_info or return_volume:
+        info = dict(D=D.value, zb=zb.value, peak=pk.value, votes=votes.value)
+        if return_volume:
+            info["volume"] = vol
+        return out, info
+    return out
+
+
+def lmshorn(P1, P2, n, A):
+    """util/horn.py:75-181: fills the 4x4 A in place; P1/P2 untouched."""
+    P1 = np.ascontiguousarray(P1, dtype=np.float64)
+    P2 = np.ascontiguousarray(P2, dtype=np.float64)
+    out = np.empty((4, 4), dtype=np.float64)
+    lib().orc_lmshorn(_p(P1), _p(P2), int(n), _p(out))
+    A[...] = out

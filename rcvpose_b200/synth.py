@@ -1,0 +1,102 @@
+"""Synthetic LINEMOD-/YCB-shaped inputs for the voting path (no datasets are available offline).
+
+The shapes follow SURVEY.md section 8d: a sphere-shaped object seen through the LINEMOD camera
+(`linemod_K`, reference AccumulatorSpace.py:59-61), depth as uint16 millimetres (the `.dpt` format,
+AccumulatorSpace.py:482-490), and one float32 radius map per keypoint in decimetres
+(AccumulatorSpace.py:388: "radius map is in decimetre").
+"""
+import numpy as np
+
+H, W = 480, 640
+
+linemod_K = np.array([[572.4114, 0.0, 325.2611],
+                      [0.0, 573.57043, 242.04899],
+                      [0.0, 0.0, 1.0]])
+
+ycb_K = np.array([[1066.778, 0.0, 312.9869],
+                  [0.0, 1067.487, 241.3109],
+                  [0.0, 0.0, 1.0]])
+
+
+def sphere_depth(K, centre_mm, radius_mm, h=H, w=W):
+    """Front ray-sphere intersection depth (mm, rounded to uint16); 0 where the ray misses."""
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    v, u = np.mgrid[0:h, 0:w].astype(np.float64)
+    dx, dy = (u - cx) / fx, (v - cy) / fy          # ray = (dx, dy, 1) * z
+    a = dx * dx + dy * dy + 1.0
+    b = dx * centre_mm[0] + dy * centre_mm[1] + centre_mm[2]
+    c = float(np.dot(centre_mm, centre_mm)) - radius_mm ** 2
+    disc = b * b - a * c
+    hit = disc > 0
+    z = np.where(hit, (b - np.sqrt(np.where(hit, disc, 0.0))) / a, 0.0)
+    return np.where(hit, np.round(z), 0).astype(np.uint16)
+
+
+def backproject_mm(K, depth):
+    """Host-side back-projection used only to *build* synthetic radius maps (same formula as
+    AccumulatorSpace.py:77-85, dense form)."""
+    h, w = depth.shape
+    v, u = np.mgrid[0:h, 0:w].astype(np.float64)
+    z = depth.astype(np.float64)
+    x = ((u - K[0, 2]) * z) / K[0, 0]
+    y = ((v - K[1, 2]) * z) / K[1, 1]
+    return np.stack([x, y, z], axis=-1)
+
+
+def radius_map_dm(K, depth, kpt_mm, rng, sigma_dm=0.01, outlier_frac=0.0, max_radius_dm=None):
+    """float32 (H,W) radius map in decimetres: 10*|p-kpt| [m] + N(0,sigma); 0 outside the mask."""
+    pts = backproject_mm(K, depth)
+    dist_dm = np.linalg.norm(pts - kpt_mm[None, None, :], axis=-1) / 100.0
+    r = dist_dm + rng.normal(0.0, sigma_dm, size=depth.shape)
+    if outlier_frac > 0:
+        out = rng.random(depth.shape) < outlier_frac
+        hi = max_radius_dm if max_radius_dm is not None else float(dist_dm[depth != 0].max())
+        r = np.where(out, rng.uniform(0.0, hi, size=depth.shape), r)
+    return np.where(depth != 0, r, 0.0).astype(np.float32)
+
+
+def config1_frame():
+    """sphere r=50mm at (20,-10,900)mm, keypoint = centre+(80,70,60)mm,
+    radius noise N(0,0.01 dm), default_rng(1234).  N=3189 px, D=86, 14,792,527 votes, peak 1215."""
+    rng = np.random.default_rng(1234)
+    centre = np.array([20.0, -10.0, 900.0])
+    depth = sphere_depth(linemod_K, centre, 50.0)
+    kpt = centre + np.array([80.0, 70.0, 60.0])
+    radius = radius_map_dm(linemod_K, depth, kpt, rng)
+    return dict(K=linemod_K, depth=depth, radius=radius[None], kpts_mm=kpt[None])
+
+
+def config3_frame(f, n_kpts=3, K=linemod_K):
+    """SURVEY 8d config 3 frame `f`: default_rng(f); object radius U(40,70)mm, centre x,y U(-150,150),
+    z U(700,1100); keypoints at 1.5-2.5x object radius in dispersed directions; sigma 0.01 dm and
+    2% uniform outliers in [0, max_radius]."""
+    rng = np.random.default_rng(f)
+    rad = rng.uniform(40.0, 70.0)
+    centre = np.array([rng.uniform(-150, 150), rng.uniform(-150, 150), rng.uniform(700, 1100)])
+    depth = sphere_depth(K, centre, rad)
+    dirs = np.array([[1.0, 0.2, 0.1], [-0.3, 1.0, 0.2], [0.2, -0.4, 1.0], [-1.0, -0.5, 0.3]])[:n_kpts]
+    dirs = dirs + rng.normal(0, 0.15, size=dirs.shape)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    kpts = centre[None] + dirs * rad * rng.uniform(1.5, 2.5, size=(n_kpts, 1))
+    pts = backproject_mm(K, depth)
+    radius, max_r = [], []
+    for k in range(n_kpts):
+        d = np.linalg.norm(pts - kpts[k][None, None], axis=-1) / 100.0
+        mr = float(d[depth != 0].max()) if (depth != 0).any() else 1.0
+        max_r.append(mr)
+        radius.append(radius_map_dm(K, depth, kpts[k], rng, 0.01, 0.02, mr))
+    return dict(K=K, depth=depth, radius=np.stack(radius), kpts_mm=kpts, max_radii_dm=np.array(max_r), obj_radius_mm=rad,
+                centre_mm=centre)
+
+
+def frame_to_points(K, depth, radius):
+    """The reference caller's glue (AccumulatorSpace.py:612-619, npy branch): masked depth ->
+    xyz in metres (N,3) float64 + radial list (N,) in the map's dtype."""
+    m = (radius != 0)
+    dm = depth * m
+    vs, us = dm.nonzero()
+    zs = dm[vs, us]
+    xs = ((us - K[0, 2]) * zs) / float(K[0, 0])
+    ys = ((vs - K[1, 2]) * zs) / float(K[1, 1])
+    xyz_mm = np.array([xs, ys, zs]).T
+    return xyz_mm / 1000, radius[dm.nonzero()]
