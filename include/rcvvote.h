@@ -1,0 +1,157 @@
+/*
+ * rcvvote.h -- C ABI of librcvvote.so: the B200-native (sm_100a) radial keypoint-voting path.
+ *
+ * The reference (aaronWool/rcvpose) has no plugin/FFI layer: the path is three Python callables
+ * (SURVEY.md section 8b).  This header is the boundary a maintainer binds instead; each entry point
+ * names the reference interface it replaces (file:line in the reference repository).
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, int status codes.  No C++ exceptions cross the boundary.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - Unless a function name ends in `_host`, every data pointer is a DEVICE pointer on the
+ *     context's device and the call is asynchronous on `stream` (outputs are valid once the
+ *     stream has completed).  `_host` variants take HOST pointers, perform the host<->device
+ *     copies on `stream` and synchronise it before returning.
+ *   - The caller owns every input/output buffer and the stream; the context owns scratch.
+ *     A context is not re-entrant; use one context per (device, stream).
+ *   - Return value: RCV_OK or a negative RCV_E_* code; rcv_last_error() gives the text.
+ *     Data-dependent conditions are reported per item in `status[]` (RCV_ST_*), never as UB.
+ */
+#ifndef RCVVOTE_H_
+#define RCVVOTE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCV_ABI_VERSION 1
+
+/* call status */
+#define RCV_OK 0
+#define RCV_E_INVALID (-1)   /* bad argument */
+#define RCV_E_CUDA (-2)      /* CUDA runtime error (see rcv_last_error) */
+#define RCV_E_CAPACITY (-3)  /* request exceeds the capacities fixed at rcv_create */
+#define RCV_E_NOGPU (-4)     /* no usable sm_100 device: there is no CPU fallback */
+
+/* per-item status bits (status[] outputs) */
+#define RCV_ST_OK 0
+#define RCV_ST_EMPTY_MASK 1      /* no surviving pixel/point: the reference raises ValueError (AccumulatorSpace.py:390) */
+#define RCV_ST_BAD_GRID 2        /* D <= 0 (np.zeros would raise) */
+#define RCV_ST_D_EXCEEDS_CAP 4   /* D > cfg.max_grid */
+#define RCV_ST_POINT_OVERFLOW 8  /* compacted points exceed cfg.max_points_total */
+#define RCV_ST_UNIT_OVERFLOW 16  /* tile work list exceeds capacity */
+
+/* grid policy: which Accumulator_3D prelude is reproduced */
+#define RCV_POLICY_LM 0      /* AccumulatorSpace.py:373-419: D = int(max) + int(rmax); centre = (idx+mean+0.5)*unit */
+#define RCV_POLICY_YCBGEN 1  /* 3DRadius_ycb.py:113-161:    D = int(max) + 1;         centre = (idx+mean)*unit+0.5 */
+
+/* element types */
+#define RCV_F32 0
+#define RCV_F64 1
+#define RCV_U16 2
+
+/* mask rule flags for rcv_vote_frames (AccumulatorSpace.py:603-618, 837-851, 1049-1053) */
+#define RCV_MASK_RADIUS_NONZERO 1   /* keep pixel iff radius != 0   (LM  npy branch :613) */
+#define RCV_MASK_RADIUS_POSITIVE 2  /* keep pixel iff radius > 0    (LMO npy branch :850) */
+#define RCV_MASK_SEM_GT 4           /* keep pixel iff sem >  sem_threshold (LM/YCB ckpt :603,:1049) */
+#define RCV_MASK_SEM_GE 8           /* keep pixel iff sem >= sem_threshold (LMO ckpt :837) */
+#define RCV_MASK_MAX_RADIUS 16      /* keep pixel iff radius <= max_radii[k] (:604,:613,:838,:849) */
+
+typedef struct rcv_ctx rcv_ctx;
+
+typedef struct rcv_config {
+  int abi_version;             /* RCV_ABI_VERSION */
+  int max_items;               /* max (frame,keypoint) items per call */
+  long long max_points_total;  /* pool for compacted points summed over the items of one call */
+  int max_grid;                /* largest accumulator side D accepted */
+  int max_units;               /* tile work-list capacity (0 = derive from max_items/max_grid) */
+} rcv_config;
+
+/* Parameters of Accumulator_3D that the reference hard-codes (AccumulatorSpace.py:374,388). */
+typedef struct rcv_vote_params {
+  double acc_unit;      /* 5   : voxel size in mm (:374) */
+  double radius_scale;  /* 100 : radius unit -> mm (decimetre maps, :388); 1000 for metre radii (3DRadius_ycb.py:124) */
+  int grid_policy;      /* RCV_POLICY_* */
+  int radius_dtype;     /* RCV_F32 or RCV_F64: radius arithmetic is done in the radius' own dtype (:388) */
+} rcv_vote_params;
+
+typedef struct rcv_frame_params {
+  int height, width;    /* 480, 640 */
+  int depth_dtype;      /* RCV_U16 (LINEMOD .dpt, :482-490), RCV_F32 or RCV_F64 (LMO png, :833) */
+  double depth_div;     /* depth is divided by this first (YCB factor_depth, :1051-1052); 1 = none */
+  double xyz_div;       /* back-projected cloud is divided by this (mm -> m, :619); 1 = none (YCB) */
+  int mask_flags;       /* RCV_MASK_* */
+  float sem_threshold;  /* 0.8 (LM, YCB) or 0.5 (LMO) */
+  int k_stride;         /* doubles between per-frame intrinsics (9), or 0 for one shared K */
+  int max_radii_stride; /* doubles between per-frame max_radii rows (n_kpts), or 0 for one shared row */
+} rcv_frame_params;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out);
+void rcv_destroy(rcv_ctx* ctx);
+const char* rcv_last_error(const rcv_ctx* ctx); /* ctx may be NULL: error of the last failed rcv_create */
+int rcv_abi_version(void);
+
+/* ---- rgbd_to_point_cloud(K, depth)  -- AccumulatorSpace.py:77-85 ------------------------------
+ * depth: (H,W) of `depth_dtype`; K: 9 doubles row-major (DEVICE).  Writes the (N,3) float64 cloud in
+ * row-major pixel order to xyz_out (capacity xyz_capacity points) and N to *n_out (device int).  */
+int rcv_backproject(rcv_ctx* ctx, const double* K, const void* depth, int depth_dtype, int height, int width,
+                    double* xyz_out, long long xyz_capacity, int* n_out, void* stream);
+
+/* ---- Accumulator_3D(xyz, radial_list)  -- AccumulatorSpace.py:373-419 ---------------------------
+ * Batched over n_items independent point clouds stored back to back:
+ *   xyz     (sum N, 3) float64, metres            radii  (sum N) of params->radius_dtype
+ *   item_offsets (n_items+1) int64 on the DEVICE: item b owns points [off[b], off[b+1]).
+ * Outputs per item (device): centre_mm[3] float64 (row 0 of the reference's result), peak = vote count of
+ * the winning voxel, votes = total votes cast inside the grid (int64), grid = D, zero_boundary = zb,
+ * status = RCV_ST_*.  Any output pointer except centre_mm/status may be NULL.
+ * volume_out (optional, n_items must be 1): int32 [D][D][D] C-order dump of the vote volume
+ * (the reference's VoteMap_3D), for parity checks; volume_capacity in int32 elements. */
+int rcv_vote_points(rcv_ctx* ctx, const double* xyz, const void* radii, const long long* item_offsets, int n_items,
+                    const rcv_vote_params* params, double* centre_mm, int* peak, long long* votes, int* grid,
+                    int* zero_boundary, int* status, int32_t* volume_out, long long volume_capacity, void* stream);
+
+/* ---- the per-frame loop body of estimate_6d_pose_*  -- AccumulatorSpace.py:601-637 (LM), 833-873 (LMO),
+ *      1048-1067 (YCB): mask rule + rgbd_to_point_cloud + radial_list gather + Accumulator_3D, fused, for
+ *      n_frames x n_kpts items.
+ *   depth   [n_frames][H][W] depth_dtype           radius [n_frames][n_kpts][H][W] float32 (decimetres)
+ *   sem     [n_frames][n_kpts][H][W] float32 or NULL
+ *   K       [n_frames or 1][9] float64             max_radii [n_frames or 1][n_kpts] float64 or NULL
+ * Outputs are indexed [frame][kpt]: centre_mm [..][3] float64, peak, votes, n_points, grid, status. */
+int rcv_vote_frames(rcv_ctx* ctx, int n_frames, int n_kpts, const void* depth, const float* radius, const float* sem,
+                    const double* K, const double* max_radii, const rcv_frame_params* fp, const rcv_vote_params* vp,
+                    double* centre_mm, int* peak, long long* votes, int* n_points, int* grid, int* status, void* stream);
+
+/* Same, HOST buffers in and out: copies inputs host->device and results device->host on `stream`,
+ * in chunks that overlap transfer with voting, and synchronises before returning.  For full
+ * bandwidth the host buffers should be page-locked (cudaHostAlloc / torch pin_memory). */
+int rcv_vote_frames_host(rcv_ctx* ctx, int n_frames, int n_kpts, const void* depth, const float* radius, const float* sem,
+                         const double* K, const double* max_radii, const rcv_frame_params* fp, const rcv_vote_params* vp,
+                         double* centre_mm, int* peak, long long* votes, int* n_points, int* grid, int* status,
+                         int frames_per_chunk, void* stream);
+
+/* ---- argwhere(V == V.max())[0]  -- AccumulatorSpace.py:406 ---------------------------------------
+ * Peak search over an int32 [D][D][D] volume: first maximum in C order.  idx_out[3], max_out (device). */
+int rcv_argmax_volume(rcv_ctx* ctx, const int32_t* volume, int grid, int* idx_out, int* max_out, void* stream);
+
+/* ---- HornPoseFitting.lmshorn(P1, P2, n, A)  -- util/horn.py:75-181 --------------------------------
+ * Batched closed-form absolute orientation: model [n_frames or 1][n][3] (model_stride = 3n or 0),
+ * est [n_frames][n][3] float64 -> RT [n_frames][4][4] float64 with est ~= R*model + T. */
+int rcv_horn_batch(rcv_ctx* ctx, const double* model, long long model_stride, const double* est, int n, int n_frames,
+                   double* RT, void* stream);
+int rcv_horn_batch_host(rcv_ctx* ctx, const double* model, long long model_stride, const double* est, int n, int n_frames,
+                        double* RT, void* stream);
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+/* Kernel launches issued by this context since creation (the bench's gpu_launches claim). */
+long long rcv_launch_count(const rcv_ctx* ctx);
+/* Device time of the vote kernel in the most recent rcv_vote_* call, in ms (CUDA events on `stream`);
+ * blocks until that call has finished.  Returns a negative value if no call was made. */
+float rcv_last_vote_kernel_ms(rcv_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCVVOTE_H_ */

@@ -1,0 +1,216 @@
+"""Host-side API over librcvvote.so: PyTorch owns device memory and streams, CUDA does the work.
+
+`VoteContext` is a thin object wrapper of the C ABI (include/rcvvote.h); every method takes CUDA
+tensors (or, for the `_host` methods, NumPy arrays) and launches asynchronously on torch's
+current stream.  Nothing here computes votes, peaks or poses on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (RCV_F32, RCV_F64, RCV_U16, RCV_POLICY_LM, RCV_POLICY_YCBGEN, RCV_MASK_RADIUS_NONZERO,  # noqa: F401
+                   RCV_MASK_RADIUS_POSITIVE, RCV_MASK_SEM_GT, RCV_MASK_SEM_GE, RCV_MASK_MAX_RADIUS, RCV_ST_OK,
+                   RCV_ST_EMPTY_MASK, RCV_ST_BAD_GRID, RCV_ST_D_EXCEEDS_CAP, RCV_ST_POINT_OVERFLOW, RCV_ST_UNIT_OVERFLOW,
+                   RCV_ST_VOLUME_SKIPPED)
+
+_DEPTH_DTYPES = {torch.uint16: RCV_U16, torch.int16: RCV_U16, torch.float32: RCV_F32, torch.float64: RCV_F64}
+_NP_DEPTH_DTYPES = {np.dtype(np.uint16): RCV_U16, np.dtype(np.float32): RCV_F32, np.dtype(np.float64): RCV_F64}
+
+# mask rules of the reference's three evaluators (AccumulatorSpace.py)
+MASK_LM_NPY = RCV_MASK_MAX_RADIUS | RCV_MASK_RADIUS_NONZERO       # :612-618
+MASK_LM_CKPT = RCV_MASK_MAX_RADIUS | RCV_MASK_SEM_GT              # :603-610  (sem > 0.8)
+MASK_LMO_NPY = RCV_MASK_MAX_RADIUS | RCV_MASK_RADIUS_POSITIVE     # :849-851
+MASK_LMO_CKPT = RCV_MASK_MAX_RADIUS | RCV_MASK_SEM_GE             # :837-840  (sem >= 0.5)
+MASK_YCB = RCV_MASK_SEM_GT                                        # :1049-1053 (sem > 0.8)
+
+
+class RcvError(RuntimeError):
+    pass
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_cuda(t, dtype=None, name="tensor"):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+        raise RcvError("%s must be a contiguous CUDA tensor" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RcvError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
+
+
+class VoteContext:
+    """One context per (device, stream); not re-entrant.  Capacities are fixed here (no allocation
+    on the hot calls)."""
+
+    def __init__(self, device=0, max_items=64, max_points_total=1 << 22, max_grid=256, max_units=0):
+        if not torch.cuda.is_available():
+            raise RcvError("no CUDA device: rcvpose_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device if isinstance(device, int) else device.index or 0)
+        cfg = _lib.rcv_config(_lib.RCV_ABI_VERSION, int(max_items), int(max_points_total), int(max_grid), int(max_units))
+        h = C.c_void_p()
+        rc = self.lib.rcv_create(self.device.index, C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise RcvError("rcv_create failed (%d): %s" % (rc, self.lib.rcv_last_error(None).decode()))
+        self.h = h
+        self.max_items, self.max_grid = int(max_items), int(max_grid)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rcv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RcvError("librcvvote error %d: %s" % (rc, self.lib.rcv_last_error(self.h).decode()))
+
+    @property
+    def launches(self):
+        return int(self.lib.rcv_launch_count(self.h))
+
+    def last_vote_kernel_ms(self):
+        return float(self.lib.rcv_last_vote_kernel_ms(self.h))
+
+    # ---- rgbd_to_point_cloud (AccumulatorSpace.py:77-85) ----
+    def backproject(self, K, depth):
+        _check_cuda(K, torch.float64, "K")
+        _check_cuda(depth, None, "depth")
+        H, W = depth.shape
+        xyz = torch.empty((H * W, 3), dtype=torch.float64, device=depth.device)
+        n = torch.zeros(1, dtype=torch.int32, device=depth.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_backproject(self.h, _ptr(K), _ptr(depth), _DEPTH_DTYPES[depth.dtype], H, W, _ptr(xyz), H * W, _ptr(n),
+                                              _stream()))
+        return xyz[: int(n.item())]
+
+    # ---- Accumulator_3D (AccumulatorSpace.py:373-419), batched ----
+    def vote_points(self, xyz, radii, item_offsets=None, acc_unit=5.0, radius_scale=100.0, policy=RCV_POLICY_LM, want_volume=False,
+                    volume_capacity=None):
+        _check_cuda(xyz, torch.float64, "xyz")
+        _check_cuda(radii, None, "radii")
+        if radii.dtype not in (torch.float32, torch.float64):
+            raise RcvError("radii must be float32 or float64")
+        dev = xyz.device
+        if item_offsets is None:
+            item_offsets = torch.tensor([0, xyz.shape[0]], dtype=torch.int64, device=dev)
+        _check_cuda(item_offsets, torch.int64, "item_offsets")
+        B = item_offsets.numel() - 1
+        out = dict(centre_mm=torch.empty((B, 3), dtype=torch.float64, device=dev), peak=torch.empty(B, dtype=torch.int32, device=dev),
+                   votes=torch.empty(B, dtype=torch.int64, device=dev), grid=torch.empty(B, dtype=torch.int32, device=dev),
+                   zero_boundary=torch.empty(B, dtype=torch.int32, device=dev), status=torch.empty(B, dtype=torch.int32, device=dev))
+        vol = None
+        if want_volume:
+            cap = int(volume_capacity if volume_capacity is not None else self.max_grid ** 3)
+            vol = torch.zeros(cap, dtype=torch.int32, device=dev)
+        vp = _lib.rcv_vote_params(float(acc_unit), float(radius_scale), int(policy), RCV_F32 if radii.dtype == torch.float32 else RCV_F64)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_vote_points(self.h, _ptr(xyz), _ptr(radii), _ptr(item_offsets), B, C.byref(vp), _ptr(out["centre_mm"]),
+                                              _ptr(out["peak"]), _ptr(out["votes"]), _ptr(out["grid"]), _ptr(out["zero_boundary"]),
+                                              _ptr(out["status"]), _ptr(vol), vol.numel() if vol is not None else 0, _stream()))
+        if vol is not None:
+            out["volume_flat"] = vol
+        return out
+
+    # ---- fused mask + back-projection + Accumulator_3D over frames x keypoints ----
+    def vote_frames(self, depth, radius, K, sem=None, max_radii=None, mask_flags=MASK_LM_NPY, sem_threshold=0.8, depth_div=1.0,
+                    xyz_div=1000.0, acc_unit=5.0, radius_scale=100.0, policy=RCV_POLICY_LM):
+        _check_cuda(depth, None, "depth")
+        _check_cuda(radius, torch.float32, "radius")
+        _check_cuda(K, torch.float64, "K")
+        B, Kp, H, W = radius.shape
+        if tuple(depth.shape) != (B, H, W):
+            raise RcvError("depth must be (B,H,W) matching radius (B,Kp,H,W)")
+        if sem is not None:
+            _check_cuda(sem, torch.float32, "sem")
+        if max_radii is not None:
+            _check_cuda(max_radii, torch.float64, "max_radii")
+        dev = radius.device
+        fp = _lib.rcv_frame_params(H, W, _DEPTH_DTYPES[depth.dtype], float(depth_div), float(xyz_div), int(mask_flags), float(sem_threshold),
+                                   9 if (K.dim() == 3 and K.shape[0] == B) else 0,
+                                   Kp if (max_radii is not None and max_radii.dim() == 2 and max_radii.shape[0] == B) else 0)
+        vp = _lib.rcv_vote_params(float(acc_unit), float(radius_scale), int(policy), RCV_F32)
+        out = dict(centre_mm=torch.empty((B, Kp, 3), dtype=torch.float64, device=dev), peak=torch.empty((B, Kp), dtype=torch.int32, device=dev),
+                   votes=torch.empty((B, Kp), dtype=torch.int64, device=dev), n_points=torch.empty((B, Kp), dtype=torch.int32, device=dev),
+                   grid=torch.empty((B, Kp), dtype=torch.int32, device=dev), status=torch.empty((B, Kp), dtype=torch.int32, device=dev))
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_vote_frames(self.h, B, Kp, _ptr(depth), _ptr(radius), _ptr(sem), _ptr(K), _ptr(max_radii), C.byref(fp),
+                                              C.byref(vp), _ptr(out["centre_mm"]), _ptr(out["peak"]), _ptr(out["votes"]), _ptr(out["n_points"]),
+                                              _ptr(out["grid"]), _ptr(out["status"]), _stream()))
+        return out
+
+    def vote_frames_host(self, depth, radius, K, sem=None, max_radii=None, mask_flags=MASK_LM_NPY, sem_threshold=0.8, depth_div=1.0,
+                         xyz_div=1000.0, acc_unit=5.0, radius_scale=100.0, policy=RCV_POLICY_LM, frames_per_chunk=256, out=None):
+        """HOST arrays in, HOST arrays out (NumPy or pinned CPU tensors' .numpy()); H2D/D2H inside."""
+        B, Kp, H, W = radius.shape
+        assert radius.dtype == np.float32 and radius.flags.c_contiguous and depth.flags.c_contiguous and tuple(depth.shape) == (B, H, W)
+        K = np.ascontiguousarray(K, dtype=np.float64)
+        mr = np.ascontiguousarray(max_radii, dtype=np.float64) if max_radii is not None else None
+        fp = _lib.rcv_frame_params(H, W, _NP_DEPTH_DTYPES[depth.dtype], float(depth_div), float(xyz_div), int(mask_flags), float(sem_threshold),
+                                   9 if (K.ndim == 3 and K.shape[0] == B) else 0,
+                                   Kp if (mr is not None and mr.ndim == 2 and mr.shape[0] == B) else 0)
+        vp = _lib.rcv_vote_params(float(acc_unit), float(radius_scale), int(policy), RCV_F32)
+        if out is None:
+            out = dict(centre_mm=np.empty((B, Kp, 3), np.float64), peak=np.empty((B, Kp), np.int32), votes=np.empty((B, Kp), np.int64),
+                       n_points=np.empty((B, Kp), np.int32), grid=np.empty((B, Kp), np.int32), status=np.empty((B, Kp), np.int32))
+        p = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None  # noqa: E731
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_vote_frames_host(self.h, B, Kp, p(depth), p(radius), p(sem), p(K), p(mr), C.byref(fp), C.byref(vp),
+                                                   p(out["centre_mm"]), p(out["peak"]), p(out["votes"]), p(out["n_points"]), p(out["grid"]),
+                                                   p(out["status"]), int(frames_per_chunk), _stream()))
+        return out
+
+    # ---- argwhere(V == V.max())[0] (AccumulatorSpace.py:406) ----
+    def argmax_volume(self, volume):
+        _check_cuda(volume, torch.int32, "volume")
+        D = volume.shape[0]
+        idx = torch.empty(3, dtype=torch.int32, device=volume.device)
+        mx = torch.empty(1, dtype=torch.int32, device=volume.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_argmax_volume(self.h, _ptr(volume), D, _ptr(idx), _ptr(mx), _stream()))
+        return idx, mx
+
+    # ---- HornPoseFitting.lmshorn, batched (util/horn.py:75-181) ----
+    def horn_batch(self, model, est):
+        """model (n,3) or (B,n,3), est (B,n,3) float64 CUDA -> RT (B,4,4)."""
+        _check_cuda(model, torch.float64, "model")
+        _check_cuda(est, torch.float64, "est")
+        B, n, _ = est.shape
+        stride = 3 * n if model.dim() == 3 else 0
+        RT = torch.empty((B, 4, 4), dtype=torch.float64, device=est.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_horn_batch(self.h, _ptr(model), stride, _ptr(est), n, B, _ptr(RT), _stream()))
+        return RT
+
+    def horn_batch_host(self, model, est):
+        model = np.ascontiguousarray(model, dtype=np.float64)
+        est = np.ascontiguousarray(est, dtype=np.float64)
+        B, n, _ = est.shape
+        RT = np.empty((B, 4, 4), np.float64)
+        p = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_horn_batch_host(self.h, p(model), 3 * n if model.ndim == 3 else 0, p(est), n, B, p(RT), _stream()))
+        return RT
+
+
+_default = {}
+
+
+def default_context(device=0, **kw):
+    """Process-wide context for the drop-in shim (created on first use)."""
+    key = (device, tuple(sorted(kw.items())))
+    if key not in _default:
+        _default[key] = VoteContext(device, **kw)
+    return _default[key]

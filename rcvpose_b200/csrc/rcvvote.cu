@@ -1,0 +1,1128 @@
+// rcvvote.cu -- CUDA kernels (sm_100a) and the C ABI of librcvvote.so.
+//
+// Pipeline for one call (all on the caller's stream, no host round trip):
+//   K1  k_frame_count / k_frame_compact : mask rule + depth back-projection + stable stream compaction
+//                                         (AccumulatorSpace.py:603-619, 77-85)      [frames API]
+//       k_points_to_voxel               : (N,3) metres -> voxel units               [points API]
+//   P   k_prelude   : numpy-pairwise means, recentre, zero boundary, grid side D, tile work list
+//                                         (AccumulatorSpace.py:373-401)
+//   K2  k_vote      : persistent CTAs, each owning a shared-memory int32 tile of the accumulator;
+//                     sphere shells are scattered with shared-memory atomics (raster_core.h) and the
+//                     tile's peak is reduced in place, so the volume never touches HBM
+//                                         (AccumulatorSpace.py:325-341 + :406)
+//   K3  k_argmax_volume : warp-shuffle + grid-level argmax over an HBM-resident int32 volume (:406)
+//   F   k_finalize  : un-shift the peak to millimetres (AccumulatorSpace.py:409-415)
+//   K4  k_horn      : batched Horn absolute orientation (util/horn.py:75-181)
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/rcvvote.h"
+#include "raster_core.h"
+
+#define RCV_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+using namespace rcv;
+
+constexpr int kVoteThreads = 512;
+constexpr int kVoteWarps = kVoteThreads / 32;
+constexpr int kSmemBytes = 232448;                        // 227 KB: the sm_100 per-CTA maximum
+constexpr int kDummyWords = 32 * kVoteWarps;              // one private sink word per lane per warp
+constexpr int kTileWords = kSmemBytes / 4 - kDummyWords - 128;   // 128 words left for static shared variables
+constexpr int kStVolumeSkipped = 32;
+
+struct ItemMeta {
+  long long off;  // first point of the item in the pool
+  int n;          // points
+  int D, Dp, zb;  // grid side, padded row stride, zero boundary
+  int ni, nj;     // tile shape (slices x rows); every tile spans all k
+  int status;
+  int pad;
+  double mean[3];
+  double rmax;
+};
+
+struct Unit {
+  int item, i0, ni, j0, nj;
+};
+
+struct Pool {
+  double *X, *Y, *Z, *Rd;  // voxel-unit coordinates (recentred in place by the prelude), radius in voxels
+  int* Ri;                 // np.around(radius) -- AccumulatorSpace.py:332
+  long long cap;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+  return __shfl_xor_sync(0xffffffffu, v, m);
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+  for (int m = 16; m; m >>= 1) { unsigned long long o = shfl_xor_u64(v, m); v = o > v ? o : v; }
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int m = 16; m; m >>= 1) v += shfl_xor_u64(v, m);
+  return v;
+}
+__device__ __forceinline__ double warp_min_f64(double v) {
+#pragma unroll
+  for (int m = 16; m; m >>= 1) { double o = __shfl_xor_sync(0xffffffffu, v, m); v = o < v ? o : v; }
+  return v;
+}
+__device__ __forceinline__ double warp_max_f64(double v) {
+#pragma unroll
+  for (int m = 16; m; m >>= 1) { double o = __shfl_xor_sync(0xffffffffu, v, m); v = o > v ? o : v; }
+  return v;
+}
+
+// (count, first C-order index) packed so that unsigned max = highest count, then smallest index:
+// exactly argwhere(V == V.max())[0] (AccumulatorSpace.py:406).
+__device__ __forceinline__ unsigned long long pack_peak(int count, unsigned lin) {
+  return ((unsigned long long)(unsigned)count << 32) | (unsigned long long)(0xffffffffu - lin);
+}
+
+// ------------------------------------------------------------------------------------------------
+// points API front end: xyz (metres) -> voxel units; radius -> voxel units in its own dtype
+// (AccumulatorSpace.py:376, :388, :332)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_items_from_offsets(const long long* __restrict__ offs, int n_items, long long cap, ItemMeta* meta) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_items) return;
+  long long o = offs[b] - offs[0], n = offs[b + 1] - offs[b];
+  ItemMeta m;
+  memset(&m, 0, sizeof(m));
+  m.off = o;
+  m.n = (int)n;
+  if (n < 0 || o + n > cap || n > 0x7fffffffLL) { m.status = RCV_ST_POINT_OVERFLOW; m.n = 0; }
+  meta[b] = m;
+}
+
+__device__ __forceinline__ void radius_to_voxel_f32(float r, float scale, float unit, double& rd, int& ri) {
+  const float rv = __fdiv_rn(__fmul_rn(r, scale), unit);
+  rd = (double)rv;
+  ri = __float2int_rn(rv);  // half-to-even, like np.around
+}
+__device__ __forceinline__ void radius_to_voxel_f64(double r, double scale, double unit, double& rd, int& ri) {
+  const double rv = __ddiv_rn(__dmul_rn(r, scale), unit);
+  rd = rv;
+  ri = __double2int_rn(rv);
+}
+
+__global__ void k_points_to_voxel(const double* __restrict__ xyz, const void* __restrict__ radii, int radius_dtype,
+                                  const long long* __restrict__ offs, int n_items, double acc_unit, double radius_scale,
+                                  Pool pool) {
+  const long long base = offs[0];
+  long long total = offs[n_items] - base;
+  if (total > pool.cap) total = pool.cap;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const double* p = xyz + 3 * (base + q);
+    pool.X[q] = __ddiv_rn(__dmul_rn(p[0], 1000.0), acc_unit);
+    pool.Y[q] = __ddiv_rn(__dmul_rn(p[1], 1000.0), acc_unit);
+    pool.Z[q] = __ddiv_rn(__dmul_rn(p[2], 1000.0), acc_unit);
+    double rd; int ri;
+    if (radius_dtype == RCV_F32) radius_to_voxel_f32(((const float*)radii)[base + q], (float)radius_scale, (float)acc_unit, rd, ri);
+    else radius_to_voxel_f64(((const double*)radii)[base + q], radius_scale, acc_unit, rd, ri);
+    pool.Rd[q] = rd;
+    pool.Ri[q] = ri;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 -- frames API front end: mask rule + back-projection + stable compaction, one CTA per item.
+// ------------------------------------------------------------------------------------------------
+struct FrameArgs {
+  const void* depth; const float* radius; const float* sem; const double* K; const double* max_radii;
+  rcv_frame_params fp;
+  double acc_unit, radius_scale;
+  int n_kpts;
+  int vec_ok;  // 128-bit loads allowed: H*W % 8 == 0 and all map pointers 16-byte aligned
+};
+
+constexpr int kCompactThreads = 512;
+constexpr int kPxPerThread = 8;
+constexpr int kPxPerIter = kCompactThreads * kPxPerThread;
+
+__device__ __forceinline__ double load_depth(const void* depth, int dtype, long long idx) {
+  if (dtype == RCV_U16) return (double)((const unsigned short*)depth)[idx];
+  if (dtype == RCV_F32) return (double)((const float*)depth)[idx];
+  return ((const double*)depth)[idx];
+}
+
+// Loads 8 consecutive pixels' validity + raw values. Vectorised (128-bit) when the group is whole.
+__device__ __forceinline__ unsigned pixel_group_mask(const FrameArgs& a, long long frame_px0, long long item_px0, int px, int npx,
+                                                     bool vec_ok, double max_r, double* zraw, float* rad) {
+  unsigned mask = 0;
+  const int flags = a.fp.mask_flags;
+  if (vec_ok && px + kPxPerThread <= npx) {
+    float s[kPxPerThread];
+    {
+      const float4* rp = reinterpret_cast<const float4*>(a.radius + item_px0 + px);
+      float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+      rad[0] = r0.x; rad[1] = r0.y; rad[2] = r0.z; rad[3] = r0.w; rad[4] = r1.x; rad[5] = r1.y; rad[6] = r1.z; rad[7] = r1.w;
+    }
+    if (a.sem) {
+      const float4* sp = reinterpret_cast<const float4*>(a.sem + item_px0 + px);
+      float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+      s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+    }
+    if (a.fp.depth_dtype == RCV_U16) {
+      const uint4 d = __ldg(reinterpret_cast<const uint4*>((const unsigned short*)a.depth + frame_px0 + px));
+      const unsigned w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { zraw[2 * q] = (double)(w[q] & 0xffffu); zraw[2 * q + 1] = (double)(w[q] >> 16); }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kPxPerThread; ++q) zraw[q] = load_depth(a.depth, a.fp.depth_dtype, frame_px0 + px + q);
+    }
+#pragma unroll
+    for (int q = 0; q < kPxPerThread; ++q) {
+      bool ok = zraw[q] != 0.0;
+      if (flags & RCV_MASK_MAX_RADIUS) ok = ok && ((double)rad[q] <= max_r);
+      if (flags & RCV_MASK_RADIUS_NONZERO) ok = ok && (rad[q] != 0.f);
+      if (flags & RCV_MASK_RADIUS_POSITIVE) ok = ok && (rad[q] > 0.f);
+      if (flags & RCV_MASK_SEM_GT) ok = ok && (s[q] > a.fp.sem_threshold);
+      if (flags & RCV_MASK_SEM_GE) ok = ok && (s[q] >= a.fp.sem_threshold);
+      mask |= (unsigned)ok << q;
+    }
+  } else {
+    for (int q = 0; q < kPxPerThread; ++q) {
+      if (px + q >= npx) break;
+      zraw[q] = load_depth(a.depth, a.fp.depth_dtype, frame_px0 + px + q);
+      rad[q] = a.radius[item_px0 + px + q];
+      const float sv = a.sem ? a.sem[item_px0 + px + q] : 0.f;
+      bool ok = zraw[q] != 0.0;
+      if (flags & RCV_MASK_MAX_RADIUS) ok = ok && ((double)rad[q] <= max_r);
+      if (flags & RCV_MASK_RADIUS_NONZERO) ok = ok && (rad[q] != 0.f);
+      if (flags & RCV_MASK_RADIUS_POSITIVE) ok = ok && (rad[q] > 0.f);
+      if (flags & RCV_MASK_SEM_GT) ok = ok && (sv > a.fp.sem_threshold);
+      if (flags & RCV_MASK_SEM_GE) ok = ok && (sv >= a.fp.sem_threshold);
+      mask |= (unsigned)ok << q;
+    }
+  }
+  return mask;
+}
+
+// WRITE=false: count survivors into cnt[item].  WRITE=true: emit them in row-major pixel order.
+template <bool WRITE>
+__global__ void __launch_bounds__(kCompactThreads) k_frame_compact(FrameArgs a, int* __restrict__ cnt, const ItemMeta* __restrict__ meta,
+                                                                  Pool pool) {
+  const int item = blockIdx.x;
+  const int frame = item / a.n_kpts, kp = item % a.n_kpts;
+  const int W = a.fp.width, npx = a.fp.height * a.fp.width;
+  const long long frame_px0 = (long long)frame * npx, item_px0 = (long long)item * npx;
+  const double max_r = a.max_radii ? a.max_radii[(long long)frame * a.fp.max_radii_stride + kp] : 0.0;
+  const bool vec_ok = a.vec_ok != 0;
+  __shared__ int s_warp[kCompactThreads / 32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long out0 = 0;
+  int n_item = 0;
+  double fx = 1, fy = 1, cx = 0, cy = 0;
+  if (WRITE) {
+    const ItemMeta m = meta[item];
+    out0 = m.off;
+    n_item = m.n;
+    if (n_item == 0) return;  // empty or overflowed item: nothing to write
+    const double* Kp = a.K + (long long)frame * a.fp.k_stride;
+    fx = Kp[0]; cx = Kp[2]; fy = Kp[4]; cy = Kp[5];
+  }
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int it0 = 0; it0 < npx; it0 += kPxPerIter) {
+    const int px = it0 + threadIdx.x * kPxPerThread;
+    double zraw[kPxPerThread];
+    float rad[kPxPerThread];
+    unsigned mask = 0;
+    if (px < npx) mask = pixel_group_mask(a, frame_px0, item_px0, px, npx, vec_ok, max_r, zraw, rad);
+    const int c = __popc(mask);
+    // block-wide exclusive scan of c (warp shuffle scan + warp totals)
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kCompactThreads / 32; ++w) { const int t = s_warp[w]; if (w < warp) wbase += t; total += t; }
+    const int base = s_base;
+    if (WRITE && c) {
+      long long o = out0 + base + wbase + incl - c;
+#pragma unroll
+      for (int q = 0; q < kPxPerThread; ++q) {
+        if (!(mask >> q & 1)) continue;
+        const int p = px + q, u = p % W, v = p / W;
+        // rgbd_to_point_cloud (AccumulatorSpace.py:77-85) then xyz_mm/1000 (:619) then *1000/acc_unit (:376)
+        const double z = __ddiv_rn(zraw[q], a.fp.depth_div);
+        double x = __ddiv_rn(__dmul_rn(__dsub_rn((double)u, cx), z), fx);
+        double y = __ddiv_rn(__dmul_rn(__dsub_rn((double)v, cy), z), fy);
+        pool.X[o] = __ddiv_rn(__dmul_rn(__ddiv_rn(x, a.fp.xyz_div), 1000.0), a.acc_unit);
+        pool.Y[o] = __ddiv_rn(__dmul_rn(__ddiv_rn(y, a.fp.xyz_div), 1000.0), a.acc_unit);
+        pool.Z[o] = __ddiv_rn(__dmul_rn(__ddiv_rn(z, a.fp.xyz_div), 1000.0), a.acc_unit);
+        double rd; int ri;
+        radius_to_voxel_f32(rad[q], (float)a.radius_scale, (float)a.acc_unit, rd, ri);
+        pool.Rd[o] = rd;
+        pool.Ri[o] = ri;
+        ++o;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = base + total;
+    __syncthreads();
+  }
+  if (!WRITE && threadIdx.x == 0) cnt[item] = s_base;
+}
+
+// Exclusive scan of per-item counts into pool offsets (one block; n_items <= a few 10^4).
+__global__ void k_scan_items(const int* __restrict__ cnt, int n_items, long long cap, ItemMeta* meta) {
+  __shared__ long long s_part[1024];
+  const int per = (n_items + blockDim.x - 1) / blockDim.x;
+  const int b0 = threadIdx.x * per, b1 = min(n_items, b0 + per);
+  long long s = 0;
+  for (int b = b0; b < b1; ++b) s += cnt[b];
+  s_part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    for (int t = 0; t < (int)blockDim.x; ++t) { long long v = s_part[t]; s_part[t] = run; run += v; }
+  }
+  __syncthreads();
+  long long o = s_part[threadIdx.x];
+  for (int b = b0; b < b1; ++b) {
+    ItemMeta m;
+    memset(&m, 0, sizeof(m));
+    m.off = o;
+    m.n = cnt[b];
+    if (o + m.n > cap) { m.status = RCV_ST_POINT_OVERFLOW; m.n = 0; m.off = 0; }
+    o += cnt[b];
+    meta[b] = m;
+  }
+}
+
+// single-image compaction for rcv_backproject (AoS float64 output, like the reference's (N,3) array)
+__global__ void __launch_bounds__(1024) k_backproject(const double* __restrict__ K, const void* __restrict__ depth, int dtype, int H, int W,
+                                                     double* __restrict__ xyz, long long cap, int* __restrict__ n_out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, npx = H * W;
+  const double fx = K[0], cx = K[2], fy = K[4], cy = K[5];
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int p0 = 0; p0 < npx; p0 += 1024) {
+    const int p = p0 + threadIdx.x;
+    double z = 0.0;
+    if (p < npx) z = load_depth(depth, dtype, p);
+    const bool ok = z != 0.0;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int w = 0; w < 32; ++w) { const int t = s_warp[w]; if (w < warp) wbase += t; total += t; }
+    const int base = s_base;
+    if (ok) {
+      const long long o = base + wbase + __popc(bal & ((1u << lane) - 1));
+      if (o < cap) {
+        const int u = p % W, v = p / W;
+        xyz[3 * o + 0] = __ddiv_rn(__dmul_rn(__dsub_rn((double)u, cx), z), fx);
+        xyz[3 * o + 1] = __ddiv_rn(__dmul_rn(__dsub_rn((double)v, cy), z), fy);
+        xyz[3 * o + 2] = z;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = base + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_out = s_base;
+}
+
+// ------------------------------------------------------------------------------------------------
+// P -- Accumulator_3D prelude (AccumulatorSpace.py:373-401), one CTA per item.
+// The per-axis means reproduce numpy's pairwise summation (np.mean -> add.reduce, blocks of <=128
+// with 8 running partial sums, recursive halving rounded down to a multiple of 8), so the recentred
+// coordinates are bit-identical to the reference's.
+// ------------------------------------------------------------------------------------------------
+struct PwLeaf { int start; short len; short adds; };
+
+__device__ double pw_leaf_sum(const double* __restrict__ a, int n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+  }
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i;
+  for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+  }
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+  return res;
+}
+
+struct PreludeArgs {
+  Pool pool; ItemMeta* meta; Unit* units; int* counters; int max_units; int max_grid; int policy; int tile_words;
+  PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
+};
+
+constexpr int kPreludeThreads = 256;
+
+__global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
+  const int item = blockIdx.x;
+  ItemMeta m = a.meta[item];
+  const int n = m.n;
+  __shared__ int s_nleaf;
+  __shared__ double s_mean[3];
+  __shared__ double s_red[3][kPreludeThreads / 32];
+  __shared__ int s_zb, s_ok, s_ubase;
+  if (n <= 0) {
+    if (threadIdx.x == 0) { if (!(m.status & RCV_ST_POINT_OVERFLOW)) m.status |= RCV_ST_EMPTY_MASK; a.meta[item] = m; }
+    return;
+  }
+  double* X = a.pool.X + m.off; double* Y = a.pool.Y + m.off; double* Z = a.pool.Z + m.off;
+  const double* Rd = a.pool.Rd + m.off;
+  // disjoint scratch window for this item's leaves: an item with n points has <= n/57 + 1 leaves
+  const long long lbase = m.off / 56 + 2LL * item;
+  PwLeaf* leaves = a.leaves + lbase;
+  double* lsum = a.leaf_sums + 3 * lbase;
+  if (threadIdx.x == 0) {
+    int st_start[40], st_len[40], st_rc[40], top = 0, nl = 0;
+    st_start[0] = 0; st_len[0] = n; st_rc[0] = 0; top = 1;
+    while (top) {
+      --top;
+      const int s = st_start[top], l = st_len[top], rc = st_rc[top];
+      if (l <= 128) { PwLeaf lf; lf.start = s; lf.len = (short)l; lf.adds = (short)rc; leaves[nl++] = lf; }
+      else {
+        int n2 = l / 2; n2 -= n2 % 8;
+        st_start[top] = s + n2; st_len[top] = l - n2; st_rc[top] = rc + 1; ++top;  // right child (popped second)
+        st_start[top] = s; st_len[top] = n2; st_rc[top] = 0; ++top;                // left child
+      }
+    }
+    s_nleaf = nl;
+  }
+  __syncthreads();
+  const int nleaf = s_nleaf;
+  for (int t = threadIdx.x; t < 3 * nleaf; t += blockDim.x) {
+    const int l = t / 3, c = t % 3;
+    const PwLeaf lf = leaves[l];
+    const double* src = (c == 0 ? X : c == 1 ? Y : Z) + lf.start;
+    lsum[3 * l + c] = pw_leaf_sum(src, lf.len);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int c = threadIdx.x;
+    double st[40]; int top = 0;
+    for (int l = 0; l < nleaf; ++l) {
+      st[top++] = lsum[3 * l + c];
+      for (int q = leaves[l].adds; q > 0; --q) { const double r = st[--top]; const double lft = st[--top]; st[top++] = __dadd_rn(lft, r); }
+    }
+    s_mean[c] = __ddiv_rn(st[0], (double)n);
+  }
+  __syncthreads();
+  const double mx = s_mean[0], my = s_mean[1], mz = s_mean[2];
+  // recentre; global min / max over all three axes; max radius
+  double vmin = INFINITY, vmax = -INFINITY, rmax = -INFINITY;
+  for (int q = threadIdx.x; q < n; q += blockDim.x) {
+    const double x = __dsub_rn(X[q], mx), y = __dsub_rn(Y[q], my), z = __dsub_rn(Z[q], mz);
+    X[q] = x; Y[q] = y; Z[q] = z;
+    vmin = fmin(vmin, fmin(x, fmin(y, z)));
+    vmax = fmax(vmax, fmax(x, fmax(y, z)));
+    rmax = fmax(rmax, Rd[q]);
+  }
+  vmin = warp_min_f64(vmin); vmax = warp_max_f64(vmax); rmax = warp_max_f64(rmax);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_red[0][warp] = vmin; s_red[1][warp] = vmax; s_red[2][warp] = rmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kPreludeThreads / 32; ++w) { vmin = fmin(vmin, s_red[0][w]); vmax = fmax(vmax, s_red[1][w]); rmax = fmax(rmax, s_red[2][w]); }
+    // zero_boundary = int(xyz_mm_min - radius_max) + 1   (int() truncates toward zero)
+    const double zbd = __dsub_rn(vmin, rmax);
+    int zb = (int)zbd + 1;  // values beyond int range are rejected below through D
+    double pmax = vmax;
+    if (zb < 0) pmax = __dsub_rn(vmax, (double)zb);  // max(x - zb) == max(x) - zb: the subtraction is monotone
+    const double Dd = (a.policy == RCV_POLICY_YCBGEN) ? trunc(pmax) + 1.0 : trunc(pmax) + trunc(rmax);
+    int status = m.status, D = 0, ok = 0;
+    if (!(fabs(zbd) < 1e9) || !(fabs(Dd) < 1e9)) status |= RCV_ST_BAD_GRID;
+    else {
+      D = (int)Dd;
+      if (D <= 0) status |= RCV_ST_BAD_GRID;
+      else if (D > a.max_grid) status |= RCV_ST_D_EXCEEDS_CAP;
+      else ok = 1;
+    }
+    m.D = D; m.zb = zb; m.rmax = rmax; m.mean[0] = mx; m.mean[1] = my; m.mean[2] = mz; m.status = status;
+    int nunits = 0;
+    if (ok) {
+      const int Dp = D | 1;  // odd row stride: consecutive rows start in different banks
+      m.Dp = Dp;
+      const long long slice = (long long)D * Dp;
+      if (slice <= a.tile_words) {
+        const int ni_max = (int)(a.tile_words / slice);
+        const int ns = (D + ni_max - 1) / ni_max;
+        m.ni = (D + ns - 1) / ns; m.nj = D;
+        nunits = (D + m.ni - 1) / m.ni;
+      } else {
+        const int nj_max = a.tile_words / Dp;
+        const int nt = (D + nj_max - 1) / nj_max;
+        m.ni = 1; m.nj = (D + nt - 1) / nt;
+        nunits = D * ((D + m.nj - 1) / m.nj);
+      }
+      const int ub = atomicAdd(&a.counters[0], nunits);
+      if (ub + nunits > a.max_units) { m.status |= RCV_ST_UNIT_OVERFLOW; ok = 0; atomicSub(&a.counters[0], nunits); }
+      s_ubase = ub;
+    }
+    s_zb = zb; s_ok = ok;
+    a.meta[item] = m;
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  const int zb = s_zb;
+  if (zb < 0) {
+    const double zbd = (double)zb;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) { X[q] = __dsub_rn(X[q], zbd); Y[q] = __dsub_rn(Y[q], zbd); Z[q] = __dsub_rn(Z[q], zbd); }
+  }
+  // tile work list
+  m = a.meta[item];
+  const int tj = (m.D + m.nj - 1) / m.nj, ti = (m.D + m.ni - 1) / m.ni;
+  for (int t = threadIdx.x; t < ti * tj; t += blockDim.x) {
+    Unit u;
+    u.item = item;
+    u.i0 = (t / tj) * m.ni; u.ni = min(m.ni, m.D - u.i0);
+    u.j0 = (t % tj) * m.nj; u.nj = min(m.nj, m.D - u.j0);
+    a.units[s_ubase + t] = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 -- the vote kernel.  Persistent: one CTA per SM pulls (item, tile) units from a global queue.
+// ------------------------------------------------------------------------------------------------
+struct VoteArgs {
+  Pool pool; const ItemMeta* meta; const Unit* units; int* counters;
+  unsigned long long* best; unsigned long long* votes;
+  int32_t* volume; long long volume_cap;
+};
+
+struct SmemEmit {
+  int* tile; int sink;
+  __device__ __forceinline__ void operator()(int off, bool vote) const { atomicAdd(&tile[vote ? off : sink], 1); }
+};
+
+struct PointData { double x, y, z; int R; };
+
+__global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
+  extern __shared__ __align__(16) int smem[];
+  int* tile = smem;
+  __shared__ int s_unit, s_next;
+  __shared__ unsigned long long s_key[kVoteWarps], s_sum[kVoteWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SmemEmit emit{tile, kTileWords + warp * 32 + lane};
+  const int n_units = a.counters[0];
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) { s_unit = atomicAdd(&a.counters[1], 1); s_next = 0; }
+    __syncthreads();
+    const int ui = s_unit;
+    if (ui >= n_units) break;
+    const Unit u = a.units[ui];
+    const ItemMeta& m = a.meta[u.item];
+    const int D = m.D, Dp = m.Dp, n = m.n;
+    const long long off = m.off;
+    const Tile t{u.i0, u.ni, u.j0, u.nj, D, Dp};
+    const int words = u.ni * u.nj * Dp;
+    {
+      int4* t4 = reinterpret_cast<int4*>(tile);
+      const int n4 = (words + 3) >> 2;
+      for (int w = threadIdx.x; w < n4; w += kVoteThreads) t4[w] = make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    // ---- scatter: each warp takes points from the CTA's queue, next point prefetched ----
+    int cur = 0;
+    if (lane == 0) cur = atomicAdd(&s_next, 1);
+    cur = __shfl_sync(0xffffffffu, cur, 0);
+    PointData pd{0, 0, 0, 0};
+    if (cur < n) { pd.x = a.pool.X[off + cur]; pd.y = a.pool.Y[off + cur]; pd.z = a.pool.Z[off + cur]; pd.R = a.pool.Ri[off + cur]; }
+    while (cur < n) {
+      int nxt = 0;
+      if (lane == 0) nxt = atomicAdd(&s_next, 1);
+      nxt = __shfl_sync(0xffffffffu, nxt, 0);
+      PointData nd{0, 0, 0, 0};
+      if (nxt < n) { nd.x = a.pool.X[off + nxt]; nd.y = a.pool.Y[off + nxt]; nd.z = a.pool.Z[off + nxt]; nd.R = a.pool.Ri[off + nxt]; }
+      PointCtx c;
+      point_setup(c, pd.x, pd.y, pd.z, pd.R);
+      int ia, ib;
+      slice_range(c, t, ia, ib);
+      if (ia <= ib) {
+        const int istar = c.ipx < ia ? ia : (c.ipx > ib ? ib : c.ipx);
+        SliceCtx s0;
+        slice_setup(c, istar, s0);
+        bool any_dense = false;
+        if (s0.a > 36.0f) {
+          const int H = ring_half_width(s0.a);
+          const int ntask = 2 * (2 * H + 1);
+          for (int base = 0; base < ntask; base += 32) {
+            LaneTask L;
+            lane_setup(c, t, H, base + lane, L);
+            for (int i = ia; i <= ib; ++i) {
+              SliceCtx s;
+              slice_setup(c, i, s);
+              if (s.kind == SLICE_RING) ring_lane(c, s, L, i, (i - t.i0) * t.nj * Dp, emit);
+              else if (s.kind == SLICE_DENSE) any_dense = true;
+            }
+          }
+        } else any_dense = true;
+        if (any_dense) {
+          for (int i = ia; i <= ib; ++i) {
+            SliceCtx s;
+            slice_setup(c, i, s);
+            if (s.kind != SLICE_DENSE) continue;
+            const int side = 2 * s.m + 1, cells = side * side;
+            for (int cell = lane; cell < ((cells + 31) & ~31); cell += 32) dense_cell(c, s, t, i, (i - t.i0) * t.nj * Dp, cell, emit);
+          }
+        }
+      }
+      cur = nxt; pd = nd;
+    }
+    __syncthreads();
+    // ---- peak of the tile (K3 fused) + vote tally + optional volume dump ----
+    unsigned long long key = 0, sum = 0;
+    const int rows = u.ni * u.nj;
+    for (int r = warp; r < rows; r += kVoteWarps) {
+      const int gi = u.i0 + r / u.nj, gj = u.j0 + r % u.nj;
+      const unsigned lin0 = ((unsigned)gi * (unsigned)D + (unsigned)gj) * (unsigned)D;
+      const int* row = tile + r * Dp;
+      for (int k = lane; k < D; k += 32) {
+        const int v = row[k];
+        const unsigned long long kk = pack_peak(v, lin0 + k);
+        key = kk > key ? kk : key;
+        sum += (unsigned)v;
+        if (a.volume && (long long)D * D * D <= a.volume_cap) a.volume[(long long)lin0 + k] = v;
+      }
+    }
+    key = warp_max_u64(key); sum = warp_sum_u64(sum);
+    if (lane == 0) { s_key[warp] = key; s_sum[warp] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kVoteWarps; ++w) { key = s_key[w] > key ? s_key[w] : key; sum += s_sum[w]; }
+      atomicMax(&a.best[u.item], key);
+      if (sum) atomicAdd(&a.votes[u.item], sum);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// F -- peak -> millimetres (AccumulatorSpace.py:409-415); scatter of per-item outputs
+// ------------------------------------------------------------------------------------------------
+struct FinalArgs {
+  const ItemMeta* meta; const unsigned long long* best; const unsigned long long* votes; int n_items;
+  double acc_unit; int policy; int want_volume; long long volume_cap;
+  double* centre_mm; int* peak; long long* votes_out; int* n_points; int* grid; int* zb; int* status;
+};
+
+__global__ void k_finalize(FinalArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.n_items) return;
+  const ItemMeta m = a.meta[b];
+  int st = m.status;
+  double c[3] = {0.0, 0.0, 0.0};
+  int pk = 0;
+  long long nv = 0;
+  if (st == RCV_ST_OK) {
+    const unsigned long long key = a.best[b];
+    pk = (int)(key >> 32);
+    const unsigned lin = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+    const unsigned D = (unsigned)m.D;
+    const int idx[3] = {(int)(lin / (D * D)), (int)((lin / D) % D), (int)(lin % D)};
+    for (int q = 0; q < 3; ++q) {
+      double v = (double)idx[q];
+      if (m.zb < 0) v = __dadd_rn(v, (double)m.zb);
+      if (a.policy == RCV_POLICY_YCBGEN) c[q] = __dadd_rn(__dmul_rn(__dadd_rn(v, m.mean[q]), a.acc_unit), 0.5);
+      else c[q] = __dmul_rn(__dadd_rn(__dadd_rn(v, m.mean[q]), 0.5), a.acc_unit);
+    }
+    nv = (long long)a.votes[b];
+    if (a.want_volume && (long long)m.D * m.D * m.D > a.volume_cap) st |= kStVolumeSkipped;
+  }
+  a.centre_mm[3 * b] = c[0]; a.centre_mm[3 * b + 1] = c[1]; a.centre_mm[3 * b + 2] = c[2];
+  if (a.peak) a.peak[b] = pk;
+  if (a.votes_out) a.votes_out[b] = nv;
+  if (a.n_points) a.n_points[b] = m.n;
+  if (a.grid) a.grid[b] = m.D;
+  if (a.zb) a.zb[b] = m.zb;
+  if (a.status) a.status[b] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 -- standalone peak search over an HBM volume (AccumulatorSpace.py:406)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_argmax_volume(const int32_t* __restrict__ vol, long long total, unsigned long long* best) {
+  unsigned long long key = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; q < total; q += stride) {
+    if (q + 3 < total && ((reinterpret_cast<uintptr_t>(vol + q) & 15) == 0)) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(vol + q));
+      unsigned long long k0 = pack_peak(v.x, (unsigned)q), k1 = pack_peak(v.y, (unsigned)q + 1), k2 = pack_peak(v.z, (unsigned)q + 2),
+                         k3 = pack_peak(v.w, (unsigned)q + 3);
+      k0 = k1 > k0 ? k1 : k0; k2 = k3 > k2 ? k3 : k2; k0 = k2 > k0 ? k2 : k0;
+      key = k0 > key ? k0 : key;
+    } else {
+      for (int e = 0; e < 4 && q + e < total; ++e) { const unsigned long long kk = pack_peak(vol[q + e], (unsigned)(q + e)); key = kk > key ? kk : key; }
+    }
+  }
+  key = warp_max_u64(key);
+  __shared__ unsigned long long s_k[8];
+  if ((threadIdx.x & 31) == 0) s_k[threadIdx.x >> 5] = key;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) key = s_k[w] > key ? s_k[w] : key;
+    atomicMax(best, key);
+  }
+}
+
+__global__ void k_argmax_unpack(const unsigned long long* best, int D, int* idx_out, int* max_out) {
+  const unsigned long long key = *best;
+  const unsigned lin = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+  idx_out[0] = (int)(lin / ((unsigned)D * D)); idx_out[1] = (int)((lin / D) % D); idx_out[2] = (int)(lin % D);
+  *max_out = (int)(key >> 32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 -- batched Horn absolute orientation (util/horn.py:75-181), one thread per frame.
+// Quaternion method: eigenvector of the largest eigenvalue of the symmetric 4x4 N built from the
+// cross-covariance sums; cyclic Jacobi with the reference's sweep order, thresholds and 50-sweep cap.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void jac_rot(double (*a)[4], int i, int j, int k, int l, double s, double tau) {
+  const double g = a[i][j], h = a[k][l];
+  a[i][j] = g - s * (h + g * tau);
+  a[k][l] = h + s * (g - h * tau);
+}
+
+__global__ void k_horn(const double* __restrict__ model, long long model_stride, const double* __restrict__ est, int n, int n_frames,
+                       double* __restrict__ RT) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  const double* P1 = model + (long long)f * model_stride;
+  const double* P2 = est + (long long)f * 3 * n;
+  double C1[3] = {0, 0, 0}, C2[3] = {0, 0, 0};
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < 3; ++j) { C1[j] += P1[3 * i + j]; C2[j] += P2[3 * i + j]; }
+  for (int j = 0; j < 3; ++j) { C1[j] /= n; C2[j] /= n; }
+  double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int i = 0; i < n; ++i) {
+    double a[3], b[3];
+    for (int j = 0; j < 3; ++j) { a[j] = P1[3 * i + j] - C1[j]; b[j] = P2[3 * i + j] - C2[j]; }
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) S[r][c] += a[r] * b[c];
+  }
+  double A[4][4], V[4][4], d[4], bq[4], zq[4];
+  A[0][0] = S[0][0] + S[1][1] + S[2][2]; A[0][1] = S[1][2] - S[2][1]; A[0][2] = S[2][0] - S[0][2]; A[0][3] = S[0][1] - S[1][0];
+  A[1][0] = A[0][1]; A[1][1] = S[0][0] - S[1][1] - S[2][2]; A[1][2] = S[0][1] + S[1][0]; A[1][3] = S[2][0] + S[0][2];
+  A[2][0] = A[0][2]; A[2][1] = A[1][2]; A[2][2] = -S[0][0] + S[1][1] - S[2][2]; A[2][3] = S[1][2] + S[2][1];
+  A[3][0] = A[0][3]; A[3][1] = A[1][3]; A[3][2] = A[2][3]; A[3][3] = -S[0][0] - S[1][1] + S[2][2];
+  for (int p = 0; p < 4; ++p) {
+    for (int q = 0; q < 4; ++q) V[p][q] = 0.0;
+    V[p][p] = 1.0;
+    bq[p] = d[p] = A[p][p];
+    zq[p] = 0.0;
+  }
+  for (int sweep = 1; sweep <= 50; ++sweep) {
+    double sm = 0.0;
+    for (int p = 0; p < 3; ++p)
+      for (int q = 0; q < 4; ++q) sm += fabs(A[p][q]);  // util/horn.py:28-30 sums whole rows, diagonal included
+    if (sm == 0.0) break;
+    const double tresh = sweep < 4 ? 0.2 * sm / 16.0 : 0.0;
+    for (int p = 0; p < 3; ++p)
+      for (int q = p + 1; q < 4; ++q) {
+        const double g = 100.0 * fabs(A[p][q]);
+        if (sweep > 4 && fabs(d[p]) + g == fabs(d[p]) && fabs(d[q]) + g == fabs(d[q])) A[p][q] = 0.0;
+        else if (fabs(A[p][q]) > tresh) {
+          double h = d[q] - d[p], t;
+          if (fabs(h) + g == fabs(h)) t = A[p][q] / h;
+          else {
+            const double theta = 0.5 * h / A[p][q];
+            t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+            if (theta < 0.0) t = -t;
+          }
+          const double c = 1.0 / sqrt(1 + t * t), s = t * c, tau = s / (1.0 + c);
+          h = t * A[p][q];
+          zq[p] -= h; zq[q] += h; d[p] -= h; d[q] += h;
+          A[p][q] = 0.0;
+          for (int j = 0; j < p; ++j) jac_rot(A, j, p, j, q, s, tau);
+          for (int j = p + 1; j < q; ++j) jac_rot(A, p, j, j, q, s, tau);
+          for (int j = q + 1; j < 4; ++j) jac_rot(A, p, j, q, j, s, tau);
+          for (int j = 0; j < 4; ++j) jac_rot(V, j, p, j, q, s, tau);
+        }
+      }
+    for (int p = 0; p < 4; ++p) { bq[p] += zq[p]; d[p] = bq[p]; zq[p] = 0.0; }
+  }
+  int me = 0;
+  for (int p = 1; p < 4; ++p)
+    if (d[p] > d[me]) me = p;
+  const double q0 = V[0][me], q1 = V[1][me], q2 = V[2][me], q3 = V[3][me];
+  double R[3][3];
+  R[0][0] = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3; R[0][1] = 2 * (q1 * q2 - q0 * q3); R[0][2] = 2 * (q1 * q3 + q0 * q2);
+  R[1][0] = 2 * (q1 * q2 + q0 * q3); R[1][1] = q0 * q0 + q2 * q2 - q1 * q1 - q3 * q3; R[1][2] = 2 * (q2 * q3 - q0 * q1);
+  R[2][0] = 2 * (q1 * q3 - q0 * q2); R[2][1] = 2 * (q2 * q3 + q0 * q1); R[2][2] = q0 * q0 + q3 * q3 - q1 * q1 - q2 * q2;
+  double* o = RT + (long long)f * 16;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) o[4 * r + c] = R[r][c];
+    o[4 * r + 3] = C2[r] - (R[r][0] * C1[0] + R[r][1] * C1[1] + R[r][2] * C1[2]);
+    o[12 + r] = 0.0;
+  }
+  o[15] = 1.0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// Context and C ABI
+// ================================================================================================
+struct rcv_ctx {
+  int device, sms;
+  rcv_config cfg;
+  Pool pool;
+  ItemMeta* meta;
+  Unit* units;
+  int* counters;  // [0] units queued, [1] queue cursor
+  int* cnt;
+  unsigned long long *best, *votes;
+  PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
+  cudaEvent_t ev0, ev1; bool timed;
+  long long launches;
+  // staging for the _host entry points
+  cudaStream_t s_in, s_run; cudaEvent_t ev_in[2], ev_done[2], ev_user;
+  void* st_depth[2]; float* st_radius[2]; float* st_sem[2]; double* st_K; double* st_maxr;
+  double* st_centre; int* st_peak; long long* st_votes; int* st_np; int* st_grid; int* st_status;
+  long long st_frames, st_kpts, st_px, st_depth_bytes; int st_has_sem; long long st_total_items;
+  double* st_horn_in; long long st_horn_cap;
+  char err[512];
+};
+
+static char g_create_err[512] = "";
+
+#define CK(ctx, call)                                                                                         \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) {                                                                                  \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return RCV_E_CUDA;                                                                                      \
+    }                                                                                                         \
+  } while (0)
+
+#define FAIL(ctx, code, ...)                                  \
+  do {                                                        \
+    snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);    \
+    return (code);                                            \
+  } while (0)
+
+RCV_EXPORT int rcv_abi_version(void) { return RCV_ABI_VERSION; }
+
+RCV_EXPORT const char* rcv_last_error(const rcv_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+RCV_EXPORT long long rcv_launch_count(const rcv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri);
+  cudaFree(c->meta); cudaFree(c->units); cudaFree(c->counters); cudaFree(c->cnt); cudaFree(c->best); cudaFree(c->votes);
+  cudaFree(c->leaves); cudaFree(c->leaf_sums);
+  for (int s = 0; s < 2; ++s) { cudaFree(c->st_depth[s]); cudaFree(c->st_radius[s]); cudaFree(c->st_sem[s]); }
+  cudaFree(c->st_K); cudaFree(c->st_maxr); cudaFree(c->st_centre); cudaFree(c->st_peak); cudaFree(c->st_votes);
+  cudaFree(c->st_np); cudaFree(c->st_grid); cudaFree(c->st_status); cudaFree(c->st_horn_in);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_user) cudaEventDestroy(c->ev_user);
+  for (int s = 0; s < 2; ++s) { if (c->ev_in[s]) cudaEventDestroy(c->ev_in[s]); if (c->ev_done[s]) cudaEventDestroy(c->ev_done[s]); }
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_run) cudaStreamDestroy(c->s_run);
+  free(c);
+}
+
+RCV_EXPORT int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out) {
+  if (!cfg || !out || cfg->abi_version != RCV_ABI_VERSION || cfg->max_items <= 0 || cfg->max_points_total <= 0 || cfg->max_grid <= 0 ||
+      cfg->max_grid > 1024) {
+    snprintf(g_create_err, sizeof(g_create_err), "rcv_create: invalid configuration");
+    return RCV_E_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    snprintf(g_create_err, sizeof(g_create_err), "rcv_create: no CUDA device %d (found %d); there is no CPU fallback", device, ndev);
+    return RCV_E_NOGPU;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    snprintf(g_create_err, sizeof(g_create_err), "rcv_create: device %d is sm_%d%d; librcvvote is built for sm_100a only", device, prop.major,
+             prop.minor);
+    return RCV_E_NOGPU;
+  }
+  rcv_ctx* c = (rcv_ctx*)calloc(1, sizeof(rcv_ctx));
+  if (!c) return RCV_E_INVALID;
+  c->device = device; c->cfg = *cfg; c->sms = prop.multiProcessorCount;
+  if (c->cfg.max_units <= 0) {
+    // worst case per item: D slices x ceil(D / rows-per-tile) tiles
+    const long long per_item = (long long)cfg->max_grid * ((cfg->max_grid * (long long)(cfg->max_grid | 1)) / kTileWords + 1);
+    long long mu = per_item * cfg->max_items;
+    if (mu > (1LL << 26)) mu = 1LL << 26;
+    c->cfg.max_units = (int)mu;
+  }
+  *out = c;
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_create_err, sizeof(g_create_err), "%s failed: %s", #call, cudaGetErrorString(e_)); rcv_destroy(c); *out = NULL; return RCV_E_CUDA; } } while (0)
+  CKC(cudaSetDevice(device));
+  const long long cap = cfg->max_points_total;
+  c->pool.cap = cap;
+  CKC(cudaMalloc(&c->pool.X, cap * 8)); CKC(cudaMalloc(&c->pool.Y, cap * 8)); CKC(cudaMalloc(&c->pool.Z, cap * 8));
+  CKC(cudaMalloc(&c->pool.Rd, cap * 8)); CKC(cudaMalloc(&c->pool.Ri, cap * 4));
+  CKC(cudaMalloc(&c->meta, sizeof(ItemMeta) * (size_t)cfg->max_items));
+  CKC(cudaMalloc(&c->units, sizeof(Unit) * (size_t)c->cfg.max_units));
+  CKC(cudaMalloc(&c->counters, 64));
+  CKC(cudaMalloc(&c->cnt, 4 * (size_t)cfg->max_items));
+  CKC(cudaMalloc(&c->best, 8 * (size_t)cfg->max_items)); CKC(cudaMalloc(&c->votes, 8 * (size_t)cfg->max_items));
+  c->leaf_cap = cap / 56 + 2LL * cfg->max_items + 8;
+  CKC(cudaMalloc(&c->leaves, sizeof(PwLeaf) * (size_t)c->leaf_cap)); CKC(cudaMalloc(&c->leaf_sums, 24 * (size_t)c->leaf_cap));
+  CKC(cudaEventCreate(&c->ev0)); CKC(cudaEventCreate(&c->ev1));
+  CKC(cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (kTileWords + kDummyWords) * 4));
+#undef CKC
+  return RCV_OK;
+}
+
+// prelude -> vote -> finalize over items already in the pool (meta[].off/n/status set)
+static int run_items(rcv_ctx* c, int n_items, const rcv_vote_params* vp, double* centre_mm, int* peak, long long* votes, int* n_points,
+                     int* grid, int* zb, int* status, int32_t* volume, long long volume_cap, cudaStream_t st) {
+  CK(c, cudaMemsetAsync(c->counters, 0, 64, st));
+  CK(c, cudaMemsetAsync(c->best, 0, 8 * (size_t)n_items, st));
+  CK(c, cudaMemsetAsync(c->votes, 0, 8 * (size_t)n_items, st));
+  PreludeArgs pa{c->pool, c->meta, c->units, c->counters, c->cfg.max_units, c->cfg.max_grid, vp->grid_policy, kTileWords,
+                 c->leaves, c->leaf_sums, c->leaf_cap};
+  k_prelude<<<n_items, kPreludeThreads, 0, st>>>(pa);
+  VoteArgs va{c->pool, c->meta, c->units, c->counters, c->best, c->votes, volume, volume_cap};
+  CK(c, cudaEventRecord(c->ev0, st));
+  k_vote<<<c->sms, kVoteThreads, (kTileWords + kDummyWords) * 4, st>>>(va);
+  CK(c, cudaEventRecord(c->ev1, st));
+  c->timed = true;
+  FinalArgs fa{c->meta, c->best, c->votes, n_items, vp->acc_unit, vp->grid_policy, volume != nullptr, volume_cap,
+               centre_mm, peak, votes, n_points, grid, zb, status};
+  k_finalize<<<(n_items + 127) / 128, 128, 0, st>>>(fa);
+  c->launches += 3;
+  CK(c, cudaGetLastError());
+  return RCV_OK;
+}
+
+static int check_vote_params(rcv_ctx* c, const rcv_vote_params* vp) {
+  if (!vp || !(vp->acc_unit > 0) || !(vp->radius_scale > 0)) FAIL(c, RCV_E_INVALID, "vote params: acc_unit and radius_scale must be positive");
+  if (vp->grid_policy != RCV_POLICY_LM && vp->grid_policy != RCV_POLICY_YCBGEN) FAIL(c, RCV_E_INVALID, "vote params: unknown grid policy %d", vp->grid_policy);
+  if (vp->radius_dtype != RCV_F32 && vp->radius_dtype != RCV_F64) FAIL(c, RCV_E_INVALID, "vote params: radius dtype must be RCV_F32 or RCV_F64");
+  return RCV_OK;
+}
+
+RCV_EXPORT int rcv_vote_points(rcv_ctx* c, const double* xyz, const void* radii, const long long* item_offsets, int n_items,
+                               const rcv_vote_params* vp, double* centre_mm, int* peak, long long* votes, int* grid, int* zero_boundary,
+                               int* status, int32_t* volume_out, long long volume_capacity, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!xyz || !radii || !item_offsets || !centre_mm || !status) FAIL(c, RCV_E_INVALID, "rcv_vote_points: null pointer");
+  if (n_items <= 0 || n_items > c->cfg.max_items) FAIL(c, RCV_E_CAPACITY, "rcv_vote_points: n_items %d outside (0, %d]", n_items, c->cfg.max_items);
+  if (volume_out && n_items != 1) FAIL(c, RCV_E_INVALID, "rcv_vote_points: volume_out needs n_items == 1");
+  int rc = check_vote_params(c, vp);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(c, cudaSetDevice(c->device));
+  k_items_from_offsets<<<(n_items + 127) / 128, 128, 0, st>>>(item_offsets, n_items, c->pool.cap, c->meta);
+  k_points_to_voxel<<<c->sms * 4, 256, 0, st>>>(xyz, radii, vp->radius_dtype, item_offsets, n_items, vp->acc_unit, vp->radius_scale, c->pool);
+  c->launches += 2;
+  return run_items(c, n_items, vp, centre_mm, peak, votes, nullptr, grid, zero_boundary, status, volume_out, volume_capacity, st);
+}
+
+static int check_frame_params(rcv_ctx* c, int n_frames, int n_kpts, const rcv_frame_params* fp, const float* sem, const double* max_radii) {
+  if (!fp || fp->height <= 0 || fp->width <= 0) FAIL(c, RCV_E_INVALID, "frame params: bad image size");
+  if (fp->depth_dtype != RCV_U16 && fp->depth_dtype != RCV_F32 && fp->depth_dtype != RCV_F64) FAIL(c, RCV_E_INVALID, "frame params: bad depth dtype");
+  if (!(fp->depth_div > 0) || !(fp->xyz_div > 0)) FAIL(c, RCV_E_INVALID, "frame params: depth_div and xyz_div must be positive");
+  if ((fp->mask_flags & (RCV_MASK_SEM_GT | RCV_MASK_SEM_GE)) && !sem) FAIL(c, RCV_E_INVALID, "frame params: sem rule without a sem map");
+  if ((fp->mask_flags & RCV_MASK_MAX_RADIUS) && !max_radii) FAIL(c, RCV_E_INVALID, "frame params: max-radius rule without max_radii");
+  if (n_frames <= 0 || n_kpts <= 0 || (long long)n_frames * n_kpts > c->cfg.max_items)
+    FAIL(c, RCV_E_CAPACITY, "n_frames*n_kpts = %lld exceeds max_items %d", (long long)n_frames * n_kpts, c->cfg.max_items);
+  return RCV_OK;
+}
+
+RCV_EXPORT int rcv_vote_frames(rcv_ctx* c, int n_frames, int n_kpts, const void* depth, const float* radius, const float* sem, const double* K,
+                               const double* max_radii, const rcv_frame_params* fp, const rcv_vote_params* vp, double* centre_mm, int* peak,
+                               long long* votes, int* n_points, int* grid, int* status, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!depth || !radius || !K || !centre_mm || !status) FAIL(c, RCV_E_INVALID, "rcv_vote_frames: null pointer");
+  int rc = check_vote_params(c, vp);
+  if (rc) return rc;
+  rc = check_frame_params(c, n_frames, n_kpts, fp, sem, max_radii);
+  if (rc) return rc;
+  if (vp->radius_dtype != RCV_F32) FAIL(c, RCV_E_INVALID, "rcv_vote_frames: radius maps are float32");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(c, cudaSetDevice(c->device));
+  const int n_items = n_frames * n_kpts;
+  const long long npx = (long long)fp->height * fp->width;
+  const int vec_ok = (npx % 8 == 0) && (((uintptr_t)depth | (uintptr_t)radius | (uintptr_t)sem) % 16 == 0);
+  FrameArgs fa{depth, radius, sem, K, max_radii, *fp, vp->acc_unit, vp->radius_scale, n_kpts, vec_ok};
+  k_frame_compact<false><<<n_items, kCompactThreads, 0, st>>>(fa, c->cnt, c->meta, c->pool);
+  k_scan_items<<<1, 1024, 0, st>>>(c->cnt, n_items, c->pool.cap, c->meta);
+  k_frame_compact<true><<<n_items, kCompactThreads, 0, st>>>(fa, c->cnt, c->meta, c->pool);
+  c->launches += 3;
+  return run_items(c, n_items, vp, centre_mm, peak, votes, n_points, grid, nullptr, status, nullptr, 0, st);
+}
+
+static int ensure_staging(rcv_ctx* c, int frames, int kpts, long long px, long long depth_bytes, int has_sem, long long total_items) {
+  if (c->st_frames >= frames && c->st_kpts == kpts && c->st_px == px && c->st_depth_bytes == depth_bytes && c->st_has_sem >= has_sem &&
+      c->st_total_items >= total_items)
+    return RCV_OK;
+  for (int s = 0; s < 2; ++s) { cudaFree(c->st_depth[s]); cudaFree(c->st_radius[s]); cudaFree(c->st_sem[s]); c->st_depth[s] = nullptr; c->st_radius[s] = nullptr; c->st_sem[s] = nullptr; }
+  cudaFree(c->st_K); cudaFree(c->st_maxr); cudaFree(c->st_centre); cudaFree(c->st_peak); cudaFree(c->st_votes); cudaFree(c->st_np);
+  cudaFree(c->st_grid); cudaFree(c->st_status);
+  c->st_K = c->st_maxr = c->st_centre = nullptr; c->st_peak = c->st_np = c->st_grid = c->st_status = nullptr; c->st_votes = nullptr;
+  c->st_frames = 0;
+  for (int s = 0; s < 2; ++s) {
+    CK(c, cudaMalloc(&c->st_depth[s], (size_t)(frames * px * depth_bytes)));
+    CK(c, cudaMalloc(&c->st_radius[s], (size_t)(frames * kpts * px * 4)));
+    if (has_sem) CK(c, cudaMalloc(&c->st_sem[s], (size_t)(frames * kpts * px * 4)));
+  }
+  const long long nf = total_items / kpts + 1;
+  CK(c, cudaMalloc(&c->st_K, (size_t)(nf * 9 * 8))); CK(c, cudaMalloc(&c->st_maxr, (size_t)(total_items + kpts) * 8));
+  CK(c, cudaMalloc(&c->st_centre, (size_t)total_items * 24)); CK(c, cudaMalloc(&c->st_peak, (size_t)total_items * 4));
+  CK(c, cudaMalloc(&c->st_votes, (size_t)total_items * 8)); CK(c, cudaMalloc(&c->st_np, (size_t)total_items * 4));
+  CK(c, cudaMalloc(&c->st_grid, (size_t)total_items * 4)); CK(c, cudaMalloc(&c->st_status, (size_t)total_items * 4));
+  if (!c->s_in) {
+    CK(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)); CK(c, cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) { CK(c, cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming)); CK(c, cudaEventCreateWithFlags(&c->ev_done[s], cudaEventDisableTiming)); }
+    CK(c, cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
+  }
+  c->st_frames = frames; c->st_kpts = kpts; c->st_px = px; c->st_depth_bytes = depth_bytes; c->st_has_sem = has_sem; c->st_total_items = total_items;
+  return RCV_OK;
+}
+
+RCV_EXPORT int rcv_vote_frames_host(rcv_ctx* c, int n_frames, int n_kpts, const void* depth, const float* radius, const float* sem,
+                                    const double* K, const double* max_radii, const rcv_frame_params* fp, const rcv_vote_params* vp,
+                                    double* centre_mm, int* peak, long long* votes, int* n_points, int* grid, int* status,
+                                    int frames_per_chunk, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!depth || !radius || !K || !centre_mm || !status) FAIL(c, RCV_E_INVALID, "rcv_vote_frames_host: null pointer");
+  int rc = check_vote_params(c, vp);
+  if (rc) return rc;
+  if (frames_per_chunk <= 0) frames_per_chunk = 256;
+  if ((long long)frames_per_chunk * n_kpts > c->cfg.max_items) frames_per_chunk = c->cfg.max_items / (n_kpts > 0 ? n_kpts : 1);
+  if (frames_per_chunk > n_frames) frames_per_chunk = n_frames;
+  rc = check_frame_params(c, frames_per_chunk, n_kpts, fp, sem, max_radii);
+  if (rc) return rc;
+  CK(c, cudaSetDevice(c->device));
+  const long long px = (long long)fp->height * fp->width;
+  const long long dbytes = fp->depth_dtype == RCV_U16 ? 2 : fp->depth_dtype == RCV_F32 ? 4 : 8;
+  const long long total_items = (long long)n_frames * n_kpts;
+  rc = ensure_staging(c, frames_per_chunk, n_kpts, px, dbytes, sem != nullptr, total_items);
+  if (rc) return rc;
+  cudaStream_t user = (cudaStream_t)stream;
+  CK(c, cudaEventRecord(c->ev_user, user));
+  CK(c, cudaStreamWaitEvent(c->s_in, c->ev_user, 0));
+  CK(c, cudaStreamWaitEvent(c->s_run, c->ev_user, 0));
+  const long long nK = fp->k_stride ? n_frames : 1, nM = fp->max_radii_stride ? n_frames : 1;
+  CK(c, cudaMemcpyAsync(c->st_K, K, (size_t)(nK * 9 * 8), cudaMemcpyHostToDevice, c->s_in));
+  if (max_radii) CK(c, cudaMemcpyAsync(c->st_maxr, max_radii, (size_t)(nM * n_kpts * 8), cudaMemcpyHostToDevice, c->s_in));
+  int chunk = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += frames_per_chunk, ++chunk) {
+    const int nf = n_frames - f0 < frames_per_chunk ? n_frames - f0 : frames_per_chunk;
+    const int s = chunk & 1;
+    if (chunk >= 2) CK(c, cudaStreamWaitEvent(c->s_in, c->ev_done[s], 0));  // slot reuse: previous occupant finished voting
+    CK(c, cudaMemcpyAsync(c->st_depth[s], (const char*)depth + (size_t)(f0 * px * dbytes), (size_t)(nf * px * dbytes), cudaMemcpyHostToDevice, c->s_in));
+    CK(c, cudaMemcpyAsync(c->st_radius[s], radius + (size_t)f0 * n_kpts * px, (size_t)(nf * n_kpts * px * 4), cudaMemcpyHostToDevice, c->s_in));
+    if (sem) CK(c, cudaMemcpyAsync(c->st_sem[s], sem + (size_t)f0 * n_kpts * px, (size_t)(nf * n_kpts * px * 4), cudaMemcpyHostToDevice, c->s_in));
+    CK(c, cudaEventRecord(c->ev_in[s], c->s_in));
+    CK(c, cudaStreamWaitEvent(c->s_run, c->ev_in[s], 0));
+    const long long i0 = (long long)f0 * n_kpts;
+    rc = rcv_vote_frames(c, nf, n_kpts, c->st_depth[s], c->st_radius[s], sem ? c->st_sem[s] : nullptr,
+                         c->st_K + (fp->k_stride ? (long long)f0 * fp->k_stride : 0),
+                         max_radii ? c->st_maxr + (fp->max_radii_stride ? (long long)f0 * fp->max_radii_stride : 0) : nullptr, fp, vp,
+                         c->st_centre + 3 * i0, c->st_peak + i0, c->st_votes + i0, c->st_np + i0, c->st_grid + i0, c->st_status + i0, c->s_run);
+    if (rc) return rc;
+    CK(c, cudaEventRecord(c->ev_done[s], c->s_run));
+  }
+  CK(c, cudaMemcpyAsync(centre_mm, c->st_centre, (size_t)total_items * 24, cudaMemcpyDeviceToHost, c->s_run));
+  CK(c, cudaMemcpyAsync(status, c->st_status, (size_t)total_items * 4, cudaMemcpyDeviceToHost, c->s_run));
+  if (peak) CK(c, cudaMemcpyAsync(peak, c->st_peak, (size_t)total_items * 4, cudaMemcpyDeviceToHost, c->s_run));
+  if (votes) CK(c, cudaMemcpyAsync(votes, c->st_votes, (size_t)total_items * 8, cudaMemcpyDeviceToHost, c->s_run));
+  if (n_points) CK(c, cudaMemcpyAsync(n_points, c->st_np, (size_t)total_items * 4, cudaMemcpyDeviceToHost, c->s_run));
+  if (grid) CK(c, cudaMemcpyAsync(grid, c->st_grid, (size_t)total_items * 4, cudaMemcpyDeviceToHost, c->s_run));
+  CK(c, cudaStreamSynchronize(c->s_in));
+  CK(c, cudaStreamSynchronize(c->s_run));
+  return RCV_OK;
+}
+
+RCV_EXPORT int rcv_backproject(rcv_ctx* c, const double* K, const void* depth, int depth_dtype, int height, int width, double* xyz_out,
+                               long long xyz_capacity, int* n_out, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!K || !depth || !xyz_out || !n_out || height <= 0 || width <= 0) FAIL(c, RCV_E_INVALID, "rcv_backproject: bad argument");
+  if (depth_dtype != RCV_U16 && depth_dtype != RCV_F32 && depth_dtype != RCV_F64) FAIL(c, RCV_E_INVALID, "rcv_backproject: bad depth dtype");
+  CK(c, cudaSetDevice(c->device));
+  k_backproject<<<1, 1024, 0, (cudaStream_t)stream>>>(K, depth, depth_dtype, height, width, xyz_out, xyz_capacity, n_out);
+  c->launches += 1;
+  CK(c, cudaGetLastError());
+  return RCV_OK;
+}
+
+RCV_EXPORT int rcv_argmax_volume(rcv_ctx* c, const int32_t* volume, int grid, int* idx_out, int* max_out, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!volume || !idx_out || !max_out || grid <= 0 || grid > 1024) FAIL(c, RCV_E_INVALID, "rcv_argmax_volume: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaMemsetAsync(c->best, 0, 8, st));
+  const long long total = (long long)grid * grid * grid;
+  long long blocks = (total / 4 + 255) / 256;
+  if (blocks > c->sms * 8) blocks = c->sms * 8;
+  if (blocks < 1) blocks = 1;
+  k_argmax_volume<<<(int)blocks, 256, 0, st>>>(volume, total, c->best);
+  k_argmax_unpack<<<1, 1, 0, st>>>(c->best, grid, idx_out, max_out);
+  c->launches += 2;
+  CK(c, cudaGetLastError());
+  return RCV_OK;
+}
+
+RCV_EXPORT int rcv_horn_batch(rcv_ctx* c, const double* model, long long model_stride, const double* est, int n, int n_frames, double* RT,
+                              void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!model || !est || !RT || n <= 0 || n_frames <= 0) FAIL(c, RCV_E_INVALID, "rcv_horn_batch: bad argument");
+  if (model_stride != 0 && model_stride != 3LL * n) FAIL(c, RCV_E_INVALID, "rcv_horn_batch: model_stride must be 0 or 3*n");
+  CK(c, cudaSetDevice(c->device));
+  k_horn<<<(n_frames + 63) / 64, 64, 0, (cudaStream_t)stream>>>(model, model_stride, est, n, n_frames, RT);
+  c->launches += 1;
+  CK(c, cudaGetLastError());
+  return RCV_OK;
+}
+
+RCV_EXPORT int rcv_horn_batch_host(rcv_ctx* c, const double* model, long long model_stride, const double* est, int n, int n_frames,
+                                   double* RT, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!model || !est || !RT || n <= 0 || n_frames <= 0) FAIL(c, RCV_E_INVALID, "rcv_horn_batch_host: bad argument");
+  CK(c, cudaSetDevice(c->device));
+  const long long nm = model_stride ? (long long)n_frames * 3 * n : 3LL * n, ne = (long long)n_frames * 3 * n, nr = (long long)n_frames * 16;
+  if (c->st_horn_cap < nm + ne + nr) {
+    cudaFree(c->st_horn_in); c->st_horn_in = nullptr; c->st_horn_cap = 0;
+    CK(c, cudaMalloc(&c->st_horn_in, (size_t)(nm + ne + nr) * 8));
+    c->st_horn_cap = nm + ne + nr;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  double *dm = c->st_horn_in, *de = dm + nm, *dr = de + ne;
+  CK(c, cudaMemcpyAsync(dm, model, (size_t)nm * 8, cudaMemcpyHostToDevice, st));
+  CK(c, cudaMemcpyAsync(de, est, (size_t)ne * 8, cudaMemcpyHostToDevice, st));
+  int rc = rcv_horn_batch(c, dm, model_stride, de, n, n_frames, dr, stream);
+  if (rc) return rc;
+  CK(c, cudaMemcpyAsync(RT, dr, (size_t)nr * 8, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  return RCV_OK;
+}
+
+RCV_EXPORT float rcv_last_vote_kernel_ms(rcv_ctx* c) {
+  if (!c || !c->timed) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.f;
+  return ms;
+}

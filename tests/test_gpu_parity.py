@@ -1,0 +1,193 @@
+"""GPU parity tests: the CUDA path (through the C ABI, librcvvote.so) against the CPU oracle and the
+golden fixtures produced by the real reference.  Integer results (vote volumes, peaks, D, zero
+boundary, point counts) must be bit-exact; float64 centres are compared exactly where the operation
+order is reproduced (they are affine in exact integers and the numpy-pairwise mean) and Horn poses to
+1e-12 absolute on rotation entries (north-star tolerance: 1e-4 relative)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from rcvpose_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def acc():
+    from rcvpose_b200 import AccumulatorSpace as A
+    return A
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from rcvpose_b200 import api
+    return api.VoteContext(0, max_items=64, max_points_total=1 << 21, max_grid=400)
+
+
+def test_library_loaded_and_device_is_sm100():
+    from rcvpose_b200 import _lib
+    L = _lib.load()
+    assert L.rcv_abi_version() == 1
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+def test_rgbd_to_point_cloud_exact(acc, golden):
+    fr = synth.config1_frame()
+    dm = fr["depth"] * (fr["radius"][0] != 0)
+    got = acc.rgbd_to_point_cloud(fr["K"], dm)
+    assert got.dtype == np.float64 and np.array_equal(got, golden["c1_xyz_mm"])
+    got64 = acc.rgbd_to_point_cloud(fr["K"], dm.astype(np.float64))
+    assert np.array_equal(got64, golden["c1_xyz_mm"])
+
+
+def test_config1_volume_bit_exact_vs_reference(acc, golden):
+    fr = synth.config1_frame()
+    xyz, rl = synth.frame_to_points(fr["K"], fr["depth"], fr["radius"][0])
+    vol, out = acc.vote_volume(xyz, rl)
+    assert vol.shape == (86, 86, 86)
+    assert np.array_equal(vol, golden["c1_volume"])            # every voxel equals the reference's VoteMap_3D
+    assert int(out["votes"].item()) == int(golden["c1_votes"])
+    assert int(out["peak"].item()) == int(golden["c1_peak"])
+    assert int(out["zero_boundary"].item()) == int(golden["c1_zb"])
+    centre, info = acc.Accumulator_3D(xyz, rl, return_info=True)
+    assert centre.shape == (1, 3) and centre.dtype == np.float64
+    assert np.array_equal(centre[0], golden["c1_centre_mm"])   # same float64 bits as the reference
+    assert info["D"] == 86 and info["votes"] == int(golden["c1_votes"])
+
+
+@pytest.mark.parametrize("t", range(8))
+def test_random_clouds_vs_reference(acc, golden, t):
+    xyz, rl = golden["r%d_xyz" % t], golden["r%d_rl" % t]
+    vol, out = acc.vote_volume(xyz, rl)
+    assert np.array_equal(vol, golden["r%d_volume" % t])
+    assert int(out["grid"].item()) == int(golden["r%d_D" % t]) and int(out["zero_boundary"].item()) == int(golden["r%d_zb" % t])
+    c = acc.Accumulator_3D(xyz, rl)
+    assert np.array_equal(c[0], golden["r%d_centre" % t][0])
+
+
+def test_frames_api_vs_reference(ctx, golden):
+    frames = [synth.config3_frame(f) for f in range(4)]
+    depth = torch.from_numpy(np.stack([f["depth"] for f in frames]).view(np.int16)).cuda()
+    radius = torch.from_numpy(np.stack([f["radius"] for f in frames])).cuda()
+    K = torch.from_numpy(synth.linemod_K).cuda()
+    from rcvpose_b200 import api
+    out = ctx.vote_frames(depth, radius, K, mask_flags=api.RCV_MASK_RADIUS_NONZERO)
+    torch.cuda.synchronize()
+    for f in range(4):
+        for k in range(3):
+            g = lambda name: golden["c3_f%d_k%d_%s" % (f, k, name)]
+            assert int(out["status"][f, k]) == 0
+            assert int(out["n_points"][f, k]) == int(g("n"))
+            assert int(out["grid"][f, k]) == int(g("D"))
+            assert int(out["votes"][f, k]) == int(g("votes"))
+            assert int(out["peak"][f, k]) == int(g("peak"))
+            assert np.array_equal(out["centre_mm"][f, k].cpu().numpy(), g("centre_mm"))
+    # host-buffer entry point gives the same answers
+    h = ctx.vote_frames_host(np.stack([f["depth"] for f in frames]), np.stack([f["radius"] for f in frames]), synth.linemod_K,
+                             mask_flags=api.RCV_MASK_RADIUS_NONZERO, frames_per_chunk=3)
+    for key in ("centre_mm", "peak", "votes", "n_points", "grid", "status"):
+        assert np.array_equal(h[key], out[key].cpu().numpy()), key
+
+
+def test_mask_rules_and_max_radius(ctx):
+    from rcvpose_b200 import api
+    fr = synth.config3_frame(11)
+    rng = np.random.default_rng(3)
+    sem = (rng.random(fr["radius"].shape) * 1.2).astype(np.float32)
+    maxr = fr["max_radii_dm"] * 0.9
+    depth = torch.from_numpy(fr["depth"][None].view(np.int16)).cuda()
+    radius = torch.from_numpy(fr["radius"][None]).cuda()
+    out = ctx.vote_frames(depth, radius, torch.from_numpy(fr["K"]).cuda(), sem=torch.from_numpy(sem[None]).cuda(),
+                          max_radii=torch.from_numpy(maxr).cuda(), mask_flags=api.MASK_LM_CKPT, sem_threshold=0.8)
+    torch.cuda.synchronize()
+    for k in range(3):
+        # reference rule AccumulatorSpace.py:603-610 with "surviving pixel = mask && depth != 0" 
+        m = (sem[k] > 0.8) & (fr["radius"][k] <= maxr[k]) & (fr["depth"] != 0)
+        xyz_mm = oracle.rgbd_to_point_cloud(fr["K"], fr["depth"] * m)
+        rl = fr["radius"][k][m]
+        want, info = oracle.Accumulator_3D(xyz_mm / 1000, rl, method="scatter", return_info=True)
+        assert int(out["n_points"][0, k]) == int(m.sum())
+        assert int(out["grid"][0, k]) == info["D"] and int(out["votes"][0, k]) == info["votes"] and int(out["peak"][0, k]) == info["peak"]
+        assert np.array_equal(out["centre_mm"][0, k].cpu().numpy(), want[0])
+
+
+def test_float64_radii_and_ycbgen_policy(acc):
+    rng = np.random.default_rng(5)
+    xyz = rng.normal(0, 0.03, size=(300, 3)) + np.array([0.1, -0.2, 0.8])
+    kp = xyz.mean(0) + np.array([0.05, 0.02, -0.04])
+    rl = np.linalg.norm(xyz - kp, axis=1) * 10
+    for policy, scale, r in ((0, 100, rl), (1, 1000, rl / 10)):
+        want, info = oracle.Accumulator_3D(xyz, r, radius_scale=scale, policy=policy, return_info=True, return_volume=True)
+        vol, out = acc.vote_volume(xyz, r, radius_scale=scale, policy=policy)
+        assert np.array_equal(vol, info["volume"])
+        got = acc.Accumulator_3D(xyz, r, radius_scale=scale, policy=policy)
+        assert np.array_equal(got, want)
+
+
+def test_large_grid_uses_row_tiles(acc):
+    # acc_unit 1.25 mm -> D ~ 300: one slice no longer fits a CTA's shared memory (ni = 1, nj < D)
+    rng = np.random.default_rng(8)
+    xyz = rng.normal(0, 0.025, size=(400, 3)) + np.array([0.0, 0.1, 0.9])
+    kp = xyz.mean(0) + np.array([0.12, 0.05, -0.08])
+    rl = (np.linalg.norm(xyz - kp, axis=1) * 10).astype(np.float32)
+    want, info = oracle.Accumulator_3D(xyz, rl, acc_unit=1.25, method="scatter", return_info=True, return_volume=True)
+    assert info["D"] > 240
+    vol, out = acc.vote_volume(xyz, rl, acc_unit=1.25)
+    assert np.array_equal(vol, info["volume"])
+    assert np.array_equal(acc.Accumulator_3D(xyz, rl, acc_unit=1.25), want)
+
+
+def test_empty_and_degenerate_inputs(acc, ctx):
+    with pytest.raises(ValueError):
+        acc.Accumulator_3D(np.zeros((0, 3)), np.zeros((0,), np.float32))
+    # all radii negative: R <= 0 never votes; the reference returns voxel (0,0,0) un-shifted (all-equal volume)
+    xyz = np.array([[0.0, 0.0, 0.5], [0.01, 0.0, 0.5], [0.0, 0.02, 0.52], [0.3, 0.1, 0.4]])
+    rl = np.array([0.01, 0.02, 0.0, 0.03], np.float32)
+    want, info = oracle.Accumulator_3D(xyz, rl, return_info=True)
+    got, ginfo = acc.Accumulator_3D(xyz, rl, return_info=True)
+    assert np.array_equal(got, want) and ginfo["D"] == info["D"] and ginfo["votes"] == info["votes"]
+    # empty mask inside a batch is a per-item status, not an error
+    from rcvpose_b200 import api
+    depth = torch.zeros((1, 480, 640), dtype=torch.int16, device="cuda")
+    radius = torch.ones((1, 1, 480, 640), dtype=torch.float32, device="cuda")
+    out = ctx.vote_frames(depth, radius, torch.from_numpy(synth.linemod_K).cuda(), mask_flags=api.RCV_MASK_RADIUS_NONZERO)
+    assert int(out["status"][0, 0]) == api.RCV_ST_EMPTY_MASK
+
+
+def test_argmax_volume_first_max_in_c_order(ctx):
+    rng = np.random.default_rng(2)
+    for D in (5, 33, 86):
+        v = rng.integers(0, 50, size=(D, D, D)).astype(np.int32)
+        v[rng.integers(0, D), rng.integers(0, D), rng.integers(0, D)] = 77
+        v.ravel()[D * D * D // 2 + 3] = 77                      # a tie: the smaller linear index must win
+        idx, mx = ctx.argmax_volume(torch.from_numpy(v).cuda())
+        want = np.argwhere(v == v.max())[0]
+        assert np.array_equal(idx.cpu().numpy(), want) and int(mx) == 77
+    z = torch.zeros((7, 7, 7), dtype=torch.int32, device="cuda")
+    idx, mx = ctx.argmax_volume(z)
+    assert idx.tolist() == [0, 0, 0] and int(mx) == 0
+
+
+@pytest.mark.parametrize("t", range(6))
+def test_horn_vs_reference(golden, t):
+    from rcvpose_b200.util.horn import HornPoseFitting
+    P1, P2, RT = golden["h%d_P1" % t], golden["h%d_P2" % t], golden["h%d_RT" % t]
+    A = np.zeros((4, 4))
+    a, b = P1.copy(), P2.copy()
+    assert HornPoseFitting().lmshorn(a, b, P1.shape[0], A) is None
+    assert np.array_equal(a, P1) and np.array_equal(b, P2)
+    np.testing.assert_allclose(A[:3, :3], RT[:3, :3], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(A[:3, 3], RT[:3, 3], rtol=1e-12, atol=1e-9)
+    assert np.array_equal(A[3], [0, 0, 0, 1])
+
+
+def test_horn_batch_device(ctx, golden):
+    P1 = torch.from_numpy(golden["h0_P1"]).cuda()
+    est = torch.from_numpy(np.stack([golden["h%d_P2" % t] for t in range(4)])).cuda()
+    mdl = torch.from_numpy(np.stack([golden["h%d_P1" % t] for t in range(4)])).cuda()
+    RT = ctx.horn_batch(mdl, est).cpu().numpy()
+    for t in range(4):
+        np.testing.assert_allclose(RT[t], golden["h%d_RT" % t], rtol=1e-12, atol=1e-9)
+    RT0 = ctx.horn_batch(P1, est[:1]).cpu().numpy()
+    np.testing.assert_allclose(RT0[0], golden["h0_RT"], rtol=1e-12, atol=1e-9)

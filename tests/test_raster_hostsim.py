@@ -1,0 +1,89 @@
+"""Fuzzes the rasteriser arithmetic (rcvpose_b200/csrc/raster_core.h, compiled for the host by
+tests/hostsim.cpp) against the oracle's brute-force restatement of fast_for
+(AccumulatorSpace.py:325-341).  The vote volume must be bit-exact: integer adds commute."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import hostsim
+
+
+def _check(p, R, D, **kw):
+    want = oracle.fast_for(p, R, D)
+    got, st = hostsim.render(p, R, D, **kw)
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, "first mismatch at %s: got %d want %d (of %d)" % (bad[0], got[tuple(bad[0])], want[tuple(bad[0])], len(bad))
+    assert st["votes"] == int(want.sum())
+    return st
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_points_all_radii(seed):
+    rng = np.random.default_rng(seed)
+    D = int(rng.integers(20, 70))
+    n = 40
+    p = rng.uniform(-3, D + 3, size=(n, 3))
+    R = rng.integers(-1, D // 2 + 4, size=n).astype(np.int32)
+    _check(p, R, D, sqrt_perturb=seed % 2)
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 6, 7, 8, 10, 13, 17, 24, 31, 40])
+def test_single_radius_many_offsets(R):
+    rng = np.random.default_rng(100 + R)
+    D = 2 * R + 9
+    p = (D / 2.0) + rng.uniform(-1.0, 1.0, size=(24, 3))
+    _check(p, np.full(24, R, np.int32), D, sqrt_perturb=1)
+
+
+def test_lattice_aligned_and_half_integer_points():
+    # adversarial: exact boundary hits (|v-p| == R exactly), half-integer ties, zero fractions
+    D = 41
+    pts, Rs = [], []
+    for R in (1, 2, 3, 5, 10, 13, 15):  # 5,10,13,15: many integer triples with x^2+y^2+z^2 == R^2
+        for off in ((0, 0, 0), (0.5, 0, 0), (0.5, 0.5, 0.5), (0.25, -0.25, 0.5), (1e-9, 0, 0), (0, -1e-12, 0.5 - 1e-12)):
+            pts.append(np.array([20.0, 20.0, 20.0]) + np.array(off))
+            Rs.append(R)
+    p, R = np.array(pts), np.array(Rs, np.int32)
+    _check(p, R, D)
+    _check(p, R, D, sqrt_perturb=1)
+
+
+def test_clipping_at_grid_faces_and_corners():
+    rng = np.random.default_rng(5)
+    D = 30
+    p = np.concatenate([rng.uniform(-2.5, 2.5, size=(10, 3)), D - 1 + rng.uniform(-2.5, 2.5, size=(10, 3)),
+                        np.array([[0.0, 15.2, 29.0], [-2.4, -2.4, -2.4], [31.9, 31.9, 31.9]])])
+    R = rng.integers(1, 20, size=p.shape[0]).astype(np.int32)
+    _check(p, R, D)
+
+
+@pytest.mark.parametrize("tile", [(0, 5, 0, 37), (5, 7, 0, 37), (30, 7, 0, 37), (11, 1, 0, 37), (11, 1, 8, 13), (3, 2, 30, 7), (0, 37, 0, 37)])
+def test_tiles_partition_the_volume(tile):
+    rng = np.random.default_rng(9)
+    D = 37
+    p = rng.uniform(5, 32, size=(30, 3))
+    R = rng.integers(1, 16, size=30).astype(np.int32)
+    want = oracle.fast_for(p, R, D)
+    i0, ni, j0, nj = tile
+    got, _ = hostsim.render(p, R, D, tile=tile, Dp=39)
+    assert np.array_equal(got, want[i0:i0 + ni, j0:j0 + nj, :])
+
+
+def test_large_radius_thick_rings():
+    rng = np.random.default_rng(21)
+    D = 120
+    p = rng.uniform(40, 80, size=(6, 3))
+    R = np.array([37, 45, 52, 58, 29, 33], np.int32)
+    want = oracle.fast_for(p, R, D, method="scatter")
+    got, st = hostsim.render(p, R, D, sqrt_perturb=1)
+    assert np.array_equal(got, want)
+
+
+def test_linemod_shaped_frame_matches_reference_volume(golden):
+    from rcvpose_b200 import synth
+    fr = synth.config1_frame()
+    xyz, rl = synth.frame_to_points(fr["K"], fr["depth"], fr["radius"][0])
+    pre = oracle.prelude(xyz, rl)
+    got, st = hostsim.render(pre["p"], pre["R"], pre["D"])
+    assert np.array_equal(got, golden["c1_volume"])   # the real reference's volume, every voxel
+    assert st["votes"] == int(golden["c1_votes"])
