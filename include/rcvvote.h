@@ -150,6 +150,13 @@ long long rcv_launch_count(const rcv_ctx* ctx);
 /* Device time of the vote kernel in the most recent rcv_vote_* call, in ms (CUDA events on `stream`);
  * blocks until that call has finished.  Returns a negative value if no call was made. */
 float rcv_last_vote_kernel_ms(rcv_ctx* ctx);
+/* Device times (ms) of the vote kernel in the most recent n (<= 64) rcv_vote_* calls, oldest first; the
+ * events were recorded on the stream each kernel was launched on.  Blocks until they have completed.
+ * Returns the number of entries written, or a negative RCV_E_* code. */
+int rcv_vote_kernel_times(rcv_ctx* ctx, float* ms_out, int n);
+/* Measures this GPU's conflict-free shared-memory atomic rate (atomic lanes per second over all SMs) with a
+ * built-in micro-benchmark on the default stream: the denominator of the vote kernel's roofline. */
+int rcv_ubench_smem_atomics(rcv_ctx* ctx, double* atomics_per_second);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ RCV_ST_VOLUME_SKIPPED = 32
 
 EXPORTS = ["rcv_create", "rcv_destroy", "rcv_last_error", "rcv_abi_version", "rcv_backproject", "rcv_vote_points", "rcv_vote_frames",
            "rcv_vote_frames_host", "rcv_argmax_volume", "rcv_horn_batch", "rcv_horn_batch_host", "rcv_launch_count",
-           "rcv_last_vote_kernel_ms"]
+           "rcv_last_vote_kernel_ms", "rcv_vote_kernel_times", "rcv_ubench_smem_atomics"]
 
 
 class rcv_config(C.Structure):
@@ -79,6 +79,10 @@ def load():
     L.rcv_launch_count.argtypes = [vp]
     L.rcv_last_vote_kernel_ms.restype = C.c_float
     L.rcv_last_vote_kernel_ms.argtypes = [vp]
+    L.rcv_vote_kernel_times.restype = C.c_int
+    L.rcv_vote_kernel_times.argtypes = [vp, vp, C.c_int]
+    L.rcv_ubench_smem_atomics.restype = C.c_int
+    L.rcv_ubench_smem_atomics.argtypes = [vp, C.POINTER(C.c_double)]
     if L.rcv_abi_version() != RCV_ABI_VERSION:
         raise RuntimeError("librcvvote.so ABI version mismatch")
     _lib = L

@@ -84,6 +84,21 @@ class VoteContext:
     def last_vote_kernel_ms(self):
         return float(self.lib.rcv_last_vote_kernel_ms(self.h))
 
+    def vote_kernel_times(self, n):
+        """Device durations (ms) of the vote kernel in the last n (<=64) calls, oldest first (syncs)."""
+        buf = (C.c_float * 64)()
+        got = self.lib.rcv_vote_kernel_times(self.h, buf, int(n))
+        if got < 0:
+            self._ck(got)
+        return [float(buf[i]) for i in range(got)]
+
+    def measure_smem_atomic_peak(self):
+        """Conflict-free shared-memory atomics per second on this GPU (built-in micro-benchmark)."""
+        v = C.c_double()
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_ubench_smem_atomics(self.h, C.byref(v)))
+        return float(v.value)
+
     # ---- rgbd_to_point_cloud (AccumulatorSpace.py:77-85) ----
     def backproject(self, K, depth):
         _check_cuda(K, torch.float64, "K")

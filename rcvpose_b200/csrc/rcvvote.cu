@@ -779,6 +779,31 @@ __global__ void k_horn(const double* __restrict__ model, long long model_stride,
   o[15] = 1.0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Roofline denominator: conflict-free shared-memory atomic rate of this GPU (one ATOMS per warp
+// instruction, 32 distinct banks), measured the same way as tools/ubench_atoms.cu.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) k_ubench_atoms(int iters, unsigned* out) {
+  extern __shared__ __align__(16) int smem[];
+  unsigned* s = reinterpret_cast<unsigned*>(smem);
+  constexpr unsigned kWords = 32768;
+  for (unsigned i = threadIdx.x; i < kWords; i += blockDim.x) s[i] = 0;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned base = warp * 997u;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (unsigned u = 0; u < 8; ++u) {
+      atomicAdd(&s[(base + ((lane + u) & 31) + 32u * u) & (kWords - 1)], 1u);
+      base += 1031u;
+    }
+  }
+  __syncthreads();
+  unsigned acc = 0;
+  for (unsigned i = threadIdx.x; i < kWords; i += blockDim.x) acc += s[i];
+  if (acc == 0xdeadbeefu) out[blockIdx.x] = acc;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -794,7 +819,7 @@ struct rcv_ctx {
   int* cnt;
   unsigned long long *best, *votes;
   PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
-  cudaEvent_t ev0, ev1; bool timed;
+  cudaEvent_t evr[64][2]; long long ev_count;   // ring of (start, stop) events around the vote kernel
   long long launches;
   // staging for the _host entry points
   cudaStream_t s_in, s_run; cudaEvent_t ev_in[2], ev_done[2], ev_user;
@@ -837,8 +862,7 @@ RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
   for (int s = 0; s < 2; ++s) { cudaFree(c->st_depth[s]); cudaFree(c->st_radius[s]); cudaFree(c->st_sem[s]); }
   cudaFree(c->st_K); cudaFree(c->st_maxr); cudaFree(c->st_centre); cudaFree(c->st_peak); cudaFree(c->st_votes);
   cudaFree(c->st_np); cudaFree(c->st_grid); cudaFree(c->st_status); cudaFree(c->st_horn_in);
-  if (c->ev0) cudaEventDestroy(c->ev0);
-  if (c->ev1) cudaEventDestroy(c->ev1);
+  for (int e = 0; e < 64; ++e) { if (c->evr[e][0]) cudaEventDestroy(c->evr[e][0]); if (c->evr[e][1]) cudaEventDestroy(c->evr[e][1]); }
   if (c->ev_user) cudaEventDestroy(c->ev_user);
   for (int s = 0; s < 2; ++s) { if (c->ev_in[s]) cudaEventDestroy(c->ev_in[s]); if (c->ev_done[s]) cudaEventDestroy(c->ev_done[s]); }
   if (c->s_in) cudaStreamDestroy(c->s_in);
@@ -882,12 +906,13 @@ RCV_EXPORT int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out) {
   CKC(cudaMalloc(&c->pool.Rd, cap * 8)); CKC(cudaMalloc(&c->pool.Ri, cap * 4));
   CKC(cudaMalloc(&c->meta, sizeof(ItemMeta) * (size_t)cfg->max_items));
   CKC(cudaMalloc(&c->units, sizeof(Unit) * (size_t)c->cfg.max_units));
-  CKC(cudaMalloc(&c->counters, 64));
+  CKC(cudaMalloc(&c->counters, 64 + 4096));
   CKC(cudaMalloc(&c->cnt, 4 * (size_t)cfg->max_items));
   CKC(cudaMalloc(&c->best, 8 * (size_t)cfg->max_items)); CKC(cudaMalloc(&c->votes, 8 * (size_t)cfg->max_items));
   c->leaf_cap = cap / 56 + 2LL * cfg->max_items + 8;
   CKC(cudaMalloc(&c->leaves, sizeof(PwLeaf) * (size_t)c->leaf_cap)); CKC(cudaMalloc(&c->leaf_sums, 24 * (size_t)c->leaf_cap));
-  CKC(cudaEventCreate(&c->ev0)); CKC(cudaEventCreate(&c->ev1));
+  for (int e = 0; e < 64; ++e) { CKC(cudaEventCreate(&c->evr[e][0])); CKC(cudaEventCreate(&c->evr[e][1])); }
+  CKC(cudaFuncSetAttribute(k_ubench_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
   CKC(cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (kTileWords + kDummyWords) * 4));
 #undef CKC
   return RCV_OK;
@@ -903,10 +928,11 @@ static int run_items(rcv_ctx* c, int n_items, const rcv_vote_params* vp, double*
                  c->leaves, c->leaf_sums, c->leaf_cap};
   k_prelude<<<n_items, kPreludeThreads, 0, st>>>(pa);
   VoteArgs va{c->pool, c->meta, c->units, c->counters, c->best, c->votes, volume, volume_cap};
-  CK(c, cudaEventRecord(c->ev0, st));
+  const int slot = (int)(c->ev_count % 64);
+  CK(c, cudaEventRecord(c->evr[slot][0], st));
   k_vote<<<c->sms, kVoteThreads, (kTileWords + kDummyWords) * 4, st>>>(va);
-  CK(c, cudaEventRecord(c->ev1, st));
-  c->timed = true;
+  CK(c, cudaEventRecord(c->evr[slot][1], st));
+  c->ev_count += 1;
   FinalArgs fa{c->meta, c->best, c->votes, n_items, vp->acc_unit, vp->grid_policy, volume != nullptr, volume_cap,
                centre_mm, peak, votes, n_points, grid, zb, status};
   k_finalize<<<(n_items + 127) / 128, 128, 0, st>>>(fa);
@@ -1119,10 +1145,41 @@ RCV_EXPORT int rcv_horn_batch_host(rcv_ctx* c, const double* model, long long mo
   return RCV_OK;
 }
 
+RCV_EXPORT int rcv_vote_kernel_times(rcv_ctx* c, float* ms_out, int n) {
+  if (!c || !ms_out || n <= 0) return RCV_E_INVALID;
+  if (n > 64) n = 64;
+  if ((long long)n > c->ev_count) n = (int)c->ev_count;
+  for (int q = 0; q < n; ++q) {
+    const int slot = (int)((c->ev_count - n + q) % 64);
+    CK(c, cudaEventSynchronize(c->evr[slot][1]));
+    CK(c, cudaEventElapsedTime(&ms_out[q], c->evr[slot][0], c->evr[slot][1]));
+  }
+  return n;
+}
+
 RCV_EXPORT float rcv_last_vote_kernel_ms(rcv_ctx* c) {
-  if (!c || !c->timed) return -1.f;
   float ms = -1.f;
-  if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.f;
-  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.f;
+  if (!c || rcv_vote_kernel_times(c, &ms, 1) != 1) return -1.f;
   return ms;
+}
+
+RCV_EXPORT int rcv_ubench_smem_atomics(rcv_ctx* c, double* atomics_per_second) {
+  if (!c || !atomics_per_second) return RCV_E_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  unsigned* out = reinterpret_cast<unsigned*>(c->counters + 8);
+  const int iters = 4096;
+  cudaEvent_t a = c->evr[63][0], b = c->evr[63][1];
+  float best = 1e30f;
+  for (int r = 0; r < 7; ++r) {
+    CK(c, cudaEventRecord(a, 0));
+    k_ubench_atoms<<<c->sms, 1024, 32768 * 4, 0>>>(iters, out);
+    CK(c, cudaEventRecord(b, 0));
+    CK(c, cudaEventSynchronize(b));
+    float ms;
+    CK(c, cudaEventElapsedTime(&ms, a, b));
+    if (r >= 2 && ms < best) best = ms;
+  }
+  c->launches += 7;
+  *atomics_per_second = (double)c->sms * 1024.0 * iters * 8.0 / (best * 1e-3);
+  return RCV_OK;
 }

@@ -100,3 +100,50 @@ def frame_to_points(K, depth, radius):
     ys = ((vs - K[1, 2]) * zs) / float(K[1, 1])
     xyz_mm = np.array([xs, ys, zs]).T
     return xyz_mm / 1000, radius[dm.nonzero()]
+
+
+def torch_batch(n_frames, n_kpts=3, seed=0, device="cuda", K=linemod_K, chunk=128, sigma_dm=0.01, outlier_frac=0.02, h=H, w=W):
+    """Config-3 shaped batch generated on the GPU: per frame an object sphere of radius
+    U(40,70) mm at x,y U(-150,150), z U(700,1100) mm; `n_kpts` keypoints at 1.5-2.5 object radii in
+    dispersed directions; radius maps (decimetres, float32) with N(0, sigma) noise and a fraction of
+    uniform outliers in [0, max radius]; depth uint16 millimetres (returned as an int16 view).
+    Returns dict(depth (B,H,W) int16-view-of-uint16, radius (B,Kp,H,W) f32, kpts_mm (B,Kp,3) f64,
+    centre_mm (B,3) f64, model_mm (B,Kp,3) f64 = keypoints in the object frame)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    dev = torch.device(device)
+    depth = torch.empty((n_frames, h, w), dtype=torch.int16, device=dev)
+    radius = torch.empty((n_frames, n_kpts, h, w), dtype=torch.float32, device=dev)
+    U = lambda *s: torch.rand(*s, generator=g, device=dev, dtype=torch.float64)  # noqa: E731
+    obj_r = 40.0 + 30.0 * U(n_frames)
+    centre = torch.stack([-150 + 300 * U(n_frames), -150 + 300 * U(n_frames), 700 + 400 * U(n_frames)], dim=1)
+    base = torch.tensor([[1.0, 0.2, 0.1], [-0.3, 1.0, 0.2], [0.2, -0.4, 1.0], [-1.0, -0.5, 0.3]], dtype=torch.float64, device=dev)[:n_kpts]
+    dirs = base[None] + 0.15 * torch.randn((n_frames, n_kpts, 3), generator=g, device=dev, dtype=torch.float64)
+    dirs = dirs / dirs.norm(dim=2, keepdim=True)
+    model = dirs * (obj_r[:, None, None] * (1.5 + U(n_frames, n_kpts, 1)))
+    kpts = centre[:, None, :] + model
+    fx, fy, cx, cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+    vv, uu = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float64), torch.arange(w, device=dev, dtype=torch.float64), indexing="ij")
+    dx, dy = (uu - cx) / fx, (vv - cy) / fy
+    a = dx * dx + dy * dy + 1.0
+    for f0 in range(0, n_frames, chunk):
+        f1 = min(n_frames, f0 + chunk)
+        c = centre[f0:f1]
+        b = dx[None] * c[:, 0, None, None] + dy[None] * c[:, 1, None, None] + c[:, 2, None, None]
+        cc = (c * c).sum(dim=1) - obj_r[f0:f1] ** 2
+        disc = b * b - a[None] * cc[:, None, None]
+        hit = disc > 0
+        z = torch.where(hit, (b - torch.sqrt(disc.clamp_min(0))) / a[None], torch.zeros_like(b)).round()
+        depth[f0:f1] = z.to(torch.int32).to(torch.int16)          # values < 32768: the int16 view equals the uint16 value
+        x = (uu[None] - cx) * z / fx
+        y = (vv[None] - cy) * z / fy
+        for k in range(n_kpts):
+            kp = kpts[f0:f1, k]
+            d = torch.sqrt((x - kp[:, 0, None, None]) ** 2 + (y - kp[:, 1, None, None]) ** 2 + (z - kp[:, 2, None, None]) ** 2) / 100.0
+            mr = torch.where(hit, d, torch.zeros_like(d)).amax(dim=(1, 2))
+            r = d + sigma_dm * torch.randn(d.shape, generator=g, device=dev, dtype=torch.float64)
+            out = torch.rand(d.shape, generator=g, device=dev) < outlier_frac
+            r = torch.where(out, mr[:, None, None] * torch.rand(d.shape, generator=g, device=dev, dtype=torch.float64), r)
+            radius[f0:f1, k] = torch.where(hit, r, torch.zeros_like(r)).to(torch.float32)
+    return dict(depth=depth, radius=radius, kpts_mm=kpts, centre_mm=centre, model_mm=model.contiguous())
