@@ -102,6 +102,7 @@ struct PointCtx {
   int ipx, ipy, ipz;  // nearest lattice point
   float fx, fy, fz;   // p - ip, |f| <= 0.5
   float R2, W, eps, dbias_m05;
+  float hW, hw_m, hw_p;  // W/2, W/2 - eps, W/2 + eps
 };
 
 RCV_HD void point_setup(PointCtx& c, double px, double py, double pz, int R) {
@@ -118,38 +119,34 @@ RCV_HD void point_setup(PointCtx& c, double px, double py, double pz, int R) {
   c.eps = f_mul(f_mul(rp2, rp2), 9.5367431640625e-07f);        // 2^-20
   const float dbias = f_add(f_mul(c.eps, 0.125f), f_mul(rp2, 9.5367431640625e-07f));
   c.dbias_m05 = f_sub(dbias, 0.5f);
+  c.hW = f_mul(c.W, 0.5f);
+  c.hw_m = f_sub(c.hW, c.eps);
+  c.hw_p = f_add(c.hW, c.eps);
 }
 
-// Per-(point, slice) constants (warp-uniform).
-enum { SLICE_SKIP = 0, SLICE_RING = 1, SLICE_DENSE = 2 };
-struct SliceCtx {
-  float a;   // R^2 - dx^2
-  int kind;
-  int m;     // candidates per arc per lane (ring) / box half-width (dense)
-};
-
-RCV_HD void slice_setup(const PointCtx& c, int i, SliceCtx& s) {
+// Per-(point, slice) classification (warp-uniform; the kernel evaluates 32 slices at once, one per
+// lane, and broadcasts (a, code) with shuffles).  code > 0: ring slice, code = candidates per arc;
+// code < 0: dense slice, -code = half-width of its bounding box; code == 0: nothing to draw.
+RCV_HD void slice_setup(const PointCtx& c, int i, float& a, int& code) {
   const float dxf = f_sub((float)(i - c.ipx), c.fx);
-  s.a = f_sub(c.R2, f_mul(dxf, dxf));
-  const float b = f_sub(s.a, c.W);
-  if (!(s.a > -c.eps)) { s.kind = SLICE_SKIP; s.m = 0; return; }
-  if (b < 4.0f || s.a <= 36.0f) {
-    s.kind = SLICE_DENSE;
-    s.m = (int)f_add(f_sqrt_fast(fmaxf(s.a, 0.f)), 1.5f);  // floor(ro + 1.5) >= ro + 0.5, with slack
+  a = f_sub(c.R2, f_mul(dxf, dxf));
+  const float b = f_sub(a, c.W);
+  if (!(a > -c.eps)) { code = 0; return; }
+  if (b < 4.0f || a <= 36.0f) {
+    code = -(int)f_add(f_sqrt_fast(fmaxf(a, 0.f)), 1.5f);  // floor(ro + 1.5) >= ro + 0.5, with slack
     return;
   }
-  s.kind = SLICE_RING;
   // Longest run of an arc inside its own pass: sqrt(a - b/2) - sqrt(b/2)  (column |du| = sqrt(b/2)).
   const float hb = f_mul(b, 0.5f);
-  const float lmax = f_sub(f_sqrt_fast(f_sub(s.a, hb)), f_sqrt_fast(hb));
-  s.m = (int)f_add(lmax, 0.02f) + 1;
+  const float lmax = f_sub(f_sqrt_fast(f_sub(a, hb)), f_sqrt_fast(hb));
+  code = (int)f_add(lmax, 0.02f) + 1;
 }
 
 // Per-lane task: one column (Z-pass) or row (Y-pass) of the ring, both arcs.
 struct LaneTask {
   float du2, thr, fv;
-  int cst;     // word offset of (u-coordinate, v = lattice base) inside a slice of the tile
-  int sv;      // word stride of the candidate axis (1 for Z-pass, Dp for Y-pass)
+  int ubase;   // offset of (lane coordinate, candidate coordinate 0) inside a slice of the tile, in `unit`s
+  int sv;      // stride of the candidate axis (1 word for Z-pass, Dp words for Y-pass), in `unit`s
   int vrel0;   // lattice base of the candidate axis relative to the tile origin
   int vn;      // extent of the candidate axis in the tile
   int ucoord;  // global index along the lane axis
@@ -161,7 +158,7 @@ struct LaneTask {
 // lies in a lane: owned => du^2 <= dv^2 and du^2 + dv^2 < a  =>  |du| < sqrt(a/2); |u| <= |du| + 0.5.
 RCV_HD int ring_half_width(float amax) { return (int)f_add(f_sqrt_fast(f_mul(amax, 0.5f)), 0.5f) + 1; }
 
-RCV_HD void lane_setup(const PointCtx& c, const Tile& t, int H, int tau, LaneTask& L) {
+RCV_HD void lane_setup(const PointCtx& c, const Tile& t, int H, int tau, int unit, LaneTask& L) {
   const int Wc = 2 * H + 1;
   L.pass = tau >= Wc;
   const int u = tau - (L.pass ? Wc : 0) - H;
@@ -176,73 +173,82 @@ RCV_HD void lane_setup(const PointCtx& c, const Tile& t, int H, int tau, LaneTas
   if (!L.pass) {
     L.ucoord = c.ipy + u;
     ok = (unsigned)(L.ucoord - t.j0) < (unsigned)t.nj;
-    L.cst = (L.ucoord - t.j0) * t.Dp + c.ipz;
-    L.sv = 1; L.vrel0 = c.ipz; L.vn = t.D;
+    L.ubase = (L.ucoord - t.j0) * t.Dp * unit;
+    L.sv = unit; L.vrel0 = c.ipz; L.vn = t.D;
   } else {
     L.ucoord = c.ipz + u;
     ok = (unsigned)L.ucoord < (unsigned)t.D;
-    L.cst = (c.ipy - t.j0) * t.Dp + L.ucoord;
-    L.sv = t.Dp; L.vrel0 = c.ipy - t.j0; L.vn = t.nj;
+    L.ubase = L.ucoord * unit;
+    L.sv = t.Dp * unit; L.vrel0 = c.ipy - t.j0; L.vn = t.nj;
   }
   L.active = ok && tau < 2 * Wc;
 }
 
-// One lane, one ring slice: emit(word_offset, vote) is called a fixed 2*m times (vote may be
-// false), plus extra calls on the rare exact path.  `slice_base` = (i - i0) * nj * Dp.
-template <class Emit>
-RCV_HD void ring_lane(const PointCtx& c, const SliceCtx& s, const LaneTask& L, int i, int slice_base, Emit& emit) {
-  const float g = f_sub(s.a, L.du2);
+// One lane, one ring slice with outer radius^2 `a` and `m` candidates per arc (THIN: m == 1).
+//   emit(offset, vote)     -- called exactly 2*m times (vote may be false): the unconditional
+//                             shared-memory atomic of the fast path;
+//   slow(i, j, k) -> bool  -- the exact float64 predicate, called only for candidates whose float32
+//                             residual is within eps of a shell boundary (rare);
+//   emit_slow(offset)      -- a vote decided on the slow path.
+// Offsets are in the units lane_setup() was given (words on the host, bytes on the device);
+// `slice_base` = (i - i0) * nj * Dp in the same units.
+template <bool THIN, class Emit, class Slow, class EmitSlow>
+RCV_HD void ring_lane(const PointCtx& c, float a, int m, const LaneTask& L, int i, int slice_base, Emit& emit, Slow& slow,
+                      EmitSlow& emit_slow) {
+  const float g = f_sub(a, L.du2);
   const bool lane_ok = L.active && (g > 0.f);
   const float zs = f_sqrt_fast(fmaxf(g, 0.f));
-  const float negW = -c.W;
+  const float hWg = f_sub(c.hW, g);
+  const int ub = L.ubase + slice_base;
+  if (THIN) m = 1;
 #pragma unroll
   for (int arc = 0; arc < 2; ++arc) {
     const float fvs = arc ? -L.fv : L.fv;
-    const float t = f_add(zs, fvs);
-    const float tm = f_add(f_add(t, c.dbias_m05), RCV_MAGIC);
+    const float tm = f_add(f_add(f_add(zs, fvs), c.dbias_m05), RCV_MAGIC);
     const int kq = f_bits(tm) - RCV_MAGIC_BITS;  // topmost candidate (>= true topmost voxel inside the outer circle)
     const float flr = f_sub(tm, RCV_MAGIC);
-    for (int cc = 0; cc < s.m; ++cc) {
-      const float dvfs = f_sub(f_sub(flr, (float)cc), fvs);
-      const float e = f_fma(dvfs, dvfs, -g);  // dv^2 + du^2 + dx^2 - R^2  (<0 inside the outer sphere)
+    const int vtop = arc ? (L.vrel0 - kq) : (L.vrel0 + kq);
+#pragma unroll 1
+    for (int cc = 0; cc < m; ++cc) {
+      const float dvfs = f_sub(THIN ? flr : f_sub(flr, (float)cc), fvs);
+      const float q = f_fma(dvfs, dvfs, hWg);              // e + W/2, e = |v-p|^2 - R^2 in float32
       const bool own = fabsf(dvfs) > L.thr;
-      const int dv = arc ? (cc - kq) : (kq - cc);
-      const bool inb = (unsigned)(L.vrel0 + dv) < (unsigned)L.vn;
-      const bool amb = (e >= -c.eps) || (fabsf(f_add(e, c.W)) <= c.eps);
-      bool hit = (e > negW) && !amb;
-      if (amb && lane_ok) {
-        const int vj = L.pass ? (c.ipy + dv) : L.ucoord;
-        const int vk = L.pass ? L.ucoord : (c.ipz + dv);
-        hit = own && inb && exact_hit(c.px, c.py, c.pz, c.R, i, vj, vk);
-        if (cc == 0 && e >= -c.eps) {
+      const int vrel = arc ? (vtop + cc) : (vtop - cc);
+      const bool inb = (unsigned)vrel < (unsigned)L.vn;
+      const bool sure = fabsf(q) < c.hw_m;                 // -W + eps < e < -eps
+      emit(ub + vrel * L.sv, sure && own && inb && lane_ok);
+      if (!sure && (q > -c.hw_p) && lane_ok) {
+        // within eps of the inner boundary, or not surely inside the outer one: decide exactly
+        const int dv = arc ? (cc - kq) : (kq - cc);
+        if (own && inb && slow(i, L.pass ? (c.ipy + dv) : L.ucoord, L.pass ? L.ucoord : (c.ipz + dv))) emit_slow(ub + vrel * L.sv);
+        if (cc == 0 && q >= c.hw_m) {
           // The top candidate may lie outside the outer sphere; the run can then reach one voxel lower.
-          const int dv2 = arc ? (s.m - kq) : (kq - s.m);
-          const float dvfs2 = f_sub(f_sub(flr, (float)s.m), fvs);
-          const bool own2 = fabsf(dvfs2) > L.thr;
-          const bool inb2 = (unsigned)(L.vrel0 + dv2) < (unsigned)L.vn;
-          const int vj2 = L.pass ? (c.ipy + dv2) : L.ucoord;
-          const int vk2 = L.pass ? L.ucoord : (c.ipz + dv2);
-          if (own2 && inb2 && exact_hit(c.px, c.py, c.pz, c.R, i, vj2, vk2)) emit(slice_base + L.cst + dv2 * L.sv, true);
+          const int dv2 = arc ? (m - kq) : (kq - m);
+          const float dvfs2 = f_sub(f_sub(flr, (float)m), fvs);
+          const int vrel2 = L.vrel0 + dv2;
+          if ((fabsf(dvfs2) > L.thr) && ((unsigned)vrel2 < (unsigned)L.vn) &&
+              slow(i, L.pass ? (c.ipy + dv2) : L.ucoord, L.pass ? L.ucoord : (c.ipz + dv2)))
+            emit_slow(ub + vrel2 * L.sv);
         }
       }
-      emit(slice_base + L.cst + dv * L.sv, hit && own && inb && lane_ok);
+      if (THIN) break;
     }
   }
 }
 
-// One lane, one cell of a dense slice's bounding box.  cell in [0, (2*hb+1)^2).
-template <class Emit>
-RCV_HD void dense_cell(const PointCtx& c, const SliceCtx& s, const Tile& t, int i, int slice_base, int cell, Emit& emit) {
-  const int side = 2 * s.m + 1;
-  const int dj = cell / side - s.m, dk = cell % side - s.m;
+// One lane, one cell (dj, dk) of a dense slice's bounding box.
+template <class Emit, class Slow>
+RCV_HD void dense_cell(const PointCtx& c, float a, const Tile& t, int i, int slice_base, int unit, int dj, int dk, bool cell_ok,
+                       Emit& emit, Slow& slow) {
   const float dyf = f_sub((float)dj, c.fy), dzf = f_sub((float)dk, c.fz);
-  const float e = f_fma(dzf, dzf, f_fma(dyf, dyf, -s.a));
+  const float q = f_add(f_fma(dzf, dzf, f_fma(dyf, dyf, -a)), c.hW);
   const int vj = c.ipy + dj, vk = c.ipz + dk;
-  const bool inb = ((unsigned)(vj - t.j0) < (unsigned)t.nj) && ((unsigned)vk < (unsigned)t.D) && (cell < side * side);
-  const bool amb = (fabsf(e) <= c.eps) || (fabsf(f_add(e, c.W)) <= c.eps);
-  bool hit = (e < 0.f) && (e > -c.W) && !amb;
-  if (amb && inb) hit = exact_hit(c.px, c.py, c.pz, c.R, i, vj, vk);
-  emit(slice_base + (vj - t.j0) * t.Dp + vk, hit && inb);
+  const bool inb = cell_ok && ((unsigned)(vj - t.j0) < (unsigned)t.nj) && ((unsigned)vk < (unsigned)t.D);
+  const bool sure = fabsf(q) < c.hw_m;
+  const bool amb = !sure && (fabsf(q) <= c.hw_p);
+  bool vote = sure && inb;
+  if (amb && inb) vote = slow(i, vj, vk);
+  emit(slice_base + ((vj - t.j0) * t.Dp + vk) * unit, vote);
 }
 
 // Slice range of point c inside tile t (inclusive); empty if ia > ib.

@@ -511,12 +511,78 @@ struct VoteArgs {
   int32_t* volume; long long volume_cap;
 };
 
+// Shared-memory atomics by 32-bit shared-window address (offsets are bytes): the fast path adds 1 to
+// the voxel or, for a lane with no vote, to the lane's private sink word, so the instruction is never
+// predicated or branched around (a predicated ATOMS compiles to a divergent branch, 3.6x slower).
+__device__ __forceinline__ void smem_inc(unsigned addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory"); }
 struct SmemEmit {
-  int* tile; int sink;
-  __device__ __forceinline__ void operator()(int off, bool vote) const { atomicAdd(&tile[vote ? off : sink], 1); }
+  unsigned base, sink;
+  __device__ __forceinline__ void operator()(int off, bool vote) const { smem_inc(vote ? base + (unsigned)off : sink); }
+};
+struct SmemEmitSlow {
+  unsigned base;
+  __device__ __forceinline__ void operator()(int off) const { smem_inc(base + (unsigned)off); }
+};
+// The exact predicate lives behind a call so the compiler cannot hoist its float64 arithmetic into the
+// hot loop (it did: 40% of the first version's instructions were speculated DADD/DMUL/DSQRT).
+__device__ __noinline__ bool exact_hit_call(double px, double py, double pz, int R, int i, int j, int k) {
+  return exact_hit(px, py, pz, R, i, j, k);
+}
+struct SlowExact {
+  double px, py, pz; int R;
+  __device__ __forceinline__ bool operator()(int i, int j, int k) const { return exact_hit_call(px, py, pz, R, i, j, k); }
 };
 
 struct PointData { double x, y, z; int R; };
+
+__device__ __forceinline__ void vote_point(const PointData& pd, const Tile& t, int lane, const SmemEmit& emit_c) {
+  SmemEmit emit = emit_c;
+  SmemEmitSlow emit_slow{emit_c.base};
+  PointCtx c;
+  point_setup(c, pd.x, pd.y, pd.z, pd.R);
+  SlowExact slow{pd.x, pd.y, pd.z, pd.R};
+  int ia, ib;
+  slice_range(c, t, ia, ib);
+  const int slice_bytes = t.nj * t.Dp * 4;
+  for (int sb = ia; sb <= ib; sb += 32) {
+    // classify 32 slices at once, one per lane
+    float a_l = 0.f; int code_l = 0;
+    if (sb + lane <= ib) slice_setup(c, sb + lane, a_l, code_l);
+    const unsigned ring_mask = __ballot_sync(0xffffffffu, code_l > 0);
+    const unsigned dense_mask = __ballot_sync(0xffffffffu, code_l < 0);
+    if (ring_mask) {
+      float amax = code_l > 0 ? a_l : 0.f;
+#pragma unroll
+      for (int m = 16; m; m >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, m));
+      const int H = ring_half_width(amax);
+      const int ntask = 2 * (2 * H + 1);
+      for (int base = 0; base < ntask; base += 32) {
+        LaneTask L;
+        lane_setup(c, t, H, base + lane, 4, L);
+        for (unsigned mk = ring_mask; mk; mk &= mk - 1) {
+          const int sl = __ffs(mk) - 1;
+          const float a = __shfl_sync(0xffffffffu, a_l, sl);
+          const int m = __shfl_sync(0xffffffffu, code_l, sl);
+          const int i = sb + sl;
+          if (m == 1) ring_lane<true>(c, a, 1, L, i, (i - t.i0) * slice_bytes, emit, slow, emit_slow);
+          else ring_lane<false>(c, a, m, L, i, (i - t.i0) * slice_bytes, emit, slow, emit_slow);
+        }
+      }
+    }
+    for (unsigned mk = dense_mask; mk; mk &= mk - 1) {
+      const int sl = __ffs(mk) - 1;
+      const float a = __shfl_sync(0xffffffffu, a_l, sl);
+      const int hb = -__shfl_sync(0xffffffffu, code_l, sl);
+      const int i = sb + sl, side = 2 * hb + 1;
+      const int lshift = side <= 16 ? 4 : 5, lpr = 1 << lshift, rpi = 32 >> lshift;   // lanes per row, rows per iteration
+      for (int r0 = 0; r0 < side; r0 += rpi)
+        for (int k0 = 0; k0 < side; k0 += lpr) {
+          const int rr = r0 + (lane >> lshift), kk = k0 + (lane & (lpr - 1));
+          dense_cell(c, a, t, i, (i - t.i0) * slice_bytes, 4, rr - hb, kk - hb, rr < side && kk < side, emit, slow);
+        }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
   extern __shared__ __align__(16) int smem[];
@@ -524,7 +590,8 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
   __shared__ int s_unit, s_next;
   __shared__ unsigned long long s_key[kVoteWarps], s_sum[kVoteWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  SmemEmit emit{tile, kTileWords + warp * 32 + lane};
+  const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
+  const SmemEmit emit{tile_s, tile_s + 4u * (unsigned)(kTileWords + warp * 32 + lane)};
   const int n_units = a.counters[0];
   for (;;) {
     __syncthreads();
@@ -556,39 +623,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
       nxt = __shfl_sync(0xffffffffu, nxt, 0);
       PointData nd{0, 0, 0, 0};
       if (nxt < n) { nd.x = a.pool.X[off + nxt]; nd.y = a.pool.Y[off + nxt]; nd.z = a.pool.Z[off + nxt]; nd.R = a.pool.Ri[off + nxt]; }
-      PointCtx c;
-      point_setup(c, pd.x, pd.y, pd.z, pd.R);
-      int ia, ib;
-      slice_range(c, t, ia, ib);
-      if (ia <= ib) {
-        const int istar = c.ipx < ia ? ia : (c.ipx > ib ? ib : c.ipx);
-        SliceCtx s0;
-        slice_setup(c, istar, s0);
-        bool any_dense = false;
-        if (s0.a > 36.0f) {
-          const int H = ring_half_width(s0.a);
-          const int ntask = 2 * (2 * H + 1);
-          for (int base = 0; base < ntask; base += 32) {
-            LaneTask L;
-            lane_setup(c, t, H, base + lane, L);
-            for (int i = ia; i <= ib; ++i) {
-              SliceCtx s;
-              slice_setup(c, i, s);
-              if (s.kind == SLICE_RING) ring_lane(c, s, L, i, (i - t.i0) * t.nj * Dp, emit);
-              else if (s.kind == SLICE_DENSE) any_dense = true;
-            }
-          }
-        } else any_dense = true;
-        if (any_dense) {
-          for (int i = ia; i <= ib; ++i) {
-            SliceCtx s;
-            slice_setup(c, i, s);
-            if (s.kind != SLICE_DENSE) continue;
-            const int side = 2 * s.m + 1, cells = side * side;
-            for (int cell = lane; cell < ((cells + 31) & ~31); cell += 32) dense_cell(c, s, t, i, (i - t.i0) * t.nj * Dp, cell, emit);
-          }
-        }
-      }
+      vote_point(pd, t, lane, emit);
       cur = nxt; pd = nd;
     }
     __syncthreads();
