@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librcvvote.so")
+LIB_PATH = os.environ.get("RCV_LIB_PATH", os.path.join(HERE, "librcvvote.so"))   # override: kernel-variant experiments only
 
 RCV_ABI_VERSION = 1
 RCV_OK = 0
@@ -43,7 +43,7 @@ def load():
         return _lib
     from . import build
     try:
-        if build.needs_build():
+        if "RCV_LIB_PATH" not in os.environ and build.needs_build():
             build.build_library()
     except Exception as e:  # no nvcc on the box: fall through to the prebuilt library if there is one
         if not os.path.exists(LIB_PATH):

@@ -182,63 +182,119 @@ RCV_HD void lane_setup(const PointCtx& c, const Tile& t, int H, int tau, int uni
     L.sv = t.Dp * unit; L.vrel0 = c.ipy - t.j0; L.vn = t.nj;
   }
   L.active = ok && tau < 2 * Wc;
+  if (!L.active) L.thr = 3.0e38f;   // an inactive lane owns nothing
 }
 
-// One lane, one ring slice with outer radius^2 `a` and `m` candidates per arc (THIN: m == 1).
-//   emit(offset, vote)     -- called exactly 2*m times (vote may be false): the unconditional
-//                             shared-memory atomic of the fast path;
-//   slow(i, j, k) -> bool  -- the exact float64 predicate, called only for candidates whose float32
-//                             residual is within eps of a shell boundary (rare);
-//   emit_slow(offset)      -- a vote decided on the slow path.
+// Fast-path vote decision of one candidate: sure = residual strictly inside the shell by more than eps,
+// own = the candidate belongs to this pass, inb = inside the tile.  Returns the offset to increment:
+// the voxel's or, when there is no vote, the lane's private sink.
+RCV_HD int pick_offset(float q, float adv, int vrel, int off, int sink, float hw_m, float thr, int vn) {
+#if defined(__CUDA_ARCH__)
+  int r;
+  asm("{\n\t.reg .pred p;\n\t.reg .f32 aq;\n\t"
+      "abs.f32 aq, %1;\n\t"
+      "setp.gt.f32 p, %2, %3;\n\t"
+      "setp.lt.and.f32 p, aq, %4, p;\n\t"
+      "setp.lt.and.u32 p, %5, %6, p;\n\t"
+      "selp.b32 %0, %7, %8, p;\n\t}"
+      : "=r"(r) : "f"(q), "f"(adv), "f"(thr), "f"(hw_m), "r"(vrel), "r"(vn), "r"(off), "r"(sink));
+  return r;
+#else
+  return ((adv > thr) && (fabsf(q) < hw_m) && ((unsigned)vrel < (unsigned)vn)) ? off : sink;
+#endif
+}
+
+// Slow path of ring_lane for one arc's candidate `cc` whose float32 residual q is not decisive.
+// (fl, vt) describe the arc: fl = float offset of the top candidate from the lattice base (mirrored for
+// the bottom arc), vt = its index along the candidate axis relative to the tile.
+template <class Slow, class EmitSlow>
+RCV_HD void ring_slow(const PointCtx& c, const LaneTask& L, int i, int ub, int m, int arc, int cc, float q, float fl, int vt, Slow& slow,
+                      EmitSlow& emit_slow) {
+  const int v = arc ? (vt + cc) : (vt - cc), dv = v - L.vrel0;
+  if (((unsigned)v < (unsigned)L.vn) && slow(i, L.pass ? (c.ipy + dv) : L.ucoord, L.pass ? L.ucoord : (c.ipz + dv))) emit_slow(ub + v * L.sv);
+  if (cc == 0 && q >= c.hw_m) {
+    // The top candidate may lie outside the outer sphere; the run can then reach one voxel lower.
+    const int v2 = arc ? (vt + m) : (vt - m), dv2 = v2 - L.vrel0;
+    const float d2 = arc ? f_add(f_sub(fl, (float)m), L.fv) : f_sub(f_sub(fl, (float)m), L.fv);
+    if ((fabsf(d2) > L.thr) && ((unsigned)v2 < (unsigned)L.vn) &&
+        slow(i, L.pass ? (c.ipy + dv2) : L.ucoord, L.pass ? L.ucoord : (c.ipz + dv2)))
+      emit_slow(ub + v2 * L.sv);
+  }
+}
+
+// ---- thin ring slices (one candidate per arc): fast part and rare part split so that the kernel can
+// interleave the fast parts of two slices (two independent dependency chains each) before a single
+// rarely-taken branch.
+struct ThinOut {
+  float q0, q1, fl0, fl1;
+  int vt0, vt1, ub;
+  bool t0, t1;   // candidate of the top / bottom arc needs the exact path
+};
+
+//   emit(offset) -- the unconditional shared-memory atomic of the fast path, called exactly twice; the
+//                   offset is the voxel's, or `sink` when there is no vote.
 // Offsets are in the units lane_setup() was given (words on the host, bytes on the device);
 // `slice_base` = (i - i0) * nj * Dp in the same units.
-template <bool THIN, class Emit, class Slow, class EmitSlow>
-RCV_HD void ring_lane(const PointCtx& c, float a, int m, const LaneTask& L, int i, int slice_base, Emit& emit, Slow& slow,
-                      EmitSlow& emit_slow) {
+template <class Emit>
+RCV_HD void thin_fast(const PointCtx& c, float a, const LaneTask& L, int slice_base, int sink, Emit& emit, ThinOut& o) {
   const float g = f_sub(a, L.du2);
-  const bool lane_ok = L.active && (g > 0.f);
+  const float zs = f_sqrt_fast(fmaxf(g, 0.f));
+  const float hWg = f_sub(c.hW, g);        // g <= 0  =>  q >= W/2: never a fast-path vote
+  o.ub = L.ubase + slice_base;
+  const float tm0 = f_add(f_add(f_add(zs, L.fv), c.dbias_m05), RCV_MAGIC);   // top arc
+  const float tm1 = f_add(f_add(f_sub(zs, L.fv), c.dbias_m05), RCV_MAGIC);   // bottom arc, mirrored
+  o.fl0 = f_sub(tm0, RCV_MAGIC); o.fl1 = f_sub(tm1, RCV_MAGIC);
+  o.vt0 = L.vrel0 + (f_bits(tm0) - RCV_MAGIC_BITS);   // topmost candidate (>= true topmost voxel under the outer circle)
+  o.vt1 = L.vrel0 - (f_bits(tm1) - RCV_MAGIC_BITS);
+  const float d0 = f_sub(o.fl0, L.fv), d1 = f_add(o.fl1, L.fv);              // dv of the two candidates
+  o.q0 = f_fma(d0, d0, hWg); o.q1 = f_fma(d1, d1, hWg);                      // e + W/2, e = |v-p|^2 - R^2 in float32
+  emit(pick_offset(o.q0, fabsf(d0), o.vt0, o.ub + o.vt0 * L.sv, sink, c.hw_m, L.thr, L.vn));
+  emit(pick_offset(o.q1, fabsf(d1), o.vt1, o.ub + o.vt1 * L.sv, sink, c.hw_m, L.thr, L.vn));
+  // not surely inside the shell, but not surely beyond the inner boundary either: decide exactly
+  o.t0 = (fabsf(d0) > L.thr) && !(fabsf(o.q0) < c.hw_m) && (o.q0 > -c.hw_p);
+  o.t1 = (fabsf(d1) > L.thr) && !(fabsf(o.q1) < c.hw_m) && (o.q1 > -c.hw_p);
+}
+
+template <class SlowArc>
+RCV_HD void thin_slow(const PointCtx& c, const LaneTask& L, int i, const ThinOut& o, SlowArc& slowarc) {
+  if (o.t0) slowarc(c, L, i, o.ub, 1, 0, 0, o.q0, o.fl0, o.vt0);
+  if (o.t1) slowarc(c, L, i, o.ub, 1, 1, 0, o.q1, o.fl1, o.vt1);
+}
+
+// One lane, one ring slice with outer radius^2 `a` and `m` >= 1 candidates per arc (general form).
+//   slowarc(...) -- ring_slow() behind a call: decides candidates whose float32 residual is within eps
+//                   of a shell boundary with the exact float64 predicate (rare).
+template <class Emit, class SlowArc>
+RCV_HD void ring_lane(const PointCtx& c, float a, int m, const LaneTask& L, int i, int slice_base, int sink, Emit& emit, SlowArc& slowarc) {
+  const float g = f_sub(a, L.du2);
   const float zs = f_sqrt_fast(fmaxf(g, 0.f));
   const float hWg = f_sub(c.hW, g);
   const int ub = L.ubase + slice_base;
-  if (THIN) m = 1;
-#pragma unroll
-  for (int arc = 0; arc < 2; ++arc) {
-    const float fvs = arc ? -L.fv : L.fv;
-    const float tm = f_add(f_add(f_add(zs, fvs), c.dbias_m05), RCV_MAGIC);
-    const int kq = f_bits(tm) - RCV_MAGIC_BITS;  // topmost candidate (>= true topmost voxel inside the outer circle)
-    const float flr = f_sub(tm, RCV_MAGIC);
-    const int vtop = arc ? (L.vrel0 - kq) : (L.vrel0 + kq);
+  const float tm0 = f_add(f_add(f_add(zs, L.fv), c.dbias_m05), RCV_MAGIC);
+  const float tm1 = f_add(f_add(f_sub(zs, L.fv), c.dbias_m05), RCV_MAGIC);
+  const float fl0 = f_sub(tm0, RCV_MAGIC), fl1 = f_sub(tm1, RCV_MAGIC);
+  const int vt0 = L.vrel0 + (f_bits(tm0) - RCV_MAGIC_BITS);
+  const int vt1 = L.vrel0 - (f_bits(tm1) - RCV_MAGIC_BITS);
 #pragma unroll 1
-    for (int cc = 0; cc < m; ++cc) {
-      const float dvfs = f_sub(THIN ? flr : f_sub(flr, (float)cc), fvs);
-      const float q = f_fma(dvfs, dvfs, hWg);              // e + W/2, e = |v-p|^2 - R^2 in float32
-      const bool own = fabsf(dvfs) > L.thr;
-      const int vrel = arc ? (vtop + cc) : (vtop - cc);
-      const bool inb = (unsigned)vrel < (unsigned)L.vn;
-      const bool sure = fabsf(q) < c.hw_m;                 // -W + eps < e < -eps
-      emit(ub + vrel * L.sv, sure && own && inb && lane_ok);
-      if (!sure && (q > -c.hw_p) && lane_ok) {
-        // within eps of the inner boundary, or not surely inside the outer one: decide exactly
-        const int dv = arc ? (cc - kq) : (kq - cc);
-        if (own && inb && slow(i, L.pass ? (c.ipy + dv) : L.ucoord, L.pass ? L.ucoord : (c.ipz + dv))) emit_slow(ub + vrel * L.sv);
-        if (cc == 0 && q >= c.hw_m) {
-          // The top candidate may lie outside the outer sphere; the run can then reach one voxel lower.
-          const int dv2 = arc ? (m - kq) : (kq - m);
-          const float dvfs2 = f_sub(f_sub(flr, (float)m), fvs);
-          const int vrel2 = L.vrel0 + dv2;
-          if ((fabsf(dvfs2) > L.thr) && ((unsigned)vrel2 < (unsigned)L.vn) &&
-              slow(i, L.pass ? (c.ipy + dv2) : L.ucoord, L.pass ? L.ucoord : (c.ipz + dv2)))
-            emit_slow(ub + vrel2 * L.sv);
-        }
-      }
-      if (THIN) break;
+  for (int cc = 0; cc < m; ++cc) {
+    const float fc = (float)cc;
+    const float d0 = f_sub(f_sub(fl0, fc), L.fv), d1 = f_add(f_sub(fl1, fc), L.fv);
+    const float q0 = f_fma(d0, d0, hWg), q1 = f_fma(d1, d1, hWg);
+    const int v0 = vt0 - cc, v1 = vt1 + cc;
+    emit(pick_offset(q0, fabsf(d0), v0, ub + v0 * L.sv, sink, c.hw_m, L.thr, L.vn));
+    emit(pick_offset(q1, fabsf(d1), v1, ub + v1 * L.sv, sink, c.hw_m, L.thr, L.vn));
+    const bool t0 = (fabsf(d0) > L.thr) && !(fabsf(q0) < c.hw_m) && (q0 > -c.hw_p);
+    const bool t1 = (fabsf(d1) > L.thr) && !(fabsf(q1) < c.hw_m) && (q1 > -c.hw_p);
+    if (t0 || t1) {
+      if (t0) slowarc(c, L, i, ub, m, 0, cc, q0, fl0, vt0);
+      if (t1) slowarc(c, L, i, ub, m, 1, cc, q1, fl1, vt1);
     }
   }
 }
 
 // One lane, one cell (dj, dk) of a dense slice's bounding box.
 template <class Emit, class Slow>
-RCV_HD void dense_cell(const PointCtx& c, float a, const Tile& t, int i, int slice_base, int unit, int dj, int dk, bool cell_ok,
+RCV_HD void dense_cell(const PointCtx& c, float a, const Tile& t, int i, int slice_base, int unit, int sink, int dj, int dk, bool cell_ok,
                        Emit& emit, Slow& slow) {
   const float dyf = f_sub((float)dj, c.fy), dzf = f_sub((float)dk, c.fz);
   const float q = f_add(f_fma(dzf, dzf, f_fma(dyf, dyf, -a)), c.hW);
@@ -248,7 +304,7 @@ RCV_HD void dense_cell(const PointCtx& c, float a, const Tile& t, int i, int sli
   const bool amb = !sure && (fabsf(q) <= c.hw_p);
   bool vote = sure && inb;
   if (amb && inb) vote = slow(i, vj, vk);
-  emit(slice_base + ((vj - t.j0) * t.Dp + vk) * unit, vote);
+  emit(vote ? slice_base + ((vj - t.j0) * t.Dp + vk) * unit : sink);
 }
 
 // Slice range of point c inside tile t (inclusive); empty if ia > ib.

@@ -29,11 +29,16 @@ namespace {
 
 using namespace rcv;
 
-constexpr int kVoteThreads = 512;
+#ifndef RCV_VOTE_THREADS
+#define RCV_VOTE_THREADS 512
+#endif
+constexpr int kVoteThreads = RCV_VOTE_THREADS;
 constexpr int kVoteWarps = kVoteThreads / 32;
 constexpr int kSmemBytes = 232448;                        // 227 KB: the sm_100 per-CTA maximum
 constexpr int kDummyWords = 32 * kVoteWarps;              // one private sink word per lane per warp
-constexpr int kTileWords = kSmemBytes / 4 - kDummyWords - 128;   // 128 words left for static shared variables
+constexpr int kTabRows = 36;                                  // 32 slices + spare rows for the prefetch
+constexpr int kTabWords = kTabRows * 4 * kVoteWarps;          // per-warp table of ring slices (int4 rows)
+constexpr int kTileWords = kSmemBytes / 4 - kDummyWords - kTabWords - 128;   // 128 words left for static shared variables
 constexpr int kStVolumeSkipped = 32;
 
 struct ItemMeta {
@@ -515,57 +520,115 @@ struct VoteArgs {
 // the voxel or, for a lane with no vote, to the lane's private sink word, so the instruction is never
 // predicated or branched around (a predicated ATOMS compiles to a divergent branch, 3.6x slower).
 __device__ __forceinline__ void smem_inc(unsigned addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory"); }
-struct SmemEmit {
-  unsigned base, sink;
-  __device__ __forceinline__ void operator()(int off, bool vote) const { smem_inc(vote ? base + (unsigned)off : sink); }
-};
-struct SmemEmitSlow {
-  unsigned base;
+struct SmemEmit {   // offsets are bytes relative to the tile; `sink` is the lane's private word after the tile
+  unsigned base; int sink;
   __device__ __forceinline__ void operator()(int off) const { smem_inc(base + (unsigned)off); }
 };
-// The exact predicate lives behind a call so the compiler cannot hoist its float64 arithmetic into the
+typedef SmemEmit SmemEmitSlow;
+// The exact float64 path lives behind a call so the compiler cannot hoist any of its arithmetic into the
 // hot loop (it did: 40% of the first version's instructions were speculated DADD/DMUL/DSQRT).
+struct SlowExact {
+  double px, py, pz; int R;
+  __device__ __forceinline__ bool operator()(int i, int j, int k) const { return exact_hit(px, py, pz, R, i, j, k); }
+};
+__device__ __noinline__ void ring_slow_call(double px, double py, double pz, int R, int ipy, int ipz, float hw_m, float fv, float thr,
+                                            int vrel0, int vn, int ucoord, int pass, int sv, int i, int ub, int m, int arc, int cc,
+                                            float q, float fl, int vt, unsigned base) {
+  PointCtx c;
+  c.px = px; c.py = py; c.pz = pz; c.R = R; c.ipy = ipy; c.ipz = ipz; c.hw_m = hw_m;
+  LaneTask L;
+  L.fv = fv; L.thr = thr; L.vrel0 = vrel0; L.vn = vn; L.ucoord = ucoord; L.pass = pass != 0; L.sv = sv;
+  SlowExact slow{px, py, pz, R};
+  SmemEmit es{base, 0};
+  ring_slow(c, L, i, ub, m, arc, cc, q, fl, vt, slow, es);
+}
+struct SlowArcCall {
+  unsigned base;
+  __device__ __forceinline__ void operator()(const PointCtx& c, const LaneTask& L, int i, int ub, int m, int arc, int cc, float q, float fl,
+                                             int vt) const {
+    ring_slow_call(c.px, c.py, c.pz, c.R, c.ipy, c.ipz, c.hw_m, L.fv, L.thr, L.vrel0, L.vn, L.ucoord, L.pass ? 1 : 0, L.sv, i, ub, m, arc, cc,
+                   q, fl, vt, base);
+  }
+};
 __device__ __noinline__ bool exact_hit_call(double px, double py, double pz, int R, int i, int j, int k) {
   return exact_hit(px, py, pz, R, i, j, k);
 }
-struct SlowExact {
+struct SlowExactCall {
   double px, py, pz; int R;
   __device__ __forceinline__ bool operator()(int i, int j, int k) const { return exact_hit_call(px, py, pz, R, i, j, k); }
 };
 
 struct PointData { double x, y, z; int R; };
 
-__device__ __forceinline__ void vote_point(const PointData& pd, const Tile& t, int lane, const SmemEmit& emit_c) {
+__device__ __forceinline__ int4 lds128(unsigned addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, int4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// One point, one tile, one warp.  `tab_s` is the shared-window address of the warp's private table of
+// ring slices (33 x int4 {a bits, candidates per arc, slice byte offset, slice index}; thin slices first).
+__device__ __forceinline__ void vote_point(const PointData& pd, const Tile& t, int lane, const SmemEmit& emit_c, unsigned tab_s) {
   SmemEmit emit = emit_c;
-  SmemEmitSlow emit_slow{emit_c.base};
+  SlowArcCall slowarc{emit_c.base};
   PointCtx c;
   point_setup(c, pd.x, pd.y, pd.z, pd.R);
-  SlowExact slow{pd.x, pd.y, pd.z, pd.R};
+  SlowExactCall slow{pd.x, pd.y, pd.z, pd.R};
   int ia, ib;
   slice_range(c, t, ia, ib);
   const int slice_bytes = t.nj * t.Dp * 4;
   for (int sb = ia; sb <= ib; sb += 32) {
-    // classify 32 slices at once, one per lane
+    // classify 32 slices at once, one per lane; ring slices are compacted into the warp's table
     float a_l = 0.f; int code_l = 0;
     if (sb + lane <= ib) slice_setup(c, sb + lane, a_l, code_l);
-    const unsigned ring_mask = __ballot_sync(0xffffffffu, code_l > 0);
+    const unsigned thin_mask = __ballot_sync(0xffffffffu, code_l == 1);
+    const unsigned thick_mask = __ballot_sync(0xffffffffu, code_l > 1);
     const unsigned dense_mask = __ballot_sync(0xffffffffu, code_l < 0);
-    if (ring_mask) {
+    if (thin_mask | thick_mask) {
       float amax = code_l > 0 ? a_l : 0.f;
 #pragma unroll
       for (int m = 16; m; m >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, m));
+      const int nthin = __popc(thin_mask), nring = nthin + __popc(thick_mask);
+      const unsigned lt = (1u << lane) - 1u;
+      __syncwarp();
+      if (code_l > 0) {
+        const int pos = code_l == 1 ? __popc(thin_mask & lt) : nthin + __popc(thick_mask & lt);
+        sts128(tab_s + 16u * pos, make_int4(__float_as_int(a_l), code_l, (sb + lane - t.i0) * slice_bytes, sb + lane));
+      }
+      __syncwarp();
       const int H = ring_half_width(amax);
       const int ntask = 2 * (2 * H + 1);
       for (int base = 0; base < ntask; base += 32) {
         LaneTask L;
         lane_setup(c, t, H, base + lane, 4, L);
-        for (unsigned mk = ring_mask; mk; mk &= mk - 1) {
-          const int sl = __ffs(mk) - 1;
-          const float a = __shfl_sync(0xffffffffu, a_l, sl);
-          const int m = __shfl_sync(0xffffffffu, code_l, sl);
-          const int i = sb + sl;
-          if (m == 1) ring_lane<true>(c, a, 1, L, i, (i - t.i0) * slice_bytes, emit, slow, emit_slow);
-          else ring_lane<false>(c, a, m, L, i, (i - t.i0) * slice_bytes, emit, slow, emit_slow);
+        int s = 0;
+        // thin slices two at a time: four independent candidate chains, one rarely-taken branch
+        int4 e0 = lds128(tab_s), e1 = lds128(tab_s + 16u);
+#pragma unroll 1
+        for (; s + 2 <= nthin; s += 2) {
+          const int4 n0 = lds128(tab_s + 16u * (s + 2)), n1 = lds128(tab_s + 16u * (s + 3));   // prefetch (table has 2 spare rows)
+          ThinOut oa, ob;
+          thin_fast(c, __int_as_float(e0.x), L, e0.z, emit.sink, emit, oa);
+          thin_fast(c, __int_as_float(e1.x), L, e1.z, emit.sink, emit, ob);
+          if (oa.t0 || oa.t1 || ob.t0 || ob.t1) {
+            if (oa.t0 || oa.t1) thin_slow(c, L, e0.w, oa, slowarc);
+            if (ob.t0 || ob.t1) thin_slow(c, L, e1.w, ob, slowarc);
+          }
+          e0 = n0; e1 = n1;
+        }
+        if (s < nthin) {
+          ThinOut oa;
+          thin_fast(c, __int_as_float(e0.x), L, e0.z, emit.sink, emit, oa);
+          if (oa.t0 || oa.t1) thin_slow(c, L, e0.w, oa, slowarc);
+          ++s;
+        }
+#pragma unroll 1
+        for (; s < nring; ++s) {
+          const int4 e = lds128(tab_s + 16u * s);
+          ring_lane(c, __int_as_float(e.x), e.y, L, e.w, e.z, emit.sink, emit, slowarc);
         }
       }
     }
@@ -578,7 +641,7 @@ __device__ __forceinline__ void vote_point(const PointData& pd, const Tile& t, i
       for (int r0 = 0; r0 < side; r0 += rpi)
         for (int k0 = 0; k0 < side; k0 += lpr) {
           const int rr = r0 + (lane >> lshift), kk = k0 + (lane & (lpr - 1));
-          dense_cell(c, a, t, i, (i - t.i0) * slice_bytes, 4, rr - hb, kk - hb, rr < side && kk < side, emit, slow);
+          dense_cell(c, a, t, i, (i - t.i0) * slice_bytes, 4, emit.sink, rr - hb, kk - hb, rr < side && kk < side, emit, slow);
         }
     }
   }
@@ -590,8 +653,10 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
   __shared__ int s_unit, s_next;
   __shared__ unsigned long long s_key[kVoteWarps], s_sum[kVoteWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
-  const SmemEmit emit{tile_s, tile_s + 4u * (unsigned)(kTileWords + warp * 32 + lane)};
+  unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
+  asm volatile("mov.u32 %0, %0;" : "+r"(tile_s));   // keep the shared-window base in a register (ptxas otherwise rematerialises it per use)
+  const SmemEmit emit{tile_s, 4 * (kTileWords + warp * 32 + lane)};
+  const unsigned tab_s = tile_s + 4u * (unsigned)(kTileWords + kDummyWords + warp * kTabRows * 4);
   const int n_units = a.counters[0];
   for (;;) {
     __syncthreads();
@@ -623,7 +688,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
       nxt = __shfl_sync(0xffffffffu, nxt, 0);
       PointData nd{0, 0, 0, 0};
       if (nxt < n) { nd.x = a.pool.X[off + nxt]; nd.y = a.pool.Y[off + nxt]; nd.z = a.pool.Z[off + nxt]; nd.R = a.pool.Ri[off + nxt]; }
-      vote_point(pd, t, lane, emit);
+      vote_point(pd, t, lane, emit, tab_s);
       cur = nxt; pd = nd;
     }
     __syncthreads();
@@ -948,7 +1013,7 @@ RCV_EXPORT int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out) {
   CKC(cudaMalloc(&c->leaves, sizeof(PwLeaf) * (size_t)c->leaf_cap)); CKC(cudaMalloc(&c->leaf_sums, 24 * (size_t)c->leaf_cap));
   for (int e = 0; e < 64; ++e) { CKC(cudaEventCreate(&c->evr[e][0])); CKC(cudaEventCreate(&c->evr[e][1])); }
   CKC(cudaFuncSetAttribute(k_ubench_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
-  CKC(cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (kTileWords + kDummyWords) * 4));
+  CKC(cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (kTileWords + kDummyWords + kTabWords) * 4));
 #undef CKC
   return RCV_OK;
 }
@@ -965,7 +1030,7 @@ static int run_items(rcv_ctx* c, int n_items, const rcv_vote_params* vp, double*
   VoteArgs va{c->pool, c->meta, c->units, c->counters, c->best, c->votes, volume, volume_cap};
   const int slot = (int)(c->ev_count % 64);
   CK(c, cudaEventRecord(c->evr[slot][0], st));
-  k_vote<<<c->sms, kVoteThreads, (kTileWords + kDummyWords) * 4, st>>>(va);
+  k_vote<<<c->sms, kVoteThreads, (kTileWords + kDummyWords + kTabWords) * 4, st>>>(va);
   CK(c, cudaEventRecord(c->evr[slot][1], st));
   c->ev_count += 1;
   FinalArgs fa{c->meta, c->best, c->votes, n_items, vp->acc_unit, vp->grid_policy, volume != nullptr, volume_cap,

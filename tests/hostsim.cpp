@@ -11,20 +11,27 @@ using namespace rcv;
 
 struct HostEmit {
   int32_t* tile; long words; long long votes = 0, calls = 0, oob = 0, slow_calls = 0;
-  void operator()(int off, bool vote) {
+  void operator()(int off) {
     ++calls;
-    if (!vote) return;
+    if (off == -1) return;                      // the sink
     if (off < 0 || off >= words) { ++oob; return; }
     tile[off] += 1; ++votes;
   }
 };
 struct HostEmitSlow {
   HostEmit* e;
-  void operator()(int off) { (*e)(off, true); --e->calls; }
+  void operator()(int off) { (*e)(off); --e->calls; }
 };
 struct HostSlow {
   const PointCtx* c; HostEmit* e;
   bool operator()(int i, int j, int k) { ++e->slow_calls; return exact_hit(c->px, c->py, c->pz, c->R, i, j, k); }
+};
+
+struct HostSlowArc {
+  HostSlow* slow; HostEmitSlow* es;
+  void operator()(const PointCtx& c, const LaneTask& L, int i, int ub, int m, int arc, int cc, float q, float fl, int vt) {
+    ring_slow(c, L, i, ub, m, arc, cc, q, fl, vt, *slow, *es);
+  }
 };
 
 extern "C" __attribute__((visibility("default")))
@@ -39,6 +46,7 @@ int hostsim_render(const double* p, const int* R, long n, int D, int Dp, int i0,
     PointCtx c;
     point_setup(c, p[3 * q], p[3 * q + 1], p[3 * q + 2], R[q]);
     HostSlow slow{&c, &emit};
+    HostSlowArc slowarc{&slow, &emit_slow};
     int ia, ib;
     slice_range(c, t, ia, ib);
     for (int sb = ia; sb <= ib; sb += 32) {
@@ -56,13 +64,24 @@ int hostsim_render(const double* p, const int* R, long n, int D, int Dp, int i0,
           for (int lane = 0; lane < 32; ++lane) {
             LaneTask L;
             lane_setup(c, t, H, base + lane, 1, L);
-            for (int sl = 0; sl < 32; ++sl) {
-              if (code_l[sl] <= 0) continue;
-              const int i = sb + sl;
-              if (lane == 0 && base == 0) ++ring_slices;
+            // thin slices first, in pairs (as the kernel does), then the general ones
+            int thin[32], nthin = 0, thick[32], nthick = 0;
+            for (int sl = 0; sl < 32; ++sl) { if (code_l[sl] == 1) thin[nthin++] = sl; else if (code_l[sl] > 1) thick[nthick++] = sl; }
+            for (int s = 0; s < nthin; s += 2) {
+              ThinOut oa, ob;
+              const int ia_ = sb + thin[s];
+              thin_fast(c, a_l[thin[s]], L, (ia_ - i0) * nj * Dp, -1, emit, oa);
+              const bool two = s + 1 < nthin;
+              const int ib_ = two ? sb + thin[s + 1] : 0;
+              if (two) thin_fast(c, a_l[thin[s + 1]], L, (ib_ - i0) * nj * Dp, -1, emit, ob);
+              if (oa.t0 || oa.t1) thin_slow(c, L, ia_, oa, slowarc);
+              if (two && (ob.t0 || ob.t1)) thin_slow(c, L, ib_, ob, slowarc);
+              lane_tasks += two ? 2 : 1;
+            }
+            for (int s = 0; s < nthick; ++s) {
+              const int i = sb + thick[s];
               ++lane_tasks;
-              if (code_l[sl] == 1) ring_lane<true>(c, a_l[sl], 1, L, i, (i - i0) * nj * Dp, emit, slow, emit_slow);
-              else ring_lane<false>(c, a_l[sl], code_l[sl], L, i, (i - i0) * nj * Dp, emit, slow, emit_slow);
+              ring_lane(c, a_l[thick[s]], code_l[thick[s]], L, i, (i - i0) * nj * Dp, -1, emit, slowarc);
             }
           }
       }
@@ -75,7 +94,7 @@ int hostsim_render(const double* p, const int* R, long n, int D, int Dp, int i0,
           for (int k0 = 0; k0 < side; k0 += lpr)
             for (int lane = 0; lane < 32; ++lane) {
               const int rr = r0 + lane / lpr, kk = k0 + lane % lpr;
-              dense_cell(c, a_l[sl], t, i, (i - i0) * nj * Dp, 1, rr - hb, kk - hb, rr < side && kk < side, emit, slow);
+              dense_cell(c, a_l[sl], t, i, (i - i0) * nj * Dp, 1, -1, rr - hb, kk - hb, rr < side && kk < side, emit, slow);
             }
       }
     }
