@@ -1,0 +1,129 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every symbol that
+include/rcvvote.h declares, refuses to run without an sm_100 GPU (no CPU fallback), and the
+frame-sharding / result-gather logic of the multi-GPU path works over gloo with world_size 2."""
+import ctypes
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "rcvvote.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rcv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rcvpose_b200 import _lib, build
+    lib = build.build_library()
+    L = ctypes.CDLL(lib)
+    names = _header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), "include/rcvvote.h declares %s but librcvvote.so does not export it" % n
+    assert sorted(_lib.EXPORTS) == names, "ctypes binding and header disagree"
+    L.rcv_abi_version.restype = ctypes.c_int
+    assert L.rcv_abi_version() == _lib.RCV_ABI_VERSION
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_gpu_means_loud_failure_not_fallback():
+    from rcvpose_b200 import _lib, api
+    with pytest.raises(Exception) as ei:
+        api.VoteContext(0, max_items=4, max_points_total=1024, max_grid=64)
+    assert "CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+    from rcvpose_b200 import AccumulatorSpace as A
+    with pytest.raises(Exception):
+        A.Accumulator_3D(np.zeros((4, 3)), np.ones(4, np.float32))
+    assert _lib.load().rcv_abi_version() == 1
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under rcvpose_b200/ may import or load it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "rcvpose_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "librcv_oracle" not in text, f
+
+
+def test_shard_range_partitions_frames():
+    from rcvpose_b200.pipeline import shard_range
+    for n in (0, 1, 7, 8, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_pack_unpack_roundtrip():
+    from rcvpose_b200.pipeline import pack_results, unpack_results
+    rng = np.random.default_rng(0)
+    B, Kp = 5, 3
+    c = torch.from_numpy(rng.normal(size=(B, Kp, 3)))
+    RT = torch.from_numpy(rng.normal(size=(B, 4, 4)))
+    peak = torch.from_numpy(rng.integers(0, 5000, size=(B, Kp)).astype(np.int32))
+    st = torch.from_numpy(rng.integers(0, 32, size=(B, Kp)).astype(np.int32))
+    rows = pack_results(c, RT, peak, st)
+    assert rows.shape == (B, 3 * Kp + 16 + 2 * Kp)
+    c2, RT2, p2, s2 = unpack_results(rows, Kp)
+    assert torch.equal(c, c2) and torch.equal(RT, RT2) and torch.equal(peak, p2) and torch.equal(st, s2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, n_frames, q):
+    import torch.distributed as dist
+    from rcvpose_b200.pipeline import gather_results, pack_results, shard_range, unpack_results
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_range(n_frames, rank, world)
+        f = torch.arange(lo, hi, dtype=torch.float64)
+        centres = (f[:, None, None] * 10 + torch.arange(3, dtype=torch.float64)[None, :, None] + torch.arange(3, dtype=torch.float64)[None, None, :] / 10)
+        RT = f[:, None, None] + torch.eye(4, dtype=torch.float64)[None]
+        peak = (f[:, None] + torch.arange(3)[None, :]).to(torch.int32)
+        st = torch.zeros((hi - lo, 3), dtype=torch.int32)
+        rows = pack_results(centres, RT, peak, st)
+        out_known = gather_results(rows, counts=[shard_range(n_frames, r, world)[1] - shard_range(n_frames, r, world)[0] for r in range(world)])
+        out_probe = gather_results(rows)                      # counts discovered by a first all_gather
+        c, R, p, s = unpack_results(out_known, 3)
+        ok = bool(torch.equal(out_known, out_probe) and out_known.shape[0] == n_frames
+                  and torch.equal(c[:, 0, 0], torch.arange(n_frames, dtype=torch.float64) * 10)
+                  and torch.equal(p[:, 2], (torch.arange(n_frames) + 2).to(torch.int32))
+                  and torch.equal(R[:, 3, 3], torch.arange(n_frames, dtype=torch.float64) + 1))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [8, 7])
+def test_gather_results_world2_gloo(n_frames):
+    """N>1 path on CPU: two ranks own contiguous (possibly unequal) frame ranges, results are gathered in frame order."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
