@@ -3,16 +3,23 @@
 // What it renders.  The reference's vote loop (AccumulatorSpace.py:325-341) increments voxel
 // (i,j,k) for point p with integer radius R iff
 //        0 < R - sqrt((i-px)^2 + (j-py)^2 + (k-pz)^2) < sqrt(3)/4        (float64, strict)
-// evaluated for EVERY voxel of the D^3 cube.  This file emits exactly that voxel set by scattering:
-// for the x-slice i of a sphere the set is a ring in the (j,k) plane with outer radius^2
-// a = R^2 - dx^2 and inner radius^2 b = a - W, W = R^2 - (R - sqrt3/4)^2.  The ring is split into
-// four arcs by the dominant axis of (dy,dz):
-//     Z-pass: one lane per column j, candidates k = topmost voxel under the outer circle and the
-//             m-1 below it (mirror image for the bottom arc); owns voxels with |dz| >= |dy|;
-//     Y-pass: one lane per row k, candidates along j; owns |dy| > |dz|.
-// In its own pass an arc crosses each column in fewer than m voxels (m = 1 for most slices), so a
-// lane tests m candidates per arc and there is no data-dependent loop.  Rings too close to the pole
-// of the sphere (b < 4 or a <= 36) are rendered densely over their small bounding box instead.
+// evaluated for EVERY voxel of the D^3 cube.  This file emits exactly that voxel set by scattering.
+// One lane owns one point.  Axes here are the rasteriser's own (A,B,C) = (x,y,z) of this file; the
+// kernel feeds it a permutation of the reference's axes (see rcvvote.cu).  For the A-slice i of a
+// sphere the set is a ring in the (B,C) plane with outer radius^2 a = R^2 - dx^2 and inner radius^2
+// b = a - W, W = R^2 - (R - sqrt3/4)^2.
+//
+//   thin rings (slice_setup code 1: no arc crosses a column of its own pass in more than one voxel,
+//   about 80 % of a sphere's slices) are drawn by two ring passes.  The ring is split into four arcs
+//   by the dominant axis of (dy,dz):
+//     Z-pass: one task per column j, candidate k = topmost voxel under the outer circle (mirror image
+//             for the bottom arc); owns voxels with |dz| >= |dy|;
+//     Y-pass: one task per row k, candidates along j; owns |dy| > |dz|.
+//   all other slices (the two polar caps of the slice axis) are drawn by the polar pass: for
+//   R >= RCV_POLAR_MIN_R a column ALONG the slice axis crosses the shell of such a slice in less than
+//   one voxel, so the thin-ring arithmetic applies with the axes rotated; a candidate votes iff its
+//   slice is one of the lane's non-thin slices (bit mask), so the two kinds of pass partition the
+//   shell exactly.  Spheres with R < RCV_POLAR_MIN_R are scanned densely over their bounding box.
 //
 // Exactness.  Candidates are classified in float32 with a proven error bound eps; a candidate whose
 // float32 residual lies within eps of either shell boundary is re-decided by exact_hit(), which
@@ -21,7 +28,7 @@
 // against the brute-force oracle, and the -m gpu tests check the CUDA build the same way.
 //
 // The header is shared by the CUDA kernel (rcvvote.cu) and the host-side test harness
-// (tests/hostsim.cpp): all float arithmetic goes through the RCV_F* wrappers, which are the
+// (tests/hostsim.cpp): all float arithmetic goes through the f_* / d_* wrappers, which are the
 // never-contracted intrinsics on the device and plain IEEE operations (-ffp-contract=off) on the host.
 #pragma once
 #include <math.h>
@@ -44,9 +51,10 @@ RCV_HD float f_add(float a, float b) { return __fadd_rn(a, b); }
 RCV_HD float f_sub(float a, float b) { return __fsub_rn(a, b); }
 RCV_HD float f_mul(float a, float b) { return __fmul_rn(a, b); }
 RCV_HD float f_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-RCV_HD float f_sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RCV_HD float f_sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // NaN for x < 0
 RCV_HD int f_bits(float x) { return __float_as_int(x); }
 RCV_HD float f_from_bits(int x) { return __int_as_float(x); }
+RCV_HD unsigned u_shr(unsigned m, int v) { unsigned r; asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(m), "r"(v)); return r; }   // 0 for v outside [0,32)
 RCV_HD double d_add(double a, double b) { return __dadd_rn(a, b); }
 RCV_HD double d_sub(double a, double b) { return __dsub_rn(a, b); }
 RCV_HD double d_mul(double a, double b) { return __dmul_rn(a, b); }
@@ -64,13 +72,14 @@ RCV_HD float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
 RCV_HD int f_bits(float x) { int i; memcpy(&i, &x, 4); return i; }
 RCV_HD float f_from_bits(int x) { float f; memcpy(&f, &x, 4); return f; }
 RCV_HD float f_sqrt_fast(float x) {
-  float r = sqrtf(x);
+  float r = sqrtf(x);   // NaN for x < 0, like the device instruction
   if (g_sqrt_perturb && r > 0.f) {
     g_sqrt_rng = g_sqrt_rng * 1664525u + 1013904223u;
     r = f_from_bits(f_bits(r) + (int)((g_sqrt_rng >> 16) % 5u) - 2);
   }
   return r;
 }
+RCV_HD unsigned u_shr(unsigned m, int v) { return ((unsigned)v < 32u) ? (m >> v) : 0u; }
 RCV_HD double d_add(double a, double b) { return a + b; }
 RCV_HD double d_sub(double a, double b) { return a - b; }
 RCV_HD double d_mul(double a, double b) { return a * b; }
@@ -80,6 +89,7 @@ RCV_HD int d_rint(double a) { return (int)nearbyint(a); }
 
 #define RCV_MAGIC 12582912.0f        // 1.5 * 2^23: adding it rounds a float to the nearest integer
 #define RCV_MAGIC_BITS 0x4B400000
+#define RCV_POLAR_MIN_R 7            // smallest R drawn by ring + polar passes (see polar_fast)
 
 // The reference predicate, operation for operation (AccumulatorSpace.py:337-338).
 RCV_HD bool exact_hit(double px, double py, double pz, int R, int i, int j, int k) {
@@ -95,7 +105,7 @@ struct Tile {
   int i0, ni, j0, nj, D, Dp;
 };
 
-// Per-point constants (warp-uniform).
+// Per-point constants (one lane).
 struct PointCtx {
   double px, py, pz;  // exact shifted voxel-unit coordinates (what the reference passes to fast_for)
   int R;
@@ -117,6 +127,7 @@ RCV_HD void point_setup(PointCtx& c, double px, double py, double pz, int R) {
   // |e_float32 - e_exact| <= 2^-21 (R+2)^2 ("error bound"); eps carries a 2x margin.
   const float rp2 = (float)(R + 2);
   c.eps = f_mul(f_mul(rp2, rp2), 9.5367431640625e-07f);        // 2^-20
+  // bias of the floor that picks the top candidate: covers the rounding of sqrt and of the additions before the floor
   const float dbias = f_add(f_mul(c.eps, 0.125f), f_mul(rp2, 9.5367431640625e-07f));
   c.dbias_m05 = f_sub(dbias, 0.5f);
   c.hW = f_mul(c.W, 0.5f);
@@ -124,9 +135,8 @@ RCV_HD void point_setup(PointCtx& c, double px, double py, double pz, int R) {
   c.hw_p = f_add(c.hW, c.eps);
 }
 
-// Per-(point, slice) classification (warp-uniform; the kernel evaluates 32 slices at once, one per
-// lane, and broadcasts (a, code) with shuffles).  code > 0: ring slice, code = candidates per arc;
-// code < 0: dense slice, -code = half-width of its bounding box; code == 0: nothing to draw.
+// Per-(point, slice) classification.  code == 1: thin ring; code > 1: thick ring (code = longest arc run);
+// code < 0: small ring, -code = half-width of its bounding box; code == 0: nothing to draw.
 RCV_HD void slice_setup(const PointCtx& c, int i, float& a, int& code) {
   const float dxf = f_sub((float)(i - c.ipx), c.fx);
   a = f_sub(c.R2, f_mul(dxf, dxf));
@@ -142,35 +152,36 @@ RCV_HD void slice_setup(const PointCtx& c, int i, float& a, int& code) {
   code = (int)f_add(lmax, 0.02f) + 1;
 }
 
-// Per-lane task: one column (Z-pass) or row (Y-pass) of the ring, both arcs.
+// One column (Z-pass) or row (Y-pass) of a lane's rings, both arcs.
 struct LaneTask {
   float du2, thr, fv;
-  int ubase;   // offset of (lane coordinate, candidate coordinate 0) inside a slice of the tile, in `unit`s
-  int sv;      // stride of the candidate axis (1 word for Z-pass, Dp words for Y-pass), in `unit`s
-  int vrel0;   // lattice base of the candidate axis relative to the tile origin
-  int vn;      // extent of the candidate axis in the tile
-  int ucoord;  // global index along the lane axis
-  bool pass;   // false: Z-pass (lane axis j, candidates along k); true: Y-pass
-  bool active;
+  float cp, cm;  // fv + dbias - 0.5 and -fv + dbias - 0.5: what is added to the half-chord before the floor
+  int ubase;     // offset of (lane coordinate, candidate coordinate 0) inside a slice of the tile, in `unit`s
+  int sv;        // stride of the candidate axis (1 word for Z-pass, Dp words for Y-pass), in `unit`s
+  int vrel0;     // lattice base of the candidate axis relative to the tile origin
+  int vn;        // extent of the candidate axis in the tile
+  int ucoord;    // global index along the lane axis
+  bool pass;     // false: Z-pass (lane axis j, candidates along k); true: Y-pass
 };
 
-// Half-width (in lanes) needed so that every owned voxel of a ring with outer radius^2 <= amax
-// lies in a lane: owned => du^2 <= dv^2 and du^2 + dv^2 < a  =>  |du| < sqrt(a/2); |u| <= |du| + 0.5.
+// Half-width (in columns) needed so that every owned voxel of a ring with outer radius^2 <= amax
+// lies in a task: owned => du^2 <= dv^2 and du^2 + dv^2 < a  =>  |du| < sqrt(a/2); |u| <= |du| + 0.5.
 RCV_HD int ring_half_width(float amax) { return (int)f_add(f_sqrt_fast(f_mul(amax, 0.5f)), 0.5f) + 1; }
 
-RCV_HD void lane_setup(const PointCtx& c, const Tile& t, int H, int tau, int unit, LaneTask& L) {
-  const int Wc = 2 * H + 1;
-  L.pass = tau >= Wc;
-  const int u = tau - (L.pass ? Wc : 0) - H;
-  const float fu = L.pass ? c.fz : c.fy;
-  L.fv = L.pass ? c.fy : c.fz;
-  const float duf = f_sub((float)u, fu);
+// Task of column/row `u` (lattice offset from the point's nearest lattice point) in pass `pass`; uf == (float)u.
+RCV_HD void lane_setup_pu(const PointCtx& c, const Tile& t, bool pass, int u, float uf, int unit, LaneTask& L) {
+  L.pass = pass;
+  const float fu = pass ? c.fz : c.fy;
+  L.fv = pass ? c.fy : c.fz;
+  L.cp = f_add(L.fv, c.dbias_m05);
+  L.cm = f_sub(c.dbias_m05, L.fv);
+  const float duf = f_sub(uf, fu);
   L.du2 = f_mul(duf, duf);
   const float ad = fabsf(duf);
   // Z-pass owns |dv| >= |du|  <=>  |dv| > pred(|du|); Y-pass owns |dv| > |du|: complementary.
-  L.thr = L.pass ? ad : (ad > 0.f ? f_from_bits(f_bits(ad) - 1) : -1.0f);
+  L.thr = pass ? ad : (ad > 0.f ? f_from_bits(f_bits(ad) - 1) : -1.0f);
   bool ok;
-  if (!L.pass) {
+  if (!pass) {
     L.ucoord = c.ipy + u;
     ok = (unsigned)(L.ucoord - t.j0) < (unsigned)t.nj;
     L.ubase = (L.ucoord - t.j0) * t.Dp * unit;
@@ -181,50 +192,56 @@ RCV_HD void lane_setup(const PointCtx& c, const Tile& t, int H, int tau, int uni
     L.ubase = L.ucoord * unit;
     L.sv = t.Dp * unit; L.vrel0 = c.ipy - t.j0; L.vn = t.nj;
   }
-  L.active = ok && tau < 2 * Wc;
-  if (!L.active) L.thr = 3.0e38f;   // an inactive lane owns nothing
+  if (!ok) L.thr = 3.0e38f;   // a task outside the tile owns nothing
 }
 
 // Fast-path vote decision of one candidate: sure = residual strictly inside the shell by more than eps,
-// own = the candidate belongs to this pass, inb = inside the tile.  Returns the offset to increment:
-// the voxel's or, when there is no vote, the lane's private sink.
+// own = the candidate belongs to this pass, inb = inside the tile (tested only if CLIP).  Returns the offset to
+// increment: the voxel's or, when there is no vote, the lane's private sink.
+template <bool CLIP>
 RCV_HD int pick_offset(float q, float adv, int vrel, int off, int sink, float hw_m, float thr, int vn) {
 #if defined(__CUDA_ARCH__)
   int r;
-  asm("{\n\t.reg .pred p;\n\t.reg .f32 aq;\n\t"
-      "abs.f32 aq, %1;\n\t"
-      "setp.gt.f32 p, %2, %3;\n\t"
-      "setp.lt.and.f32 p, aq, %4, p;\n\t"
-      "setp.lt.and.u32 p, %5, %6, p;\n\t"
-      "selp.b32 %0, %7, %8, p;\n\t}"
-      : "=r"(r) : "f"(q), "f"(adv), "f"(thr), "f"(hw_m), "r"(vrel), "r"(vn), "r"(off), "r"(sink));
+  if (CLIP)
+    asm("{\n\t.reg .pred p;\n\t.reg .f32 aq;\n\t"
+        "abs.f32 aq, %1;\n\t"
+        "setp.gt.f32 p, %2, %3;\n\t"
+        "setp.lt.and.f32 p, aq, %4, p;\n\t"
+        "setp.lt.and.u32 p, %5, %6, p;\n\t"
+        "selp.b32 %0, %7, %8, p;\n\t}"
+        : "=r"(r) : "f"(q), "f"(adv), "f"(thr), "f"(hw_m), "r"(vrel), "r"(vn), "r"(off), "r"(sink));
+  else
+    asm("{\n\t.reg .pred p;\n\t.reg .f32 aq;\n\t"
+        "abs.f32 aq, %1;\n\t"
+        "setp.gt.f32 p, %2, %3;\n\t"
+        "setp.lt.and.f32 p, aq, %4, p;\n\t"
+        "selp.b32 %0, %5, %6, p;\n\t}"
+        : "=r"(r) : "f"(q), "f"(adv), "f"(thr), "f"(hw_m), "r"(off), "r"(sink));
   return r;
 #else
-  return ((adv > thr) && (fabsf(q) < hw_m) && ((unsigned)vrel < (unsigned)vn)) ? off : sink;
+  return ((adv > thr) && (fabsf(q) < hw_m) && (!CLIP || ((unsigned)vrel < (unsigned)vn))) ? off : sink;
 #endif
 }
 
-// Slow path of ring_lane for one arc's candidate `cc` whose float32 residual q is not decisive.
+// Slow path for one arc's top candidate whose float32 residual q is not decisive.
 // (fl, vt) describe the arc: fl = float offset of the top candidate from the lattice base (mirrored for
 // the bottom arc), vt = its index along the candidate axis relative to the tile.
 template <class Slow, class EmitSlow>
-RCV_HD void ring_slow(const PointCtx& c, const LaneTask& L, int i, int ub, int m, int arc, int cc, float q, float fl, int vt, Slow& slow,
-                      EmitSlow& emit_slow) {
-  const int v = arc ? (vt + cc) : (vt - cc), dv = v - L.vrel0;
-  if (((unsigned)v < (unsigned)L.vn) && slow(i, L.pass ? (c.ipy + dv) : L.ucoord, L.pass ? L.ucoord : (c.ipz + dv))) emit_slow(ub + v * L.sv);
-  if (cc == 0 && q >= c.hw_m) {
+RCV_HD void ring_slow(const PointCtx& c, const LaneTask& L, int i, int ub, int arc, float q, float fl, int vt, Slow& slow, EmitSlow& emit_slow) {
+  const int dv = vt - L.vrel0;
+  if (((unsigned)vt < (unsigned)L.vn) && slow(i, L.pass ? (c.ipy + dv) : L.ucoord, L.pass ? L.ucoord : (c.ipz + dv))) emit_slow(ub + vt * L.sv);
+  if (q >= c.hw_m) {
     // The top candidate may lie outside the outer sphere; the run can then reach one voxel lower.
-    const int v2 = arc ? (vt + m) : (vt - m), dv2 = v2 - L.vrel0;
-    const float d2 = arc ? f_add(f_sub(fl, (float)m), L.fv) : f_sub(f_sub(fl, (float)m), L.fv);
+    const int v2 = arc ? (vt + 1) : (vt - 1), dv2 = v2 - L.vrel0;
+    const float d2 = arc ? f_add(f_sub(fl, 1.0f), L.fv) : f_sub(f_sub(fl, 1.0f), L.fv);
     if ((fabsf(d2) > L.thr) && ((unsigned)v2 < (unsigned)L.vn) &&
         slow(i, L.pass ? (c.ipy + dv2) : L.ucoord, L.pass ? L.ucoord : (c.ipz + dv2)))
       emit_slow(ub + v2 * L.sv);
   }
 }
 
-// ---- thin ring slices (one candidate per arc): fast part and rare part split so that the kernel can
-// interleave the fast parts of two slices (two independent dependency chains each) before a single
-// rarely-taken branch.
+// ---- thin rings: fast part and rare part split so that the kernel can issue the fast parts of several
+// slices (independent dependency chains) before a single rarely-taken branch.
 struct ThinOut {
   float q0, q1, fl0, fl1;
   int vt0, vt1, ub;
@@ -233,23 +250,25 @@ struct ThinOut {
 
 //   emit(offset) -- the unconditional shared-memory atomic of the fast path, called exactly twice; the
 //                   offset is the voxel's, or `sink` when there is no vote.
-// Offsets are in the units lane_setup() was given (words on the host, bytes on the device);
-// `slice_base` = (i - i0) * nj * Dp in the same units.
-template <class Emit>
+// Offsets are in the units lane_setup_pu() was given (words on the host, bytes on the device);
+// `slice_base` = (i - i0) * nj * Dp in the same units.  `a` = outer radius^2 of the lane's ring in this slice,
+// or NaN if the slice is not a thin ring of this lane: NaN never votes and never asks for the exact path
+// (every comparison with it is false), and neither does a column outside the outer circle (sqrt of a negative).
+template <bool CLIP, class Emit>
 RCV_HD void thin_fast(const PointCtx& c, float a, const LaneTask& L, int slice_base, int sink, Emit& emit, ThinOut& o) {
   const float g = f_sub(a, L.du2);
-  const float zs = f_sqrt_fast(fmaxf(g, 0.f));
-  const float hWg = f_sub(c.hW, g);        // g <= 0  =>  q >= W/2: never a fast-path vote
+  const float zs = f_sqrt_fast(g);
+  const float hWg = f_sub(c.hW, g);
   o.ub = L.ubase + slice_base;
-  const float tm0 = f_add(f_add(f_add(zs, L.fv), c.dbias_m05), RCV_MAGIC);   // top arc
-  const float tm1 = f_add(f_add(f_sub(zs, L.fv), c.dbias_m05), RCV_MAGIC);   // bottom arc, mirrored
+  const float tm0 = f_add(f_add(zs, L.cp), RCV_MAGIC);   // top arc
+  const float tm1 = f_add(f_add(zs, L.cm), RCV_MAGIC);   // bottom arc, mirrored
   o.fl0 = f_sub(tm0, RCV_MAGIC); o.fl1 = f_sub(tm1, RCV_MAGIC);
   o.vt0 = L.vrel0 + (f_bits(tm0) - RCV_MAGIC_BITS);   // topmost candidate (>= true topmost voxel under the outer circle)
   o.vt1 = L.vrel0 - (f_bits(tm1) - RCV_MAGIC_BITS);
   const float d0 = f_sub(o.fl0, L.fv), d1 = f_add(o.fl1, L.fv);              // dv of the two candidates
   o.q0 = f_fma(d0, d0, hWg); o.q1 = f_fma(d1, d1, hWg);                      // e + W/2, e = |v-p|^2 - R^2 in float32
-  emit(pick_offset(o.q0, fabsf(d0), o.vt0, o.ub + o.vt0 * L.sv, sink, c.hw_m, L.thr, L.vn));
-  emit(pick_offset(o.q1, fabsf(d1), o.vt1, o.ub + o.vt1 * L.sv, sink, c.hw_m, L.thr, L.vn));
+  emit(pick_offset<CLIP>(o.q0, fabsf(d0), o.vt0, o.ub + o.vt0 * L.sv, sink, c.hw_m, L.thr, L.vn));
+  emit(pick_offset<CLIP>(o.q1, fabsf(d1), o.vt1, o.ub + o.vt1 * L.sv, sink, c.hw_m, L.thr, L.vn));
   // not surely inside the shell, but not surely beyond the inner boundary either: decide exactly
   o.t0 = (fabsf(d0) > L.thr) && !(fabsf(o.q0) < c.hw_m) && (o.q0 > -c.hw_p);
   o.t1 = (fabsf(d1) > L.thr) && !(fabsf(o.q1) < c.hw_m) && (o.q1 > -c.hw_p);
@@ -257,42 +276,11 @@ RCV_HD void thin_fast(const PointCtx& c, float a, const LaneTask& L, int slice_b
 
 template <class SlowArc>
 RCV_HD void thin_slow(const PointCtx& c, const LaneTask& L, int i, const ThinOut& o, SlowArc& slowarc) {
-  if (o.t0) slowarc(c, L, i, o.ub, 1, 0, 0, o.q0, o.fl0, o.vt0);
-  if (o.t1) slowarc(c, L, i, o.ub, 1, 1, 0, o.q1, o.fl1, o.vt1);
+  if (o.t0) slowarc(c, L, i, o.ub, 0, o.q0, o.fl0, o.vt0);
+  if (o.t1) slowarc(c, L, i, o.ub, 1, o.q1, o.fl1, o.vt1);
 }
 
-// One lane, one ring slice with outer radius^2 `a` and `m` >= 1 candidates per arc (general form).
-//   slowarc(...) -- ring_slow() behind a call: decides candidates whose float32 residual is within eps
-//                   of a shell boundary with the exact float64 predicate (rare).
-template <class Emit, class SlowArc>
-RCV_HD void ring_lane(const PointCtx& c, float a, int m, const LaneTask& L, int i, int slice_base, int sink, Emit& emit, SlowArc& slowarc) {
-  const float g = f_sub(a, L.du2);
-  const float zs = f_sqrt_fast(fmaxf(g, 0.f));
-  const float hWg = f_sub(c.hW, g);
-  const int ub = L.ubase + slice_base;
-  const float tm0 = f_add(f_add(f_add(zs, L.fv), c.dbias_m05), RCV_MAGIC);
-  const float tm1 = f_add(f_add(f_sub(zs, L.fv), c.dbias_m05), RCV_MAGIC);
-  const float fl0 = f_sub(tm0, RCV_MAGIC), fl1 = f_sub(tm1, RCV_MAGIC);
-  const int vt0 = L.vrel0 + (f_bits(tm0) - RCV_MAGIC_BITS);
-  const int vt1 = L.vrel0 - (f_bits(tm1) - RCV_MAGIC_BITS);
-#pragma unroll 1
-  for (int cc = 0; cc < m; ++cc) {
-    const float fc = (float)cc;
-    const float d0 = f_sub(f_sub(fl0, fc), L.fv), d1 = f_add(f_sub(fl1, fc), L.fv);
-    const float q0 = f_fma(d0, d0, hWg), q1 = f_fma(d1, d1, hWg);
-    const int v0 = vt0 - cc, v1 = vt1 + cc;
-    emit(pick_offset(q0, fabsf(d0), v0, ub + v0 * L.sv, sink, c.hw_m, L.thr, L.vn));
-    emit(pick_offset(q1, fabsf(d1), v1, ub + v1 * L.sv, sink, c.hw_m, L.thr, L.vn));
-    const bool t0 = (fabsf(d0) > L.thr) && !(fabsf(q0) < c.hw_m) && (q0 > -c.hw_p);
-    const bool t1 = (fabsf(d1) > L.thr) && !(fabsf(q1) < c.hw_m) && (q1 > -c.hw_p);
-    if (t0 || t1) {
-      if (t0) slowarc(c, L, i, ub, m, 0, cc, q0, fl0, vt0);
-      if (t1) slowarc(c, L, i, ub, m, 1, cc, q1, fl1, vt1);
-    }
-  }
-}
-
-// One lane, one cell (dj, dk) of a dense slice's bounding box.
+// One lane, one cell (dj, dk) of a small sphere's slice bounding box (R < RCV_POLAR_MIN_R only).
 template <class Emit, class Slow>
 RCV_HD void dense_cell(const PointCtx& c, float a, const Tile& t, int i, int slice_base, int unit, int sink, int dj, int dk, bool cell_ok,
                        Emit& emit, Slow& slow) {
@@ -307,11 +295,102 @@ RCV_HD void dense_cell(const PointCtx& c, float a, const Tile& t, int i, int sli
   emit(vote ? slice_base + ((vj - t.j0) * t.Dp + vk) * unit : sink);
 }
 
+// ---- polar pass --------------------------------------------------------------------------------------
+// Slices whose ring is not thin (slice_setup code != 1) lie in the polar caps of the slice axis.  For
+// R >= RCV_POLAR_MIN_R every such slice has |dx| >= (W+1)/2, so a column ALONG the slice axis through the
+// in-plane cell (j,k) crosses the shell in less than one voxel: the only candidate of the + side is the topmost
+// voxel under the outer sphere (mirror image for the - side).  A candidate votes iff its slice is one of the
+// lane's non-thin slices in this tile (bit masks mplus / mminus, bit v = slice t.i0 + v; a tile has <= 32 slices).
+struct PolarOut {
+  float q0, q1;
+  int vt0, vt1;
+  bool t0, t1;
+};
+
+RCV_HD bool mask_bit(unsigned m, int v) { return (u_shr(m, v) & 1u) != 0u; }
+
+// s = dB^2 + dC^2 of the cell, cell = its offset inside a slice, ok = the cell is inside the tile and the lane
+// takes part; sstride = slice stride (same units as cell).  SIDES: bit 0 = + side, bit 1 = - side.
+// cpx / cmx = fx + dbias - 0.5 and -fx + dbias - 0.5.
+template <int SIDES, class Emit>
+RCV_HD void polar_fast(const PointCtx& c, const Tile& t, float cpx, float cmx, float s, int cell, bool ok, unsigned mplus, unsigned mminus,
+                       int sstride, int sink, Emit& emit, PolarOut& o) {
+  const float g = f_sub(c.R2, s);
+  const float zs = f_sqrt_fast(g);         // NaN outside the sphere's shadow: no vote, no exact path
+  const float hWg = f_sub(c.hW, g);
+  const int vrel0 = c.ipx - t.i0;
+  o.t0 = false; o.t1 = false; o.q0 = 0.f; o.q1 = 0.f; o.vt0 = 0; o.vt1 = 0;
+  if (SIDES & 1) {
+    const float tm0 = f_add(f_add(zs, cpx), RCV_MAGIC);
+    const float fl0 = f_sub(tm0, RCV_MAGIC);
+    o.vt0 = vrel0 + (f_bits(tm0) - RCV_MAGIC_BITS);
+    const float d0 = f_sub(fl0, c.fx);
+    o.q0 = f_fma(d0, d0, hWg);
+    const bool sure = fabsf(o.q0) < c.hw_m;
+    const bool vote = sure & ok & mask_bit(mplus, o.vt0);
+    emit(vote ? cell + o.vt0 * sstride : sink);
+    o.t0 = ok & !sure & (o.q0 > -c.hw_p);
+  }
+  if (SIDES & 2) {
+    const float tm1 = f_add(f_add(zs, cmx), RCV_MAGIC);
+    const float fl1 = f_sub(tm1, RCV_MAGIC);
+    o.vt1 = vrel0 - (f_bits(tm1) - RCV_MAGIC_BITS);
+    const float d1 = f_add(fl1, c.fx);
+    o.q1 = f_fma(d1, d1, hWg);
+    const bool sure = fabsf(o.q1) < c.hw_m;
+    const bool vote = sure & ok & mask_bit(mminus, o.vt1);
+    emit(vote ? cell + o.vt1 * sstride : sink);
+    o.t1 = ok & !sure & (o.q1 > -c.hw_p);
+  }
+}
+
+// Column range of row `db2` (= dB^2) of the polar pass: the lane's non-thin rings of this tile lie in the annulus
+// s_lo < dB^2 + dC^2 < s_hi (s_hi = largest outer radius^2, s_lo = smallest inner radius^2), so only cells with
+// ci <= |uc| <= co can hold a candidate (|uc| differs from |dC| by at most 0.5; co < 0: the row is empty).
+RCV_HD void polar_row_range(float s_lo, float s_hi, float db2, bool lane_on, int& ci, int& co) {
+  const float rem_hi = f_sub(s_hi, db2), rem_lo = f_sub(s_lo, db2);
+  co = -1; ci = 0x7fffffff;
+  if (lane_on && rem_hi > 0.f) {
+    co = (int)f_add(f_sqrt_fast(rem_hi), 0.6f);
+    ci = rem_lo > 1.0f ? (int)f_sub(f_sqrt_fast(rem_lo), 0.6f) : 0;
+    if (ci < 0) ci = 0;
+  }
+}
+
+// Exact decision of the candidates polar_fast() could not decide; (jb, kc) = in-plane lattice coordinates of the cell.
+template <class Slow, class EmitSlow>
+RCV_HD void polar_slow(float hw_m, int ti0, const PolarOut& o, int jb, int kc, int cell, unsigned mplus, unsigned mminus, int sstride, Slow& slow,
+                       EmitSlow& emit_slow) {
+  if (o.t0) {
+    if (mask_bit(mplus, o.vt0) && slow(ti0 + o.vt0, jb, kc)) emit_slow(cell + o.vt0 * sstride);
+    if (o.q0 >= hw_m) {   // the top candidate may lie outside the outer sphere; the voxel below it can then be inside
+      const int v2 = o.vt0 - 1;
+      if (mask_bit(mplus, v2) && slow(ti0 + v2, jb, kc)) emit_slow(cell + v2 * sstride);
+    }
+  }
+  if (o.t1) {
+    if (mask_bit(mminus, o.vt1) && slow(ti0 + o.vt1, jb, kc)) emit_slow(cell + o.vt1 * sstride);
+    if (o.q1 >= hw_m) {
+      const int v2 = o.vt1 + 1;
+      if (mask_bit(mminus, v2) && slow(ti0 + v2, jb, kc)) emit_slow(cell + v2 * sstride);
+    }
+  }
+}
+
+// Half-width (in rows) of the polar pass for a lane whose largest non-thin ring has outer radius^2 amax.
+RCV_HD int polar_half_width(float amax) { return (int)f_add(f_sqrt_fast(fmaxf(amax, 0.f)), 0.6f); }
+
 // Slice range of point c inside tile t (inclusive); empty if ia > ib.
 RCV_HD void slice_range(const PointCtx& c, const Tile& t, int& ia, int& ib) {
   ia = c.ipx - c.R - 1; if (ia < t.i0) ia = t.i0;
   ib = c.ipx + c.R + 1; if (ib > t.i0 + t.ni - 1) ib = t.i0 + t.ni - 1;
   if (c.R <= 0) { ia = 1; ib = 0; }
+}
+
+// True if no candidate of the lane's ring passes can fall outside the tile along a candidate axis
+// (candidates lie within R + 1 of the nearest lattice point), so the per-candidate bounds test can be skipped.
+RCV_HD bool ring_noclip(const PointCtx& c, const Tile& t) {
+  return (c.ipz - c.R - 2 >= 0) && (c.ipz + c.R + 2 < t.D) && (c.ipy - c.R - 2 >= t.j0) && (c.ipy + c.R + 2 < t.j0 + t.nj);
 }
 
 }  // namespace rcv

@@ -36,9 +36,7 @@ constexpr int kVoteThreads = RCV_VOTE_THREADS;
 constexpr int kVoteWarps = kVoteThreads / 32;
 constexpr int kSmemBytes = 232448;                        // 227 KB: the sm_100 per-CTA maximum
 constexpr int kDummyWords = 32 * kVoteWarps;              // one private sink word per lane per warp
-constexpr int kTabRows = 36;                                  // 32 slices + spare rows for the prefetch
-constexpr int kTabWords = kTabRows * 4 * kVoteWarps;          // per-warp table of ring slices (int4 rows)
-constexpr int kTileWords = kSmemBytes / 4 - kDummyWords - kTabWords - 128;   // 128 words left for static shared variables
+constexpr int kTileWords = kSmemBytes / 4 - kDummyWords - 128;   // 128 words left for static shared variables
 constexpr int kStVolumeSkipped = 32;
 
 struct ItemMeta {
@@ -471,7 +469,8 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
       m.Dp = Dp;
       const long long slice = (long long)D * Dp;
       if (slice <= a.tile_words) {
-        const int ni_max = (int)(a.tile_words / slice);
+        int ni_max = (int)(a.tile_words / slice);
+        if (ni_max > 32) ni_max = 32;   // the polar pass keeps one mask bit per slice of a tile
         const int ns = (D + ni_max - 1) / ni_max;
         m.ni = (D + ns - 1) / ns; m.nj = D;
         nunits = (D + m.ni - 1) / m.ni;
@@ -524,125 +523,177 @@ struct SmemEmit {   // offsets are bytes relative to the tile; `sink` is the lan
   unsigned base; int sink;
   __device__ __forceinline__ void operator()(int off) const { smem_inc(base + (unsigned)off); }
 };
-typedef SmemEmit SmemEmitSlow;
+// Internal axes.  The rasteriser walks "slices" along its first axis A; the kernel feeds it (A,B,C) = (y,x,z)
+// of the reference so that the 32 points of a warp -- consecutive surviving pixels of an image row -- share
+// their slice geometry (same y up to a voxel).  exact_hit() gets the coordinates back in reference order
+// because the float64 sum dx^2 + dy^2 + dz^2 is order-sensitive.
 // The exact float64 path lives behind a call so the compiler cannot hoist any of its arithmetic into the
 // hot loop (it did: 40% of the first version's instructions were speculated DADD/DMUL/DSQRT).
-struct SlowExact {
-  double px, py, pz; int R;
-  __device__ __forceinline__ bool operator()(int i, int j, int k) const { return exact_hit(px, py, pz, R, i, j, k); }
+__device__ __noinline__ bool exact_hit_call(double px, double py, double pz, int R, int i, int j, int k) {
+  return exact_hit(px, py, pz, R, i, j, k);
+}
+struct SlowExactCall {   // arguments are internal (A,B,C) indices
+  double pa, pb, pc; int R;
+  __device__ __forceinline__ bool operator()(int ia, int ib, int ic) const { return exact_hit_call(pb, pa, pc, R, ib, ia, ic); }
 };
 __device__ __noinline__ void ring_slow_call(double px, double py, double pz, int R, int ipy, int ipz, float hw_m, float fv, float thr,
-                                            int vrel0, int vn, int ucoord, int pass, int sv, int i, int ub, int m, int arc, int cc,
-                                            float q, float fl, int vt, unsigned base) {
+                                            int vrel0, int vn, int ucoord, int pass, int sv, int i, int ub, int arc, float q, float fl, int vt,
+                                            unsigned base) {
   PointCtx c;
   c.px = px; c.py = py; c.pz = pz; c.R = R; c.ipy = ipy; c.ipz = ipz; c.hw_m = hw_m;
   LaneTask L;
   L.fv = fv; L.thr = thr; L.vrel0 = vrel0; L.vn = vn; L.ucoord = ucoord; L.pass = pass != 0; L.sv = sv;
-  SlowExact slow{px, py, pz, R};
+  SlowExactCall slow{px, py, pz, R};
   SmemEmit es{base, 0};
-  ring_slow(c, L, i, ub, m, arc, cc, q, fl, vt, slow, es);
+  ring_slow(c, L, i, ub, arc, q, fl, vt, slow, es);
 }
 struct SlowArcCall {
   unsigned base;
-  __device__ __forceinline__ void operator()(const PointCtx& c, const LaneTask& L, int i, int ub, int m, int arc, int cc, float q, float fl,
-                                             int vt) const {
-    ring_slow_call(c.px, c.py, c.pz, c.R, c.ipy, c.ipz, c.hw_m, L.fv, L.thr, L.vrel0, L.vn, L.ucoord, L.pass ? 1 : 0, L.sv, i, ub, m, arc, cc,
-                   q, fl, vt, base);
+  __device__ __forceinline__ void operator()(const PointCtx& c, const LaneTask& L, int i, int ub, int arc, float q, float fl, int vt) const {
+    ring_slow_call(c.px, c.py, c.pz, c.R, c.ipy, c.ipz, c.hw_m, L.fv, L.thr, L.vrel0, L.vn, L.ucoord, L.pass ? 1 : 0, L.sv, i, ub, arc, q, fl, vt, base);
   }
 };
-__device__ __noinline__ bool exact_hit_call(double px, double py, double pz, int R, int i, int j, int k) {
-  return exact_hit(px, py, pz, R, i, j, k);
-}
-struct SlowExactCall {
-  double px, py, pz; int R;
-  __device__ __forceinline__ bool operator()(int i, int j, int k) const { return exact_hit_call(px, py, pz, R, i, j, k); }
-};
 
-struct PointData { double x, y, z; int R; };
+__device__ __forceinline__ int warp_max_i32(int v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_min_i32(int v) { return __reduce_min_sync(0xffffffffu, v); }
 
-__device__ __forceinline__ int4 lds128(unsigned addr) {
-  int4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(unsigned addr, int4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// One point, one tile, one warp.  `tab_s` is the shared-window address of the warp's private table of
-// ring slices (33 x int4 {a bits, candidates per arc, slice byte offset, slice index}; thin slices first).
-__device__ __forceinline__ void vote_point(const PointData& pd, const Tile& t, int lane, const SmemEmit& emit_c, unsigned tab_s) {
+// One pass over a chunk of NC consecutive slices for a warp whose 32 lanes each own one point: every lane walks the
+// columns (rows) u = -H..H of ITS thin rings (one candidate per arc); the lane task of column u is shared by the
+// chunk's slices.  a4[s] is NaN for a slice that is not a thin ring of this lane (NaN never votes, never asks for
+// the exact path).  H is the maximum over the warp.  CLIP = some lane's candidates may leave the tile.
+template <bool PASS, bool CLIP, int NC>
+__device__ __forceinline__ void ring_pass(const PointCtx& c, const Tile& t, const float (&a4)[NC], int H, int i0c, int sbase0, int slice_bytes,
+                                          const SmemEmit& emit_c, const SlowArcCall& slowarc_c) {
   SmemEmit emit = emit_c;
-  SlowArcCall slowarc{emit_c.base};
-  PointCtx c;
-  point_setup(c, pd.x, pd.y, pd.z, pd.R);
-  SlowExactCall slow{pd.x, pd.y, pd.z, pd.R};
-  int ia, ib;
-  slice_range(c, t, ia, ib);
-  const int slice_bytes = t.nj * t.Dp * 4;
-  for (int sb = ia; sb <= ib; sb += 32) {
-    // classify 32 slices at once, one per lane; ring slices are compacted into the warp's table
-    float a_l = 0.f; int code_l = 0;
-    if (sb + lane <= ib) slice_setup(c, sb + lane, a_l, code_l);
-    const unsigned thin_mask = __ballot_sync(0xffffffffu, code_l == 1);
-    const unsigned thick_mask = __ballot_sync(0xffffffffu, code_l > 1);
-    const unsigned dense_mask = __ballot_sync(0xffffffffu, code_l < 0);
-    if (thin_mask | thick_mask) {
-      float amax = code_l > 0 ? a_l : 0.f;
+  SlowArcCall slowarc = slowarc_c;
+  float uf = (float)(-H);
+#pragma unroll 1
+  for (int u = -H; u <= H; ++u, uf += 1.0f) {
+    LaneTask L;
+    lane_setup_pu(c, t, PASS, u, uf, 4, L);
+    ThinOut o[NC];
 #pragma unroll
-      for (int m = 16; m; m >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, m));
-      const int nthin = __popc(thin_mask), nring = nthin + __popc(thick_mask);
-      const unsigned lt = (1u << lane) - 1u;
-      __syncwarp();
-      if (code_l > 0) {
-        const int pos = code_l == 1 ? __popc(thin_mask & lt) : nthin + __popc(thick_mask & lt);
-        sts128(tab_s + 16u * pos, make_int4(__float_as_int(a_l), code_l, (sb + lane - t.i0) * slice_bytes, sb + lane));
-      }
-      __syncwarp();
-      const int H = ring_half_width(amax);
-      const int ntask = 2 * (2 * H + 1);
-      for (int base = 0; base < ntask; base += 32) {
-        LaneTask L;
-        lane_setup(c, t, H, base + lane, 4, L);
-        int s = 0;
-        // thin slices two at a time: four independent candidate chains, one rarely-taken branch
-        int4 e0 = lds128(tab_s), e1 = lds128(tab_s + 16u);
+    for (int sidx = 0; sidx < NC; ++sidx) thin_fast<CLIP>(c, a4[sidx], L, sbase0 + sidx * slice_bytes, emit.sink, emit, o[sidx]);
+    bool any = false;
+#pragma unroll
+    for (int sidx = 0; sidx < NC; ++sidx) any |= o[sidx].t0 | o[sidx].t1;
+    if (any) {
+#pragma unroll
+      for (int sidx = 0; sidx < NC; ++sidx)
+        if (o[sidx].t0 || o[sidx].t1) thin_slow(c, L, i0c + sidx, o[sidx], slowarc);
+    }
+  }
+}
+
+__device__ __noinline__ void polar_slow_call(double pa, double pb, double pc, int R, float hw_m, int ti0, float q0, float q1, int vt0, int vt1,
+                                             int t01, int jb, int kc, int cell, unsigned mplus, unsigned mminus, int sstride, unsigned base) {
+  PolarOut o;
+  o.q0 = q0; o.q1 = q1; o.vt0 = vt0; o.vt1 = vt1; o.t0 = (t01 & 1) != 0; o.t1 = (t01 & 2) != 0;
+  SlowExactCall slow{pa, pb, pc, R};
+  SmemEmit es{base, 0};
+  polar_slow(hw_m, ti0, o, jb, kc, cell, mplus, mminus, sstride, slow, es);
+}
+
+// Polar pass of a warp: rows ub = -Hp..Hp around each lane's own point; in every row only the columns of the annulus
+// that holds the lane's non-thin rings (polar_row_range), bounds taken over the warp.
+template <int SIDES>
+__device__ __forceinline__ void polar_segment(const PointCtx& c, const Tile& t, float cpx, float cmx, int uc0, int uc1, float db2, int jb, bool row_ok,
+                                              int rowoff, unsigned mplus, unsigned mminus, int slice_bytes, const SmemEmit& emit) {
+  float ucf = (float)uc0;
+#pragma unroll 2
+  for (int uc = uc0; uc <= uc1; ++uc, ucf += 1.0f) {
+    const float dc = f_sub(ucf, c.fz);
+    const float s2 = f_fma(dc, dc, db2);
+    const int kc = c.ipz + uc;
+    const bool ok = row_ok & ((unsigned)kc < (unsigned)t.D);
+    const int cell = rowoff + kc * 4;
+    PolarOut o;
+    polar_fast<SIDES>(c, t, cpx, cmx, s2, cell, ok, mplus, mminus, slice_bytes, emit.sink, emit, o);
+    if (o.t0 || o.t1)
+      polar_slow_call(c.px, c.py, c.pz, c.R, c.hw_m, t.i0, o.q0, o.q1, o.vt0, o.vt1, (o.t0 ? 1 : 0) | (o.t1 ? 2 : 0), jb, kc, cell, mplus, mminus,
+                      slice_bytes, emit.base);
+  }
+}
+
+template <int SIDES>
+__device__ __forceinline__ void polar_pass(const PointCtx& c, const Tile& t, int Hp, float s_lo, float s_hi, unsigned mplus, unsigned mminus,
+                                           int slice_bytes, const SmemEmit& emit_c) {
+  SmemEmit emit = emit_c;
+  const bool lane_on = (mplus | mminus) != 0u;
+  const float cpx = f_add(c.fx, c.dbias_m05), cmx = f_sub(c.dbias_m05, c.fx);
+  float ubf = (float)(-Hp);
 #pragma unroll 1
-        for (; s + 2 <= nthin; s += 2) {
-          const int4 n0 = lds128(tab_s + 16u * (s + 2)), n1 = lds128(tab_s + 16u * (s + 3));   // prefetch (table has 2 spare rows)
-          ThinOut oa, ob;
-          thin_fast(c, __int_as_float(e0.x), L, e0.z, emit.sink, emit, oa);
-          thin_fast(c, __int_as_float(e1.x), L, e1.z, emit.sink, emit, ob);
-          if (oa.t0 || oa.t1 || ob.t0 || ob.t1) {
-            if (oa.t0 || oa.t1) thin_slow(c, L, e0.w, oa, slowarc);
-            if (ob.t0 || ob.t1) thin_slow(c, L, e1.w, ob, slowarc);
+  for (int ub = -Hp; ub <= Hp; ++ub, ubf += 1.0f) {
+    const float db = f_sub(ubf, c.fy);
+    const float db2 = f_mul(db, db);
+    int ci, co;
+    polar_row_range(s_lo, s_hi, db2, lane_on, ci, co);
+    const int CO = warp_max_i32(co), CI = warp_min_i32(ci);
+    if (CO < 0) continue;
+    const int jb = c.ipy + ub;
+    const bool row_ok = lane_on & ((unsigned)(jb - t.j0) < (unsigned)t.nj);
+    const int rowoff = (jb - t.j0) * t.Dp * 4;
+    if (CI > 1) {
+      polar_segment<SIDES>(c, t, cpx, cmx, -CO, -CI, db2, jb, row_ok, rowoff, mplus, mminus, slice_bytes, emit);
+      polar_segment<SIDES>(c, t, cpx, cmx, CI, CO, db2, jb, row_ok, rowoff, mplus, mminus, slice_bytes, emit);
+    } else {
+      polar_segment<SIDES>(c, t, cpx, cmx, -CO, CO, db2, jb, row_ok, rowoff, mplus, mminus, slice_bytes, emit);
+    }
+  }
+}
+
+// Ring passes of one warp over the slices [wa, wb] of the tile, in chunks of NC slices that tile the slab from its
+// first slice; collects the lane's non-thin slices (masks, annulus) for the polar pass and scans small spheres densely.
+template <int NC>
+__device__ __forceinline__ void ring_chunks(const PointCtx& c, const Tile& t, int ia, int ib, int wa, int wb, int slice_bytes, bool noclip,
+                                            const SlowExactCall& slow_c, const SmemEmit& emit, const SlowArcCall& slowarc, unsigned& mplus,
+                                            unsigned& mminus, float& s_lo, float& s_hi) {
+  SlowExactCall slow = slow_c;
+  const bool polar_lane = c.R >= RCV_POLAR_MIN_R;
+  const int first = t.i0 + ((wa - t.i0) / NC) * NC;
+#pragma unroll 1
+  for (int i0c = first; i0c <= wb; i0c += NC) {
+    float a4[NC];
+    int abits = 0;
+#pragma unroll
+    for (int sidx = 0; sidx < NC; ++sidx) {
+      const int i = i0c + sidx;
+      float ar = 0.f; int code = 0;
+      if (i >= ia && i <= ib) slice_setup(c, i, ar, code);
+      const bool thin = code == 1;
+      a4[sidx] = thin ? ar : __int_as_float(0x7fc00000);
+      if (thin) abits = max(abits, __float_as_int(ar));   // thin => a > 36 > 0: bit order = value order
+      int dl = 0;
+      if (polar_lane) {
+        if (code > 1 || code < 0) {
+          if (i > c.ipx) mplus |= 1u << (i - t.i0); else mminus |= 1u << (i - t.i0);
+          s_hi = fmaxf(s_hi, ar);
+          s_lo = fminf(s_lo, f_sub(ar, c.W));
+        }
+      } else dl = -code;
+      const int dmax = warp_max_i32(dl);
+      if (dmax > 0) {   // spheres too small for the polar pass (R < RCV_POLAR_MIN_R): bounding-box scan of the slice
+        const int sbase = (i - t.i0) * slice_bytes;
+#pragma unroll 1
+        for (int rr = -dmax; rr <= dmax; ++rr)
+#pragma unroll 1
+          for (int kk = -dmax; kk <= dmax; ++kk) {
+            const bool ok = dl > 0 && rr >= -dl && rr <= dl && kk >= -dl && kk <= dl;
+            dense_cell(c, ar, t, i, sbase, 4, emit.sink, rr, kk, ok, emit, slow);
           }
-          e0 = n0; e1 = n1;
-        }
-        if (s < nthin) {
-          ThinOut oa;
-          thin_fast(c, __int_as_float(e0.x), L, e0.z, emit.sink, emit, oa);
-          if (oa.t0 || oa.t1) thin_slow(c, L, e0.w, oa, slowarc);
-          ++s;
-        }
-#pragma unroll 1
-        for (; s < nring; ++s) {
-          const int4 e = lds128(tab_s + 16u * s);
-          ring_lane(c, __int_as_float(e.x), e.y, L, e.w, e.z, emit.sink, emit, slowarc);
-        }
       }
     }
-    for (unsigned mk = dense_mask; mk; mk &= mk - 1) {
-      const int sl = __ffs(mk) - 1;
-      const float a = __shfl_sync(0xffffffffu, a_l, sl);
-      const int hb = -__shfl_sync(0xffffffffu, code_l, sl);
-      const int i = sb + sl, side = 2 * hb + 1;
-      const int lshift = side <= 16 ? 4 : 5, lpr = 1 << lshift, rpi = 32 >> lshift;   // lanes per row, rows per iteration
-      for (int r0 = 0; r0 < side; r0 += rpi)
-        for (int k0 = 0; k0 < side; k0 += lpr) {
-          const int rr = r0 + (lane >> lshift), kk = k0 + (lane & (lpr - 1));
-          dense_cell(c, a, t, i, (i - t.i0) * slice_bytes, 4, emit.sink, rr - hb, kk - hb, rr < side && kk < side, emit, slow);
-        }
+    const int amax_bits = warp_max_i32(abits);
+    if (amax_bits > 0) {
+      const int H = ring_half_width(__int_as_float(amax_bits));
+      const int sbase0 = (i0c - t.i0) * slice_bytes;
+      if (noclip) {
+        ring_pass<false, false, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
+        ring_pass<true, false, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
+      } else {
+        ring_pass<false, true, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
+        ring_pass<true, true, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
+      }
     }
   }
 }
@@ -656,7 +707,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
   unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
   asm volatile("mov.u32 %0, %0;" : "+r"(tile_s));   // keep the shared-window base in a register (ptxas otherwise rematerialises it per use)
   const SmemEmit emit{tile_s, 4 * (kTileWords + warp * 32 + lane)};
-  const unsigned tab_s = tile_s + 4u * (unsigned)(kTileWords + kDummyWords + warp * kTabRows * 4);
+  const SlowArcCall slowarc{tile_s};
   const int n_units = a.counters[0];
   for (;;) {
     __syncthreads();
@@ -676,28 +727,44 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
       for (int w = threadIdx.x; w < n4; w += kVoteThreads) t4[w] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();
-    // ---- scatter: each warp takes points from the CTA's queue, next point prefetched ----
-    int cur = 0;
-    if (lane == 0) cur = atomicAdd(&s_next, 1);
-    cur = __shfl_sync(0xffffffffu, cur, 0);
-    PointData pd{0, 0, 0, 0};
-    if (cur < n) { pd.x = a.pool.X[off + cur]; pd.y = a.pool.Y[off + cur]; pd.z = a.pool.Z[off + cur]; pd.R = a.pool.Ri[off + cur]; }
-    while (cur < n) {
-      int nxt = 0;
-      if (lane == 0) nxt = atomicAdd(&s_next, 1);
-      nxt = __shfl_sync(0xffffffffu, nxt, 0);
-      PointData nd{0, 0, 0, 0};
-      if (nxt < n) { nd.x = a.pool.X[off + nxt]; nd.y = a.pool.Y[off + nxt]; nd.z = a.pool.Z[off + nxt]; nd.R = a.pool.Ri[off + nxt]; }
-      vote_point(pd, t, lane, emit, tab_s);
-      cur = nxt; pd = nd;
+    // ---- scatter: each warp takes 32 consecutive points from the CTA's queue, one point per lane ----
+    const int slice_bytes = u.nj * Dp * 4;
+    for (;;) {
+      int cur = 0;
+      if (lane == 0) cur = atomicAdd(&s_next, 32);
+      cur = __shfl_sync(0xffffffffu, cur, 0);
+      if (cur >= n) break;
+      const int q = cur + lane;
+      double pa = 0.0, pb = 0.0, pc = 0.0; int R = 0;
+      if (q < n) { pb = a.pool.X[off + q]; pa = a.pool.Y[off + q]; pc = a.pool.Z[off + q]; R = a.pool.Ri[off + q]; }
+      PointCtx c;
+      point_setup(c, pa, pb, pc, R);
+      SlowExactCall slow{pa, pb, pc, R};
+      int ia, ib;
+      slice_range(c, t, ia, ib);
+      const int wa = warp_min_i32(ia <= ib ? ia : 0x7fffffff), wb = warp_max_i32(ia <= ib ? ib : -0x7fffffff);
+      if (wa > wb) continue;
+      const bool noclip = __all_sync(0xffffffffu, ring_noclip(c, t));
+      unsigned mplus = 0u, mminus = 0u;
+      float s_hi = 0.f, s_lo = 3.0e38f;
+      if (u.ni % 4 != 0 && u.ni % 3 == 0) ring_chunks<3>(c, t, ia, ib, wa, wb, slice_bytes, noclip, slow, emit, slowarc, mplus, mminus, s_lo, s_hi);
+      else ring_chunks<4>(c, t, ia, ib, wa, wb, slice_bytes, noclip, slow, emit, slowarc, mplus, mminus, s_lo, s_hi);
+      const int Hp = warp_max_i32((mplus | mminus) ? polar_half_width(s_hi) : -1);
+      if (Hp >= 0) {
+        const bool anyp = __any_sync(0xffffffffu, mplus != 0u), anym = __any_sync(0xffffffffu, mminus != 0u);
+        if (anyp && anym) polar_pass<3>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);
+        else if (anyp) polar_pass<1>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);
+        else polar_pass<2>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);
+      }
     }
     __syncthreads();
     // ---- peak of the tile (K3 fused) + vote tally + optional volume dump ----
+    // tile row r = (A - i0) * nj + (B - j0) holds reference voxels (i, j, k) = (B, A, k)
     unsigned long long key = 0, sum = 0;
     const int rows = u.ni * u.nj;
     for (int r = warp; r < rows; r += kVoteWarps) {
-      const int gi = u.i0 + r / u.nj, gj = u.j0 + r % u.nj;
-      const unsigned lin0 = ((unsigned)gi * (unsigned)D + (unsigned)gj) * (unsigned)D;
+      const int ga = u.i0 + r / u.nj, gb = u.j0 + r % u.nj;
+      const unsigned lin0 = ((unsigned)gb * (unsigned)D + (unsigned)ga) * (unsigned)D;
       const int* row = tile + r * Dp;
       for (int k = lane; k < D; k += 32) {
         const int v = row[k];
@@ -1013,7 +1080,7 @@ RCV_EXPORT int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out) {
   CKC(cudaMalloc(&c->leaves, sizeof(PwLeaf) * (size_t)c->leaf_cap)); CKC(cudaMalloc(&c->leaf_sums, 24 * (size_t)c->leaf_cap));
   for (int e = 0; e < 64; ++e) { CKC(cudaEventCreate(&c->evr[e][0])); CKC(cudaEventCreate(&c->evr[e][1])); }
   CKC(cudaFuncSetAttribute(k_ubench_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
-  CKC(cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (kTileWords + kDummyWords + kTabWords) * 4));
+  CKC(cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (kTileWords + kDummyWords) * 4));
 #undef CKC
   return RCV_OK;
 }
@@ -1030,7 +1097,7 @@ static int run_items(rcv_ctx* c, int n_items, const rcv_vote_params* vp, double*
   VoteArgs va{c->pool, c->meta, c->units, c->counters, c->best, c->votes, volume, volume_cap};
   const int slot = (int)(c->ev_count % 64);
   CK(c, cudaEventRecord(c->evr[slot][0], st));
-  k_vote<<<c->sms, kVoteThreads, (kTileWords + kDummyWords + kTabWords) * 4, st>>>(va);
+  k_vote<<<c->sms, kVoteThreads, (kTileWords + kDummyWords) * 4, st>>>(va);
   CK(c, cudaEventRecord(c->evr[slot][1], st));
   c->ev_count += 1;
   FinalArgs fa{c->meta, c->best, c->votes, n_items, vp->acc_unit, vp->grid_policy, volume != nullptr, volume_cap,

@@ -1,8 +1,8 @@
 // Host-side harness for rcvpose_b200/csrc/raster_core.h (TEST INFRASTRUCTURE ONLY).
-// Executes the rasteriser's per-lane code on the CPU, one simulated lane at a time, in the same
-// loop structure as the CUDA kernel (k_vote in rcvvote.cu: 32-slice groups, lane chunks, ring slices
-// then dense slices), so the exactness of the voxel set can be fuzzed against the oracle in the
-// CPU-only container.  It is never loaded by the product.
+// Executes the rasteriser's per-lane code on the CPU with 32 simulated lanes in lockstep, in the same loop
+// structure as the CUDA kernel (k_vote in rcvvote.cu: lane = point, slice chunks, ring passes, polar pass), with
+// the trip counts taken as warp maxima exactly as the kernel's warp reductions do, so the exactness of the voxel
+// set can be fuzzed against the oracle in the CPU-only container.  It is never loaded by the product.
 #include <cstdint>
 #include <cstdio>
 #include "../rcvpose_b200/csrc/raster_core.h"
@@ -22,83 +22,147 @@ struct HostEmitSlow {
   HostEmit* e;
   void operator()(int off) { (*e)(off); --e->calls; }
 };
-struct HostSlow {
+// Internal axes are (A,B,C) = (y,x,z) of the reference: the tile is a slab of A-slices, buffer layout
+// [A-i0][B-j0][C].  exact_hit() needs the reference's operand order (dx^2 + dy^2 + dz^2 is order-sensitive).
+struct HostSlowPerm {
   const PointCtx* c; HostEmit* e;
-  bool operator()(int i, int j, int k) { ++e->slow_calls; return exact_hit(c->px, c->py, c->pz, c->R, i, j, k); }
+  bool operator()(int i, int j, int k) { ++e->slow_calls; return exact_hit(c->py, c->px, c->pz, c->R, j, i, k); }
 };
-
-struct HostSlowArc {
-  HostSlow* slow; HostEmitSlow* es;
-  void operator()(const PointCtx& c, const LaneTask& L, int i, int ub, int m, int arc, int cc, float q, float fl, int vt) {
-    ring_slow(c, L, i, ub, m, arc, cc, q, fl, vt, *slow, *es);
+struct HostSlowArcPerm {
+  HostSlowPerm* slow; HostEmitSlow* es;
+  void operator()(const PointCtx& c, const LaneTask& L, int i, int ub, int arc, float q, float fl, int vt) {
+    ring_slow(c, L, i, ub, arc, q, fl, vt, *slow, *es);
   }
 };
 
-extern "C" __attribute__((visibility("default")))
-int hostsim_render(const double* p, const int* R, long n, int D, int Dp, int i0, int ni, int j0, int nj,
-                   int32_t* tile, int sqrt_perturb, long long* stats) {
-  g_sqrt_perturb = sqrt_perturb;
-  Tile t{i0, ni, j0, nj, D, Dp};
-  HostEmit emit{tile, (long)ni * nj * Dp};
-  HostEmitSlow emit_slow{&emit};
-  long long ring_slices = 0, dense_slices = 0, lane_tasks = 0;
-  for (long q = 0; q < n; ++q) {
-    PointCtx c;
-    point_setup(c, p[3 * q], p[3 * q + 1], p[3 * q + 2], R[q]);
-    HostSlow slow{&c, &emit};
-    HostSlowArc slowarc{&slow, &emit_slow};
-    int ia, ib;
-    slice_range(c, t, ia, ib);
-    for (int sb = ia; sb <= ib; sb += 32) {
-      float a_l[32]; int code_l[32];
-      float amax = 0.f; bool any_ring = false;
-      for (int lane = 0; lane < 32; ++lane) {
-        a_l[lane] = 0.f; code_l[lane] = 0;
-        if (sb + lane <= ib) slice_setup(c, sb + lane, a_l[lane], code_l[lane]);
-        if (code_l[lane] > 0) { any_ring = true; if (a_l[lane] > amax) amax = a_l[lane]; }
-      }
-      if (any_ring) {
-        const int H = ring_half_width(amax);
-        const int ntask = 2 * (2 * H + 1);
-        for (int base = 0; base < ntask; base += 32)
-          for (int lane = 0; lane < 32; ++lane) {
-            LaneTask L;
-            lane_setup(c, t, H, base + lane, 1, L);
-            // thin slices first, in pairs (as the kernel does), then the general ones
-            int thin[32], nthin = 0, thick[32], nthick = 0;
-            for (int sl = 0; sl < 32; ++sl) { if (code_l[sl] == 1) thin[nthin++] = sl; else if (code_l[sl] > 1) thick[nthick++] = sl; }
-            for (int s = 0; s < nthin; s += 2) {
-              ThinOut oa, ob;
-              const int ia_ = sb + thin[s];
-              thin_fast(c, a_l[thin[s]], L, (ia_ - i0) * nj * Dp, -1, emit, oa);
-              const bool two = s + 1 < nthin;
-              const int ib_ = two ? sb + thin[s + 1] : 0;
-              if (two) thin_fast(c, a_l[thin[s + 1]], L, (ib_ - i0) * nj * Dp, -1, emit, ob);
-              if (oa.t0 || oa.t1) thin_slow(c, L, ia_, oa, slowarc);
-              if (two && (ob.t0 || ob.t1)) thin_slow(c, L, ib_, ob, slowarc);
-              lane_tasks += two ? 2 : 1;
-            }
-            for (int s = 0; s < nthick; ++s) {
-              const int i = sb + thick[s];
-              ++lane_tasks;
-              ring_lane(c, a_l[thick[s]], code_l[thick[s]], L, i, (i - i0) * nj * Dp, -1, emit, slowarc);
-            }
+template <int NC>
+static void ring_chunks(PointCtx* c, const int* ia, const int* ib, const Tile& t, int wa, int wb, unsigned* mplus, unsigned* mminus,
+                        float* smax, float* slo, HostEmit& emit, HostEmitSlow& emit_slow, long long* counters) {
+  const int slice_words = t.nj * t.Dp;
+  const float kNaN = __builtin_nanf("");
+  bool noclip = true;
+  for (int l = 0; l < 32; ++l) noclip = noclip && ring_noclip(c[l], t);
+  const int first = t.i0 + ((wa - t.i0) / NC) * NC;          // chunks tile the slab from its first slice
+  for (int i0c = first; i0c <= wb; i0c += NC) {
+    float a4[32][NC]; float amax = 0.f; bool any_thin = false;
+    for (int sidx = 0; sidx < NC; ++sidx) {
+      const int i = i0c + sidx;
+      int dmax = 0; float ad[32]; int code[32];
+      for (int l = 0; l < 32; ++l) {
+        ad[l] = 0.f; code[l] = 0;
+        if (i >= ia[l] && i <= ib[l]) slice_setup(c[l], i, ad[l], code[l]);
+        const bool thin = code[l] == 1;
+        a4[l][sidx] = thin ? ad[l] : kNaN;
+        if (thin) { any_thin = true; if (ad[l] > amax) amax = ad[l]; }
+        if (c[l].R >= RCV_POLAR_MIN_R) {
+          if (code[l] > 1 || code[l] < 0) {
+            if (i > c[l].ipx) mplus[l] |= 1u << (i - t.i0); else mminus[l] |= 1u << (i - t.i0);
+            if (ad[l] > smax[l]) smax[l] = ad[l];
+            const float bl = f_sub(ad[l], c[l].W);
+            if (bl < slo[l]) slo[l] = bl;
           }
+        } else if (-code[l] > dmax) dmax = -code[l];
       }
-      for (int sl = 0; sl < 32; ++sl) {
-        if (code_l[sl] >= 0) continue;
-        const int i = sb + sl, hb = -code_l[sl], side = 2 * hb + 1;
-        ++dense_slices;
-        const int lpr = side <= 16 ? 16 : 32, rpi = 32 / lpr;   // lanes per row, rows per warp iteration
-        for (int r0 = 0; r0 < side; r0 += rpi)
-          for (int k0 = 0; k0 < side; k0 += lpr)
-            for (int lane = 0; lane < 32; ++lane) {
-              const int rr = r0 + lane / lpr, kk = k0 + lane % lpr;
-              dense_cell(c, a_l[sl], t, i, (i - i0) * nj * Dp, 1, -1, rr - hb, kk - hb, rr < side && kk < side, emit, slow);
+      if (dmax > 0) {
+        ++counters[1];
+        const int sbase = (i - t.i0) * slice_words;
+        for (int rr = -dmax; rr <= dmax; ++rr)
+          for (int kk = -dmax; kk <= dmax; ++kk)
+            for (int l = 0; l < 32; ++l) {
+              HostSlowPerm slow{&c[l], &emit};
+              const int hb = c[l].R < RCV_POLAR_MIN_R ? -code[l] : 0;
+              const bool ok = hb > 0 && rr >= -hb && rr <= hb && kk >= -hb && kk <= hb;
+              dense_cell(c[l], ad[l], t, i, sbase, 1, -1, rr, kk, ok, emit, slow);
             }
       }
     }
+    if (any_thin) {
+      ++counters[0];
+      const int H = ring_half_width(amax);
+      for (int pass = 0; pass < 2; ++pass)
+        for (int u = -H; u <= H; ++u)
+          for (int l = 0; l < 32; ++l) {
+            HostSlowPerm slow{&c[l], &emit};
+            HostSlowArcPerm slowarc{&slow, &emit_slow};
+            LaneTask L;
+            lane_setup_pu(c[l], t, pass != 0, u, (float)u, 1, L);
+            ++counters[2];
+            for (int sidx = 0; sidx < NC; ++sidx) {
+              const int i = i0c + sidx;
+              ThinOut o;
+              if (noclip) thin_fast<false>(c[l], a4[l][sidx], L, (i - t.i0) * slice_words, -1, emit, o);
+              else thin_fast<true>(c[l], a4[l][sidx], L, (i - t.i0) * slice_words, -1, emit, o);
+              if (o.t0 || o.t1) thin_slow(c[l], L, i, o, slowarc);
+            }
+          }
+    }
   }
-  if (stats) { stats[0] = emit.votes; stats[1] = emit.calls; stats[2] = emit.oob; stats[3] = ring_slices; stats[4] = dense_slices; stats[5] = lane_tasks; stats[6] = emit.slow_calls; }
+}
+
+extern "C" __attribute__((visibility("default")))
+int hostsim_render_v6(const double* p, const int* R, long n, int D, int Dp, int i0, int ni, int j0, int nj,
+                      int32_t* tile, int sqrt_perturb, long long* stats) {
+  g_sqrt_perturb = sqrt_perturb;
+  if (ni > 32) return 2;                       // the polar pass keeps one bit per slice of the tile
+  Tile t{i0, ni, j0, nj, D, Dp};
+  HostEmit emit{tile, (long)ni * nj * Dp};
+  HostEmitSlow emit_slow{&emit};
+  long long counters[3] = {0, 0, 0}, polar_cells = 0;
+  const int slice_words = nj * Dp;
+  for (long g0 = 0; g0 < n; g0 += 32) {
+    PointCtx c[32]; int ia[32], ib[32];
+    unsigned mplus[32], mminus[32]; float smax[32], slo[32];
+    int wa = 1 << 30, wb = -(1 << 30);
+    for (int l = 0; l < 32; ++l) {
+      const long q = g0 + l;
+      if (q < n) point_setup(c[l], p[3 * q + 1], p[3 * q], p[3 * q + 2], R[q]);   // (A,B,C) = (y,x,z)
+      else point_setup(c[l], 0.0, 0.0, 0.0, 0);
+      slice_range(c[l], t, ia[l], ib[l]);
+      if (ia[l] <= ib[l]) { if (ia[l] < wa) wa = ia[l]; if (ib[l] > wb) wb = ib[l]; }
+      mplus[l] = mminus[l] = 0u; smax[l] = 0.f; slo[l] = 3.0e38f;
+    }
+    if (wa > wb) continue;
+    if (ni % 4 != 0 && ni % 3 == 0) ring_chunks<3>(c, ia, ib, t, wa, wb, mplus, mminus, smax, slo, emit, emit_slow, counters);
+    else ring_chunks<4>(c, ia, ib, t, wa, wb, mplus, mminus, smax, slo, emit, emit_slow, counters);
+    // polar pass over the tile's non-thin slices
+    int Hp = -1; bool anyp = false, anym = false;
+    for (int l = 0; l < 32; ++l) {
+      if (mplus[l] | mminus[l]) { const int h = polar_half_width(smax[l]); if (h > Hp) Hp = h; }
+      anyp |= mplus[l] != 0u; anym |= mminus[l] != 0u;
+    }
+    if (Hp >= 0) {
+      for (int ub = -Hp; ub <= Hp; ++ub) {
+        float db2[32]; int CI = 0x7fffffff, CO = -1;
+        for (int l = 0; l < 32; ++l) {
+          const float db = f_sub((float)ub, c[l].fy);
+          db2[l] = f_mul(db, db);
+          int ci, co;
+          polar_row_range(slo[l], smax[l], db2[l], (mplus[l] | mminus[l]) != 0u, ci, co);
+          if (ci < CI) CI = ci;
+          if (co > CO) CO = co;
+        }
+        if (CO < 0) continue;
+        for (int uc = -CO; uc <= CO; ++uc) {
+          if (CI > 1 && uc > -CI && uc < CI) continue;
+          for (int l = 0; l < 32; ++l) {
+            HostSlowPerm slow{&c[l], &emit};
+            const float cpx = f_add(c[l].fx, c[l].dbias_m05), cmx = f_sub(c[l].dbias_m05, c[l].fx);
+            const float dc = f_sub((float)uc, c[l].fz);
+            const float s2 = f_fma(dc, dc, db2[l]);
+            const int jb = c[l].ipy + ub, kc = c[l].ipz + uc;
+            const bool ok = ((mplus[l] | mminus[l]) != 0u) && ((unsigned)(jb - j0) < (unsigned)nj) && ((unsigned)kc < (unsigned)D);
+            const int cell = (jb - j0) * Dp + kc;
+            PolarOut o;
+            ++polar_cells;
+            if (anyp && anym) polar_fast<3>(c[l], t, cpx, cmx, s2, cell, ok, mplus[l], mminus[l], slice_words, -1, emit, o);
+            else if (anyp) polar_fast<1>(c[l], t, cpx, cmx, s2, cell, ok, mplus[l], mminus[l], slice_words, -1, emit, o);
+            else polar_fast<2>(c[l], t, cpx, cmx, s2, cell, ok, mplus[l], mminus[l], slice_words, -1, emit, o);
+            if (o.t0 || o.t1) polar_slow(c[l].hw_m, t.i0, o, jb, kc, cell, mplus[l], mminus[l], slice_words, slow, emit_slow);
+          }
+        }
+      }
+    }
+  }
+  if (stats) { stats[0] = emit.votes; stats[1] = emit.calls; stats[2] = emit.oob; stats[3] = counters[0]; stats[4] = counters[1]; stats[5] = counters[2]; stats[6] = emit.slow_calls; stats[7] = polar_cells; }
   return emit.oob ? 1 : 0;
 }

@@ -87,3 +87,44 @@ def test_linemod_shaped_frame_matches_reference_volume(golden):
     got, st = hostsim.render(pre["p"], pre["R"], pre["D"])
     assert np.array_equal(got, golden["c1_volume"])   # the real reference's volume, every voxel
     assert st["votes"] == int(golden["c1_votes"])
+
+
+@pytest.mark.parametrize("slab", [1, 3, 4, 6, 7, 12, 32])
+def test_slab_thickness_and_chunking(slab):
+    """The kernel walks a slab in chunks of 3 or 4 slices and draws the polar caps once per slab: every slab
+    thickness must give the same volume (exercises chunk alignment, polar masks and the annulus row ranges)."""
+    rng = np.random.default_rng(40 + slab)
+    D = 64
+    n = 70
+    p = rng.uniform(14, 50, size=(n, 3))
+    R = rng.integers(5, 30, size=n).astype(np.int32)
+    want = oracle.fast_for(p, R, D, method="scatter")
+    got, st = hostsim.render(p, R, D, slab=slab, sqrt_perturb=slab % 2)
+    assert np.array_equal(got, want)
+    assert st["polar_cells"] > 0 and st["lane_tasks"] > 0
+
+
+@pytest.mark.parametrize("R", [6, 7, 8, 9, 11, 12, 14, 19])
+def test_polar_threshold_radii(R):
+    """R = RCV_POLAR_MIN_R - 1 (dense scan), R = RCV_POLAR_MIN_R and just above (polar pass, one voxel per column)."""
+    rng = np.random.default_rng(300 + R)
+    D = 2 * R + 12
+    p = (D / 2.0) + rng.uniform(-2.0, 2.0, size=(64, 3))
+    for slab in (5, 32):
+        want = oracle.fast_for(p, np.full(64, R, np.int32), D)
+        got, _ = hostsim.render(p, np.full(64, R, np.int32), D, slab=slab, sqrt_perturb=1)
+        assert np.array_equal(got, want)
+
+
+def test_surface_patch_like_a_frame_row():
+    """Points of one warp like consecutive pixels of an image row (close in y, spread in x, varying R)."""
+    rng = np.random.default_rng(77)
+    D = 90
+    n = 96
+    x = np.linspace(30, 50, n) + rng.normal(0, 0.05, n)
+    p = np.stack([x, 40 + rng.normal(0, 0.3, n), 45 + 0.02 * (x - 40) ** 2], axis=1)
+    R = np.round(np.linalg.norm(p - np.array([60.0, 55.0, 30.0]), axis=1)).astype(np.int32)
+    want = oracle.fast_for(p, R, D, method="scatter")
+    for slab in (6, 9):
+        got, _ = hostsim.render(p, R, D, slab=slab)
+        assert np.array_equal(got, want)
