@@ -312,6 +312,24 @@ RCV_HD bool mask_bit(unsigned m, int v) { return (u_shr(m, v) & 1u) != 0u; }
 // s = dB^2 + dC^2 of the cell, cell = its offset inside a slice, ok = the cell is inside the tile and the lane
 // takes part; sstride = slice stride (same units as cell).  SIDES: bit 0 = + side, bit 1 = - side.
 // cpx / cmx = fx + dbias - 0.5 and -fx + dbias - 0.5.
+// vote = |q| < hw_m  &&  ok  &&  bit v of mask  (one predicate chain, one select)
+RCV_HD int polar_pick(float q, float hw_m, bool ok, unsigned mask, int v, int off, int sink) {
+#if defined(__CUDA_ARCH__)
+  int r;
+  asm("{\n\t.reg .pred p;\n\t.reg .f32 aq;\n\t.reg .b32 sh;\n\t"
+      "abs.f32 aq, %1;\n\t"
+      "shr.u32 sh, %4, %5;\n\t"
+      "and.b32 sh, sh, %3;\n\t"
+      "setp.ne.b32 p, sh, 0;\n\t"
+      "setp.lt.and.f32 p, aq, %2, p;\n\t"
+      "selp.b32 %0, %6, %7, p;\n\t}"
+      : "=r"(r) : "f"(q), "f"(hw_m), "r"(ok ? 1 : 0), "r"(mask), "r"(v), "r"(off), "r"(sink));
+  return r;
+#else
+  return ((fabsf(q) < hw_m) && ok && mask_bit(mask, v)) ? off : sink;
+#endif
+}
+
 template <int SIDES, class Emit>
 RCV_HD void polar_fast(const PointCtx& c, const Tile& t, float cpx, float cmx, float s, int cell, bool ok, unsigned mplus, unsigned mminus,
                        int sstride, int sink, Emit& emit, PolarOut& o) {
@@ -326,10 +344,8 @@ RCV_HD void polar_fast(const PointCtx& c, const Tile& t, float cpx, float cmx, f
     o.vt0 = vrel0 + (f_bits(tm0) - RCV_MAGIC_BITS);
     const float d0 = f_sub(fl0, c.fx);
     o.q0 = f_fma(d0, d0, hWg);
-    const bool sure = fabsf(o.q0) < c.hw_m;
-    const bool vote = sure & ok & mask_bit(mplus, o.vt0);
-    emit(vote ? cell + o.vt0 * sstride : sink);
-    o.t0 = ok & !sure & (o.q0 > -c.hw_p);
+    emit(polar_pick(o.q0, c.hw_m, ok, mplus, o.vt0, cell + o.vt0 * sstride, sink));
+    o.t0 = ok & !(fabsf(o.q0) < c.hw_m) & (o.q0 > -c.hw_p);
   }
   if (SIDES & 2) {
     const float tm1 = f_add(f_add(zs, cmx), RCV_MAGIC);
@@ -337,18 +353,19 @@ RCV_HD void polar_fast(const PointCtx& c, const Tile& t, float cpx, float cmx, f
     o.vt1 = vrel0 - (f_bits(tm1) - RCV_MAGIC_BITS);
     const float d1 = f_add(fl1, c.fx);
     o.q1 = f_fma(d1, d1, hWg);
-    const bool sure = fabsf(o.q1) < c.hw_m;
-    const bool vote = sure & ok & mask_bit(mminus, o.vt1);
-    emit(vote ? cell + o.vt1 * sstride : sink);
-    o.t1 = ok & !sure & (o.q1 > -c.hw_p);
+    emit(polar_pick(o.q1, c.hw_m, ok, mminus, o.vt1, cell + o.vt1 * sstride, sink));
+    o.t1 = ok & !(fabsf(o.q1) < c.hw_m) & (o.q1 > -c.hw_p);
   }
 }
 
 // Column range of row `db2` (= dB^2) of the polar pass: the lane's non-thin rings of this tile lie in the annulus
 // s_lo < dB^2 + dC^2 < s_hi (s_hi = largest outer radius^2, s_lo = smallest inner radius^2), so only cells with
 // ci <= |uc| <= co can hold a candidate (|uc| differs from |dC| by at most 0.5; co < 0: the row is empty).
-RCV_HD void polar_row_range(float s_lo, float s_hi, float db2, bool lane_on, int& ci, int& co) {
-  const float rem_hi = f_sub(s_hi, db2), rem_lo = f_sub(s_lo, db2);
+RCV_HD void polar_row_range(float s_lo, float s_hi, float eps, float db2, bool lane_on, int& ci, int& co) {
+  // the annulus is widened by 2 eps: a cell whose float32 s sits exactly on a ring boundary can still hold a vote
+  // (it is then decided by the exact path)
+  const float m = f_add(eps, eps);
+  const float rem_hi = f_sub(f_add(s_hi, m), db2), rem_lo = f_sub(f_sub(s_lo, m), db2);
   co = -1; ci = 0x7fffffff;
   if (lane_on && rem_hi > 0.f) {
     co = (int)f_add(f_sqrt_fast(rem_hi), 0.6f);
@@ -378,13 +395,22 @@ RCV_HD void polar_slow(float hw_m, int ti0, const PolarOut& o, int jb, int kc, i
 }
 
 // Half-width (in rows) of the polar pass for a lane whose largest non-thin ring has outer radius^2 amax.
-RCV_HD int polar_half_width(float amax) { return (int)f_add(f_sqrt_fast(fmaxf(amax, 0.f)), 0.6f); }
+RCV_HD int polar_half_width(float amax, float eps) { return (int)f_add(f_sqrt_fast(fmaxf(f_add(amax, f_add(eps, eps)), 0.f)), 0.6f); }
 
 // Slice range of point c inside tile t (inclusive); empty if ia > ib.
 RCV_HD void slice_range(const PointCtx& c, const Tile& t, int& ia, int& ib) {
   ia = c.ipx - c.R - 1; if (ia < t.i0) ia = t.i0;
   ib = c.ipx + c.R + 1; if (ib > t.i0 + t.ni - 1) ib = t.i0 + t.ni - 1;
   if (c.R <= 0) { ia = 1; ib = 0; }
+}
+
+// Slices per chunk of the ring passes for a slab of ni slices: 3 or 4, whichever pads the slab less.
+RCV_HD int ring_chunk(int ni) { return (((ni + 2) / 3) * 3 < ((ni + 3) / 4) * 4) ? 3 : 4; }
+// Largest slab thickness <= ni_max that is a multiple of 3 or 4 (no padding in the ring passes).
+RCV_HD int slab_thickness(int ni_max) {
+  if (ni_max < 3) return ni_max;
+  const int a3 = (ni_max / 3) * 3, a4 = (ni_max / 4) * 4;
+  return a3 > a4 ? a3 : a4;
 }
 
 // True if no candidate of the lane's ring passes can fall outside the tile along a candidate axis

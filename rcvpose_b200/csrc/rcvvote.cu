@@ -471,8 +471,9 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
       if (slice <= a.tile_words) {
         int ni_max = (int)(a.tile_words / slice);
         if (ni_max > 32) ni_max = 32;   // the polar pass keeps one mask bit per slice of a tile
-        const int ns = (D + ni_max - 1) / ni_max;
-        m.ni = (D + ns - 1) / ns; m.nj = D;
+        if (ni_max > D) ni_max = D;
+        m.ni = ni_max >= D ? D : slab_thickness(ni_max);   // a multiple of 3 or 4: the ring passes walk a slab in chunks
+        m.nj = D;
         nunits = (D + m.ni - 1) / m.ni;
       } else {
         const int nj_max = a.tile_words / Dp;
@@ -594,18 +595,19 @@ __device__ __noinline__ void polar_slow_call(double pa, double pb, double pc, in
   polar_slow(hw_m, ti0, o, jb, kc, cell, mplus, mminus, sstride, slow, es);
 }
 
-// Polar pass of a warp: rows ub = -Hp..Hp around each lane's own point; in every row only the columns of the annulus
-// that holds the lane's non-thin rings (polar_row_range), bounds taken over the warp.
+// Polar pass of a warp: rows ub = -Hp..Hp around each lane's own point; in every row each lane walks the two column
+// segments [-co,-ci] and [max(ci,1),co] of ITS OWN annulus (polar_row_range); the trip count is the warp maximum.
 template <int SIDES>
-__device__ __forceinline__ void polar_segment(const PointCtx& c, const Tile& t, float cpx, float cmx, int uc0, int uc1, float db2, int jb, bool row_ok,
-                                              int rowoff, unsigned mplus, unsigned mminus, int slice_bytes, const SmemEmit& emit) {
+__device__ __forceinline__ void polar_segment(const PointCtx& c, const Tile& t, float cpx, float cmx, int uc0, int ucl, int T, float db2, int jb,
+                                              bool row_ok, int rowoff, unsigned mplus, unsigned mminus, int slice_bytes, const SmemEmit& emit) {
   float ucf = (float)uc0;
+  int kc = c.ipz + uc0;
+  const int kcl = c.ipz + ucl;
 #pragma unroll 2
-  for (int uc = uc0; uc <= uc1; ++uc, ucf += 1.0f) {
+  for (int tt = 0; tt < T; ++tt, ucf += 1.0f, ++kc) {
     const float dc = f_sub(ucf, c.fz);
     const float s2 = f_fma(dc, dc, db2);
-    const int kc = c.ipz + uc;
-    const bool ok = row_ok & ((unsigned)kc < (unsigned)t.D);
+    const bool ok = row_ok & (kc <= kcl) & ((unsigned)kc < (unsigned)t.D);
     const int cell = rowoff + kc * 4;
     PolarOut o;
     polar_fast<SIDES>(c, t, cpx, cmx, s2, cell, ok, mplus, mminus, slice_bytes, emit.sink, emit, o);
@@ -627,18 +629,16 @@ __device__ __forceinline__ void polar_pass(const PointCtx& c, const Tile& t, int
     const float db = f_sub(ubf, c.fy);
     const float db2 = f_mul(db, db);
     int ci, co;
-    polar_row_range(s_lo, s_hi, db2, lane_on, ci, co);
-    const int CO = warp_max_i32(co), CI = warp_min_i32(ci);
-    if (CO < 0) continue;
+    polar_row_range(s_lo, s_hi, c.eps, db2, lane_on, ci, co);
+    const int c1 = ci > 1 ? ci : 1;
+    const int T0 = warp_max_i32(co >= 0 ? co - ci + 1 : 0), T1 = warp_max_i32(co >= 0 ? co - c1 + 1 : 0);
+    if (T0 <= 0) continue;
     const int jb = c.ipy + ub;
-    const bool row_ok = lane_on & ((unsigned)(jb - t.j0) < (unsigned)t.nj);
+    const bool row_ok = (co >= 0) & ((unsigned)(jb - t.j0) < (unsigned)t.nj);
     const int rowoff = (jb - t.j0) * t.Dp * 4;
-    if (CI > 1) {
-      polar_segment<SIDES>(c, t, cpx, cmx, -CO, -CI, db2, jb, row_ok, rowoff, mplus, mminus, slice_bytes, emit);
-      polar_segment<SIDES>(c, t, cpx, cmx, CI, CO, db2, jb, row_ok, rowoff, mplus, mminus, slice_bytes, emit);
-    } else {
-      polar_segment<SIDES>(c, t, cpx, cmx, -CO, CO, db2, jb, row_ok, rowoff, mplus, mminus, slice_bytes, emit);
-    }
+    polar_segment<SIDES>(c, t, cpx, cmx, co >= 0 ? -co : 0, co >= 0 ? -ci : -1, T0, db2, jb, row_ok, rowoff, mplus, mminus, slice_bytes, emit);
+    if (T1 > 0)
+      polar_segment<SIDES>(c, t, cpx, cmx, co >= 0 ? c1 : 0, co >= 0 ? co : -1, T1, db2, jb, row_ok, rowoff, mplus, mminus, slice_bytes, emit);
   }
 }
 
@@ -747,9 +747,9 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
       const bool noclip = __all_sync(0xffffffffu, ring_noclip(c, t));
       unsigned mplus = 0u, mminus = 0u;
       float s_hi = 0.f, s_lo = 3.0e38f;
-      if (u.ni % 4 != 0 && u.ni % 3 == 0) ring_chunks<3>(c, t, ia, ib, wa, wb, slice_bytes, noclip, slow, emit, slowarc, mplus, mminus, s_lo, s_hi);
+      if (ring_chunk(u.ni) == 3) ring_chunks<3>(c, t, ia, ib, wa, wb, slice_bytes, noclip, slow, emit, slowarc, mplus, mminus, s_lo, s_hi);
       else ring_chunks<4>(c, t, ia, ib, wa, wb, slice_bytes, noclip, slow, emit, slowarc, mplus, mminus, s_lo, s_hi);
-      const int Hp = warp_max_i32((mplus | mminus) ? polar_half_width(s_hi) : -1);
+      const int Hp = warp_max_i32((mplus | mminus) ? polar_half_width(s_hi, c.eps) : -1);
       if (Hp >= 0) {
         const bool anyp = __any_sync(0xffffffffu, mplus != 0u), anym = __any_sync(0xffffffffu, mminus != 0u);
         if (anyp && anym) polar_pass<3>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);

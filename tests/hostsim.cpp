@@ -122,43 +122,53 @@ int hostsim_render_v6(const double* p, const int* R, long n, int D, int Dp, int 
       mplus[l] = mminus[l] = 0u; smax[l] = 0.f; slo[l] = 3.0e38f;
     }
     if (wa > wb) continue;
-    if (ni % 4 != 0 && ni % 3 == 0) ring_chunks<3>(c, ia, ib, t, wa, wb, mplus, mminus, smax, slo, emit, emit_slow, counters);
+    if (ring_chunk(ni) == 3) ring_chunks<3>(c, ia, ib, t, wa, wb, mplus, mminus, smax, slo, emit, emit_slow, counters);
     else ring_chunks<4>(c, ia, ib, t, wa, wb, mplus, mminus, smax, slo, emit, emit_slow, counters);
     // polar pass over the tile's non-thin slices
     int Hp = -1; bool anyp = false, anym = false;
     for (int l = 0; l < 32; ++l) {
-      if (mplus[l] | mminus[l]) { const int h = polar_half_width(smax[l]); if (h > Hp) Hp = h; }
+      if (mplus[l] | mminus[l]) { const int h = polar_half_width(smax[l], c[l].eps); if (h > Hp) Hp = h; }
       anyp |= mplus[l] != 0u; anym |= mminus[l] != 0u;
     }
     if (Hp >= 0) {
       for (int ub = -Hp; ub <= Hp; ++ub) {
-        float db2[32]; int CI = 0x7fffffff, CO = -1;
+        float db2[32]; int CI = 0x7fffffff, CO = -1, ci_l[32], co_l[32];
         for (int l = 0; l < 32; ++l) {
           const float db = f_sub((float)ub, c[l].fy);
           db2[l] = f_mul(db, db);
-          int ci, co;
-          polar_row_range(slo[l], smax[l], db2[l], (mplus[l] | mminus[l]) != 0u, ci, co);
-          if (ci < CI) CI = ci;
-          if (co > CO) CO = co;
+          polar_row_range(slo[l], smax[l], c[l].eps, db2[l], (mplus[l] | mminus[l]) != 0u, ci_l[l], co_l[l]);
+          if (ci_l[l] < CI) CI = ci_l[l];
+          if (co_l[l] > CO) CO = co_l[l];
         }
         if (CO < 0) continue;
-        for (int uc = -CO; uc <= CO; ++uc) {
-          if (CI > 1 && uc > -CI && uc < CI) continue;
+        // every lane walks ITS OWN annulus segments [-co,-ci] and [max(ci,1),co]; trip counts are warp maxima
+        for (int seg = 0; seg < 2; ++seg) {
+          int T = 0, uc0[32], ucl[32];
           for (int l = 0; l < 32; ++l) {
-            HostSlowPerm slow{&c[l], &emit};
-            const float cpx = f_add(c[l].fx, c[l].dbias_m05), cmx = f_sub(c[l].dbias_m05, c[l].fx);
-            const float dc = f_sub((float)uc, c[l].fz);
-            const float s2 = f_fma(dc, dc, db2[l]);
-            const int jb = c[l].ipy + ub, kc = c[l].ipz + uc;
-            const bool ok = ((mplus[l] | mminus[l]) != 0u) && ((unsigned)(jb - j0) < (unsigned)nj) && ((unsigned)kc < (unsigned)D);
-            const int cell = (jb - j0) * Dp + kc;
-            PolarOut o;
-            ++polar_cells;
-            if (anyp && anym) polar_fast<3>(c[l], t, cpx, cmx, s2, cell, ok, mplus[l], mminus[l], slice_words, -1, emit, o);
-            else if (anyp) polar_fast<1>(c[l], t, cpx, cmx, s2, cell, ok, mplus[l], mminus[l], slice_words, -1, emit, o);
-            else polar_fast<2>(c[l], t, cpx, cmx, s2, cell, ok, mplus[l], mminus[l], slice_words, -1, emit, o);
-            if (o.t0 || o.t1) polar_slow(c[l].hw_m, t.i0, o, jb, kc, cell, mplus[l], mminus[l], slice_words, slow, emit_slow);
+            uc0[l] = 0; ucl[l] = -1;
+            if (co_l[l] >= 0) {
+              if (seg == 0) { uc0[l] = -co_l[l]; ucl[l] = -ci_l[l]; }
+              else { uc0[l] = ci_l[l] > 1 ? ci_l[l] : 1; ucl[l] = co_l[l]; }
+            }
+            if (ucl[l] - uc0[l] + 1 > T) T = ucl[l] - uc0[l] + 1;
           }
+          for (int tt = 0; tt < T; ++tt)
+            for (int l = 0; l < 32; ++l) {
+              HostSlowPerm slow{&c[l], &emit};
+              const float cpx = f_add(c[l].fx, c[l].dbias_m05), cmx = f_sub(c[l].dbias_m05, c[l].fx);
+              const int uc = uc0[l] + tt;
+              const float dc = f_sub((float)uc, c[l].fz);
+              const float s2 = f_fma(dc, dc, db2[l]);
+              const int jb = c[l].ipy + ub, kc = c[l].ipz + uc;
+              const bool ok = uc <= ucl[l] && ((unsigned)(jb - j0) < (unsigned)nj) && ((unsigned)kc < (unsigned)D);
+              const int cell = (jb - j0) * Dp + kc;
+              PolarOut o;
+              ++polar_cells;
+              if (anyp && anym) polar_fast<3>(c[l], t, cpx, cmx, s2, cell, ok, mplus[l], mminus[l], slice_words, -1, emit, o);
+              else if (anyp) polar_fast<1>(c[l], t, cpx, cmx, s2, cell, ok, mplus[l], mminus[l], slice_words, -1, emit, o);
+              else polar_fast<2>(c[l], t, cpx, cmx, s2, cell, ok, mplus[l], mminus[l], slice_words, -1, emit, o);
+              if (o.t0 || o.t1) polar_slow(c[l].hw_m, t.i0, o, jb, kc, cell, mplus[l], mminus[l], slice_words, slow, emit_slow);
+            }
         }
       }
     }
