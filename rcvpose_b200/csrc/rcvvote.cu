@@ -57,6 +57,7 @@ struct Unit {
 struct Pool {
   double *X, *Y, *Z, *Rd;  // voxel-unit coordinates (recentred in place by the prelude), radius in voxels
   int* Ri;                 // np.around(radius) -- AccumulatorSpace.py:332
+  int* perm;               // per item: its points ordered by (y voxel, R) so that the 32 points of a warp of k_vote draw alike
   long long cap;
 };
 
@@ -379,6 +380,7 @@ struct PreludeArgs {
 };
 
 constexpr int kPreludeThreads = 256;
+constexpr int kSortBins = 8192;   // bins of the (y voxel, R) counting sort that orders an item's points for k_vote
 
 __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
   const int item = blockIdx.x;
@@ -494,6 +496,61 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
   if (zb < 0) {
     const double zbd = (double)zb;
     for (int q = threadIdx.x; q < n; q += blockDim.x) { X[q] = __dsub_rn(X[q], zbd); Y[q] = __dsub_rn(Y[q], zbd); Z[q] = __dsub_rn(Z[q], zbd); }
+  }
+  // ---- vote order: counting sort of the item's points by (nearest y voxel, integer radius) ----
+  // k_vote gives every lane of a warp one point; lanes that share the slice coordinate and the radius have the same
+  // ring class and size in every slice, so no lane idles while another draws.  (Votes are integer adds: order-free.)
+  {
+    __shared__ int s_hist[kSortBins];
+    __shared__ int s_mm[4];
+    __shared__ int s_wsum[kPreludeThreads / 32];
+    if (threadIdx.x == 0) { s_mm[0] = 0x7fffffff; s_mm[1] = -0x7fffffff; s_mm[2] = 0x7fffffff; s_mm[3] = 0; }
+    __syncthreads();
+    int amin = 0x7fffffff, amax = -0x7fffffff, rmin = 0x7fffffff, rmx = 0;
+    const int* Ri = a.pool.Ri + m.off;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+      const int ya = __double2int_rn(Y[q]), r = max(Ri[q], 0);
+      amin = min(amin, ya); amax = max(amax, ya); rmin = min(rmin, r); rmx = max(rmx, r);
+    }
+    amin = __reduce_min_sync(0xffffffffu, amin); amax = __reduce_max_sync(0xffffffffu, amax);
+    rmin = __reduce_min_sync(0xffffffffu, rmin); rmx = __reduce_max_sync(0xffffffffu, rmx);
+    if (lane == 0) { atomicMin(&s_mm[0], amin); atomicMax(&s_mm[1], amax); atomicMin(&s_mm[2], rmin); atomicMax(&s_mm[3], rmx); }
+    __syncthreads();
+    amin = s_mm[0]; amax = s_mm[1]; rmin = s_mm[2]; rmx = s_mm[3];
+    const long long nA = (long long)amax - amin + 1;
+    int sh = 0, ash = 0;
+    while (nA > (kSortBins >> 1) && ((nA >> ash) > (kSortBins >> 1))) ++ash;                       // degenerate extents only
+    const int nAq = (int)(((long long)amax - amin) >> ash) + 1;
+    while ((long long)nAq * (((rmx - rmin) >> sh) + 1) > kSortBins) ++sh;
+    const int nRq = ((rmx - rmin) >> sh) + 1, NB = nAq * nRq;
+    for (int b = threadIdx.x; b < NB; b += blockDim.x) s_hist[b] = 0;
+    __syncthreads();
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+      const int ya = __double2int_rn(Y[q]), r = max(Ri[q], 0);
+      atomicAdd(&s_hist[((ya - amin) >> ash) * nRq + ((r - rmin) >> sh)], 1);
+    }
+    __syncthreads();
+    // exclusive scan of the bins: each thread owns a run of consecutive bins
+    const int per = (NB + kPreludeThreads - 1) / kPreludeThreads;
+    const int b0 = min(NB, (int)threadIdx.x * per), b1 = min(NB, b0 + per);
+    int tsum = 0;
+    for (int b = b0; b < b1; ++b) tsum += s_hist[b];
+    int incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += s_wsum[w];
+    int run = wbase + incl - tsum;
+    for (int b = b0; b < b1; ++b) { const int v = s_hist[b]; s_hist[b] = run; run += v; }
+    __syncthreads();
+    int* perm = a.pool.perm + m.off;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+      const int ya = __double2int_rn(Y[q]), r = max(Ri[q], 0);
+      const int pos = atomicAdd(&s_hist[((ya - amin) >> ash) * nRq + ((r - rmin) >> sh)], 1);
+      perm[pos] = q;
+    }
   }
   // tile work list
   m = a.meta[item];
@@ -734,9 +791,11 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
       if (lane == 0) cur = atomicAdd(&s_next, 32);
       cur = __shfl_sync(0xffffffffu, cur, 0);
       if (cur >= n) break;
-      const int q = cur + lane;
       double pa = 0.0, pb = 0.0, pc = 0.0; int R = 0;
-      if (q < n) { pb = a.pool.X[off + q]; pa = a.pool.Y[off + q]; pc = a.pool.Z[off + q]; R = a.pool.Ri[off + q]; }
+      if (cur + lane < n) {
+        const long long q = off + a.pool.perm[off + cur + lane];
+        pb = a.pool.X[q]; pa = a.pool.Y[q]; pc = a.pool.Z[q]; R = a.pool.Ri[q];
+      }
       PointCtx c;
       point_setup(c, pa, pb, pc, R);
       SlowExactCall slow{pa, pb, pc, R};
@@ -1023,7 +1082,7 @@ RCV_EXPORT long long rcv_launch_count(const rcv_ctx* ctx) { return ctx ? ctx->la
 RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri);
+  cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri); cudaFree(c->pool.perm);
   cudaFree(c->meta); cudaFree(c->units); cudaFree(c->counters); cudaFree(c->cnt); cudaFree(c->best); cudaFree(c->votes);
   cudaFree(c->leaves); cudaFree(c->leaf_sums);
   for (int s = 0; s < 2; ++s) { cudaFree(c->st_depth[s]); cudaFree(c->st_radius[s]); cudaFree(c->st_sem[s]); }
@@ -1070,7 +1129,7 @@ RCV_EXPORT int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out) {
   const long long cap = cfg->max_points_total;
   c->pool.cap = cap;
   CKC(cudaMalloc(&c->pool.X, cap * 8)); CKC(cudaMalloc(&c->pool.Y, cap * 8)); CKC(cudaMalloc(&c->pool.Z, cap * 8));
-  CKC(cudaMalloc(&c->pool.Rd, cap * 8)); CKC(cudaMalloc(&c->pool.Ri, cap * 4));
+  CKC(cudaMalloc(&c->pool.Rd, cap * 8)); CKC(cudaMalloc(&c->pool.Ri, cap * 4)); CKC(cudaMalloc(&c->pool.perm, cap * 4));
   CKC(cudaMalloc(&c->meta, sizeof(ItemMeta) * (size_t)cfg->max_items));
   CKC(cudaMalloc(&c->units, sizeof(Unit) * (size_t)c->cfg.max_units));
   CKC(cudaMalloc(&c->counters, 64 + 4096));
