@@ -1,0 +1,158 @@
+// head1x1.cu -- K5: the producer's final 1x1 convolution (models/fcnresnet.py:118,187-189 of the reference:
+// conv8 = Conv2d(32 -> 2, 1x1, bias); seg = out[:,0:1], radial = out[:,1:2]) as a tcgen05 tensor-core kernel.
+//
+//   out[b][n][p] = bias[n] + sum_k bf16(w[n][k]) * up[b][k][p]        n = 0,1   k = 0..31   p = 0..H*W-1
+//
+// GEMM view per tile: D[128 pixels x 16] = A[128 x 32] * B[16 x 32]^T, bf16 operands, fp32 accumulation in TMEM
+// (N is padded from 2 to 16, the smallest N of an M = 128 UMMA).  The input is NCHW, so a tile of A is 32 channel
+// rows of 128 contiguous pixels: exactly the canonical MN-major no-swizzle UMMA layout when each 16-byte chunk
+// (8 pixels of one channel) is placed at  (pixel group) * 128 B + (channel % 8) * 16 B + (channel / 8) * 2048 B.
+// cp.async moves the chunks global -> shared without touching registers (4-stage ring, 8 KB per stage); one thread
+// issues the two K = 16 MMAs of a tile, tcgen05.commit signals an mbarrier, and the four warps read their 32 TMEM
+// lanes back with tcgen05.ld, add the bias and store both planes with fully coalesced 128-pixel rows.
+// The kernel is HBM-bound: 64 B read + 8 B written per pixel, 39 MFLOP per 640x480 map.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace rcv_head {
+
+constexpr int kThreads = 128;
+constexpr int kStages = 4;
+constexpr int kTileM = 128;                 // pixels per tile = UMMA M
+constexpr int kC = 32;                      // input channels = 2 x UMMA K
+constexpr int kN = 16;                      // UMMA N (2 real outputs)
+constexpr int kATile = kC * kTileM * 2;     // 8192 bytes
+constexpr int kBTile = kN * kC * 2;         // 1024 bytes
+constexpr int kTmemCols = 32;
+constexpr int kSmemBytes = kStages * kATile + kBTile + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  // UMMA shared-memory descriptor, SWIZZLE_NONE: start address, leading / stride byte offsets (all >> 4), version 1
+  return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, A MN-major, B K-major, N = 16, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+__global__ void __launch_bounds__(kThreads) k_head1x1(const __nv_bfloat16* __restrict__ up, const float* __restrict__ w, const float* __restrict__ bias,
+                                                     float* __restrict__ out, long long HW, int tiles_per_image, long long n_tiles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kATile;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + kBTile);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(sB + kBTile + 16);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  // weights -> canonical K-major no-swizzle tile: (n % 8) * 16 + (n / 8) * 512 + (k % 8) * 2 + (k / 8) * 128
+  for (int e = tid; e < kN * kC; e += kThreads) {
+    const int n = e / kC, k = e % kC;
+    const float v = n < 2 ? w[n * kC + k] : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(sB + (n % 8) * 16 + (n / 8) * 512 + (k % 8) * 2 + (k / 8) * 128) = __float2bfloat16_rn(v);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tslot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the weight tile was written through the generic proxy
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tslot;
+  const float bias0 = bias[0], bias1 = bias[1];
+
+  const long long step = gridDim.x;
+  auto issue = [&](long long tile, int stage) {
+    if (tile < n_tiles) {
+      const long long b = tile / tiles_per_image;
+      const long long m0 = (tile - b * tiles_per_image) * kTileM;
+      const __nv_bfloat16* src0 = up + b * kC * HW;
+      const uint32_t dst0 = smem_u32(sA + stage * kATile);
+#pragma unroll
+      for (int j = 0; j < (kC * kTileM / 8) / kThreads; ++j) {
+        const int chunk = tid + j * kThreads, k = chunk >> 4, mi = chunk & 15;
+        const long long pix = m0 + mi * 8;
+        const bool valid = pix < HW;
+        const __nv_bfloat16* src = src0 + (long long)k * HW + (valid ? pix : 0);
+        const uint32_t dst = dst0 + mi * 128 + (k & 7) * 16 + (k >> 3) * 2048;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const long long tile0 = blockIdx.x;
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) issue(tile0 + s * step, s);
+  uint32_t phase = 0;
+  int it = 0;
+  for (long long tile = tile0; tile < n_tiles; tile += step, ++it) {
+    issue(tile + (kStages - 1) * step, (it + kStages - 1) % kStages);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a0 = smem_u32(sA + (it % kStages) * kATile), b0 = smem_u32(sB);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        const uint64_t da = make_desc(a0 + kb * 4096, 2048, 128);   // MN-major: 8-channel groups 2048 B apart, 8-pixel groups 128 B apart
+        const uint64_t db = make_desc(b0 + kb * 256, 128, 512);     // K-major:  8-element K chunks 128 B apart, 8-row groups 512 B apart
+        const uint32_t accumulate = kb;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+    }
+    uint32_t done;
+    do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(smem_u32(mbar)), "r"(phase) : "memory");
+    } while (!done);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t r0, r1;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(tmem + ((uint32_t)(warp * 32) << 16)) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const long long b = tile / tiles_per_image;
+    const long long pix = (tile - b * tiles_per_image) * kTileM + tid;
+    if (pix < HW) {
+      float* o = out + b * 2 * HW + pix;
+      o[0] = __uint_as_float(r0) + bias0;
+      o[HW] = __uint_as_float(r1) + bias1;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();   // TMEM and the stage buffer are free again
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+}  // namespace rcv_head
+
+// Called by the C ABI (rcvvote.cu: rcv_head_1x1).  Returns a cudaError_t as int.
+extern "C" int rcv_head1x1_launch(const void* up_bf16, const float* weight, const float* bias, float* out, int n_images, long long hw, int sms,
+                                  void* stream) {
+  using namespace rcv_head;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_head1x1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int tiles_per_image = (int)((hw + kTileM - 1) / kTileM);
+  const long long n_tiles = (long long)n_images * tiles_per_image;
+  long long grid = (long long)sms * 4;   // 4 CTAs per SM keep ~100 KB of loads in flight per SM
+  if (grid > n_tiles) grid = n_tiles;
+  k_head1x1<<<(int)grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>((const __nv_bfloat16*)up_bf16, weight, bias, out, hw, tiles_per_image, n_tiles);
+  return (int)cudaGetLastError();
+}

@@ -613,7 +613,6 @@ struct SlowArcCall {
 };
 
 __device__ __forceinline__ int warp_max_i32(int v) { return __reduce_max_sync(0xffffffffu, v); }
-__device__ __forceinline__ int warp_min_i32(int v) { return __reduce_min_sync(0xffffffffu, v); }
 
 // One pass over a chunk of NC consecutive slices for a warp whose 32 lanes each own one point: every lane walks the
 // columns (rows) u = -H..H of ITS thin rings (one candidate per arc); the lane task of column u is shared by the
@@ -699,58 +698,64 @@ __device__ __forceinline__ void polar_pass(const PointCtx& c, const Tile& t, int
   }
 }
 
-// Ring passes of one warp over the slices [wa, wb] of the tile, in chunks of NC slices that tile the slab from its
-// first slice; collects the lane's non-thin slices (masks, annulus) for the polar pass and scans small spheres densely.
+// Ring work of one warp for ONE chunk of NC slices of the slab (chunks tile the slab from its first slice): thin rings
+// by the two ring passes, spheres too small for the polar pass by a dense scan.
 template <int NC>
-__device__ __forceinline__ void ring_chunks(const PointCtx& c, const Tile& t, int ia, int ib, int wa, int wb, int slice_bytes, bool noclip,
-                                            const SlowExactCall& slow_c, const SmemEmit& emit, const SlowArcCall& slowarc, unsigned& mplus,
-                                            unsigned& mminus, float& s_lo, float& s_hi) {
+__device__ __forceinline__ void ring_chunk_work(const PointCtx& c, const Tile& t, int ia, int ib, int i0c, int slice_bytes, bool noclip,
+                                                const SlowExactCall& slow_c, const SmemEmit& emit, const SlowArcCall& slowarc) {
   SlowExactCall slow = slow_c;
   const bool polar_lane = c.R >= RCV_POLAR_MIN_R;
-  const int first = t.i0 + ((wa - t.i0) / NC) * NC;
-#pragma unroll 1
-  for (int i0c = first; i0c <= wb; i0c += NC) {
-    float a4[NC];
-    int abits = 0;
+  float a4[NC];
+  int abits = 0;
 #pragma unroll
-    for (int sidx = 0; sidx < NC; ++sidx) {
-      const int i = i0c + sidx;
-      float ar = 0.f; int code = 0;
-      if (i >= ia && i <= ib) slice_setup(c, i, ar, code);
-      const bool thin = code == 1;
-      a4[sidx] = thin ? ar : __int_as_float(0x7fc00000);
-      if (thin) abits = max(abits, __float_as_int(ar));   // thin => a > 36 > 0: bit order = value order
-      int dl = 0;
-      if (polar_lane) {
-        if (code > 1 || code < 0) {
-          if (i > c.ipx) mplus |= 1u << (i - t.i0); else mminus |= 1u << (i - t.i0);
-          s_hi = fmaxf(s_hi, ar);
-          s_lo = fminf(s_lo, f_sub(ar, c.W));
+  for (int sidx = 0; sidx < NC; ++sidx) {
+    const int i = i0c + sidx;
+    float ar = 0.f; int code = 0;
+    if (i >= ia && i <= ib) slice_setup(c, i, ar, code);
+    const bool thin = code == 1;
+    a4[sidx] = thin ? ar : __int_as_float(0x7fc00000);
+    if (thin) abits = max(abits, __float_as_int(ar));   // thin => a > 36 > 0: bit order = value order
+    const int dl = polar_lane ? 0 : -code;
+    const int dmax = warp_max_i32(dl);
+    if (dmax > 0) {   // spheres too small for the polar pass (R < RCV_POLAR_MIN_R): bounding-box scan of the slice
+      const int sbase = (i - t.i0) * slice_bytes;
+#pragma unroll 1
+      for (int rr = -dmax; rr <= dmax; ++rr)
+#pragma unroll 1
+        for (int kk = -dmax; kk <= dmax; ++kk) {
+          const bool ok = dl > 0 && rr >= -dl && rr <= dl && kk >= -dl && kk <= dl;
+          dense_cell(c, ar, t, i, sbase, 4, emit.sink, rr, kk, ok, emit, slow);
         }
-      } else dl = -code;
-      const int dmax = warp_max_i32(dl);
-      if (dmax > 0) {   // spheres too small for the polar pass (R < RCV_POLAR_MIN_R): bounding-box scan of the slice
-        const int sbase = (i - t.i0) * slice_bytes;
-#pragma unroll 1
-        for (int rr = -dmax; rr <= dmax; ++rr)
-#pragma unroll 1
-          for (int kk = -dmax; kk <= dmax; ++kk) {
-            const bool ok = dl > 0 && rr >= -dl && rr <= dl && kk >= -dl && kk <= dl;
-            dense_cell(c, ar, t, i, sbase, 4, emit.sink, rr, kk, ok, emit, slow);
-          }
-      }
     }
-    const int amax_bits = warp_max_i32(abits);
-    if (amax_bits > 0) {
-      const int H = ring_half_width(__int_as_float(amax_bits));
-      const int sbase0 = (i0c - t.i0) * slice_bytes;
-      if (noclip) {
-        ring_pass<false, false, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
-        ring_pass<true, false, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
-      } else {
-        ring_pass<false, true, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
-        ring_pass<true, true, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
-      }
+  }
+  const int amax_bits = warp_max_i32(abits);
+  if (amax_bits > 0) {
+    const int H = ring_half_width(__int_as_float(amax_bits));
+    const int sbase0 = (i0c - t.i0) * slice_bytes;
+    if (noclip) {
+      ring_pass<false, false, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
+      ring_pass<true, false, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
+    } else {
+      ring_pass<false, true, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
+      ring_pass<true, true, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
+    }
+  }
+}
+
+// The lane's non-thin slices in the slab: masks (bit v = slice t.i0 + v, by side of the pole) and the annulus
+// s_lo < dB^2 + dC^2 < s_hi that holds their rings.
+__device__ __forceinline__ void polar_collect(const PointCtx& c, const Tile& t, int ia, int ib, unsigned& mplus, unsigned& mminus, float& s_lo,
+                                              float& s_hi) {
+  mplus = 0u; mminus = 0u; s_hi = 0.f; s_lo = 3.0e38f;
+  if (c.R < RCV_POLAR_MIN_R) return;
+#pragma unroll 1
+  for (int i = ia; i <= ib; ++i) {
+    float ar; int code;
+    slice_setup(c, i, ar, code);
+    if (code > 1 || code < 0) {
+      if (i > c.ipx) mplus |= 1u << (i - t.i0); else mminus |= 1u << (i - t.i0);
+      s_hi = fmaxf(s_hi, ar);
+      s_lo = fminf(s_lo, f_sub(ar, c.W));
     }
   }
 }
@@ -784,13 +789,17 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
       for (int w = threadIdx.x; w < n4; w += kVoteThreads) t4[w] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();
-    // ---- scatter: each warp takes 32 consecutive points from the CTA's queue, one point per lane ----
+    // ---- scatter: a work item is (phase, group of 32 consecutive points of the vote order), one point per lane.
+    // Phase 0 draws the polar caps of the group's spheres inside the slab, phase 1 + c the thin rings of chunk c.
     const int slice_bytes = u.nj * Dp * 4;
+    const int NC = ring_chunk(u.ni);
+    const int ngroups = (n + 31) >> 5, nwork = ngroups * (1 + (u.ni + NC - 1) / NC);
     for (;;) {
-      int cur = 0;
-      if (lane == 0) cur = atomicAdd(&s_next, 32);
-      cur = __shfl_sync(0xffffffffu, cur, 0);
-      if (cur >= n) break;
+      int w = 0;
+      if (lane == 0) w = atomicAdd(&s_next, 1);
+      w = __shfl_sync(0xffffffffu, w, 0);
+      if (w >= nwork) break;
+      const int phase = w / ngroups, cur = (w - phase * ngroups) << 5;
       double pa = 0.0, pb = 0.0, pc = 0.0; int R = 0;
       if (cur + lane < n) {
         const long long q = off + a.pool.perm[off + cur + lane];
@@ -798,22 +807,27 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
       }
       PointCtx c;
       point_setup(c, pa, pb, pc, R);
-      SlowExactCall slow{pa, pb, pc, R};
       int ia, ib;
       slice_range(c, t, ia, ib);
-      const int wa = warp_min_i32(ia <= ib ? ia : 0x7fffffff), wb = warp_max_i32(ia <= ib ? ib : -0x7fffffff);
-      if (wa > wb) continue;
-      const bool noclip = __all_sync(0xffffffffu, ring_noclip(c, t));
-      unsigned mplus = 0u, mminus = 0u;
-      float s_hi = 0.f, s_lo = 3.0e38f;
-      if (ring_chunk(u.ni) == 3) ring_chunks<3>(c, t, ia, ib, wa, wb, slice_bytes, noclip, slow, emit, slowarc, mplus, mminus, s_lo, s_hi);
-      else ring_chunks<4>(c, t, ia, ib, wa, wb, slice_bytes, noclip, slow, emit, slowarc, mplus, mminus, s_lo, s_hi);
-      const int Hp = warp_max_i32((mplus | mminus) ? polar_half_width(s_hi, c.eps) : -1);
-      if (Hp >= 0) {
-        const bool anyp = __any_sync(0xffffffffu, mplus != 0u), anym = __any_sync(0xffffffffu, mminus != 0u);
-        if (anyp && anym) polar_pass<3>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);
-        else if (anyp) polar_pass<1>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);
-        else polar_pass<2>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);
+      if (phase == 0) {
+        unsigned mplus, mminus;
+        float s_lo, s_hi;
+        polar_collect(c, t, ia, ib, mplus, mminus, s_lo, s_hi);
+        const int Hp = warp_max_i32((mplus | mminus) ? polar_half_width(s_hi, c.eps) : -1);
+        if (Hp >= 0) {
+          const bool anyp = __any_sync(0xffffffffu, mplus != 0u), anym = __any_sync(0xffffffffu, mminus != 0u);
+          if (anyp && anym) polar_pass<3>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);
+          else if (anyp) polar_pass<1>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);
+          else polar_pass<2>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);
+        }
+      } else {
+        const int i0c = t.i0 + (phase - 1) * NC;
+        const bool here = ia <= ib && ib >= i0c && ia < i0c + NC;
+        if (!__any_sync(0xffffffffu, here)) continue;
+        const bool noclip = __all_sync(0xffffffffu, ring_noclip(c, t));
+        SlowExactCall slow{pa, pb, pc, R};
+        if (NC == 3) ring_chunk_work<3>(c, t, ia, ib, i0c, slice_bytes, noclip, slow, emit, slowarc);
+        else ring_chunk_work<4>(c, t, ia, ib, i0c, slice_bytes, noclip, slow, emit, slowarc);
       }
     }
     __syncthreads();
