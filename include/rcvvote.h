@@ -144,6 +144,15 @@ int rcv_horn_batch(rcv_ctx* ctx, const double* model, long long model_stride, co
 int rcv_horn_batch_host(rcv_ctx* ctx, const double* model, long long model_stride, const double* est, int n, int n_frames,
                         double* RT, void* stream);
 
+/* ---- conv8 of the radius-map producer  -- models/fcnresnet.py:118 (definition), :187-189 (use) -----------
+ * out[b][n][p] = bias[n] + sum_k bf16(weight[n][k]) * up[b][k][p],  n = 0 (seg), 1 (radial), k = 0..31.
+ * The 1x1 head as a tcgen05 tensor-core kernel (bf16 operands, fp32 accumulation in tensor memory).
+ *   up      [n_images][32][hw] bfloat16 (the NCHW output of conv7 + BN + ReLU), 16-byte aligned, hw % 8 == 0
+ *   weight  [2][32] float32 (rounded to bf16 inside, as a bf16 module holds it), bias [2] float32
+ *   out     [n_images][2][hw] float32: plane 0 = seg map, plane 1 = radius map (the inputs of rcv_vote_frames) */
+int rcv_head_1x1(rcv_ctx* ctx, const void* up_bf16, const float* weight, const float* bias, float* out, int n_images, long long hw,
+                 void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (the bench's gpu_launches claim). */
 long long rcv_launch_count(const rcv_ctx* ctx);

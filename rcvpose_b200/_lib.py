@@ -15,7 +15,7 @@ RCV_ST_OK, RCV_ST_EMPTY_MASK, RCV_ST_BAD_GRID, RCV_ST_D_EXCEEDS_CAP, RCV_ST_POIN
 RCV_ST_VOLUME_SKIPPED = 32
 
 EXPORTS = ["rcv_create", "rcv_destroy", "rcv_last_error", "rcv_abi_version", "rcv_backproject", "rcv_vote_points", "rcv_vote_frames",
-           "rcv_vote_frames_host", "rcv_argmax_volume", "rcv_horn_batch", "rcv_horn_batch_host", "rcv_launch_count",
+           "rcv_vote_frames_host", "rcv_argmax_volume", "rcv_head_1x1", "rcv_horn_batch", "rcv_horn_batch_host", "rcv_launch_count",
            "rcv_last_vote_kernel_ms", "rcv_vote_kernel_times", "rcv_ubench_smem_atomics"]
 
 
@@ -75,6 +75,8 @@ def load():
     L.rcv_horn_batch.argtypes = [vp, vp, C.c_longlong, vp, C.c_int, C.c_int, vp, vp]
     L.rcv_horn_batch_host.restype = C.c_int
     L.rcv_horn_batch_host.argtypes = [vp, vp, C.c_longlong, vp, C.c_int, C.c_int, vp, vp]
+    L.rcv_head_1x1.restype = C.c_int
+    L.rcv_head_1x1.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_longlong, vp]
     L.rcv_launch_count.restype = C.c_longlong
     L.rcv_launch_count.argtypes = [vp]
     L.rcv_last_vote_kernel_ms.restype = C.c_float

@@ -209,6 +209,23 @@ class VoteContext:
             self._ck(self.lib.rcv_horn_batch(self.h, _ptr(model), stride, _ptr(est), n, B, _ptr(RT), _stream()))
         return RT
 
+    def head_1x1(self, up, weight, bias):
+        """conv8 of the reference's producer (models/fcnresnet.py:118,187-189) on the tensor cores.
+        up (B,32,H,W) bfloat16 NCHW, weight (2,32[,1,1]) and bias (2,) float32 -> out (B,2,H,W) float32:
+        out[:,0] = seg map, out[:,1] = radius map."""
+        if isinstance(up, torch.Tensor):
+            up = up.contiguous()
+        _check_cuda(up, torch.bfloat16, "up")
+        B, Cin, H, W = up.shape
+        if Cin != 32:
+            raise ValueError("head_1x1: the head has 32 input channels")
+        weight = weight.reshape(2, 32).to(device=up.device, dtype=torch.float32).contiguous()
+        bias = bias.reshape(2).to(device=up.device, dtype=torch.float32).contiguous()
+        out = torch.empty((B, 2, H, W), dtype=torch.float32, device=up.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_head_1x1(self.h, _ptr(up), _ptr(weight), _ptr(bias), _ptr(out), B, H * W, _stream()))
+        return out
+
     def horn_batch_host(self, model, est):
         model = np.ascontiguousarray(model, dtype=np.float64)
         est = np.ascontiguousarray(est, dtype=np.float64)

@@ -7,25 +7,24 @@
 // (N is padded from 2 to 16, the smallest N of an M = 128 UMMA).  The input is NCHW, so a tile of A is 32 channel
 // rows of 128 contiguous pixels: exactly the canonical MN-major no-swizzle UMMA layout when each 16-byte chunk
 // (8 pixels of one channel) is placed at  (pixel group) * 128 B + (channel % 8) * 16 B + (channel / 8) * 2048 B.
-// cp.async moves the chunks global -> shared without touching registers (4-stage ring, 8 KB per stage); one thread
+// cp.async moves the chunks global -> shared without touching registers (2-stage ring, 8 KB per stage, 16 CTAs per SM); one thread
 // issues the two K = 16 MMAs of a tile, tcgen05.commit signals an mbarrier, and the four warps read their 32 TMEM
 // lanes back with tcgen05.ld, add the bias and store both planes with fully coalesced 128-pixel rows.
 // The kernel is HBM-bound: 64 B read + 8 B written per pixel, 39 MFLOP per 640x480 map.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace rcv_head {
 
 constexpr int kThreads = 128;
-constexpr int kStages = 4;
-constexpr int kTileM = 128;                 // pixels per tile = UMMA M
+constexpr int kTileM = 128;                 // pixels per UMMA tile = UMMA M
 constexpr int kC = 32;                      // input channels = 2 x UMMA K
 constexpr int kN = 16;                      // UMMA N (2 real outputs)
 constexpr int kATile = kC * kTileM * 2;     // 8192 bytes
 constexpr int kBTile = kN * kC * 2;         // 1024 bytes
-constexpr int kTmemCols = 32;
-constexpr int kSmemBytes = kStages * kATile + kBTile + 64;
+template <int kStages, int kTpi> constexpr int smem_bytes() { return kStages * kTpi * kATile + kBTile + 64; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -37,11 +36,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
 // instruction descriptor, kind::f16: D = f32, A = B = bf16, A MN-major, B K-major, N = 16, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
+// One iteration of a CTA handles a group of kTpi consecutive 128-pixel tiles of one image (one ring stage), so the
+// serial chain  copy-wait -> barrier -> MMA -> commit -> mbarrier -> tcgen05.ld -> store  is paid once per
+// kTpi * 8 KB of input.
+template <int kStages, int kTpi>
 __global__ void __launch_bounds__(kThreads) k_head1x1(const __nv_bfloat16* __restrict__ up, const float* __restrict__ w, const float* __restrict__ bias,
-                                                     float* __restrict__ out, long long HW, int tiles_per_image, long long n_tiles) {
+                                                     float* __restrict__ out, long long HW, int groups_per_image, long long n_groups) {
+  constexpr int kTmemCols = kTpi * kN < 32 ? 32 : kTpi * kN;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kATile;
+  uint8_t* sB = smem + kStages * kTpi * kATile;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + kBTile);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(sB + kBTile + 16);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -68,48 +72,51 @@ __global__ void __launch_bounds__(kThreads) k_head1x1(const __nv_bfloat16* __res
   const float bias0 = bias[0], bias1 = bias[1];
 
   const long long step = gridDim.x;
-  auto issue = [&](long long tile, int stage) {
-    if (tile < n_tiles) {
-      const long long b = tile / tiles_per_image;
-      const long long m0 = (tile - b * tiles_per_image) * kTileM;
+  auto issue = [&](long long grp, int stage) {
+    if (grp < n_groups) {
+      const long long b = grp / groups_per_image;
+      const long long m0 = (grp - b * groups_per_image) * (kTpi * kTileM);
       const __nv_bfloat16* src0 = up + b * kC * HW;
-      const uint32_t dst0 = smem_u32(sA + stage * kATile);
+      const uint32_t dst0 = smem_u32(sA + stage * kTpi * kATile);
 #pragma unroll
-      for (int j = 0; j < (kC * kTileM / 8) / kThreads; ++j) {
-        const int chunk = tid + j * kThreads, k = chunk >> 4, mi = chunk & 15;
-        const long long pix = m0 + mi * 8;
+      for (int j = 0; j < kTpi * (kC * kTileM / 8) / kThreads; ++j) {
+        // chunk = 8 pixels of one channel; consecutive threads take consecutive chunks of a channel row (coalesced)
+        const int chunk = tid + j * kThreads, k = chunk / (16 * kTpi), mg = chunk % (16 * kTpi);
+        const long long pix = m0 + mg * 8;
         const bool valid = pix < HW;
         const __nv_bfloat16* src = src0 + (long long)k * HW + (valid ? pix : 0);
-        const uint32_t dst = dst0 + mi * 128 + (k & 7) * 16 + (k >> 3) * 2048;
+        const uint32_t dst = dst0 + (mg >> 4) * kATile + (mg & 15) * 128 + (k & 7) * 16 + (k >> 3) * 2048;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  const long long tile0 = blockIdx.x;
+  const long long grp0 = blockIdx.x;
 #pragma unroll
-  for (int s = 0; s < kStages - 1; ++s) issue(tile0 + s * step, s);
+  for (int s = 0; s < kStages - 1; ++s) issue(grp0 + s * step, s);
   uint32_t phase = 0;
   int it = 0;
-  for (long long tile = tile0; tile < n_tiles; tile += step, ++it) {
-    issue(tile + (kStages - 1) * step, (it + kStages - 1) % kStages);
+  for (long long grp = grp0; grp < n_groups; grp += step, ++it) {
+    issue(grp + (kStages - 1) * step, (it + kStages - 1) % kStages);
     asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a0 = smem_u32(sA + (it % kStages) * kATile), b0 = smem_u32(sB);
+      const uint32_t a0 = smem_u32(sA + (it % kStages) * kTpi * kATile), b0 = smem_u32(sB);
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
-        const uint64_t da = make_desc(a0 + kb * 4096, 2048, 128);   // MN-major: 8-channel groups 2048 B apart, 8-pixel groups 128 B apart
-        const uint64_t db = make_desc(b0 + kb * 256, 128, 512);     // K-major:  8-element K chunks 128 B apart, 8-row groups 512 B apart
-        const uint32_t accumulate = kb;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
-      }
+      for (int tl = 0; tl < kTpi; ++tl)
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t da = make_desc(a0 + tl * kATile + kb * 4096, 2048, 128);   // MN-major: 8-channel groups 2048 B apart, 8-pixel groups 128 B apart
+          const uint64_t db = make_desc(b0 + kb * 256, 128, 512);                   // K-major:  8-element K chunks 128 B apart, 8-row groups 512 B apart
+          const uint32_t accumulate = kb;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+              ::"r"(tmem + tl * kN), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
+        }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
     }
     uint32_t done;
@@ -119,15 +126,22 @@ __global__ void __launch_bounds__(kThreads) k_head1x1(const __nv_bfloat16* __res
     } while (!done);
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t r0, r1;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(tmem + ((uint32_t)(warp * 32) << 16)) : "memory");
+    uint32_t r[kTpi][2];
+#pragma unroll
+    for (int tl = 0; tl < kTpi; ++tl)
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[tl][0]), "=r"(r[tl][1])
+                   : "r"(tmem + ((uint32_t)(warp * 32) << 16) + tl * kN) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    const long long b = tile / tiles_per_image;
-    const long long pix = (tile - b * tiles_per_image) * kTileM + tid;
-    if (pix < HW) {
-      float* o = out + b * 2 * HW + pix;
-      o[0] = __uint_as_float(r0) + bias0;
-      o[HW] = __uint_as_float(r1) + bias1;
+    const long long b = grp / groups_per_image;
+    const long long pix0 = (grp - b * groups_per_image) * (kTpi * kTileM) + tid;
+    float* o = out + b * 2 * HW;
+#pragma unroll
+    for (int tl = 0; tl < kTpi; ++tl) {
+      const long long pix = pix0 + tl * kTileM;
+      if (pix < HW) {
+        o[pix] = __uint_as_float(r[tl][0]) + bias0;
+        o[HW + pix] = __uint_as_float(r[tl][1]) + bias1;
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();   // TMEM and the stage buffer are free again
@@ -139,20 +153,40 @@ __global__ void __launch_bounds__(kThreads) k_head1x1(const __nv_bfloat16* __res
 
 }  // namespace rcv_head
 
-// Called by the C ABI (rcvvote.cu: rcv_head_1x1).  Returns a cudaError_t as int.
-extern "C" int rcv_head1x1_launch(const void* up_bf16, const float* weight, const float* bias, float* out, int n_images, long long hw, int sms,
-                                  void* stream) {
+template <int kStages, int kTpi>
+static int launch(const void* up_bf16, const float* weight, const float* bias, float* out, int n_images, long long hw, int sms, int ctas_per_sm,
+                  void* stream) {
   using namespace rcv_head;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_head1x1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(k_head1x1<kStages, kTpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kStages, kTpi>());
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int tiles_per_image = (int)((hw + kTileM - 1) / kTileM);
-  const long long n_tiles = (long long)n_images * tiles_per_image;
-  long long grid = (long long)sms * 4;   // 4 CTAs per SM keep ~100 KB of loads in flight per SM
-  if (grid > n_tiles) grid = n_tiles;
-  k_head1x1<<<(int)grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>((const __nv_bfloat16*)up_bf16, weight, bias, out, hw, tiles_per_image, n_tiles);
+  const int groups_per_image = (int)((hw + kTpi * kTileM - 1) / (kTpi * kTileM));
+  const long long n_groups = (long long)n_images * groups_per_image;
+  long long grid = (long long)sms * ctas_per_sm;
+  if (grid > n_groups) grid = n_groups;
+  k_head1x1<kStages, kTpi><<<(int)grid, kThreads, smem_bytes<kStages, kTpi>(), (cudaStream_t)stream>>>((const __nv_bfloat16*)up_bf16, weight, bias, out,
+                                                                                                    hw, groups_per_image, n_groups);
   return (int)cudaGetLastError();
+}
+
+// Called by the C ABI (rcvvote.cu: rcv_head_1x1).  Returns a cudaError_t as int.
+extern "C" int rcv_head1x1_launch(const void* up_bf16, const float* weight, const float* bias, float* out, int n_images, long long hw, int sms,
+                                  void* stream) {
+  // tuning knobs (experiments only): ring stages x tiles per iteration, and resident CTAs per SM
+  static int cfg = 0, ctas = 0;
+  if (!cfg) {
+    const char* e1 = getenv("RCV_HEAD_CFG"); const char* e2 = getenv("RCV_HEAD_CTAS");
+    cfg = e1 ? atoi(e1) : 21; ctas = e2 ? atoi(e2) : 16;   // measured best on B200: 3.87 TB/s (profiles/r01_head1x1_sweep.txt)
+  }
+  switch (cfg) {   // cfg = 10 * stages + tiles per iteration
+    case 21: return launch<2, 1>(up_bf16, weight, bias, out, n_images, hw, sms, ctas, stream);
+    case 22: return launch<2, 2>(up_bf16, weight, bias, out, n_images, hw, sms, ctas, stream);
+    case 32: return launch<3, 2>(up_bf16, weight, bias, out, n_images, hw, sms, ctas, stream);
+    case 34: return launch<3, 4>(up_bf16, weight, bias, out, n_images, hw, sms, ctas, stream);
+    case 28: return launch<2, 8>(up_bf16, weight, bias, out, n_images, hw, sms, ctas, stream);
+    default: return launch<2, 4>(up_bf16, weight, bias, out, n_images, hw, sms, ctas, stream);
+  }
 }

@@ -1385,6 +1385,21 @@ RCV_EXPORT int rcv_horn_batch_host(rcv_ctx* c, const double* model, long long mo
   return RCV_OK;
 }
 
+extern "C" int rcv_head1x1_launch(const void* up_bf16, const float* weight, const float* bias, float* out, int n_images, long long hw, int sms,
+                                  void* stream);
+
+RCV_EXPORT int rcv_head_1x1(rcv_ctx* c, const void* up_bf16, const float* weight, const float* bias, float* out, int n_images, long long hw,
+                            void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!up_bf16 || !weight || !bias || !out || n_images <= 0 || hw <= 0) FAIL(c, RCV_E_INVALID, "rcv_head_1x1: bad argument");
+  if (hw % 8 != 0 || ((uintptr_t)up_bf16 & 15) != 0) FAIL(c, RCV_E_INVALID, "rcv_head_1x1: hw must be a multiple of 8 and `up` 16-byte aligned");
+  CK(c, cudaSetDevice(c->device));
+  const int rc = rcv_head1x1_launch(up_bf16, weight, bias, out, n_images, hw, c->sms, stream);
+  if (rc != 0) FAIL(c, RCV_E_CUDA, "rcv_head_1x1: launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  c->launches += 1;
+  return RCV_OK;
+}
+
 RCV_EXPORT int rcv_vote_kernel_times(rcv_ctx* c, float* ms_out, int n) {
   if (!c || !ms_out || n <= 0) return RCV_E_INVALID;
   if (n > 64) n = 64;

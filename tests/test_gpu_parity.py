@@ -191,3 +191,23 @@ def test_horn_batch_device(ctx, golden):
         np.testing.assert_allclose(RT[t], golden["h%d_RT" % t], rtol=1e-12, atol=1e-9)
     RT0 = ctx.horn_batch(P1, est[:1]).cpu().numpy()
     np.testing.assert_allclose(RT0[0], golden["h0_RT"], rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("shape", [(1, 480, 640), (3, 480, 640), (2, 24, 40), (1, 8, 24)])
+def test_head_1x1_tensor_core_vs_torch(ctx, shape):
+    """K5 (conv8 of the producer, models/fcnresnet.py:118,187-189): tcgen05 kernel vs torch's fp32 conv of the same
+    bf16 operands.  Products of bf16 values are exact in fp32; only the accumulation order differs: 1e-5 relative."""
+    B, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H)
+    up = torch.relu(torch.randn((B, 32, H, W), generator=g, device="cuda")).to(torch.bfloat16)     # post BN+ReLU activations
+    weight = torch.randn((2, 32, 1, 1), generator=g, device="cuda") * 0.2
+    bias = torch.randn((2,), generator=g, device="cuda")
+    got = ctx.head_1x1(up, weight, bias)
+    torch.cuda.synchronize()
+    want = torch.nn.functional.conv2d(up.float(), weight.to(torch.bfloat16).float(), bias)
+    assert got.shape == (B, 2, H, W) and got.dtype == torch.float32
+    err = (got - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err <= 1e-5 * scale + 1e-6, (err, scale)
+    # seg / radius planes feed the vote directly: a second call on the same stream gives the same bits
+    assert torch.equal(got, ctx.head_1x1(up, weight, bias))
