@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU session: tests, bench, ncu launch list, ncu full capture of the vote kernel.  Usage: tools/gpu_round.sh <tag> [skip-tests]
+# One GPU session: tests, bench, ncu launch list, ncu full capture of the vote kernel and the head.  Usage: tools/gpu_round.sh <tag> [skip-tests]
 TAG=${1:-r01}
 mkdir -p gpurun_out
 if [ "$2" != "skip-tests" ]; then
@@ -7,9 +7,14 @@ if [ "$2" != "skip-tests" ]; then
 fi
 timeout 900 python bench.py 2> gpurun_out/${TAG}_bench.err | tee gpurun_out/${TAG}_bench.json
 tail -5 gpurun_out/${TAG}_bench.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2> gpurun_out/${TAG}_ref.err | tee gpurun_out/${TAG}_bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
   python bench.py --steps 2 --warmup 1 --frames 512 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_vote -s 3 -c 1 -f -o gpurun_out/${TAG}_vote \
   python bench.py --steps 1 --warmup 1 --frames 256 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_vote.log 2>&1
 tail -3 gpurun_out/${TAG}_ncu_vote.log
+timeout 300 python tools/head_bw.py | tee gpurun_out/${TAG}_head_bw.json
+RCV_HEAD_IMAGES=48 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_head -s 3 -c 1 -f -o gpurun_out/${TAG}_head \
+  python tools/head_bw.py > gpurun_out/${TAG}_ncu_head.log 2>&1
+tail -3 gpurun_out/${TAG}_ncu_head.log
 ls -la gpurun_out/
