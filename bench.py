@@ -112,7 +112,7 @@ def run_reference(args):
             "gvotes_per_s": votes / tot / 1e9,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -287,13 +287,26 @@ def run_ours(args):
                                  "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                                  "algorithmic_bytes_per_step": alg_bytes},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "cpu_baseline": cpu, "parity_spot_check": parity}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else a library prints (NCCL's version banner, ...)
+    was diverted to stderr in main()."""
+    os.write(_JSON_OUT if _JSON_OUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _JSON_OUT
     args = parse()
+    sys.stdout.flush()
+    _JSON_OUT = os.dup(1)          # keep stdout for the JSON line only
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
