@@ -280,6 +280,120 @@ RCV_HD void thin_slow(const PointCtx& c, const LaneTask& L, int i, const ThinOut
   if (o.t1) slowarc(c, L, i, o.ub, 1, o.q1, o.fl1, o.vt1);
 }
 
+// ---- fast ring pass ("ring2"): thin rings of a warp whose candidates cannot leave the tile (ring_noclip) ----------
+// Same candidates and the same float32 arithmetic as thin_fast(), reorganised so that one candidate costs about a
+// dozen instructions on the device (rcvvote.cu issues it as one PTX block per column):
+//   * the address is  bits(tm) * sv + K : the float -> int conversion of the magic-number floor, the lattice base and
+//     the tile offset are folded into one multiply-add.  In the Z-pass the column is folded in as well by adding
+//     MAGIC + u*Dp instead of MAGIC (both are integers below 2^24, so the rounding to an integer is unchanged except
+//     for the parity of exact ties, which the bias of the floor makes irrelevant: a tie candidate is never a sure vote);
+//   * columns with du^2 < b/2 - 1 (b = smallest inner radius^2 among the chunk's rings) are "interior": a
+//     candidate that is surely inside the shell has dv^2 > b - du^2 > du^2, so the ownership test |dv| > |du| is
+//     implied and only evaluated in the few boundary columns (OWN);
+//   * a candidate that needs the exact path is flagged as  lo != sure  (sure implies lo); the rare branch re-derives
+//     the column with ring2_slow_column(), which applies the ownership test in every case.
+struct Ring2Cand {
+  float q, fl, d;
+  unsigned bits;
+};
+RCV_HD void ring2_magic(bool pass, int u, int Dp, float& m0, float& m1) {
+  const float s = pass ? 0.f : (float)(u * Dp);   // exact: |u * Dp| < 2^22
+  m0 = f_add(RCV_MAGIC, s);
+  m1 = f_sub(RCV_MAGIC, s);
+}
+// cpm = +-fv + dbias - 0.5, mu = magic constant of the arc, sfv = -fv (top arc) or +fv (bottom arc, mirrored)
+RCV_HD void ring2_cand(float zs, float cpm, float mu, float sfv, float hWg, Ring2Cand& o) {
+  const float tm = f_add(f_add(zs, cpm), mu);
+  o.bits = (unsigned)f_bits(tm);
+  o.fl = f_sub(tm, mu);
+  o.d = f_add(o.fl, sfv);
+  o.q = f_fma(o.d, o.d, hWg);
+}
+// Address constants of slice `slice_base` (units as in lane_setup_pu) for column u0: top arc address = bits*sv + K0,
+// bottom arc address = K1 - bits*sv.  In the Y-pass K0/K1 advance by `unit` per column, in the Z-pass they are constant.
+RCV_HD void ring2_consts(const PointCtx& c, const Tile& t, bool pass, int u0, unsigned slice_base, unsigned unit, unsigned& K0, unsigned& K1,
+                         unsigned& sv) {
+  const unsigned MB = (unsigned)RCV_MAGIC_BITS;
+  if (!pass) {
+    sv = unit;
+    const unsigned row = (unsigned)((c.ipy - t.j0) * t.Dp + c.ipz);
+    K0 = slice_base + (row - MB) * unit;
+    K1 = slice_base + (row + MB) * unit;
+  } else {
+    sv = (unsigned)t.Dp * unit;
+    const unsigned col = slice_base + (unsigned)(c.ipz + u0) * unit;
+    K0 = col + ((unsigned)(c.ipy - t.j0) - MB) * sv;
+    K1 = col + ((unsigned)(c.ipy - t.j0) + MB) * sv;
+  }
+}
+// Ownership threshold of a column (as in lane_setup_pu, tile bounds aside): Z-pass owns |dv| >= |du|, Y-pass |dv| > |du|.
+RCV_HD float ring2_thr(bool pass, float duf) {
+  const float ad = fabsf(duf);
+  return pass ? ad : (ad > 0.f ? f_from_bits(f_bits(ad) - 1) : -1.0f);
+}
+// Interior half-width of a lane: columns |u| <= Hin have du^2 < bmin/2 - 1 (|du| <= |u| + 0.5); -1 if there is none.
+RCV_HD int ring2_interior(float bmin) {
+  const float h = f_sub(f_mul(bmin, 0.5f), 1.0f);
+  if (!(h > 0.3f)) return -1;
+  const float v = f_sub(f_sqrt_fast(h), 0.51f);
+  return v >= 0.f ? (int)v : -1;
+}
+// One slice of one column, both arcs: two emits (vote address or sink); returns true if a candidate needs the exact path.
+template <bool OWN, class Emit>
+RCV_HD bool ring2_fast(const PointCtx& c, float a, float du2, float thr, float cp, float cm, float fv, float mu0, float mu1, unsigned K0,
+                       unsigned K1, unsigned sv, unsigned sink, Emit& emit) {
+  const float g = f_sub(a, du2);
+  const float zs = f_sqrt_fast(g);
+  const float hWg = f_sub(c.hW, g);
+  Ring2Cand c0, c1;
+  ring2_cand(zs, cp, mu0, -fv, hWg, c0);
+  ring2_cand(zs, cm, mu1, fv, hWg, c1);
+  const bool o0 = !OWN || (fabsf(c0.d) > thr), o1 = !OWN || (fabsf(c1.d) > thr);
+  const bool s0 = o0 && (fabsf(c0.q) < c.hw_m), s1 = o1 && (fabsf(c1.q) < c.hw_m);
+  const bool l0 = o0 && (c0.q > -c.hw_p), l1 = o1 && (c1.q > -c.hw_p);
+  emit((int)(s0 ? c0.bits * sv + K0 : sink));
+  emit((int)(s1 ? K1 - c1.bits * sv : sink));
+  return (l0 != s0) || (l1 != s1);
+}
+// The rare branch of the fast ring pass, for one lane: exact decisions for the candidates of column u that the fast
+// path could not decide.  Re-derives the candidates of the chunk's slices with the same arithmetic (fast and slow path
+// must agree on which voxel is the candidate), applies the ownership test in every case, and decides like
+// ring_slow(): the candidate exactly, and -- if it may lie outside the outer sphere -- the voxel one step inwards.
+//   ipl / ipc = nearest lattice coordinate of the point along the lane / candidate axis, a[s] = outer radius^2 of
+//   slice i0c + s (NaN: not a thin ring of this lane), K0/K1/sv as in ring2_consts.  No bounds tests: the pass is
+//   only used when no candidate can leave the tile (ring_noclip).  slow(iA, iB, iC) is the exact predicate.
+template <class Slow, class EmitSlow>
+RCV_HD void ring2_slow_lane(bool pass, int nc, int ipl, int ipc, int u, int i0c, float hW, float hw_m, float hw_p, float duf, float cp, float cm,
+                            float fv, float mu0, float mu1, unsigned sv, const float* a, const unsigned* K0, const unsigned* K1, Slow& slow,
+                            EmitSlow& emit_slow) {
+  const float du2 = f_mul(duf, duf);
+  const float thr = ring2_thr(pass, duf);
+  const int lc = ipl + u;
+  for (int sidx = 0; sidx < nc; ++sidx) {
+    const float as = a[sidx];
+    if (!(as == as)) continue;
+    const int i = i0c + sidx;
+    const float g = f_sub(as, du2);
+    const float zs = f_sqrt_fast(g);
+    const float hWg = f_sub(hW, g);
+    for (int arc = 0; arc < 2; ++arc) {
+      Ring2Cand cd;
+      const float sfv = arc ? fv : -fv;
+      ring2_cand(zs, arc ? cm : cp, arc ? mu1 : mu0, sfv, hWg, cd);
+      if (!((fabsf(cd.d) > thr) && !(fabsf(cd.q) < hw_m) && (cd.q > -hw_p))) continue;
+      const int n = (int)cd.fl, dir = arc ? 1 : -1;
+      const int cc = arc ? ipc - n : ipc + n;
+      const unsigned addr = arc ? K1[sidx] - cd.bits * sv : cd.bits * sv + K0[sidx];
+      if (slow(i, pass ? cc : lc, pass ? lc : cc)) emit_slow((int)addr);
+      if (cd.q >= hw_m) {   // the candidate may lie outside the outer sphere: the voxel one step inwards can then be inside
+        const float d2 = f_add(f_sub(cd.fl, 1.0f), sfv);
+        const int cc2 = cc + dir;
+        if ((fabsf(d2) > thr) && slow(i, pass ? cc2 : lc, pass ? lc : cc2)) emit_slow((int)(arc ? addr + sv : addr - sv));
+      }
+    }
+  }
+}
+
 // One lane, one cell (dj, dk) of a small sphere's slice bounding box (R < RCV_POLAR_MIN_R only).
 template <class Emit, class Slow>
 RCV_HD void dense_cell(const PointCtx& c, float a, const Tile& t, int i, int slice_base, int unit, int sink, int dj, int dk, bool cell_ok,
@@ -416,6 +530,7 @@ RCV_HD int slab_thickness(int ni_max) {
 // True if no candidate of the lane's ring passes can fall outside the tile along a candidate axis
 // (candidates lie within R + 1 of the nearest lattice point), so the per-candidate bounds test can be skipped.
 RCV_HD bool ring_noclip(const PointCtx& c, const Tile& t) {
+  if (c.R <= 0) return true;   // draws nothing (padding lanes of a warp's last group)
   return (c.ipz - c.R - 2 >= 0) && (c.ipz + c.R + 2 < t.D) && (c.ipy - c.R - 2 >= t.j0) && (c.ipy + c.R + 2 < t.j0 + t.nj);
 }
 

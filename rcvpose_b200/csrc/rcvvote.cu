@@ -642,6 +642,102 @@ __device__ __forceinline__ void ring_pass(const PointCtx& c, const Tile& t, cons
   }
 }
 
+// ---- fast ring pass (raster_core.h "ring2"): one PTX block per column of a chunk ---------------------------------
+// Operands: %0 any (out) | %1 du2 %2 mu0 %3 mu1 %4 hW %5 cp %6 cm %7 fv %8 hw_m %9 -hw_p %10 sink %11 sv %12 thr %13 -sv |
+// a[NC], K0[NC], K1[NC].  Per candidate: 5 float ops, one multiply-add for the address, two or three FSETP, one
+// select, one shared-memory atomic and one predicate op; per slice: one subtract, one MUFU.SQRT, one subtract.
+#define R2_DECL "{\n\t.reg .pred pv, pl, po, pa;\n\t.reg .f32 g, zs, hwg, t, tm, fl, d, q, aq, ad;\n\t.reg .b32 bi, adr;\n\tsetp.ne.u32 pa, %10, %10;\n\t"
+#define R2_SLICE_HEAD(A) "sub.rn.f32 g, " A ", %1;\n\tsqrt.approx.ftz.f32 zs, g;\n\tsub.rn.f32 hwg, %4, g;\n\t"
+#define R2_CAND_ARITH(CPM, MU, DOP) \
+  "add.rn.f32 t, zs, " CPM ";\n\tadd.rn.f32 tm, t, " MU ";\n\tsub.rn.f32 fl, tm, " MU ";\n\t" DOP ".rn.f32 d, fl, %7;\n\t" \
+  "fma.rn.f32 q, d, d, hwg;\n\tabs.f32 aq, q;\n\tmov.b32 bi, tm;\n\t"
+#define R2_CAND_VOTE_INT "setp.lt.f32 pv, aq, %8;\n\tsetp.gt.f32 pl, q, %9;\n\t"
+#define R2_CAND_VOTE_OWN "abs.f32 ad, d;\n\tsetp.gt.f32 po, ad, %12;\n\tsetp.lt.and.f32 pv, aq, %8, po;\n\tsetp.gt.and.f32 pl, q, %9, po;\n\t"
+#define R2_CAND_EMIT(SV, K) \
+  "mad.lo.u32 adr, bi, " SV ", " K ";\n\tselp.u32 adr, adr, %10, pv;\n\tred.shared.add.u32 [adr], 1;\n\txor.pred pl, pl, pv;\n\tor.pred pa, pa, pl;\n\t"
+#define R2_SLICE(A, K0, K1, VOTE) \
+  R2_SLICE_HEAD(A) R2_CAND_ARITH("%5", "%2", "sub") VOTE R2_CAND_EMIT("%11", K0) R2_CAND_ARITH("%6", "%3", "add") VOTE R2_CAND_EMIT("%13", K1)
+#define R2_TAIL "selp.u32 %0, 1, 0, pa;\n\t}"
+#define R2_BODY3(VOTE) R2_DECL R2_SLICE("%14", "%17", "%20", VOTE) R2_SLICE("%15", "%18", "%21", VOTE) R2_SLICE("%16", "%19", "%22", VOTE) R2_TAIL
+#define R2_BODY4(VOTE) \
+  R2_DECL R2_SLICE("%14", "%18", "%22", VOTE) R2_SLICE("%15", "%19", "%23", VOTE) R2_SLICE("%16", "%20", "%24", VOTE) R2_SLICE("%17", "%21", "%25", VOTE) R2_TAIL
+#define R2_COMMON_IN "f"(du2), "f"(mu0), "f"(mu1), "f"(hW), "f"(cp), "f"(cm), "f"(fv), "f"(hw_m), "f"(nhw_p), "r"(sink), "r"(sv), "f"(thr), "r"(nsv)
+
+template <bool OWN, int NC>
+__device__ __forceinline__ unsigned ring2_asm(float du2, float mu0, float mu1, float hW, float cp, float cm, float fv, float hw_m, float nhw_p,
+                                              unsigned sink, unsigned sv, unsigned nsv, float thr, const float (&a)[NC], const unsigned (&K0)[NC],
+                                              const unsigned (&K1)[NC]) {
+  unsigned any;
+  if constexpr (NC == 3) {
+    if constexpr (OWN)
+      asm volatile(R2_BODY3(R2_CAND_VOTE_OWN) : "=r"(any) : R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]),
+                   "r"(K1[0]), "r"(K1[1]), "r"(K1[2]) : "memory");
+    else
+      asm volatile(R2_BODY3(R2_CAND_VOTE_INT) : "=r"(any) : R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]),
+                   "r"(K1[0]), "r"(K1[1]), "r"(K1[2]) : "memory");
+  } else {
+    if constexpr (OWN)
+      asm volatile(R2_BODY4(R2_CAND_VOTE_OWN) : "=r"(any) : R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "r"(K0[0]), "r"(K0[1]),
+                   "r"(K0[2]), "r"(K0[3]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), "r"(K1[3]) : "memory");
+    else
+      asm volatile(R2_BODY4(R2_CAND_VOTE_INT) : "=r"(any) : R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "r"(K0[0]), "r"(K0[1]),
+                   "r"(K0[2]), "r"(K0[3]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), "r"(K1[3]) : "memory");
+  }
+  return any;
+}
+
+// The rare branch of the fast ring pass (one lane, out of line): everything it needs arrives in scalars so that the hot
+// loop keeps nothing alive for it and nothing is re-derived from the point.
+__device__ __noinline__ void ring2_slow_call(double pa, double pb, double pc, int R, int ipl, int ipc, int u, int i0c, int pass_nc, float hW,
+                                             float hw_m, float hw_p, float duf, float cp, float cm, float fv, float mu0, float mu1, unsigned sv,
+                                             float a0, float a1, float a2, float a3, unsigned k00, unsigned k01, unsigned k02, unsigned k03,
+                                             unsigned k10, unsigned k11, unsigned k12, unsigned k13) {
+  const float a[4] = {a0, a1, a2, a3};
+  const unsigned K0[4] = {k00, k01, k02, k03}, K1[4] = {k10, k11, k12, k13};
+  SlowExactCall slow{pa, pb, pc, R};
+  SmemEmit es{0u, 0};   // addresses are absolute
+  ring2_slow_lane((pass_nc & 1) != 0, pass_nc >> 1, ipl, ipc, u, i0c, hW, hw_m, hw_p, duf, cp, cm, fv, mu0, mu1, sv, a, K0, K1, slow, es);
+}
+
+// Fast ring pass of one chunk for a warp whose candidates cannot leave the tile.  H = half-width (warp maximum),
+// Hin = interior half-width (warp minimum, -1 = none).
+template <bool PASS, int NC>
+__device__ __forceinline__ void ring_pass2(const PointCtx& c, const Tile& t, const float (&a4)[NC], int H, int Hin, int i0c, int sbase0,
+                                           int slice_bytes, unsigned base, unsigned sink_abs) {
+  const float fu = PASS ? c.fz : c.fy, fv = PASS ? c.fy : c.fz;
+  const float cp = f_add(fv, c.dbias_m05), cm = f_sub(c.dbias_m05, fv);
+  const float nhw_p = -c.hw_p;
+  unsigned K0[NC], K1[NC], sv = 0;
+#pragma unroll
+  for (int sidx = 0; sidx < NC; ++sidx) ring2_consts(c, t, PASS, -H, base + (unsigned)(sbase0 + sidx * slice_bytes), 4u, K0[sidx], K1[sidx], sv);
+  const unsigned nsv = 0u - sv;
+  float mu0, mu1;
+  ring2_magic(PASS, -H, t.Dp, mu0, mu1);
+  const float mstep = (float)t.Dp;
+  const int ioff = Hin >= 0 ? Hin : 0x40000000;
+  const unsigned ispan = Hin >= 0 ? 2u * (unsigned)Hin : 0u;
+  float uf = (float)(-H);
+#pragma unroll 1
+  for (int u = -H; u <= H; ++u, uf += 1.0f) {
+    const float duf = f_sub(uf, fu);
+    const float du2 = f_mul(duf, duf);
+    unsigned any;
+    if ((unsigned)(u + ioff) <= ispan) any = ring2_asm<false, NC>(du2, mu0, mu1, c.hW, cp, cm, fv, c.hw_m, nhw_p, sink_abs, sv, nsv, 0.f, a4, K0, K1);
+    else any = ring2_asm<true, NC>(du2, mu0, mu1, c.hW, cp, cm, fv, c.hw_m, nhw_p, sink_abs, sv, nsv, ring2_thr(PASS, duf), a4, K0, K1);
+    if (any)
+      ring2_slow_call(c.px, c.py, c.pz, c.R, PASS ? c.ipz : c.ipy, PASS ? c.ipy : c.ipz, u, i0c, (PASS ? 1 : 0) | (NC << 1), c.hW, c.hw_m, c.hw_p, duf,
+                      cp, cm, fv, mu0, mu1, sv, a4[0], a4[1], a4[2], NC > 3 ? a4[NC - 1] : a4[0], K0[0], K0[1], K0[2], NC > 3 ? K0[NC - 1] : 0u, K1[0],
+                      K1[1], K1[2], NC > 3 ? K1[NC - 1] : 0u);
+    if (PASS) {
+#pragma unroll
+      for (int sidx = 0; sidx < NC; ++sidx) { K0[sidx] += 4u; K1[sidx] += 4u; }
+    } else {
+      mu0 = f_add(mu0, mstep);
+      mu1 = f_sub(mu1, mstep);
+    }
+  }
+}
+
 __device__ __noinline__ void polar_slow_call(double pa, double pb, double pc, int R, float hw_m, int ti0, float q0, float q1, int vt0, int vt1,
                                              int t01, int jb, int kc, int cell, unsigned mplus, unsigned mminus, int sstride, unsigned base) {
   PolarOut o;
@@ -733,8 +829,14 @@ __device__ __forceinline__ void ring_chunk_work(const PointCtx& c, const Tile& t
     const int H = ring_half_width(__int_as_float(amax_bits));
     const int sbase0 = (i0c - t.i0) * slice_bytes;
     if (noclip) {
-      ring_pass<false, false, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
-      ring_pass<true, false, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
+      // interior half-width: warp minimum over the lanes that draw (a lane without thin rings does not constrain it)
+      float amin = 3.0e38f;
+#pragma unroll
+      for (int sidx = 0; sidx < NC; ++sidx) amin = fminf(amin, a4[sidx]);   // fminf ignores the NaN of a non-thin slice
+      const int hin_l = amin < 3.0e38f ? ring2_interior(f_sub(amin, c.W)) : 0x7fffffff;
+      const int Hin = __reduce_min_sync(0xffffffffu, hin_l);
+      ring_pass2<false, NC>(c, t, a4, H, Hin, i0c, sbase0, slice_bytes, emit.base, emit.base + (unsigned)emit.sink);
+      ring_pass2<true, NC>(c, t, a4, H, Hin, i0c, sbase0, slice_bytes, emit.base, emit.base + (unsigned)emit.sink);
     } else {
       ring_pass<false, true, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
       ring_pass<true, true, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);

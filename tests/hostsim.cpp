@@ -79,22 +79,58 @@ static void ring_chunks(PointCtx* c, const int* ia, const int* ib, const Tile& t
     if (any_thin) {
       ++counters[0];
       const int H = ring_half_width(amax);
-      for (int pass = 0; pass < 2; ++pass)
-        for (int u = -H; u <= H; ++u)
-          for (int l = 0; l < 32; ++l) {
-            HostSlowPerm slow{&c[l], &emit};
-            HostSlowArcPerm slowarc{&slow, &emit_slow};
-            LaneTask L;
-            lane_setup_pu(c[l], t, pass != 0, u, (float)u, 1, L);
-            ++counters[2];
-            for (int sidx = 0; sidx < NC; ++sidx) {
-              const int i = i0c + sidx;
-              ThinOut o;
-              if (noclip) thin_fast<false>(c[l], a4[l][sidx], L, (i - t.i0) * slice_words, -1, emit, o);
-              else thin_fast<true>(c[l], a4[l][sidx], L, (i - t.i0) * slice_words, -1, emit, o);
-              if (o.t0 || o.t1) thin_slow(c[l], L, i, o, slowarc);
+      if (noclip) {
+        // fast ring pass (ring2): interior columns skip the ownership test; Hin is the warp minimum
+        int Hin = 1 << 30;
+        for (int l = 0; l < 32; ++l) {
+          float amin = 3.0e38f; bool any_l = false;
+          for (int sidx = 0; sidx < NC; ++sidx) if (a4[l][sidx] == a4[l][sidx]) { any_l = true; if (a4[l][sidx] < amin) amin = a4[l][sidx]; }
+          if (any_l) { const int h = ring2_interior(f_sub(amin, c[l].W)); if (h < Hin) Hin = h; }
+        }
+        for (int pass = 0; pass < 2; ++pass)
+          for (int u = -H; u <= H; ++u) {
+            const bool interior = Hin >= 0 && u >= -Hin && u <= Hin;
+            for (int l = 0; l < 32; ++l) {
+              HostSlowPerm slow{&c[l], &emit};
+              HostSlowArcPerm slowarc{&slow, &emit_slow};
+              const float fu = pass ? c[l].fz : c[l].fy, fv = pass ? c[l].fy : c[l].fz;
+              const float cp = f_add(fv, c[l].dbias_m05), cm = f_sub(c[l].dbias_m05, fv);
+              const float duf = f_sub((float)u, fu), du2 = f_mul(duf, duf);
+              const float thr = ring2_thr(pass != 0, duf);
+              float mu0, mu1;
+              ring2_magic(pass != 0, u, t.Dp, mu0, mu1);
+              ++counters[2]; ++counters[3];
+              bool any = false;
+              unsigned K0[NC], K1[NC], sv = 0;
+              float arow[NC];
+              for (int sidx = 0; sidx < NC; ++sidx) {
+                arow[sidx] = a4[l][sidx];
+                ring2_consts(c[l], t, pass != 0, u, (unsigned)((i0c + sidx - t.i0) * slice_words), 1u, K0[sidx], K1[sidx], sv);
+                if (interior) any |= ring2_fast<false>(c[l], arow[sidx], du2, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
+                else any |= ring2_fast<true>(c[l], arow[sidx], du2, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
+              }
+              if (any)
+                ring2_slow_lane(pass != 0, NC, pass ? c[l].ipz : c[l].ipy, pass ? c[l].ipy : c[l].ipz, u, i0c, c[l].hW, c[l].hw_m, c[l].hw_p, duf,
+                                cp, cm, fv, mu0, mu1, sv, arow, K0, K1, slow, emit_slow);
             }
           }
+      } else {
+        for (int pass = 0; pass < 2; ++pass)
+          for (int u = -H; u <= H; ++u)
+            for (int l = 0; l < 32; ++l) {
+              HostSlowPerm slow{&c[l], &emit};
+              HostSlowArcPerm slowarc{&slow, &emit_slow};
+              LaneTask L;
+              lane_setup_pu(c[l], t, pass != 0, u, (float)u, 1, L);
+              ++counters[2];
+              for (int sidx = 0; sidx < NC; ++sidx) {
+                const int i = i0c + sidx;
+                ThinOut o;
+                thin_fast<true>(c[l], a4[l][sidx], L, (i - t.i0) * slice_words, -1, emit, o);
+                if (o.t0 || o.t1) thin_slow(c[l], L, i, o, slowarc);
+              }
+            }
+      }
     }
   }
 }
@@ -107,7 +143,7 @@ int hostsim_render_v6(const double* p, const int* R, long n, int D, int Dp, int 
   Tile t{i0, ni, j0, nj, D, Dp};
   HostEmit emit{tile, (long)ni * nj * Dp};
   HostEmitSlow emit_slow{&emit};
-  long long counters[3] = {0, 0, 0}, polar_cells = 0;
+  long long counters[4] = {0, 0, 0, 0}, polar_cells = 0;
   const int slice_words = nj * Dp;
   for (long g0 = 0; g0 < n; g0 += 32) {
     PointCtx c[32]; int ia[32], ib[32];
@@ -173,6 +209,6 @@ int hostsim_render_v6(const double* p, const int* R, long n, int D, int Dp, int 
       }
     }
   }
-  if (stats) { stats[0] = emit.votes; stats[1] = emit.calls; stats[2] = emit.oob; stats[3] = counters[0]; stats[4] = counters[1]; stats[5] = counters[2]; stats[6] = emit.slow_calls; stats[7] = polar_cells; }
+  if (stats) { stats[0] = emit.votes; stats[1] = emit.calls; stats[2] = emit.oob; stats[3] = counters[0]; stats[4] = counters[1]; stats[5] = counters[2]; stats[6] = emit.slow_calls; stats[7] = polar_cells; stats[8] = counters[3]; }
   return emit.oob ? 1 : 0;
 }

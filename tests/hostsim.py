@@ -36,8 +36,8 @@ def render(p, R, D, tile=None, Dp=None, sqrt_perturb=0, slab=32):
     R = np.ascontiguousarray(R, dtype=np.int32)
     i0, ni, j0, nj = tile if tile is not None else (0, D, 0, D)
     Dp = Dp or (D | 1)
-    stats = np.zeros(8, dtype=np.int64)
-    parts, tot = [], np.zeros(8, dtype=np.int64)
+    stats = np.zeros(10, dtype=np.int64)
+    parts, tot = [], np.zeros(10, dtype=np.int64)
     for a0 in range(j0, j0 + nj, slab):
         na = min(slab, j0 + nj - a0)
         part = np.zeros((na, ni, Dp), dtype=np.int32)
@@ -51,4 +51,4 @@ def render(p, R, D, tile=None, Dp=None, sqrt_perturb=0, slab=32):
     assert not buf[:, :, D:].any()
     buf = np.ascontiguousarray(buf.transpose(1, 0, 2))
     return buf[:, :, :D], dict(votes=int(stats[0]), calls=int(stats[1]), ring_chunks=int(stats[3]), dense_slices=int(stats[4]),
-                               lane_tasks=int(stats[5]), polar_cells=int(stats[7]), slow_calls=int(stats[6]))
+                               lane_tasks=int(stats[5]), polar_cells=int(stats[7]), slow_calls=int(stats[6]), ring2_tasks=int(stats[8]))

@@ -7,6 +7,8 @@ import pytest
 from oracle import oracle
 from tests import hostsim
 
+RCV_MIN_R = 1
+
 
 def _check(p, R, D, **kw):
     want = oracle.fast_for(p, R, D)
@@ -128,3 +130,37 @@ def test_surface_patch_like_a_frame_row():
     for slab in (6, 9):
         got, _ = hostsim.render(p, R, D, slab=slab)
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fast_ring_pass_interior_spheres(seed):
+    """Spheres that cannot leave the tile take the fast ring pass (ring2: magic-number addresses, interior columns
+    without the ownership test); groups of 32 like a warp, mixed radii, device-like sqrt error."""
+    rng = np.random.default_rng(700 + seed)
+    Rmax = int(rng.integers(8, 30))
+    D = 2 * Rmax + 12
+    n = 64
+    R = rng.integers(RCV_MIN_R, Rmax + 1, size=n).astype(np.int32)
+    lo = R[:, None] + 3.0
+    p = lo + rng.uniform(0, 1, size=(n, 3)) * (D - 1 - 2 * lo)
+    if seed % 2:                                  # a warp that shares (y voxel, R) like the kernel's vote order
+        R[:] = Rmax
+        p = (D / 2.0) + rng.uniform(-1.0, 1.0, size=(n, 3))
+    st = _check(p, R, D, sqrt_perturb=seed % 3 != 0)
+    assert st["ring2_tasks"] > 0
+
+
+def test_fast_ring_pass_lattice_ties():
+    # lattice-aligned and half-integer points: exact ties of the magic-number rounding and exact boundary hits
+    D = 64
+    pts, Rs = [], []
+    for R in (7, 10, 13, 15, 17, 25):
+        for off in ((0, 0, 0), (0.5, 0, 0), (0.5, 0.5, 0.5), (0.25, -0.25, 0.5), (1e-9, 0, 0), (0, -1e-12, 0.5 - 1e-12), (-0.5, 0.5, 0)):
+            pts.append(np.array([31.0, 32.0, 31.0]) + np.array(off))
+            Rs.append(R)
+    while len(pts) % 32:
+        pts.append(np.array([31.5, 31.25, 32.0])); Rs.append(12)
+    p, R = np.array(pts), np.array(Rs, np.int32)
+    for perturb in (0, 1):
+        st = _check(p, R, D, sqrt_perturb=perturb)
+        assert st["ring2_tasks"] > 0
