@@ -90,6 +90,9 @@ RCV_HD int d_rint(double a) { return (int)nearbyint(a); }
 #define RCV_MAGIC 12582912.0f        // 1.5 * 2^23: adding it rounds a float to the nearest integer
 #define RCV_MAGIC_BITS 0x4B400000
 #define RCV_POLAR_MIN_R 7            // smallest R drawn by ring + polar passes (see polar_fast)
+#ifndef RCV_RING2_MAX_CODE
+#define RCV_RING2_MAX_CODE 2         // the fast ring pass draws rings of slice_setup code 1..2 (up to 2 candidates per arc)
+#endif
 
 // The reference predicate, operation for operation (AccumulatorSpace.py:337-338).
 RCV_HD bool exact_hit(double px, double py, double pz, int R, int i, int j, int k) {
@@ -338,32 +341,49 @@ RCV_HD int ring2_interior(float bmin) {
   const float v = f_sub(f_sqrt_fast(h), 0.51f);
   return v >= 0.f ? (int)v : -1;
 }
-// One slice of one column, both arcs: two emits (vote address or sink); returns true if a candidate needs the exact path.
-template <bool OWN, class Emit>
+// One slice of one column, both arcs, M candidates per arc (the topmost voxel under the outer circle and the M - 1
+// voxels inwards of it: a ring with slice_setup code <= M crosses a column of its own pass in at most M voxels):
+// 2 M emits (vote address or sink); returns true if a candidate needs the exact path.
+template <bool OWN, int M, class Emit>
 RCV_HD bool ring2_fast(const PointCtx& c, float a, float du2, float thr, float cp, float cm, float fv, float mu0, float mu1, unsigned K0,
                        unsigned K1, unsigned sv, unsigned sink, Emit& emit) {
   const float g = f_sub(a, du2);
   const float zs = f_sqrt_fast(g);
   const float hWg = f_sub(c.hW, g);
-  Ring2Cand c0, c1;
-  ring2_cand(zs, cp, mu0, -fv, hWg, c0);
-  ring2_cand(zs, cm, mu1, fv, hWg, c1);
-  const bool o0 = !OWN || (fabsf(c0.d) > thr), o1 = !OWN || (fabsf(c1.d) > thr);
-  const bool s0 = o0 && (fabsf(c0.q) < c.hw_m), s1 = o1 && (fabsf(c1.q) < c.hw_m);
-  const bool l0 = o0 && (c0.q > -c.hw_p), l1 = o1 && (c1.q > -c.hw_p);
-  emit((int)(s0 ? c0.bits * sv + K0 : sink));
-  emit((int)(s1 ? K1 - c1.bits * sv : sink));
-  return (l0 != s0) || (l1 != s1);
+  bool any = false;
+  for (int arc = 0; arc < 2; ++arc) {
+    Ring2Cand cd;
+    const float sfv = arc ? fv : -fv;
+    ring2_cand(zs, arc ? cm : cp, arc ? mu1 : mu0, sfv, hWg, cd);
+    unsigned addr = arc ? K1 - cd.bits * sv : cd.bits * sv + K0;
+    float fl = cd.fl, d = cd.d, q = cd.q;
+    for (int m = 0; m < M; ++m) {
+      if (m) {   // one voxel inwards: (integer - 1) -+ fraction, one rounding like every other coordinate difference
+        fl = f_sub(fl, 1.0f);
+        d = f_add(fl, sfv);
+        q = f_fma(d, d, hWg);
+        addr = arc ? addr + sv : addr - sv;
+      }
+      const bool o = !OWN || (fabsf(d) > thr);
+      const bool sure = o && (fabsf(q) < c.hw_m);
+      const bool lo = o && (q > -c.hw_p);
+      emit((int)(sure ? addr : sink));
+      any |= (lo != sure);
+    }
+  }
+  return any;
 }
+
 // The rare branch of the fast ring pass, for one lane: exact decisions for the candidates of column u that the fast
 // path could not decide.  Re-derives the candidates of the chunk's slices with the same arithmetic (fast and slow path
 // must agree on which voxel is the candidate), applies the ownership test in every case, and decides like
-// ring_slow(): the candidate exactly, and -- if it may lie outside the outer sphere -- the voxel one step inwards.
+// ring_slow(): the undecided candidates exactly, and -- if the topmost one may lie outside the outer sphere -- the
+// voxel one step inwards of the last candidate.
 //   ipl / ipc = nearest lattice coordinate of the point along the lane / candidate axis, a[s] = outer radius^2 of
 //   slice i0c + s (NaN: not a thin ring of this lane), K0/K1/sv as in ring2_consts.  No bounds tests: the pass is
 //   only used when no candidate can leave the tile (ring_noclip).  slow(iA, iB, iC) is the exact predicate.
 template <class Slow, class EmitSlow>
-RCV_HD void ring2_slow_lane(bool pass, int nc, int ipl, int ipc, int u, int i0c, float hW, float hw_m, float hw_p, float duf, float cp, float cm,
+RCV_HD void ring2_slow_lane(bool pass, int nc, int M, int ipl, int ipc, int u, int i0c, float hW, float hw_m, float hw_p, float duf, float cp, float cm,
                             float fv, float mu0, float mu1, unsigned sv, const float* a, const unsigned* K0, const unsigned* K1, Slow& slow,
                             EmitSlow& emit_slow) {
   const float du2 = f_mul(duf, duf);
@@ -380,15 +400,21 @@ RCV_HD void ring2_slow_lane(bool pass, int nc, int ipl, int ipc, int u, int i0c,
       Ring2Cand cd;
       const float sfv = arc ? fv : -fv;
       ring2_cand(zs, arc ? cm : cp, arc ? mu1 : mu0, sfv, hWg, cd);
-      if (!((fabsf(cd.d) > thr) && !(fabsf(cd.q) < hw_m) && (cd.q > -hw_p))) continue;
       const int n = (int)cd.fl, dir = arc ? 1 : -1;
-      const int cc = arc ? ipc - n : ipc + n;
-      const unsigned addr = arc ? K1[sidx] - cd.bits * sv : cd.bits * sv + K0[sidx];
-      if (slow(i, pass ? cc : lc, pass ? lc : cc)) emit_slow((int)addr);
-      if (cd.q >= hw_m) {   // the candidate may lie outside the outer sphere: the voxel one step inwards can then be inside
-        const float d2 = f_add(f_sub(cd.fl, 1.0f), sfv);
-        const int cc2 = cc + dir;
-        if ((fabsf(d2) > thr) && slow(i, pass ? cc2 : lc, pass ? lc : cc2)) emit_slow((int)(arc ? addr + sv : addr - sv));
+      const unsigned addr0 = arc ? K1[sidx] - cd.bits * sv : cd.bits * sv + K0[sidx];
+      // candidates m = 0 .. M-1 were seen by the fast path: decide those it could not.  If the topmost one may lie
+      // outside the outer sphere the run can reach one voxel further inwards (m = M), which the fast path never saw.
+      const int mend = (cd.q >= hw_m) ? M : M - 1;
+      for (int m = 0; m <= mend; ++m) {
+        const float fl = f_sub(cd.fl, (float)m);                 // exact: small integers
+        const float d = m ? f_add(fl, sfv) : cd.d;
+        if (!(fabsf(d) > thr)) continue;
+        if (m < M) {
+          const float q = m ? f_fma(d, d, hWg) : cd.q;
+          if ((fabsf(q) < hw_m) || !(q > -hw_p)) continue;       // decided by the fast path
+        }
+        const int cc = arc ? ipc - n + m : ipc + n - m;
+        if (slow(i, pass ? cc : lc, pass ? lc : cc)) emit_slow((int)(addr0 + (unsigned)(m * dir) * sv));
       }
     }
   }

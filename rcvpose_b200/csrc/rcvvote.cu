@@ -29,6 +29,12 @@ namespace {
 
 using namespace rcv;
 
+#ifndef RCV_RING2_INTERIOR
+#define RCV_RING2_INTERIOR 0   // 1: columns well inside a ring skip the ownership test (one more copy of the column body)
+#endif
+#ifndef RCV_RING2_SYNCWARP
+#define RCV_RING2_SYNCWARP 1
+#endif
 #ifndef RCV_VOTE_THREADS
 #define RCV_VOTE_THREADS 512
 #endif
@@ -618,26 +624,29 @@ __device__ __forceinline__ int warp_max_i32(int v) { return __reduce_max_sync(0x
 // columns (rows) u = -H..H of ITS thin rings (one candidate per arc); the lane task of column u is shared by the
 // chunk's slices.  a4[s] is NaN for a slice that is not a thin ring of this lane (NaN never votes, never asks for
 // the exact path).  H is the maximum over the warp.  CLIP = some lane's candidates may leave the tile.
-template <bool PASS, bool CLIP, int NC>
+template <bool CLIP, int NC>
 __device__ __forceinline__ void ring_pass(const PointCtx& c, const Tile& t, const float (&a4)[NC], int H, int i0c, int sbase0, int slice_bytes,
                                           const SmemEmit& emit_c, const SlowArcCall& slowarc_c) {
   SmemEmit emit = emit_c;
   SlowArcCall slowarc = slowarc_c;
-  float uf = (float)(-H);
 #pragma unroll 1
-  for (int u = -H; u <= H; ++u, uf += 1.0f) {
-    LaneTask L;
-    lane_setup_pu(c, t, PASS, u, uf, 4, L);
-    ThinOut o[NC];
+  for (int pass = 0; pass < 2; ++pass) {   // one copy of the code for both passes (instruction cache)
+    float uf = (float)(-H);
+#pragma unroll 1
+    for (int u = -H; u <= H; ++u, uf += 1.0f) {
+      LaneTask L;
+      lane_setup_pu(c, t, pass != 0, u, uf, 4, L);
+      ThinOut o[NC];
 #pragma unroll
-    for (int sidx = 0; sidx < NC; ++sidx) thin_fast<CLIP>(c, a4[sidx], L, sbase0 + sidx * slice_bytes, emit.sink, emit, o[sidx]);
-    bool any = false;
+      for (int sidx = 0; sidx < NC; ++sidx) thin_fast<CLIP>(c, a4[sidx], L, sbase0 + sidx * slice_bytes, emit.sink, emit, o[sidx]);
+      bool any = false;
 #pragma unroll
-    for (int sidx = 0; sidx < NC; ++sidx) any |= o[sidx].t0 | o[sidx].t1;
-    if (any) {
+      for (int sidx = 0; sidx < NC; ++sidx) any |= o[sidx].t0 | o[sidx].t1;
+      if (any) {
 #pragma unroll
-      for (int sidx = 0; sidx < NC; ++sidx)
-        if (o[sidx].t0 || o[sidx].t1) thin_slow(c, L, i0c + sidx, o[sidx], slowarc);
+        for (int sidx = 0; sidx < NC; ++sidx)
+          if (o[sidx].t0 || o[sidx].t1) thin_slow(c, L, i0c + sidx, o[sidx], slowarc);
+      }
     }
   }
 }
@@ -646,42 +655,53 @@ __device__ __forceinline__ void ring_pass(const PointCtx& c, const Tile& t, cons
 // Operands: %0 any (out) | %1 du2 %2 mu0 %3 mu1 %4 hW %5 cp %6 cm %7 fv %8 hw_m %9 -hw_p %10 sink %11 sv %12 thr %13 -sv |
 // a[NC], K0[NC], K1[NC].  Per candidate: 5 float ops, one multiply-add for the address, two or three FSETP, one
 // select, one shared-memory atomic and one predicate op; per slice: one subtract, one MUFU.SQRT, one subtract.
-#define R2_DECL "{\n\t.reg .pred pv, pl, po, pa;\n\t.reg .f32 g, zs, hwg, t, tm, fl, d, q, aq, ad;\n\t.reg .b32 bi, adr;\n\tsetp.ne.u32 pa, %10, %10;\n\t"
+#define R2_DECL "{\n\t.reg .pred pv, pl, po, pa;\n\t.reg .f32 g, zs, hwg, t, tm, fl, d, q, aq, ad;\n\t.reg .b32 bi, adr, adu;\n\tsetp.ne.u32 pa, %10, %10;\n\t"
 #define R2_SLICE_HEAD(A) "sub.rn.f32 g, " A ", %1;\n\tsqrt.approx.ftz.f32 zs, g;\n\tsub.rn.f32 hwg, %4, g;\n\t"
 #define R2_CAND_ARITH(CPM, MU, DOP) \
   "add.rn.f32 t, zs, " CPM ";\n\tadd.rn.f32 tm, t, " MU ";\n\tsub.rn.f32 fl, tm, " MU ";\n\t" DOP ".rn.f32 d, fl, %7;\n\t" \
   "fma.rn.f32 q, d, d, hwg;\n\tabs.f32 aq, q;\n\tmov.b32 bi, tm;\n\t"
 #define R2_CAND_VOTE_INT "setp.lt.f32 pv, aq, %8;\n\tsetp.gt.f32 pl, q, %9;\n\t"
 #define R2_CAND_VOTE_OWN "abs.f32 ad, d;\n\tsetp.gt.f32 po, ad, %12;\n\tsetp.lt.and.f32 pv, aq, %8, po;\n\tsetp.gt.and.f32 pl, q, %9, po;\n\t"
+// second candidate of an arc: one voxel inwards (address -+ sv: %13 = -sv for the top arc, %11 = +sv for the bottom arc)
+#define R2_CAND2_ARITH(DOP, STEP) \
+  "add.rn.f32 fl, fl, 0fBF800000;\n\t" DOP ".rn.f32 d, fl, %7;\n\tfma.rn.f32 q, d, d, hwg;\n\tabs.f32 aq, q;\n\tadd.u32 adu, adu, " STEP ";\n\t"
 #define R2_CAND_EMIT(SV, K) \
-  "mad.lo.u32 adr, bi, " SV ", " K ";\n\tselp.u32 adr, adr, %10, pv;\n\tred.shared.add.u32 [adr], 1;\n\txor.pred pl, pl, pv;\n\tor.pred pa, pa, pl;\n\t"
-#define R2_SLICE(A, K0, K1, VOTE) \
+  "mad.lo.u32 adu, bi, " SV ", " K ";\n\tselp.u32 adr, adu, %10, pv;\n\tred.shared.add.u32 [adr], 1;\n\txor.pred pl, pl, pv;\n\tor.pred pa, pa, pl;\n\t"
+#define R2_CAND2_EMIT "selp.u32 adr, adu, %10, pv;\n\tred.shared.add.u32 [adr], 1;\n\txor.pred pl, pl, pv;\n\tor.pred pa, pa, pl;\n\t"
+#define R2_SLICE1(A, K0, K1, VOTE) \
   R2_SLICE_HEAD(A) R2_CAND_ARITH("%5", "%2", "sub") VOTE R2_CAND_EMIT("%11", K0) R2_CAND_ARITH("%6", "%3", "add") VOTE R2_CAND_EMIT("%13", K1)
+#define R2_SLICE2(A, K0, K1, VOTE) \
+  R2_SLICE_HEAD(A) R2_CAND_ARITH("%5", "%2", "sub") VOTE R2_CAND_EMIT("%11", K0) R2_CAND2_ARITH("sub", "%13") VOTE R2_CAND2_EMIT \
+  R2_CAND_ARITH("%6", "%3", "add") VOTE R2_CAND_EMIT("%13", K1) R2_CAND2_ARITH("add", "%11") VOTE R2_CAND2_EMIT
 #define R2_TAIL "selp.u32 %0, 1, 0, pa;\n\t}"
-#define R2_BODY3(VOTE) R2_DECL R2_SLICE("%14", "%17", "%20", VOTE) R2_SLICE("%15", "%18", "%21", VOTE) R2_SLICE("%16", "%19", "%22", VOTE) R2_TAIL
-#define R2_BODY4(VOTE) \
-  R2_DECL R2_SLICE("%14", "%18", "%22", VOTE) R2_SLICE("%15", "%19", "%23", VOTE) R2_SLICE("%16", "%20", "%24", VOTE) R2_SLICE("%17", "%21", "%25", VOTE) R2_TAIL
+#define R2_BODY3(SL, VOTE) R2_DECL SL("%14", "%17", "%20", VOTE) SL("%15", "%18", "%21", VOTE) SL("%16", "%19", "%22", VOTE) R2_TAIL
+#define R2_BODY4(SL, VOTE) R2_DECL SL("%14", "%18", "%22", VOTE) SL("%15", "%19", "%23", VOTE) SL("%16", "%20", "%24", VOTE) SL("%17", "%21", "%25", VOTE) R2_TAIL
 #define R2_COMMON_IN "f"(du2), "f"(mu0), "f"(mu1), "f"(hW), "f"(cp), "f"(cm), "f"(fv), "f"(hw_m), "f"(nhw_p), "r"(sink), "r"(sv), "f"(thr), "r"(nsv)
+#define R2_IN3 R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2])
+#define R2_IN4 \
+  R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]), "r"(K0[3]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), "r"(K1[3])
 
-template <bool OWN, int NC>
+template <bool OWN, int NC, int M>
 __device__ __forceinline__ unsigned ring2_asm(float du2, float mu0, float mu1, float hW, float cp, float cm, float fv, float hw_m, float nhw_p,
                                               unsigned sink, unsigned sv, unsigned nsv, float thr, const float (&a)[NC], const unsigned (&K0)[NC],
                                               const unsigned (&K1)[NC]) {
   unsigned any;
   if constexpr (NC == 3) {
-    if constexpr (OWN)
-      asm volatile(R2_BODY3(R2_CAND_VOTE_OWN) : "=r"(any) : R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]),
-                   "r"(K1[0]), "r"(K1[1]), "r"(K1[2]) : "memory");
-    else
-      asm volatile(R2_BODY3(R2_CAND_VOTE_INT) : "=r"(any) : R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]),
-                   "r"(K1[0]), "r"(K1[1]), "r"(K1[2]) : "memory");
+    if constexpr (M == 1) {
+      if constexpr (OWN) asm volatile(R2_BODY3(R2_SLICE1, R2_CAND_VOTE_OWN) : "=r"(any) : R2_IN3 : "memory");
+      else asm volatile(R2_BODY3(R2_SLICE1, R2_CAND_VOTE_INT) : "=r"(any) : R2_IN3 : "memory");
+    } else {
+      if constexpr (OWN) asm volatile(R2_BODY3(R2_SLICE2, R2_CAND_VOTE_OWN) : "=r"(any) : R2_IN3 : "memory");
+      else asm volatile(R2_BODY3(R2_SLICE2, R2_CAND_VOTE_INT) : "=r"(any) : R2_IN3 : "memory");
+    }
   } else {
-    if constexpr (OWN)
-      asm volatile(R2_BODY4(R2_CAND_VOTE_OWN) : "=r"(any) : R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "r"(K0[0]), "r"(K0[1]),
-                   "r"(K0[2]), "r"(K0[3]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), "r"(K1[3]) : "memory");
-    else
-      asm volatile(R2_BODY4(R2_CAND_VOTE_INT) : "=r"(any) : R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "r"(K0[0]), "r"(K0[1]),
-                   "r"(K0[2]), "r"(K0[3]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), "r"(K1[3]) : "memory");
+    if constexpr (M == 1) {
+      if constexpr (OWN) asm volatile(R2_BODY4(R2_SLICE1, R2_CAND_VOTE_OWN) : "=r"(any) : R2_IN4 : "memory");
+      else asm volatile(R2_BODY4(R2_SLICE1, R2_CAND_VOTE_INT) : "=r"(any) : R2_IN4 : "memory");
+    } else {
+      if constexpr (OWN) asm volatile(R2_BODY4(R2_SLICE2, R2_CAND_VOTE_OWN) : "=r"(any) : R2_IN4 : "memory");
+      else asm volatile(R2_BODY4(R2_SLICE2, R2_CAND_VOTE_INT) : "=r"(any) : R2_IN4 : "memory");
+    }
   }
   return any;
 }
@@ -696,38 +716,44 @@ __device__ __noinline__ void ring2_slow_call(double pa, double pb, double pc, in
   const unsigned K0[4] = {k00, k01, k02, k03}, K1[4] = {k10, k11, k12, k13};
   SlowExactCall slow{pa, pb, pc, R};
   SmemEmit es{0u, 0};   // addresses are absolute
-  ring2_slow_lane((pass_nc & 1) != 0, pass_nc >> 1, ipl, ipc, u, i0c, hW, hw_m, hw_p, duf, cp, cm, fv, mu0, mu1, sv, a, K0, K1, slow, es);
+  ring2_slow_lane((pass_nc & 1) != 0, (pass_nc >> 1) & 7, pass_nc >> 4, ipl, ipc, u, i0c, hW, hw_m, hw_p, duf, cp, cm, fv, mu0, mu1, sv, a, K0, K1, slow, es);
 }
 
 // Fast ring pass of one chunk for a warp whose candidates cannot leave the tile.  H = half-width (warp maximum),
 // Hin = interior half-width (warp minimum, -1 = none).
-template <bool PASS, int NC>
+template <bool PASS, int NC, int M>
 __device__ __forceinline__ void ring_pass2(const PointCtx& c, const Tile& t, const float (&a4)[NC], int H, int Hin, int i0c, int sbase0,
                                            int slice_bytes, unsigned base, unsigned sink_abs) {
+  const float nhw_p = -c.hw_p;
+  const float mstep = (float)t.Dp;
+  const int ioff = Hin >= 0 ? Hin : 0x40000000;
+  const unsigned ispan = Hin >= 0 ? 2u * (unsigned)Hin : 0u;
+  // PASS = false: Z-pass (lane axis B, candidates along C); true: Y-pass (lane axis C, candidates along B)
   const float fu = PASS ? c.fz : c.fy, fv = PASS ? c.fy : c.fz;
   const float cp = f_add(fv, c.dbias_m05), cm = f_sub(c.dbias_m05, fv);
-  const float nhw_p = -c.hw_p;
   unsigned K0[NC], K1[NC], sv = 0;
 #pragma unroll
   for (int sidx = 0; sidx < NC; ++sidx) ring2_consts(c, t, PASS, -H, base + (unsigned)(sbase0 + sidx * slice_bytes), 4u, K0[sidx], K1[sidx], sv);
   const unsigned nsv = 0u - sv;
   float mu0, mu1;
   ring2_magic(PASS, -H, t.Dp, mu0, mu1);
-  const float mstep = (float)t.Dp;
-  const int ioff = Hin >= 0 ? Hin : 0x40000000;
-  const unsigned ispan = Hin >= 0 ? 2u * (unsigned)Hin : 0u;
   float uf = (float)(-H);
 #pragma unroll 1
   for (int u = -H; u <= H; ++u, uf += 1.0f) {
     const float duf = f_sub(uf, fu);
     const float du2 = f_mul(duf, duf);
     unsigned any;
-    if ((unsigned)(u + ioff) <= ispan) any = ring2_asm<false, NC>(du2, mu0, mu1, c.hW, cp, cm, fv, c.hw_m, nhw_p, sink_abs, sv, nsv, 0.f, a4, K0, K1);
-    else any = ring2_asm<true, NC>(du2, mu0, mu1, c.hW, cp, cm, fv, c.hw_m, nhw_p, sink_abs, sv, nsv, ring2_thr(PASS, duf), a4, K0, K1);
+    if (RCV_RING2_INTERIOR && (unsigned)(u + ioff) <= ispan)
+      any = ring2_asm<false, NC, M>(du2, mu0, mu1, c.hW, cp, cm, fv, c.hw_m, nhw_p, sink_abs, sv, nsv, 0.f, a4, K0, K1);
+    else
+      any = ring2_asm<true, NC, M>(du2, mu0, mu1, c.hW, cp, cm, fv, c.hw_m, nhw_p, sink_abs, sv, nsv, ring2_thr(PASS, duf), a4, K0, K1);
     if (any)
-      ring2_slow_call(c.px, c.py, c.pz, c.R, PASS ? c.ipz : c.ipy, PASS ? c.ipy : c.ipz, u, i0c, (PASS ? 1 : 0) | (NC << 1), c.hW, c.hw_m, c.hw_p, duf,
-                      cp, cm, fv, mu0, mu1, sv, a4[0], a4[1], a4[2], NC > 3 ? a4[NC - 1] : a4[0], K0[0], K0[1], K0[2], NC > 3 ? K0[NC - 1] : 0u, K1[0],
-                      K1[1], K1[2], NC > 3 ? K1[NC - 1] : 0u);
+      ring2_slow_call(c.px, c.py, c.pz, c.R, PASS ? c.ipz : c.ipy, PASS ? c.ipy : c.ipz, u, i0c, (PASS ? 1 : 0) | (NC << 1) | (M << 4), c.hW, c.hw_m,
+                      c.hw_p, duf, cp, cm, fv, mu0, mu1, sv, a4[0], a4[1], a4[2], NC > 3 ? a4[NC - 1] : a4[0], K0[0], K0[1], K0[2],
+                      NC > 3 ? K0[NC - 1] : 0u, K1[0], K1[1], K1[2], NC > 3 ? K1[NC - 1] : 0u);
+#if RCV_RING2_SYNCWARP
+    __syncwarp();   // a lane that took the exact path must rejoin here: measured, it otherwise walks the rest of the loop alone
+#endif
     if (PASS) {
 #pragma unroll
       for (int sidx = 0; sidx < NC; ++sidx) { K0[sidx] += 4u; K1[sidx] += 4u; }
@@ -801,16 +827,17 @@ __device__ __forceinline__ void ring_chunk_work(const PointCtx& c, const Tile& t
                                                 const SlowExactCall& slow_c, const SmemEmit& emit, const SlowArcCall& slowarc) {
   SlowExactCall slow = slow_c;
   const bool polar_lane = c.R >= RCV_POLAR_MIN_R;
+  const int maxcode = noclip ? RCV_RING2_MAX_CODE : 1;
   float a4[NC];
-  int abits = 0;
+  int abits = 0, mc = 1;
 #pragma unroll
   for (int sidx = 0; sidx < NC; ++sidx) {
     const int i = i0c + sidx;
     float ar = 0.f; int code = 0;
     if (i >= ia && i <= ib) slice_setup(c, i, ar, code);
-    const bool thin = code == 1;
+    const bool thin = code >= 1 && code <= maxcode;      // rings the ring passes draw; the rest belongs to the polar pass
     a4[sidx] = thin ? ar : __int_as_float(0x7fc00000);
-    if (thin) abits = max(abits, __float_as_int(ar));   // thin => a > 36 > 0: bit order = value order
+    if (thin) { abits = max(abits, __float_as_int(ar)); mc = max(mc, code); }   // thin => a > 36 > 0: bit order = value order
     const int dl = polar_lane ? 0 : -code;
     const int dmax = warp_max_i32(dl);
     if (dmax > 0) {   // spheres too small for the polar pass (R < RCV_POLAR_MIN_R): bounding-box scan of the slice
@@ -835,26 +862,31 @@ __device__ __forceinline__ void ring_chunk_work(const PointCtx& c, const Tile& t
       for (int sidx = 0; sidx < NC; ++sidx) amin = fminf(amin, a4[sidx]);   // fminf ignores the NaN of a non-thin slice
       const int hin_l = amin < 3.0e38f ? ring2_interior(f_sub(amin, c.W)) : 0x7fffffff;
       const int Hin = __reduce_min_sync(0xffffffffu, hin_l);
-      ring_pass2<false, NC>(c, t, a4, H, Hin, i0c, sbase0, slice_bytes, emit.base, emit.base + (unsigned)emit.sink);
-      ring_pass2<true, NC>(c, t, a4, H, Hin, i0c, sbase0, slice_bytes, emit.base, emit.base + (unsigned)emit.sink);
+      const unsigned sink_abs = emit.base + (unsigned)emit.sink;
+      if (warp_max_i32(mc) == 1) {   // one candidate per arc
+        ring_pass2<false, NC, 1>(c, t, a4, H, Hin, i0c, sbase0, slice_bytes, emit.base, sink_abs);
+        ring_pass2<true, NC, 1>(c, t, a4, H, Hin, i0c, sbase0, slice_bytes, emit.base, sink_abs);
+      } else {                       // some ring of the chunk crosses a column in two voxels: two candidates per arc
+        ring_pass2<false, NC, 2>(c, t, a4, H, Hin, i0c, sbase0, slice_bytes, emit.base, sink_abs);
+        ring_pass2<true, NC, 2>(c, t, a4, H, Hin, i0c, sbase0, slice_bytes, emit.base, sink_abs);
+      }
     } else {
-      ring_pass<false, true, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
-      ring_pass<true, true, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
+      ring_pass<true, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);
     }
   }
 }
 
 // The lane's non-thin slices in the slab: masks (bit v = slice t.i0 + v, by side of the pole) and the annulus
 // s_lo < dB^2 + dC^2 < s_hi that holds their rings.
-__device__ __forceinline__ void polar_collect(const PointCtx& c, const Tile& t, int ia, int ib, unsigned& mplus, unsigned& mminus, float& s_lo,
-                                              float& s_hi) {
+__device__ __forceinline__ void polar_collect(const PointCtx& c, const Tile& t, int ia, int ib, int maxcode, unsigned& mplus, unsigned& mminus,
+                                              float& s_lo, float& s_hi) {
   mplus = 0u; mminus = 0u; s_hi = 0.f; s_lo = 3.0e38f;
   if (c.R < RCV_POLAR_MIN_R) return;
 #pragma unroll 1
   for (int i = ia; i <= ib; ++i) {
     float ar; int code;
     slice_setup(c, i, ar, code);
-    if (code > 1 || code < 0) {
+    if (code > maxcode || code < 0) {
       if (i > c.ipx) mplus |= 1u << (i - t.i0); else mminus |= 1u << (i - t.i0);
       s_hi = fmaxf(s_hi, ar);
       s_lo = fminf(s_lo, f_sub(ar, c.W));
@@ -914,7 +946,8 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
       if (phase == 0) {
         unsigned mplus, mminus;
         float s_lo, s_hi;
-        polar_collect(c, t, ia, ib, mplus, mminus, s_lo, s_hi);
+        const bool noclip = __all_sync(0xffffffffu, ring_noclip(c, t));   // same partition as the ring phases of this group
+        polar_collect(c, t, ia, ib, noclip ? RCV_RING2_MAX_CODE : 1, mplus, mminus, s_lo, s_hi);
         const int Hp = warp_max_i32((mplus | mminus) ? polar_half_width(s_hi, c.eps) : -1);
         if (Hp >= 0) {
           const bool anyp = __any_sync(0xffffffffu, mplus != 0u), anym = __any_sync(0xffffffffu, mminus != 0u);

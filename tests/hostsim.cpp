@@ -42,20 +42,21 @@ static void ring_chunks(PointCtx* c, const int* ia, const int* ib, const Tile& t
   const float kNaN = __builtin_nanf("");
   bool noclip = true;
   for (int l = 0; l < 32; ++l) noclip = noclip && ring_noclip(c[l], t);
+  const int maxcode = noclip ? RCV_RING2_MAX_CODE : 1;   // rings the ring passes draw; the rest goes to the polar pass
   const int first = t.i0 + ((wa - t.i0) / NC) * NC;          // chunks tile the slab from its first slice
   for (int i0c = first; i0c <= wb; i0c += NC) {
-    float a4[32][NC]; float amax = 0.f; bool any_thin = false;
+    float a4[32][NC]; float amax = 0.f; bool any_thin = false; int mcand = 1;
     for (int sidx = 0; sidx < NC; ++sidx) {
       const int i = i0c + sidx;
       int dmax = 0; float ad[32]; int code[32];
       for (int l = 0; l < 32; ++l) {
         ad[l] = 0.f; code[l] = 0;
         if (i >= ia[l] && i <= ib[l]) slice_setup(c[l], i, ad[l], code[l]);
-        const bool thin = code[l] == 1;
+        const bool thin = code[l] >= 1 && code[l] <= maxcode;
         a4[l][sidx] = thin ? ad[l] : kNaN;
-        if (thin) { any_thin = true; if (ad[l] > amax) amax = ad[l]; }
+        if (thin) { any_thin = true; if (ad[l] > amax) amax = ad[l]; if (code[l] > mcand) mcand = code[l]; }
         if (c[l].R >= RCV_POLAR_MIN_R) {
-          if (code[l] > 1 || code[l] < 0) {
+          if (code[l] > maxcode || code[l] < 0) {
             if (i > c[l].ipx) mplus[l] |= 1u << (i - t.i0); else mminus[l] |= 1u << (i - t.i0);
             if (ad[l] > smax[l]) smax[l] = ad[l];
             const float bl = f_sub(ad[l], c[l].W);
@@ -106,11 +107,16 @@ static void ring_chunks(PointCtx* c, const int* ia, const int* ib, const Tile& t
               for (int sidx = 0; sidx < NC; ++sidx) {
                 arow[sidx] = a4[l][sidx];
                 ring2_consts(c[l], t, pass != 0, u, (unsigned)((i0c + sidx - t.i0) * slice_words), 1u, K0[sidx], K1[sidx], sv);
-                if (interior) any |= ring2_fast<false>(c[l], arow[sidx], du2, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
-                else any |= ring2_fast<true>(c[l], arow[sidx], du2, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
+                if (mcand == 1) {
+                  if (interior) any |= ring2_fast<false, 1>(c[l], arow[sidx], du2, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
+                  else any |= ring2_fast<true, 1>(c[l], arow[sidx], du2, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
+                } else {
+                  if (interior) any |= ring2_fast<false, 2>(c[l], arow[sidx], du2, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
+                  else any |= ring2_fast<true, 2>(c[l], arow[sidx], du2, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
+                }
               }
               if (any)
-                ring2_slow_lane(pass != 0, NC, pass ? c[l].ipz : c[l].ipy, pass ? c[l].ipy : c[l].ipz, u, i0c, c[l].hW, c[l].hw_m, c[l].hw_p, duf,
+                ring2_slow_lane(pass != 0, NC, mcand, pass ? c[l].ipz : c[l].ipy, pass ? c[l].ipy : c[l].ipz, u, i0c, c[l].hW, c[l].hw_m, c[l].hw_p, duf,
                                 cp, cm, fv, mu0, mu1, sv, arow, K0, K1, slow, emit_slow);
             }
           }
