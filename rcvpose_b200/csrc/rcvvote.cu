@@ -642,7 +642,7 @@ __device__ __forceinline__ void ring_pass(const PointCtx& c, const Tile& t, cons
       bool any = false;
 #pragma unroll
       for (int sidx = 0; sidx < NC; ++sidx) any |= o[sidx].t0 | o[sidx].t1;
-      if (any) {
+      if (__builtin_expect(any, 0)) {
 #pragma unroll
         for (int sidx = 0; sidx < NC; ++sidx)
           if (o[sidx].t0 || o[sidx].t1) thin_slow(c, L, i0c + sidx, o[sidx], slowarc);
@@ -673,37 +673,36 @@ __device__ __forceinline__ void ring_pass(const PointCtx& c, const Tile& t, cons
 #define R2_SLICE2(A, K0, K1, VOTE) \
   R2_SLICE_HEAD(A) R2_CAND_ARITH("%5", "%2", "sub") VOTE R2_CAND_EMIT("%11", K0) R2_CAND2_ARITH("sub", "%13") VOTE R2_CAND2_EMIT \
   R2_CAND_ARITH("%6", "%3", "add") VOTE R2_CAND_EMIT("%13", K1) R2_CAND2_ARITH("add", "%11") VOTE R2_CAND2_EMIT
-#define R2_TAIL "selp.u32 %0, 1, 0, pa;\n\t}"
-#define R2_BODY3(SL, VOTE) R2_DECL SL("%14", "%17", "%20", VOTE) SL("%15", "%18", "%21", VOTE) SL("%16", "%19", "%22", VOTE) R2_TAIL
-#define R2_BODY4(SL, VOTE) R2_DECL SL("%14", "%18", "%22", VOTE) SL("%15", "%19", "%23", VOTE) SL("%16", "%20", "%24", VOTE) SL("%17", "%21", "%25", VOTE) R2_TAIL
+#define R2_TAIL(BIT) "@pa or.b32 %0, %0, " BIT ";\n\t}"
+#define R2_BODY3(SL, VOTE) R2_DECL SL("%14", "%17", "%20", VOTE) SL("%15", "%18", "%21", VOTE) SL("%16", "%19", "%22", VOTE) R2_TAIL("%23")
+#define R2_BODY4(SL, VOTE) R2_DECL SL("%14", "%18", "%22", VOTE) SL("%15", "%19", "%23", VOTE) SL("%16", "%20", "%24", VOTE) SL("%17", "%21", "%25", VOTE) R2_TAIL("%26")
 #define R2_COMMON_IN "f"(du2), "f"(mu0), "f"(mu1), "f"(hW), "f"(cp), "f"(cm), "f"(fv), "f"(hw_m), "f"(nhw_p), "r"(sink), "r"(sv), "f"(thr), "r"(nsv)
-#define R2_IN3 R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2])
+#define R2_IN3 R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), "r"(bit)
 #define R2_IN4 \
-  R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]), "r"(K0[3]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), "r"(K1[3])
+  R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]), "r"(K0[3]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), "r"(K1[3]), "r"(bit)
 
+// Adds `bit` to `flags` if a candidate of the column needs the exact path.
 template <bool OWN, int NC, int M>
-__device__ __forceinline__ unsigned ring2_asm(float du2, float mu0, float mu1, float hW, float cp, float cm, float fv, float hw_m, float nhw_p,
-                                              unsigned sink, unsigned sv, unsigned nsv, float thr, const float (&a)[NC], const unsigned (&K0)[NC],
-                                              const unsigned (&K1)[NC]) {
-  unsigned any;
+__device__ __forceinline__ void ring2_asm(unsigned& flags, unsigned bit, float du2, float mu0, float mu1, float hW, float cp, float cm, float fv,
+                                          float hw_m, float nhw_p, unsigned sink, unsigned sv, unsigned nsv, float thr, const float (&a)[NC],
+                                          const unsigned (&K0)[NC], const unsigned (&K1)[NC]) {
   if constexpr (NC == 3) {
     if constexpr (M == 1) {
-      if constexpr (OWN) asm volatile(R2_BODY3(R2_SLICE1, R2_CAND_VOTE_OWN) : "=r"(any) : R2_IN3 : "memory");
-      else asm volatile(R2_BODY3(R2_SLICE1, R2_CAND_VOTE_INT) : "=r"(any) : R2_IN3 : "memory");
+      if constexpr (OWN) asm volatile(R2_BODY3(R2_SLICE1, R2_CAND_VOTE_OWN) : "+r"(flags) : R2_IN3 : "memory");
+      else asm volatile(R2_BODY3(R2_SLICE1, R2_CAND_VOTE_INT) : "+r"(flags) : R2_IN3 : "memory");
     } else {
-      if constexpr (OWN) asm volatile(R2_BODY3(R2_SLICE2, R2_CAND_VOTE_OWN) : "=r"(any) : R2_IN3 : "memory");
-      else asm volatile(R2_BODY3(R2_SLICE2, R2_CAND_VOTE_INT) : "=r"(any) : R2_IN3 : "memory");
+      if constexpr (OWN) asm volatile(R2_BODY3(R2_SLICE2, R2_CAND_VOTE_OWN) : "+r"(flags) : R2_IN3 : "memory");
+      else asm volatile(R2_BODY3(R2_SLICE2, R2_CAND_VOTE_INT) : "+r"(flags) : R2_IN3 : "memory");
     }
   } else {
     if constexpr (M == 1) {
-      if constexpr (OWN) asm volatile(R2_BODY4(R2_SLICE1, R2_CAND_VOTE_OWN) : "=r"(any) : R2_IN4 : "memory");
-      else asm volatile(R2_BODY4(R2_SLICE1, R2_CAND_VOTE_INT) : "=r"(any) : R2_IN4 : "memory");
+      if constexpr (OWN) asm volatile(R2_BODY4(R2_SLICE1, R2_CAND_VOTE_OWN) : "+r"(flags) : R2_IN4 : "memory");
+      else asm volatile(R2_BODY4(R2_SLICE1, R2_CAND_VOTE_INT) : "+r"(flags) : R2_IN4 : "memory");
     } else {
-      if constexpr (OWN) asm volatile(R2_BODY4(R2_SLICE2, R2_CAND_VOTE_OWN) : "=r"(any) : R2_IN4 : "memory");
-      else asm volatile(R2_BODY4(R2_SLICE2, R2_CAND_VOTE_INT) : "=r"(any) : R2_IN4 : "memory");
+      if constexpr (OWN) asm volatile(R2_BODY4(R2_SLICE2, R2_CAND_VOTE_OWN) : "+r"(flags) : R2_IN4 : "memory");
+      else asm volatile(R2_BODY4(R2_SLICE2, R2_CAND_VOTE_INT) : "+r"(flags) : R2_IN4 : "memory");
     }
   }
-  return any;
 }
 
 // The rare branch of the fast ring pass (one lane, out of line): everything it needs arrives in scalars so that the hot
@@ -738,29 +737,44 @@ __device__ __forceinline__ void ring_pass2(const PointCtx& c, const Tile& t, con
   float mu0, mu1;
   ring2_magic(PASS, -H, t.Dp, mu0, mu1);
   float uf = (float)(-H);
+  // Columns are walked in blocks of 32; a column with an undecided candidate only sets its bit, and the exact path runs
+  // after the block for all flagged (lane, column) pairs at once: the hot loop has one branch (its back edge) and the
+  // lanes of a warp that need the exact path in the same block take it together.
 #pragma unroll 1
-  for (int u = -H; u <= H; ++u, uf += 1.0f) {
-    const float duf = f_sub(uf, fu);
-    const float du2 = f_mul(duf, duf);
-    unsigned any;
-    if (RCV_RING2_INTERIOR && (unsigned)(u + ioff) <= ispan)
-      any = ring2_asm<false, NC, M>(du2, mu0, mu1, c.hW, cp, cm, fv, c.hw_m, nhw_p, sink_abs, sv, nsv, 0.f, a4, K0, K1);
-    else
-      any = ring2_asm<true, NC, M>(du2, mu0, mu1, c.hW, cp, cm, fv, c.hw_m, nhw_p, sink_abs, sv, nsv, ring2_thr(PASS, duf), a4, K0, K1);
-    if (any)
-      ring2_slow_call(c.px, c.py, c.pz, c.R, PASS ? c.ipz : c.ipy, PASS ? c.ipy : c.ipz, u, i0c, (PASS ? 1 : 0) | (NC << 1) | (M << 4), c.hW, c.hw_m,
-                      c.hw_p, duf, cp, cm, fv, mu0, mu1, sv, a4[0], a4[1], a4[2], NC > 3 ? a4[NC - 1] : a4[0], K0[0], K0[1], K0[2],
-                      NC > 3 ? K0[NC - 1] : 0u, K1[0], K1[1], K1[2], NC > 3 ? K1[NC - 1] : 0u);
-#if RCV_RING2_SYNCWARP
-    __syncwarp();   // a lane that took the exact path must rejoin here: measured, it otherwise walks the rest of the loop alone
-#endif
-    if (PASS) {
+  for (int ub0 = -H; ub0 <= H; ub0 += 32) {
+    const int ue = min(ub0 + 31, H);
+    unsigned flags = 0u, bit = 1u;
+#pragma unroll 1
+    for (int u = ub0; u <= ue; ++u, uf += 1.0f, bit <<= 1) {
+      const float duf = f_sub(uf, fu);
+      const float du2 = f_mul(duf, duf);
+      if (RCV_RING2_INTERIOR && (unsigned)(u + ioff) <= ispan)
+        ring2_asm<false, NC, M>(flags, bit, du2, mu0, mu1, c.hW, cp, cm, fv, c.hw_m, nhw_p, sink_abs, sv, nsv, 0.f, a4, K0, K1);
+      else
+        ring2_asm<true, NC, M>(flags, bit, du2, mu0, mu1, c.hW, cp, cm, fv, c.hw_m, nhw_p, sink_abs, sv, nsv, ring2_thr(PASS, duf), a4, K0, K1);
+      if (PASS) {
 #pragma unroll
-      for (int sidx = 0; sidx < NC; ++sidx) { K0[sidx] += 4u; K1[sidx] += 4u; }
-    } else {
-      mu0 = f_add(mu0, mstep);
-      mu1 = f_sub(mu1, mstep);
+        for (int sidx = 0; sidx < NC; ++sidx) { K0[sidx] += 4u; K1[sidx] += 4u; }
+      } else {
+        mu0 = f_add(mu0, mstep);
+        mu1 = f_sub(mu1, mstep);
+      }
     }
+    if (__builtin_expect(flags != 0u, 0)) {
+      do {
+        const int j = __ffs((int)flags) - 1;
+        flags &= flags - 1u;
+        const int u = ub0 + j;
+        const unsigned kback = PASS ? 4u * (unsigned)(ue + 1 - u) : 0u;   // K0/K1 now stand at column ue + 1
+        float m0, m1;
+        ring2_magic(PASS, u, t.Dp, m0, m1);
+        ring2_slow_call(c.px, c.py, c.pz, c.R, PASS ? c.ipz : c.ipy, PASS ? c.ipy : c.ipz, u, i0c, (PASS ? 1 : 0) | (NC << 1) | (M << 4), c.hW,
+                        c.hw_m, c.hw_p, f_sub((float)u, fu), cp, cm, fv, m0, m1, sv, a4[0], a4[1], a4[2], NC > 3 ? a4[NC - 1] : a4[0],
+                        K0[0] - kback, K0[1] - kback, K0[2] - kback, NC > 3 ? K0[NC - 1] - kback : 0u, K1[0] - kback, K1[1] - kback,
+                        K1[2] - kback, NC > 3 ? K1[NC - 1] - kback : 0u);
+      } while (flags);
+    }
+    __syncwarp();   // lanes that took the exact path rejoin here (measured: they otherwise walk the rest of the pass alone)
   }
 }
 
@@ -789,7 +803,7 @@ __device__ __forceinline__ void polar_segment(const PointCtx& c, const Tile& t, 
     const int cell = rowoff + kc * 4;
     PolarOut o;
     polar_fast<SIDES>(c, t, cpx, cmx, s2, cell, ok, mplus, mminus, slice_bytes, emit.sink, emit, o);
-    if (o.t0 || o.t1)
+    if (__builtin_expect(o.t0 || o.t1, 0))
       polar_slow_call(c.px, c.py, c.pz, c.R, c.hw_m, t.i0, o.q0, o.q1, o.vt0, o.vt1, (o.t0 ? 1 : 0) | (o.t1 ? 2 : 0), jb, kc, cell, mplus, mminus,
                       slice_bytes, emit.base);
   }
