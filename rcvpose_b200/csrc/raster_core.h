@@ -286,6 +286,8 @@ RCV_HD void thin_slow(const PointCtx& c, const LaneTask& L, int i, const ThinOut
 // ---- fast ring pass ("ring2"): thin rings of a warp whose candidates cannot leave the tile (ring_noclip) ----------
 // Same candidates and the same float32 arithmetic as thin_fast(), reorganised so that one candidate costs about a
 // dozen instructions on the device (rcvvote.cu issues it as one PTX block per column):
+//   * g = a - du^2 is formed with one rounding (fused); ptxas contracts the packed multiply and subtract into an
+//     FFMA2 even when both carry .rn, so the fused form is the one both sides of the parity use;
 //   * the address is  bits(tm) * sv + K : the float -> int conversion of the magic-number floor, the lattice base and
 //     the tile offset are folded into one multiply-add.  In the Z-pass the column is folded in as well by adding
 //     MAGIC + u*Dp instead of MAGIC (both are integers below 2^24, so the rounding to an integer is unchanged except
@@ -331,8 +333,10 @@ RCV_HD void ring2_consts(const PointCtx& c, const Tile& t, bool pass, int u0, un
 }
 // Ownership threshold of a column (as in lane_setup_pu, tile bounds aside): Z-pass owns |dv| >= |du|, Y-pass |dv| > |du|.
 RCV_HD float ring2_thr(bool pass, float duf) {
-  const float ad = fabsf(duf);
-  return pass ? ad : (ad > 0.f ? f_from_bits(f_bits(ad) - 1) : -1.0f);
+  // Y-pass: |du|.  Z-pass: the float just below |du| (so that > means >=), and -1 for du == 0; branch-free: the bit
+  // pattern of |du| minus one wraps to 0xffffffff for du == 0 and the unsigned minimum maps that to -1.0f.
+  const unsigned b = (unsigned)f_bits(fabsf(duf)) - (pass ? 0u : 1u);
+  return f_from_bits((int)(b < 0xBF800000u ? b : 0xBF800000u));
 }
 // Interior half-width of a lane: columns |u| <= Hin have du^2 < bmin/2 - 1 (|du| <= |u| + 0.5); -1 if there is none.
 RCV_HD int ring2_interior(float bmin) {
@@ -345,9 +349,9 @@ RCV_HD int ring2_interior(float bmin) {
 // voxels inwards of it: a ring with slice_setup code <= M crosses a column of its own pass in at most M voxels):
 // 2 M emits (vote address or sink); returns true if a candidate needs the exact path.
 template <bool OWN, int M, class Emit>
-RCV_HD bool ring2_fast(const PointCtx& c, float a, float du2, float thr, float cp, float cm, float fv, float mu0, float mu1, unsigned K0,
+RCV_HD bool ring2_fast(const PointCtx& c, float a, float duf, float thr, float cp, float cm, float fv, float mu0, float mu1, unsigned K0,
                        unsigned K1, unsigned sv, unsigned sink, Emit& emit) {
-  const float g = f_sub(a, du2);
+  const float g = f_fma(-duf, duf, a);   // a - du^2 with ONE rounding (the device issues it as a packed FFMA2)
   const float zs = f_sqrt_fast(g);
   const float hWg = f_sub(c.hW, g);
   bool any = false;
@@ -386,14 +390,13 @@ template <class Slow, class EmitSlow>
 RCV_HD void ring2_slow_lane(bool pass, int nc, int M, int ipl, int ipc, int u, int i0c, float hW, float hw_m, float hw_p, float duf, float cp, float cm,
                             float fv, float mu0, float mu1, unsigned sv, const float* a, const unsigned* K0, const unsigned* K1, Slow& slow,
                             EmitSlow& emit_slow) {
-  const float du2 = f_mul(duf, duf);
   const float thr = ring2_thr(pass, duf);
   const int lc = ipl + u;
   for (int sidx = 0; sidx < nc; ++sidx) {
     const float as = a[sidx];
     if (!(as == as)) continue;
     const int i = i0c + sidx;
-    const float g = f_sub(as, du2);
+    const float g = f_fma(-duf, duf, as);   // like ring2_fast
     const float zs = f_sqrt_fast(g);
     const float hWg = f_sub(hW, g);
     for (int arc = 0; arc < 2; ++arc) {

@@ -652,55 +652,79 @@ __device__ __forceinline__ void ring_pass(const PointCtx& c, const Tile& t, cons
 }
 
 // ---- fast ring pass (raster_core.h "ring2"): one PTX block per column of a chunk ---------------------------------
-// Operands: %0 any (out) | %1 du2 %2 mu0 %3 mu1 %4 hW %5 cp %6 cm %7 fv %8 hw_m %9 -hw_p %10 sink %11 sv %12 thr %13 -sv |
-// a[NC], K0[NC], K1[NC].  Per candidate: 5 float ops, one multiply-add for the address, two or three FSETP, one
-// select, one shared-memory atomic and one predicate op; per slice: one subtract, one MUFU.SQRT, one subtract.
-#define R2_DECL "{\n\t.reg .pred pv, pl, po, pa;\n\t.reg .f32 g, zs, hwg, t, tm, fl, d, q, aq, ad;\n\t.reg .b32 bi, adr, adu;\n\tsetp.ne.u32 pa, %10, %10;\n\t"
-#define R2_SLICE_HEAD(A) "sub.rn.f32 g, " A ", %1;\n\tsqrt.approx.ftz.f32 zs, g;\n\tsub.rn.f32 hwg, %4, g;\n\t"
-#define R2_CAND_ARITH(CPM, MU, DOP) \
-  "add.rn.f32 t, zs, " CPM ";\n\tadd.rn.f32 tm, t, " MU ";\n\tsub.rn.f32 fl, tm, " MU ";\n\t" DOP ".rn.f32 d, fl, %7;\n\t" \
-  "fma.rn.f32 q, d, d, hwg;\n\tabs.f32 aq, q;\n\tmov.b32 bi, tm;\n\t"
-#define R2_CAND_VOTE_INT "setp.lt.f32 pv, aq, %8;\n\tsetp.gt.f32 pl, q, %9;\n\t"
-#define R2_CAND_VOTE_OWN "abs.f32 ad, d;\n\tsetp.gt.f32 po, ad, %12;\n\tsetp.lt.and.f32 pv, aq, %8, po;\n\tsetp.gt.and.f32 pl, q, %9, po;\n\t"
-// second candidate of an arc: one voxel inwards (address -+ sv: %13 = -sv for the top arc, %11 = +sv for the bottom arc)
-#define R2_CAND2_ARITH(DOP, STEP) \
-  "add.rn.f32 fl, fl, 0fBF800000;\n\t" DOP ".rn.f32 d, fl, %7;\n\tfma.rn.f32 q, d, d, hwg;\n\tabs.f32 aq, q;\n\tadd.u32 adu, adu, " STEP ";\n\t"
-#define R2_CAND_EMIT(SV, K) \
-  "mad.lo.u32 adu, bi, " SV ", " K ";\n\tselp.u32 adr, adu, %10, pv;\n\tred.shared.add.u32 [adr], 1;\n\txor.pred pl, pl, pv;\n\tor.pred pa, pa, pl;\n\t"
-#define R2_CAND2_EMIT "selp.u32 adr, adu, %10, pv;\n\tred.shared.add.u32 [adr], 1;\n\txor.pred pl, pl, pv;\n\tor.pred pa, pa, pl;\n\t"
-#define R2_SLICE1(A, K0, K1, VOTE) \
-  R2_SLICE_HEAD(A) R2_CAND_ARITH("%5", "%2", "sub") VOTE R2_CAND_EMIT("%11", K0) R2_CAND_ARITH("%6", "%3", "add") VOTE R2_CAND_EMIT("%13", K1)
+// The two arcs of a slice run through the same float sequence with mirrored constants, so they are issued as packed
+// fp32 pairs (sm_100 FADD2 / FFMA2: one issue slot for two IEEE-rounded results -- measured in tools/ubench_f32x2.cu:
+// the packed op takes the FMA pipe for two cycles but one issue slot, which is what this issue-bound loop is short of).
+// Pair operands (lo = top arc, hi = bottom arc):
+//   %1 (du, du)     %2 (mu0, mu1)   %3 (hW, hW)   %4 (cp, cm)   %5 (-fv, +fv)   a2[s] = (a_s, a_s)
+// Scalars: %0 flags (in/out) | %6 hw_m %7 -hw_p %8 sink %9 sv %10 thr %11 -sv | a2[NC], K0[NC], K1[NC], bit.
+// g = a - du^2 is ONE packed fma (ptxas would contract a packed multiply + subtract anyway, .rn or not; the host mirror
+// ring2_fast() uses the fused form too).  Per slice: packed fma + packed subtract + MUFU.SQRT + 5 packed ops (+3 for the second candidates); per candidate: one
+// multiply-add for the address, two or three FSETP, one select, one shared-memory atomic, one predicate op.
+#define R2_DECL \
+  "{\n\t.reg .pred pv, pl, po, pa;\n\t.reg .f32 zs, q0, q1, d0, d1, aq, ad, glo, ghi;\n\t.reg .b32 b0, b1, adr, adu;\n\t" \
+  ".reg .b64 g2, zs2, hwg2, t2, tm2, fl2, d2, q2, m1, nd2, z2;\n\tsetp.ne.u32 pa, %8, %8;\n\tmov.b64 m1, 0xBF800000BF800000;\n\t" \
+  "mov.b64 z2, 0;\n\tsub.rn.f32x2 nd2, z2, %1;\n\t"
+#define R2_SLICE_HEAD(A) \
+  "fma.rn.f32x2 g2, nd2, %1, " A ";\n\tmov.b64 {glo, ghi}, g2;\n\tsqrt.approx.ftz.f32 zs, glo;\n\tmov.b64 zs2, {zs, zs};\n\tsub.rn.f32x2 hwg2, %3, g2;\n\t" \
+  "add.rn.f32x2 t2, zs2, %4;\n\tadd.rn.f32x2 tm2, t2, %2;\n\tsub.rn.f32x2 fl2, tm2, %2;\n\tadd.rn.f32x2 d2, fl2, %5;\n\t" \
+  "fma.rn.f32x2 q2, d2, d2, hwg2;\n\tmov.b64 {q0, q1}, q2;\n\tmov.b64 {d0, d1}, d2;\n\tmov.b64 {b0, b1}, tm2;\n\t"
+// candidates one voxel inwards of both arcs: (integer - 1) -+ fraction, one rounding like every coordinate difference
+#define R2_SLICE_HEAD2 \
+  "add.rn.f32x2 fl2, fl2, m1;\n\tadd.rn.f32x2 d2, fl2, %5;\n\tfma.rn.f32x2 q2, d2, d2, hwg2;\n\tmov.b64 {q0, q1}, q2;\n\tmov.b64 {d0, d1}, d2;\n\t"
+#define R2_VOTE_INT(Q) "abs.f32 aq, " Q ";\n\tsetp.lt.f32 pv, aq, %6;\n\tsetp.gt.f32 pl, " Q ", %7;\n\t"
+#define R2_VOTE_OWN(Q, D) \
+  "abs.f32 aq, " Q ";\n\tabs.f32 ad, " D ";\n\tsetp.gt.f32 po, ad, %10;\n\tsetp.lt.and.f32 pv, aq, %6, po;\n\tsetp.gt.and.f32 pl, " Q ", %7, po;\n\t"
+#define R2_EMIT_TAIL "selp.u32 adr, adu, %8, pv;\n\tred.shared.add.u32 [adr], 1;\n\txor.pred pl, pl, pv;\n\tor.pred pa, pa, pl;\n\t"
+#define R2_EMIT(B, SV, K) "mad.lo.u32 adu, " B ", " SV ", " K ";\n\t" R2_EMIT_TAIL
+#define R2_EMIT_INWARD(ADU, STEP) "add.u32 " ADU ", " ADU ", " STEP ";\n\tmov.b32 adu, " ADU ";\n\t" R2_EMIT_TAIL
+// VOTE is a macro name taking (Q, D): R2_V_INT or R2_V_OWN
+#define R2_V_INT(Q, D) R2_VOTE_INT(Q)
+#define R2_V_OWN(Q, D) R2_VOTE_OWN(Q, D)
+#define R2_SLICE1(A, K0, K1, VOTE) R2_SLICE_HEAD(A) VOTE("q0", "d0") R2_EMIT("b0", "%9", K0) VOTE("q1", "d1") R2_EMIT("b1", "%11", K1)
+// two candidates per arc: the unselected addresses of the first candidates are kept (au0 / au1) and stepped inwards
 #define R2_SLICE2(A, K0, K1, VOTE) \
-  R2_SLICE_HEAD(A) R2_CAND_ARITH("%5", "%2", "sub") VOTE R2_CAND_EMIT("%11", K0) R2_CAND2_ARITH("sub", "%13") VOTE R2_CAND2_EMIT \
-  R2_CAND_ARITH("%6", "%3", "add") VOTE R2_CAND_EMIT("%13", K1) R2_CAND2_ARITH("add", "%11") VOTE R2_CAND2_EMIT
+  R2_SLICE_HEAD(A) VOTE("q0", "d0") "mad.lo.u32 au0, b0, %9, " K0 ";\n\tmov.b32 adu, au0;\n\t" R2_EMIT_TAIL \
+  VOTE("q1", "d1") "mad.lo.u32 au1, b1, %11, " K1 ";\n\tmov.b32 adu, au1;\n\t" R2_EMIT_TAIL \
+  R2_SLICE_HEAD2 VOTE("q0", "d0") R2_EMIT_INWARD("au0", "%11") VOTE("q1", "d1") R2_EMIT_INWARD("au1", "%9")
 #define R2_TAIL(BIT) "@pa or.b32 %0, %0, " BIT ";\n\t}"
-#define R2_BODY3(SL, VOTE) R2_DECL SL("%14", "%17", "%20", VOTE) SL("%15", "%18", "%21", VOTE) SL("%16", "%19", "%22", VOTE) R2_TAIL("%23")
-#define R2_BODY4(SL, VOTE) R2_DECL SL("%14", "%18", "%22", VOTE) SL("%15", "%19", "%23", VOTE) SL("%16", "%20", "%24", VOTE) SL("%17", "%21", "%25", VOTE) R2_TAIL("%26")
-#define R2_COMMON_IN "f"(du2), "f"(mu0), "f"(mu1), "f"(hW), "f"(cp), "f"(cm), "f"(fv), "f"(hw_m), "f"(nhw_p), "r"(sink), "r"(sv), "f"(thr), "r"(nsv)
-#define R2_IN3 R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), "r"(bit)
+#define R2_DECL2 ".reg .b32 au0, au1;\n\t"
+#define R2_BODY3(SL, VOTE) R2_DECL R2_DECL2 SL("%12", "%15", "%18", VOTE) SL("%13", "%16", "%19", VOTE) SL("%14", "%17", "%20", VOTE) R2_TAIL("%21")
+#define R2_BODY4(SL, VOTE) \
+  R2_DECL R2_DECL2 SL("%12", "%16", "%20", VOTE) SL("%13", "%17", "%21", VOTE) SL("%14", "%18", "%22", VOTE) SL("%15", "%19", "%23", VOTE) R2_TAIL("%24")
+#define R2_COMMON_IN "l"(duf2), "l"(mu2), "l"(hW2), "l"(cpm2), "l"(sfv2), "f"(hw_m), "f"(nhw_p), "r"(sink), "r"(sv), "f"(thr), "r"(nsv)
+#define R2_IN3 R2_COMMON_IN, "l"(a2[0]), "l"(a2[1]), "l"(a2[2]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), "r"(bit)
 #define R2_IN4 \
-  R2_COMMON_IN, "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]), "r"(K0[3]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), "r"(K1[3]), "r"(bit)
+  R2_COMMON_IN, "l"(a2[0]), "l"(a2[1]), "l"(a2[2]), "l"(a2[3]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]), "r"(K0[3]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), \
+      "r"(K1[3]), "r"(bit)
+
+typedef unsigned long long f32x2_t;   // two floats in an aligned register pair: lo = top arc, hi = bottom arc
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ float lo2(f32x2_t a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return lo; }
 
 // Adds `bit` to `flags` if a candidate of the column needs the exact path.
 template <bool OWN, int NC, int M>
-__device__ __forceinline__ void ring2_asm(unsigned& flags, unsigned bit, float du2, float mu0, float mu1, float hW, float cp, float cm, float fv,
-                                          float hw_m, float nhw_p, unsigned sink, unsigned sv, unsigned nsv, float thr, const float (&a)[NC],
+__device__ __forceinline__ void ring2_asm(unsigned& flags, unsigned bit, f32x2_t duf2, f32x2_t mu2, f32x2_t hW2, f32x2_t cpm2, f32x2_t sfv2, float hw_m,
+                                          float nhw_p, unsigned sink, unsigned sv, unsigned nsv, float thr, const f32x2_t (&a2)[NC],
                                           const unsigned (&K0)[NC], const unsigned (&K1)[NC]) {
   if constexpr (NC == 3) {
     if constexpr (M == 1) {
-      if constexpr (OWN) asm volatile(R2_BODY3(R2_SLICE1, R2_CAND_VOTE_OWN) : "+r"(flags) : R2_IN3 : "memory");
-      else asm volatile(R2_BODY3(R2_SLICE1, R2_CAND_VOTE_INT) : "+r"(flags) : R2_IN3 : "memory");
+      if constexpr (OWN) asm volatile(R2_BODY3(R2_SLICE1, R2_V_OWN) : "+r"(flags) : R2_IN3 : "memory");
+      else asm volatile(R2_BODY3(R2_SLICE1, R2_V_INT) : "+r"(flags) : R2_IN3 : "memory");
     } else {
-      if constexpr (OWN) asm volatile(R2_BODY3(R2_SLICE2, R2_CAND_VOTE_OWN) : "+r"(flags) : R2_IN3 : "memory");
-      else asm volatile(R2_BODY3(R2_SLICE2, R2_CAND_VOTE_INT) : "+r"(flags) : R2_IN3 : "memory");
+      if constexpr (OWN) asm volatile(R2_BODY3(R2_SLICE2, R2_V_OWN) : "+r"(flags) : R2_IN3 : "memory");
+      else asm volatile(R2_BODY3(R2_SLICE2, R2_V_INT) : "+r"(flags) : R2_IN3 : "memory");
     }
   } else {
     if constexpr (M == 1) {
-      if constexpr (OWN) asm volatile(R2_BODY4(R2_SLICE1, R2_CAND_VOTE_OWN) : "+r"(flags) : R2_IN4 : "memory");
-      else asm volatile(R2_BODY4(R2_SLICE1, R2_CAND_VOTE_INT) : "+r"(flags) : R2_IN4 : "memory");
+      if constexpr (OWN) asm volatile(R2_BODY4(R2_SLICE1, R2_V_OWN) : "+r"(flags) : R2_IN4 : "memory");
+      else asm volatile(R2_BODY4(R2_SLICE1, R2_V_INT) : "+r"(flags) : R2_IN4 : "memory");
     } else {
-      if constexpr (OWN) asm volatile(R2_BODY4(R2_SLICE2, R2_CAND_VOTE_OWN) : "+r"(flags) : R2_IN4 : "memory");
-      else asm volatile(R2_BODY4(R2_SLICE2, R2_CAND_VOTE_INT) : "+r"(flags) : R2_IN4 : "memory");
+      if constexpr (OWN) asm volatile(R2_BODY4(R2_SLICE2, R2_V_OWN) : "+r"(flags) : R2_IN4 : "memory");
+      else asm volatile(R2_BODY4(R2_SLICE2, R2_V_INT) : "+r"(flags) : R2_IN4 : "memory");
     }
   }
 }
@@ -724,19 +748,26 @@ template <bool PASS, int NC, int M>
 __device__ __forceinline__ void ring_pass2(const PointCtx& c, const Tile& t, const float (&a4)[NC], int H, int Hin, int i0c, int sbase0,
                                            int slice_bytes, unsigned base, unsigned sink_abs) {
   const float nhw_p = -c.hw_p;
-  const float mstep = (float)t.Dp;
   const int ioff = Hin >= 0 ? Hin : 0x40000000;
   const unsigned ispan = Hin >= 0 ? 2u * (unsigned)Hin : 0u;
-  // PASS = false: Z-pass (lane axis B, candidates along C); true: Y-pass (lane axis C, candidates along B)
+  // PASS = false: Z-pass (lane axis B, candidates along C; the column is carried by the magic constants, which step by
+  // Dp), true: Y-pass (lane axis C, candidates along B; the column is carried by K0/K1, which step by 4 bytes).
   const float fu = PASS ? c.fz : c.fy, fv = PASS ? c.fy : c.fz;
   const float cp = f_add(fv, c.dbias_m05), cm = f_sub(c.dbias_m05, fv);
+  const float mstep = (float)t.Dp;
+  const f32x2_t mstep2 = pack2(mstep, -mstep), fu2 = pack2(fu, fu), one2 = pack2(1.0f, 1.0f);
+  const f32x2_t hW2 = pack2(c.hW, c.hW), cpm2 = pack2(cp, cm), sfv2 = pack2(-fv, fv);
   unsigned K0[NC], K1[NC], sv = 0;
+  f32x2_t a2[NC];
+#pragma unroll
+  for (int sidx = 0; sidx < NC; ++sidx) a2[sidx] = pack2(a4[sidx], a4[sidx]);
 #pragma unroll
   for (int sidx = 0; sidx < NC; ++sidx) ring2_consts(c, t, PASS, -H, base + (unsigned)(sbase0 + sidx * slice_bytes), 4u, K0[sidx], K1[sidx], sv);
   const unsigned nsv = 0u - sv;
   float mu0, mu1;
   ring2_magic(PASS, -H, t.Dp, mu0, mu1);
-  float uf = (float)(-H);
+  f32x2_t mu2 = pack2(mu0, mu1);
+  f32x2_t uf2 = pack2((float)(-H), (float)(-H));
   // Columns are walked in blocks of 32; a column with an undecided candidate only sets its bit, and the exact path runs
   // after the block for all flagged (lane, column) pairs at once: the hot loop has one branch (its back edge) and the
   // lanes of a warp that need the exact path in the same block take it together.
@@ -745,20 +776,19 @@ __device__ __forceinline__ void ring_pass2(const PointCtx& c, const Tile& t, con
     const int ue = min(ub0 + 31, H);
     unsigned flags = 0u, bit = 1u;
 #pragma unroll 1
-    for (int u = ub0; u <= ue; ++u, uf += 1.0f, bit <<= 1) {
-      const float duf = f_sub(uf, fu);
-      const float du2 = f_mul(duf, duf);
+    for (int u = ub0; u <= ue; ++u, bit <<= 1) {
+      const f32x2_t duf2 = sub2(uf2, fu2);           // (u - fu) in both halves; uf2 holds exact integers
       if (RCV_RING2_INTERIOR && (unsigned)(u + ioff) <= ispan)
-        ring2_asm<false, NC, M>(flags, bit, du2, mu0, mu1, c.hW, cp, cm, fv, c.hw_m, nhw_p, sink_abs, sv, nsv, 0.f, a4, K0, K1);
+        ring2_asm<false, NC, M>(flags, bit, duf2, mu2, hW2, cpm2, sfv2, c.hw_m, nhw_p, sink_abs, sv, nsv, 0.f, a2, K0, K1);
       else
-        ring2_asm<true, NC, M>(flags, bit, du2, mu0, mu1, c.hW, cp, cm, fv, c.hw_m, nhw_p, sink_abs, sv, nsv, ring2_thr(PASS, duf), a4, K0, K1);
+        ring2_asm<true, NC, M>(flags, bit, duf2, mu2, hW2, cpm2, sfv2, c.hw_m, nhw_p, sink_abs, sv, nsv, ring2_thr(PASS, lo2(duf2)), a2, K0, K1);
       if (PASS) {
 #pragma unroll
         for (int sidx = 0; sidx < NC; ++sidx) { K0[sidx] += 4u; K1[sidx] += 4u; }
       } else {
-        mu0 = f_add(mu0, mstep);
-        mu1 = f_sub(mu1, mstep);
+        mu2 = add2(mu2, mstep2);                     // (mu0 + Dp, mu1 - Dp): exact integers
       }
+      uf2 = add2(uf2, one2);
     }
     if (__builtin_expect(flags != 0u, 0)) {
       do {

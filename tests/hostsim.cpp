@@ -9,6 +9,9 @@
 
 using namespace rcv;
 
+static long long* g_cat = nullptr;
+extern "C" __attribute__((visibility("default"))) void hostsim_set_census(long long* p) { g_cat = p; }
+
 struct HostEmit {
   int32_t* tile; long words; long long votes = 0, calls = 0, oob = 0, slow_calls = 0;
   void operator()(int off) {
@@ -96,7 +99,7 @@ static void ring_chunks(PointCtx* c, const int* ia, const int* ib, const Tile& t
               HostSlowArcPerm slowarc{&slow, &emit_slow};
               const float fu = pass ? c[l].fz : c[l].fy, fv = pass ? c[l].fy : c[l].fz;
               const float cp = f_add(fv, c[l].dbias_m05), cm = f_sub(c[l].dbias_m05, fv);
-              const float duf = f_sub((float)u, fu), du2 = f_mul(duf, duf);
+              const float duf = f_sub((float)u, fu);
               const float thr = ring2_thr(pass != 0, duf);
               float mu0, mu1;
               ring2_magic(pass != 0, u, t.Dp, mu0, mu1);
@@ -106,13 +109,20 @@ static void ring_chunks(PointCtx* c, const int* ia, const int* ib, const Tile& t
               float arow[NC];
               for (int sidx = 0; sidx < NC; ++sidx) {
                 arow[sidx] = a4[l][sidx];
+                if (g_cat) {   // candidate census (analysis only)
+                  const float gg = f_fma(-duf, duf, arow[sidx]);
+                  const int ncand = 2 * mcand;
+                  if (!(arow[sidx] == arow[sidx])) g_cat[c[l].R > 0 ? 0 : 4] += ncand;      // slice not drawn by this lane (or padding lane)
+                  else if (!(gg >= 0.f)) g_cat[1] += ncand;                                    // column outside the ring
+                  else g_cat[2] += ncand;                                                      // live candidates
+                }
                 ring2_consts(c[l], t, pass != 0, u, (unsigned)((i0c + sidx - t.i0) * slice_words), 1u, K0[sidx], K1[sidx], sv);
                 if (mcand == 1) {
-                  if (interior) any |= ring2_fast<false, 1>(c[l], arow[sidx], du2, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
-                  else any |= ring2_fast<true, 1>(c[l], arow[sidx], du2, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
+                  if (interior) any |= ring2_fast<false, 1>(c[l], arow[sidx], duf, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
+                  else any |= ring2_fast<true, 1>(c[l], arow[sidx], duf, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
                 } else {
-                  if (interior) any |= ring2_fast<false, 2>(c[l], arow[sidx], du2, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
-                  else any |= ring2_fast<true, 2>(c[l], arow[sidx], du2, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
+                  if (interior) any |= ring2_fast<false, 2>(c[l], arow[sidx], duf, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
+                  else any |= ring2_fast<true, 2>(c[l], arow[sidx], duf, thr, cp, cm, fv, mu0, mu1, K0[sidx], K1[sidx], sv, 0xffffffffu, emit);
                 }
               }
               if (any)
