@@ -338,6 +338,20 @@ RCV_HD float ring2_thr(bool pass, float duf) {
   const unsigned b = (unsigned)f_bits(fabsf(duf)) - (pass ? 0u : 1u);
   return f_from_bits((int)(b < 0xBF800000u ? b : 0xBF800000u));
 }
+// Bias of the magic-number floor for one lane and one chunk, minus 0.5 (what point_setup() stores in dbias_m05 for the
+// general case).  The floor must not miss the topmost voxel under the outer circle, so the bias has to cover the error of
+// zs = sqrt(g): 2 ulp of the approximate square root and the two additions before the floor ((R + 2) 2^-20, as in
+// point_setup) plus |g_float - g_exact| / (2 zs) with |g_float - g_exact| <= eps / 2.  point_setup() assumes zs >= 2; an
+// OWNED candidate of a ring with outer radius^2 a has dv^2 >= du^2, hence g = a - du^2 >= a/2 - 1 and zs >= sqrt(amin/2 - 1)
+// for the smallest ring of the chunk (amin > 36).  A candidate with g < amin/2 - 1 has du^2 - dv^2 > 2: it and the voxel
+// above it belong to the other pass, so a miss there is harmless.  The smaller bias makes "candidate above the outer
+// circle" -- 90 % of the trips to the exact path -- about three times rarer.  (1.25 = margin on the eps/2 bound.)
+RCV_HD float ring2_dbias_m05(const PointCtx& c, float amin) {
+  const float zmin = f_sub(f_sqrt_fast(f_sub(f_mul(amin, 0.5f), 1.0f)), 0.1f);   // amin > 36: zmin > 4
+  const float rp2 = (float)(c.R + 2);
+  const float dbias = f_add(f_mul(c.eps, 0.3125f) / zmin, f_mul(rp2, 9.5367431640625e-07f));
+  return f_sub(dbias, 0.5f);
+}
 // Interior half-width of a lane: columns |u| <= Hin have du^2 < bmin/2 - 1 (|du| <= |u| + 0.5); -1 if there is none.
 RCV_HD int ring2_interior(float bmin) {
   const float h = f_sub(f_mul(bmin, 0.5f), 1.0f);

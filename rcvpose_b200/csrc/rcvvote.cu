@@ -745,7 +745,7 @@ __device__ __noinline__ void ring2_slow_call(double pa, double pb, double pc, in
 // Fast ring pass of one chunk for a warp whose candidates cannot leave the tile.  H = half-width (warp maximum),
 // Hin = interior half-width (warp minimum, -1 = none).
 template <bool PASS, int NC, int M>
-__device__ __forceinline__ void ring_pass2(const PointCtx& c, const Tile& t, const float (&a4)[NC], int H, int Hin, int i0c, int sbase0,
+__device__ __forceinline__ void ring_pass2(const PointCtx& c, const Tile& t, const float (&a4)[NC], int H, int Hin, float dbm, int i0c, int sbase0,
                                            int slice_bytes, unsigned base, unsigned sink_abs) {
   const float nhw_p = -c.hw_p;
   const int ioff = Hin >= 0 ? Hin : 0x40000000;
@@ -753,7 +753,7 @@ __device__ __forceinline__ void ring_pass2(const PointCtx& c, const Tile& t, con
   // PASS = false: Z-pass (lane axis B, candidates along C; the column is carried by the magic constants, which step by
   // Dp), true: Y-pass (lane axis C, candidates along B; the column is carried by K0/K1, which step by 4 bytes).
   const float fu = PASS ? c.fz : c.fy, fv = PASS ? c.fy : c.fz;
-  const float cp = f_add(fv, c.dbias_m05), cm = f_sub(c.dbias_m05, fv);
+  const float cp = f_add(fv, dbm), cm = f_sub(dbm, fv);
   const float mstep = (float)t.Dp;
   const f32x2_t mstep2 = pack2(mstep, -mstep), fu2 = pack2(fu, fu), one2 = pack2(1.0f, 1.0f);
   const f32x2_t hW2 = pack2(c.hW, c.hW), cpm2 = pack2(cp, cm), sfv2 = pack2(-fv, fv);
@@ -906,13 +906,14 @@ __device__ __forceinline__ void ring_chunk_work(const PointCtx& c, const Tile& t
       for (int sidx = 0; sidx < NC; ++sidx) amin = fminf(amin, a4[sidx]);   // fminf ignores the NaN of a non-thin slice
       const int hin_l = amin < 3.0e38f ? ring2_interior(f_sub(amin, c.W)) : 0x7fffffff;
       const int Hin = __reduce_min_sync(0xffffffffu, hin_l);
+      const float dbm = amin < 3.0e38f ? ring2_dbias_m05(c, amin) : c.dbias_m05;   // floor bias of this lane for this chunk
       const unsigned sink_abs = emit.base + (unsigned)emit.sink;
       if (warp_max_i32(mc) == 1) {   // one candidate per arc
-        ring_pass2<false, NC, 1>(c, t, a4, H, Hin, i0c, sbase0, slice_bytes, emit.base, sink_abs);
-        ring_pass2<true, NC, 1>(c, t, a4, H, Hin, i0c, sbase0, slice_bytes, emit.base, sink_abs);
+        ring_pass2<false, NC, 1>(c, t, a4, H, Hin, dbm, i0c, sbase0, slice_bytes, emit.base, sink_abs);
+        ring_pass2<true, NC, 1>(c, t, a4, H, Hin, dbm, i0c, sbase0, slice_bytes, emit.base, sink_abs);
       } else {                       // some ring of the chunk crosses a column in two voxels: two candidates per arc
-        ring_pass2<false, NC, 2>(c, t, a4, H, Hin, i0c, sbase0, slice_bytes, emit.base, sink_abs);
-        ring_pass2<true, NC, 2>(c, t, a4, H, Hin, i0c, sbase0, slice_bytes, emit.base, sink_abs);
+        ring_pass2<false, NC, 2>(c, t, a4, H, Hin, dbm, i0c, sbase0, slice_bytes, emit.base, sink_abs);
+        ring_pass2<true, NC, 2>(c, t, a4, H, Hin, dbm, i0c, sbase0, slice_bytes, emit.base, sink_abs);
       }
     } else {
       ring_pass<true, NC>(c, t, a4, H, i0c, sbase0, slice_bytes, emit, slowarc);

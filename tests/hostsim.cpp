@@ -86,10 +86,12 @@ static void ring_chunks(PointCtx* c, const int* ia, const int* ib, const Tile& t
       if (noclip) {
         // fast ring pass (ring2): interior columns skip the ownership test; Hin is the warp minimum
         int Hin = 1 << 30;
+        float dbm[32];
         for (int l = 0; l < 32; ++l) {
           float amin = 3.0e38f; bool any_l = false;
           for (int sidx = 0; sidx < NC; ++sidx) if (a4[l][sidx] == a4[l][sidx]) { any_l = true; if (a4[l][sidx] < amin) amin = a4[l][sidx]; }
           if (any_l) { const int h = ring2_interior(f_sub(amin, c[l].W)); if (h < Hin) Hin = h; }
+          dbm[l] = any_l ? ring2_dbias_m05(c[l], amin) : c[l].dbias_m05;
         }
         for (int pass = 0; pass < 2; ++pass)
           for (int u = -H; u <= H; ++u) {
@@ -98,7 +100,7 @@ static void ring_chunks(PointCtx* c, const int* ia, const int* ib, const Tile& t
               HostSlowPerm slow{&c[l], &emit};
               HostSlowArcPerm slowarc{&slow, &emit_slow};
               const float fu = pass ? c[l].fz : c[l].fy, fv = pass ? c[l].fy : c[l].fz;
-              const float cp = f_add(fv, c[l].dbias_m05), cm = f_sub(c[l].dbias_m05, fv);
+              const float cp = f_add(fv, dbm[l]), cm = f_sub(dbm[l], fv);
               const float duf = f_sub((float)u, fu);
               const float thr = ring2_thr(pass != 0, duf);
               float mu0, mu1;
