@@ -551,6 +551,85 @@ RCV_HD void polar_slow(float hw_m, int ti0, const PolarOut& o, int jb, int kc, i
   }
 }
 
+// ---- fast polar pass ("polar2"): the polar caps of a warp whose candidates cannot leave the tile ------------------
+// Same candidates as polar_fast() for ONE side of the pole at a time, reorganised like ring2: the address is
+// bits(tm) * smul + K, and "the candidate's slice is one of the lane's polar slices of this tile" is a range test on the
+// integer-valued float fl = n instead of a bit-mask test (the polar slices of one side are consecutive; the kernel
+// checks that and otherwise falls back to polar_fast()).  n counts slices away from the point's own slice: slice =
+// ipx + sgn * n.  Votes need n in [nlo, nhi]; the exact path is asked for when n is in [nlo, nhi + 1] (the candidate may
+// lie outside the outer sphere, then the voxel one step inwards, n - 1, can be a vote: polar_slow()) and the float
+// residual is not decisive.  g = R^2 - dB^2 - dC^2 is formed as fma(-dC, dC, R^2 - dB^2).
+struct Polar2Side {
+  float cx, sfx;          // +-fx + dbias - 0.5 and -+fx (d = n + sfx)
+  float nmidw, nhalfw;    // centre and half-width of the wide range [nlo, nhi + 1]; NaN centre = the lane has no slice here
+  float nhi;              // (float)nhi
+  int nlo, nhi_i, sgn;
+};
+// mask = polar slices of the lane on this side (bit v = slice t.i0 + v).  Returns false if the set bits are not consecutive.
+RCV_HD bool polar2_side(const PointCtx& c, const Tile& t, unsigned mask, bool plus, Polar2Side& s) {
+  s.sgn = plus ? 1 : -1;
+  s.cx = plus ? f_add(c.fx, c.dbias_m05) : f_sub(c.dbias_m05, c.fx);
+  s.sfx = plus ? -c.fx : c.fx;
+  if (mask == 0u) {
+    s.nlo = 1; s.nhi_i = 0; s.nhi = 0.f; s.nmidw = f_from_bits(0x7fc00000); s.nhalfw = 0.f;
+    return true;
+  }
+#if defined(__CUDA_ARCH__)
+  const int vlo = __ffs((int)mask) - 1, vhi = 31 - __clz((int)mask);
+#else
+  int vlo = 0, vhi = 31;
+  while (!((mask >> vlo) & 1u)) ++vlo;
+  while (!((mask >> vhi) & 1u)) --vhi;
+#endif
+  const unsigned full = (vhi - vlo == 31) ? 0xffffffffu : (((1u << (vhi - vlo + 1)) - 1u) << vlo);
+  const int vrel0 = c.ipx - t.i0;
+  s.nlo = plus ? vlo - vrel0 : vrel0 - vhi;
+  s.nhi_i = plus ? vhi - vrel0 : vrel0 - vlo;
+  s.nhi = (float)s.nhi_i;
+  s.nmidw = f_mul((float)(s.nlo + s.nhi_i + 1), 0.5f);
+  s.nhalfw = f_mul((float)(s.nhi_i + 1 - s.nlo), 0.5f);
+  return mask == full;
+}
+struct Polar2Cell {
+  float q, fl;
+  unsigned bits;
+  bool wide, sure, vote, amb;
+};
+// One cell (lattice column offset ucf from the point's nearest lattice point along C), r2mdb2 = R^2 - dB^2 of its row.
+RCV_HD void polar2_cell(const PointCtx& c, const Polar2Side& s, float ucf, float r2mdb2, Polar2Cell& o) {
+  const float dc = f_sub(ucf, c.fz);
+  const float g = f_fma(-dc, dc, r2mdb2);
+  const float zs = f_sqrt_fast(g);          // NaN outside the sphere's shadow: no vote, no exact path
+  const float hWg = f_sub(c.hW, g);
+  const float tm = f_add(f_add(zs, s.cx), RCV_MAGIC);
+  o.bits = (unsigned)f_bits(tm);
+  o.fl = f_sub(tm, RCV_MAGIC);
+  const float d = f_add(o.fl, s.sfx);
+  o.q = f_fma(d, d, hWg);
+  const float r = f_sub(o.fl, s.nmidw);
+  o.wide = fabsf(r) <= s.nhalfw;
+  o.sure = o.wide && (fabsf(o.q) < c.hw_m);
+  o.vote = o.sure && (o.fl <= s.nhi);
+  const bool lo = o.wide && (o.q > -c.hw_p);
+  o.amb = lo != o.sure;
+}
+// Exact decisions for one flagged cell: (jb, kc) = its lattice coordinates, K = its address constant (address of
+// slice n = bits * smul + K with smul = sgn * slice stride).  slow(iA, iB, iC) is the exact predicate.
+template <class Slow, class EmitSlow>
+RCV_HD void polar2_slow_cell(const PointCtx& c, const Polar2Side& s, float ucf, float r2mdb2, int jb, int kc, unsigned smul, unsigned K, Slow& slow,
+                             EmitSlow& emit_slow) {
+  Polar2Cell o;
+  polar2_cell(c, s, ucf, r2mdb2, o);
+  if (!o.amb) return;
+  const int n = (int)o.fl;
+  const unsigned addr = o.bits * smul + K;
+  if (n >= s.nlo && n <= s.nhi_i && slow(c.ipx + s.sgn * n, jb, kc)) emit_slow((int)addr);
+  if (o.q >= c.hw_m) {   // the candidate may lie outside the outer sphere: the voxel one step inwards can then be inside
+    const int n2 = n - 1;
+    if (n2 >= s.nlo && n2 <= s.nhi_i && slow(c.ipx + s.sgn * n2, jb, kc)) emit_slow((int)(addr - smul));
+  }
+}
+
 // Half-width (in rows) of the polar pass for a lane whose largest non-thin ring has outer radius^2 amax.
 RCV_HD int polar_half_width(float amax, float eps) { return (int)f_add(f_sqrt_fast(fmaxf(f_add(amax, f_add(eps, eps)), 0.f)), 0.6f); }
 

@@ -864,6 +864,100 @@ __device__ __forceinline__ void polar_pass(const PointCtx& c, const Tile& t, int
   }
 }
 
+// ---- fast polar pass (raster_core.h "polar2"): one PTX block per PAIR of adjacent cells of a row, one side of the pole --
+// Operands: %0 flags (in/out) | pairs: %1 (uc, uc+1) %2 (fz, fz) %3 (R^2 - dB^2) x2 %4 (hW, hW) %5 (cx, cx) %6 (sfx, sfx)
+// %7 (nmidw, nmidw) | %8 nhalfw %9 nhi %10 hw_m %11 -hw_p %12 sink %13 smul %14 K (cell uc) %15 bit.
+#define P2_CELL(R, Q, F, B, OFS, ACC) \
+  "abs.f32 ar, " R ";\n\tsetp.le.f32 pw, ar, %8;\n\tabs.f32 aq, " Q ";\n\tsetp.lt.and.f32 ps, aq, %10, pw;\n\tsetp.le.and.f32 pv, " F ", %9, ps;\n\t" \
+  "setp.gt.and.f32 pl, " Q ", %11, pw;\n\t" ACC "mad.lo.u32 adu, " B ", %13, %14;\n\t" OFS "selp.u32 adr, adu, %12, pv;\n\tred.shared.add.u32 [adr], 1;\n\t"
+#define P2_BODY \
+  "{\n\t.reg .pred pw, ps, pv, pl, pa;\n\t.reg .f32 glo, ghi, z0, z1, q0, q1, f0, f1, r0, r1, aq, ar;\n\t.reg .b32 b0, b1, adu, adr;\n\t" \
+  ".reg .b64 dc2, nd2, g2, zs2, hwg2, t2, tm2, fl2, d2, q2, rr2, mg, z2;\n\t" \
+  "mov.b64 mg, 0x4B4000004B400000;\n\tmov.b64 z2, 0;\n\tsub.rn.f32x2 dc2, %1, %2;\n\tsub.rn.f32x2 nd2, z2, dc2;\n\tfma.rn.f32x2 g2, nd2, dc2, %3;\n\t" \
+  "mov.b64 {glo, ghi}, g2;\n\tsqrt.approx.ftz.f32 z0, glo;\n\tsqrt.approx.ftz.f32 z1, ghi;\n\tmov.b64 zs2, {z0, z1};\n\tsub.rn.f32x2 hwg2, %4, g2;\n\t" \
+  "add.rn.f32x2 t2, zs2, %5;\n\tadd.rn.f32x2 tm2, t2, mg;\n\tsub.rn.f32x2 fl2, tm2, mg;\n\tadd.rn.f32x2 d2, fl2, %6;\n\tfma.rn.f32x2 q2, d2, d2, hwg2;\n\t" \
+  "sub.rn.f32x2 rr2, fl2, %7;\n\tmov.b64 {q0, q1}, q2;\n\tmov.b64 {f0, f1}, fl2;\n\tmov.b64 {r0, r1}, rr2;\n\tmov.b64 {b0, b1}, tm2;\n\t" \
+  P2_CELL("r0", "q0", "f0", "b0", "", "xor.pred pa, pl, ps;\n\t") \
+  P2_CELL("r1", "q1", "f1", "b1", "add.u32 adu, adu, 4;\n\t", "xor.pred pl, pl, ps;\n\tor.pred pa, pa, pl;\n\t") "@pa or.b32 %0, %0, %15;\n\t}"
+
+// The rare branch of the fast polar pass: exact decisions for the two cells of a flagged pair (one lane, out of line).
+__device__ __noinline__ void polar2_slow_call(double pa, double pb, double pc, int R, int ipx, int jb, int kc0, int nlo, int nhi, int sgn, float fz,
+                                              float hW, float hw_m, float hw_p, float cx, float sfx, float ucf0, float r2m, unsigned smul, unsigned K) {
+  PointCtx c;
+  c.px = pa; c.py = pb; c.pz = pc; c.R = R; c.ipx = ipx; c.fz = fz; c.hW = hW; c.hw_m = hw_m; c.hw_p = hw_p;
+  Polar2Side S;
+  S.cx = cx; S.sfx = sfx; S.nlo = nlo; S.nhi_i = nhi; S.sgn = sgn; S.nhi = (float)nhi;
+  S.nmidw = f_mul((float)(nlo + nhi + 1), 0.5f);
+  S.nhalfw = f_mul((float)(nhi + 1 - nlo), 0.5f);
+  SlowExactCall slow{pa, pb, pc, R};
+  SmemEmit es{0u, 0};   // addresses are absolute
+  polar2_slow_cell(c, S, ucf0, r2m, jb, kc0, smul, K, slow, es);
+  polar2_slow_cell(c, S, f_add(ucf0, 1.0f), r2m, jb, kc0 + 1, smul, K + 4u, slow, es);
+}
+
+// Fast polar pass of a warp that cannot leave the tile, both sides of the pole through ONE copy of the loops.
+// Rows ub = -Hp..Hp around each lane's own point; in a row every lane walks the two column segments of ITS annulus,
+// [..,-ci] and [max(ci,1),..], in pairs of cells; the trip count is the warp maximum and surplus cells lie OUTWARDS of the
+// annulus, where the candidate's slice is never one of the lane's polar slices (so no per-cell validity test is needed).
+__device__ __forceinline__ void polar_pass2(const PointCtx& c, const Tile& t, int Hp, float s_lo, float s_hi, bool lane_on, const Polar2Side& Sp,
+                                            const Polar2Side& Sm, bool anyp, bool anym, int slice_bytes, unsigned base, unsigned sink_abs) {
+  const f32x2_t hW2 = pack2(c.hW, c.hW), fz2 = pack2(c.fz, c.fz), two2 = pack2(2.0f, 2.0f);
+  const float nhw_p = -c.hw_p;
+  const unsigned MB = (unsigned)RCV_MAGIC_BITS, vrel0 = (unsigned)(c.ipx - t.i0);
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {
+    if (side == 0 ? !anyp : !anym) continue;
+    const Polar2Side& S = side == 0 ? Sp : Sm;
+    const float cx = side == 0 ? Sp.cx : Sm.cx, sfx = side == 0 ? Sp.sfx : Sm.sfx, nmidw = side == 0 ? Sp.nmidw : Sm.nmidw;
+    const float nhalfw = side == 0 ? Sp.nhalfw : Sm.nhalfw, nhi = side == 0 ? Sp.nhi : Sm.nhi;
+    const int nlo_i = side == 0 ? Sp.nlo : Sm.nlo, nhi_i = side == 0 ? Sp.nhi_i : Sm.nhi_i;
+    const f32x2_t cx2 = pack2(cx, cx), sfx2 = pack2(sfx, sfx), nmidw2 = pack2(nmidw, nmidw);
+    const unsigned smul = side == 0 ? (unsigned)slice_bytes : 0u - (unsigned)slice_bytes;
+    const unsigned Kside = base + (side == 0 ? vrel0 - MB : vrel0 + MB) * (unsigned)slice_bytes;
+    (void)S;
+    float ubf = (float)(-Hp);
+#pragma unroll 1
+    for (int ub = -Hp; ub <= Hp; ++ub, ubf += 1.0f) {
+      const float db = f_sub(ubf, c.fy);
+      const float db2 = f_mul(db, db);
+      int ci, co;
+      polar_row_range(s_lo, s_hi, c.eps, db2, lane_on, ci, co);
+      const int c1 = ci > 1 ? ci : 1;
+      const int T0 = warp_max_i32(co >= 0 ? co - ci + 1 : 0), T1 = warp_max_i32(co >= 0 ? co - c1 + 1 : 0);
+      if (T0 <= 0) continue;
+      const float r2m = f_sub(c.R2, db2);
+      const f32x2_t r2m2 = pack2(r2m, r2m);
+      const int jb = c.ipy + ub;
+      const unsigned rowK = Kside + (unsigned)((jb - t.j0) * t.Dp) * 4u;
+#pragma unroll 1
+      for (int seg = 0; seg < 2; ++seg) {
+        const int np = ((seg ? T1 : T0) + 1) >> 1;
+        if (np <= 0) continue;
+        const int start = seg == 0 ? (co >= 0 ? -ci : -1) - 2 * np + 1 : (co >= 0 ? c1 : 1);
+        unsigned K = rowK + (unsigned)(c.ipz + start) * 4u;
+        f32x2_t uc2 = pack2((float)start, (float)(start + 1));
+        unsigned flags = 0u, bit = 1u;
+#pragma unroll 1
+        for (int p = 0; p < np; ++p, bit <<= 1, K += 8u) {
+          asm volatile(P2_BODY : "+r"(flags) : "l"(uc2), "l"(fz2), "l"(r2m2), "l"(hW2), "l"(cx2), "l"(sfx2), "l"(nmidw2), "f"(nhalfw), "f"(nhi),
+                       "f"(c.hw_m), "f"(nhw_p), "r"(sink_abs), "r"(smul), "r"(K), "r"(bit) : "memory");
+          uc2 = add2(uc2, two2);
+        }
+        if (__builtin_expect(flags != 0u, 0)) {
+          do {
+            const int j = __ffs((int)flags) - 1;
+            flags &= flags - 1u;
+            const int uc = start + 2 * j;
+            polar2_slow_call(c.px, c.py, c.pz, c.R, c.ipx, jb, c.ipz + uc, nlo_i, nhi_i, side == 0 ? 1 : -1, c.fz, c.hW, c.hw_m, c.hw_p, cx, sfx,
+                             (float)uc, r2m, smul, K - 8u * (unsigned)(np - j));
+          } while (flags);
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 // Ring work of one warp for ONE chunk of NC slices of the slab (chunks tile the slab from its first slice): thin rings
 // by the two ring passes, spheres too small for the polar pass by a dense scan.
 template <int NC>
@@ -996,9 +1090,12 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
         const int Hp = warp_max_i32((mplus | mminus) ? polar_half_width(s_hi, c.eps) : -1);
         if (Hp >= 0) {
           const bool anyp = __any_sync(0xffffffffu, mplus != 0u), anym = __any_sync(0xffffffffu, mminus != 0u);
-          if (anyp && anym) polar_pass<3>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);
-          else if (anyp) polar_pass<1>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);
-          else polar_pass<2>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);
+          Polar2Side Sp, Sm;
+          const bool cont = polar2_side(c, t, mplus, true, Sp) & polar2_side(c, t, mminus, false, Sm);   // consecutive slices on each side
+          if (noclip && __all_sync(0xffffffffu, cont))
+            polar_pass2(c, t, Hp, s_lo, s_hi, (mplus | mminus) != 0u, Sp, Sm, anyp, anym, slice_bytes, emit.base, emit.base + (unsigned)emit.sink);
+          else
+            polar_pass<3>(c, t, Hp, s_lo, s_hi, mplus, mminus, slice_bytes, emit);   // clipped warps: the general polar pass
         }
       } else {
         const int i0c = t.i0 + (phase - 1) * NC;

@@ -178,13 +178,62 @@ int hostsim_render_v6(const double* p, const int* R, long n, int D, int Dp, int 
     if (wa > wb) continue;
     if (ring_chunk(ni) == 3) ring_chunks<3>(c, ia, ib, t, wa, wb, mplus, mminus, smax, slo, emit, emit_slow, counters);
     else ring_chunks<4>(c, ia, ib, t, wa, wb, mplus, mminus, smax, slo, emit, emit_slow, counters);
-    // polar pass over the tile's non-thin slices
+    // polar pass over the tile's polar slices
     int Hp = -1; bool anyp = false, anym = false;
     for (int l = 0; l < 32; ++l) {
       if (mplus[l] | mminus[l]) { const int h = polar_half_width(smax[l], c[l].eps); if (h > Hp) Hp = h; }
       anyp |= mplus[l] != 0u; anym |= mminus[l] != 0u;
     }
-    if (Hp >= 0) {
+    bool p2 = true;   // fast polar pass: nobody can leave the tile and everybody's polar slices are consecutive
+    Polar2Side sp[32], sm[32];
+    for (int l = 0; l < 32; ++l) {
+      p2 = p2 && ring_noclip(c[l], t);
+      p2 = polar2_side(c[l], t, mplus[l], true, sp[l]) && p2;
+      p2 = polar2_side(c[l], t, mminus[l], false, sm[l]) && p2;
+    }
+    if (Hp >= 0 && p2) {
+      const unsigned MB = (unsigned)RCV_MAGIC_BITS;
+      for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? !anyp : !anym) continue;
+        for (int ub = -Hp; ub <= Hp; ++ub) {
+          float r2m[32]; int ci_l[32], co_l[32], T[2] = {0, 0};
+          for (int l = 0; l < 32; ++l) {
+            const float db = f_sub((float)ub, c[l].fy);
+            const float db2 = f_mul(db, db);
+            r2m[l] = f_sub(c[l].R2, db2);
+            polar_row_range(slo[l], smax[l], c[l].eps, db2, (mplus[l] | mminus[l]) != 0u, ci_l[l], co_l[l]);
+            if (co_l[l] >= 0) {
+              const int c1 = ci_l[l] > 1 ? ci_l[l] : 1;
+              if (co_l[l] - ci_l[l] + 1 > T[0]) T[0] = co_l[l] - ci_l[l] + 1;
+              if (co_l[l] - c1 + 1 > T[1]) T[1] = co_l[l] - c1 + 1;
+            }
+          }
+          if (T[0] <= 0) continue;
+          for (int seg = 0; seg < 2; ++seg) {
+            const int ncell = 2 * ((T[seg] + 1) / 2);      // the device walks pairs of cells
+            if (ncell <= 0) continue;
+            for (int tt = 0; tt < ncell; ++tt)
+              for (int l = 0; l < 32; ++l) {
+                HostSlowPerm slow{&c[l], &emit};
+                const Polar2Side& S = side == 0 ? sp[l] : sm[l];
+                // segments end (seg 0) or start (seg 1) at the lane's own inner bound; surplus cells lie outwards
+                const int start = seg == 0 ? (co_l[l] >= 0 ? -ci_l[l] : -1) - ncell + 1 : (co_l[l] >= 0 ? (ci_l[l] > 1 ? ci_l[l] : 1) : 1);
+                const int uc = start + tt;
+                const int jb = c[l].ipy + ub, kc = c[l].ipz + uc;
+                const unsigned cellbase = (unsigned)((jb - j0) * Dp + kc);
+                const unsigned vrel0 = (unsigned)(c[l].ipx - t.i0);
+                const unsigned smul = side == 0 ? (unsigned)slice_words : 0u - (unsigned)slice_words;
+                const unsigned K = cellbase + (side == 0 ? (vrel0 - MB) : (vrel0 + MB)) * (unsigned)slice_words;
+                Polar2Cell o;
+                ++polar_cells;
+                polar2_cell(c[l], S, (float)uc, r2m[l], o);
+                emit(o.vote ? (int)(o.bits * smul + K) : -1);
+                if (o.amb) polar2_slow_cell(c[l], S, (float)uc, r2m[l], jb, kc, smul, K, slow, emit_slow);
+              }
+          }
+        }
+      }
+    } else if (Hp >= 0) {
       for (int ub = -Hp; ub <= Hp; ++ub) {
         float db2[32]; int CI = 0x7fffffff, CO = -1, ci_l[32], co_l[32];
         for (int l = 0; l < 32; ++l) {
