@@ -138,6 +138,58 @@ def test_large_grid_uses_row_tiles(acc):
     assert np.array_equal(acc.Accumulator_3D(xyz, rl, acc_unit=1.25), want)
 
 
+def test_ycb_shaped_frame_both_grid_policies():
+    """BASELINE configs[3]: YCB-Video geometry (camera, uint16 depth with factor_depth 10000, metres), a large object so that
+    N ~ 24 k points, R up to ~100 voxels (outliers), D ~ 235: the frames entry point against the oracle fed the same maps, LM grid policy
+    (what estimate_6d_pose_ycb calls, AccumulatorSpace.py:1067) and the YCBGEN policy (3DRadius_ycb.py:113-141, metre radii)."""
+    from rcvpose_b200 import api
+    K = synth.ycb_K
+    centre = np.array([40.0, -25.0, 820.0])
+    depth_mm = synth.sphere_depth(K, centre, 95.0)                        # uint16 millimetres
+    kpt_mm = centre + np.array([170.0, 110.0, -130.0])
+    rng = np.random.default_rng(77)
+    radius_dm = synth.radius_map_dm(K, depth_mm, kpt_mm, rng, sigma_dm=0.01, outlier_frac=0.01, max_radius_dm=5.0)
+    vv, uu = np.indices(radius_dm.shape)
+    radius_dm[(vv + uu) % 2 == 1] = 0.0                                   # checkerboard mask: keeps the oracle's run time in seconds
+    depth_raw = (depth_mm.astype(np.uint32) * 10).astype(np.uint16)          # factor_depth = 10000 -> metres
+    ctx = api.VoteContext(0, max_items=2, max_points_total=1 << 17, max_grid=320)
+    Kd = torch.from_numpy(K).cuda()
+    d_t = torch.from_numpy(depth_raw.view(np.int16))[None].cuda()
+    for policy, scale, rmap in ((api.RCV_POLICY_LM, 100.0, radius_dm), (api.RCV_POLICY_YCBGEN, 1000.0, (radius_dm / 10).astype(np.float32))):
+        out = ctx.vote_frames(d_t, torch.from_numpy(rmap)[None, None].cuda(), Kd, mask_flags=api.RCV_MASK_RADIUS_NONZERO, depth_div=10000.0,
+                              xyz_div=1.0, radius_scale=scale, policy=policy)
+        torch.cuda.synchronize()
+        m = (rmap != 0) & (depth_raw != 0)
+        xyz = oracle.rgbd_to_point_cloud(K, np.where(m, depth_raw / 10000.0, 0.0))
+        rl = rmap[np.nonzero(np.where(m, depth_raw, 0))]
+        want, info = oracle.Accumulator_3D(xyz, rl, radius_scale=scale, policy=policy, method="scatter", return_info=True)
+        assert int(out["status"][0, 0]) == 0
+        assert int(out["n_points"][0, 0]) == xyz.shape[0] and xyz.shape[0] > 20000
+        assert int(out["grid"][0, 0]) == info["D"] and info["D"] > 120
+        assert int(out["votes"][0, 0]) == info["votes"]
+        assert int(out["peak"][0, 0]) == info["peak"]
+        assert np.array_equal(out["centre_mm"][0, 0].cpu().numpy(), want[0])
+
+
+def test_fine_voxel_stress_grid_512(acc):
+    """BASELINE configs[4]: accumulator resolution sweep up to a ~512^3 grid (acc_unit 1.2 mm): a slice no longer fits one CTA's
+    shared memory, tiles are single slices x row bands and the volume lives in HBM only for this parity dump."""
+    rng = np.random.default_rng(11)
+    n = 400
+    xyz = rng.normal(0, 0.02, size=(n, 3)) + np.array([0.05, -0.02, 0.85])
+    kp = xyz.mean(0) + np.array([0.11, 0.06, -0.09])
+    rl = (np.linalg.norm(xyz - kp, axis=1) * 10 + rng.normal(0, 0.005, n)).astype(np.float32)
+    for unit in (2.5, 1.2):
+        want, info = oracle.Accumulator_3D(xyz, rl, acc_unit=unit, method="scatter", return_info=True, return_volume=True)
+        got, ginfo = acc.Accumulator_3D(xyz, rl, acc_unit=unit, return_info=True)
+        assert ginfo["D"] == info["D"] and ginfo["votes"] == info["votes"] and ginfo["peak"] == info["peak"]
+        assert np.array_equal(got, want)
+        if unit == 1.2:
+            assert 440 < info["D"] <= 640
+            vol, out = acc.vote_volume(xyz, rl, acc_unit=unit)
+            assert np.array_equal(vol, info["volume"])
+
+
 def test_empty_and_degenerate_inputs(acc, ctx):
     with pytest.raises(ValueError):
         acc.Accumulator_3D(np.zeros((0, 3)), np.zeros((0,), np.float32))
