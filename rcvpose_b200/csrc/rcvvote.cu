@@ -1,7 +1,7 @@
 // rcvvote.cu -- CUDA kernels (sm_100a) and the C ABI of librcvvote.so.
 //
 // Pipeline for one call (all on the caller's stream, no host round trip):
-//   K1  k_frame_count / k_frame_compact : mask rule + depth back-projection + stable stream compaction
+//   K1  k_frame_mask / k_frame_emit / k_points_from_pixels : mask rule + stable stream compaction + depth back-projection
 //                                         (AccumulatorSpace.py:603-619, 77-85)      [frames API]
 //       k_points_to_voxel               : (N,3) metres -> voxel units               [points API]
 //   P   k_prelude   : numpy-pairwise means, recentre, zero boundary, grid side D, tile work list
@@ -221,74 +221,104 @@ __device__ __forceinline__ unsigned pixel_group_mask(const FrameArgs& a, long lo
   return mask;
 }
 
-// WRITE=false: count survivors into cnt[item].  WRITE=true: emit them in row-major pixel order.
-template <bool WRITE>
-__global__ void __launch_bounds__(kCompactThreads) k_frame_compact(FrameArgs a, int* __restrict__ cnt, const ItemMeta* __restrict__ meta,
-                                                                  Pool pool) {
+// ---- K1, streaming form: mask bits -> scan -> pixel indices -> dense conversion ----------------------------------
+// The first version (one kernel run twice: count, then re-read + convert inside the divergent compaction loop) read every
+// map twice and its write pass ran at 0.95 TB/s.  Here the maps are streamed ONCE (k_frame_mask: 128-bit loads, one survival bit per
+// pixel, no block-wide scan), the row-major compaction works on the bit masks only (k_frame_emit: 1/48 of the bytes)
+// and the float64 back-projection runs with one thread per surviving pixel, all lanes busy (k_points_from_pixels).
+__global__ void __launch_bounds__(kCompactThreads) k_frame_mask(FrameArgs a, int* __restrict__ cnt, unsigned* __restrict__ bits, int words_per_item) {
   const int item = blockIdx.x;
   const int frame = item / a.n_kpts, kp = item % a.n_kpts;
-  const int W = a.fp.width, npx = a.fp.height * a.fp.width;
+  const int npx = a.fp.height * a.fp.width;
   const long long frame_px0 = (long long)frame * npx, item_px0 = (long long)item * npx;
   const double max_r = a.max_radii ? a.max_radii[(long long)frame * a.fp.max_radii_stride + kp] : 0.0;
   const bool vec_ok = a.vec_ok != 0;
-  __shared__ int s_warp[kCompactThreads / 32];
-  __shared__ int s_base;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  long long out0 = 0;
-  int n_item = 0;
-  double fx = 1, fy = 1, cx = 0, cy = 0;
-  if (WRITE) {
-    const ItemMeta m = meta[item];
-    out0 = m.off;
-    n_item = m.n;
-    if (n_item == 0) return;  // empty or overflowed item: nothing to write
-    const double* Kp = a.K + (long long)frame * a.fp.k_stride;
-    fx = Kp[0]; cx = Kp[2]; fy = Kp[4]; cy = Kp[5];
-  }
-  if (threadIdx.x == 0) s_base = 0;
-  __syncthreads();
-  for (int it0 = 0; it0 < npx; it0 += kPxPerIter) {
-    const int px = it0 + threadIdx.x * kPxPerThread;
+  unsigned* out = bits + (long long)item * words_per_item;
+  const int lane = threadIdx.x & 31;
+  int n = 0;
+  // a warp covers 256 consecutive pixels per step (lane = one group of 8): lanes 4k..4k+3 make up one 32-bit word
+  for (int px = threadIdx.x * kPxPerThread; px < words_per_item * 32; px += kPxPerIter) {
     double zraw[kPxPerThread];
     float rad[kPxPerThread];
-    unsigned mask = 0;
-    if (px < npx) mask = pixel_group_mask(a, frame_px0, item_px0, px, npx, vec_ok, max_r, zraw, rad);
-    const int c = __popc(mask);
-    // block-wide exclusive scan of c (warp shuffle scan + warp totals)
+    unsigned m = 0;
+    if (px < npx) m = pixel_group_mask(a, frame_px0, item_px0, px, npx, vec_ok, max_r, zraw, rad);
+    n += __popc(m);
+    unsigned w = m << ((lane & 3) * 8);
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    if ((lane & 3) == 0) out[px >> 5] = w;
+  }
+  __shared__ int s_n[kCompactThreads / 32];
+  n = __reduce_add_sync(0xffffffffu, n);
+  if (lane == 0) s_n[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kCompactThreads / 32; ++w) t += s_n[w];
+    cnt[item] = t;
+  }
+}
+
+// Survivors' pixel indices in row-major order: pix[off .. off + n) for every item (pix aliases the pool's perm array).
+__global__ void __launch_bounds__(kCompactThreads) k_frame_emit(const unsigned* __restrict__ bits, int words_per_item, const ItemMeta* __restrict__ meta,
+                                                               int* __restrict__ pix) {
+  const int item = blockIdx.x;
+  const ItemMeta m = meta[item];
+  if (m.n == 0) return;   // empty or overflowed item
+  const unsigned* in = bits + (long long)item * words_per_item;
+  int* out = pix + m.off;
+  __shared__ int s_warp[kCompactThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int base = 0;
+  for (int w0 = 0; w0 < words_per_item; w0 += kCompactThreads) {
+    const int wi = w0 + threadIdx.x;
+    unsigned w = wi < words_per_item ? in[wi] : 0u;
+    const int c = __popc(w);
     int incl = c;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     int wbase = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < kCompactThreads / 32; ++w) { const int t = s_warp[w]; if (w < warp) wbase += t; total += t; }
-    const int base = s_base;
-    if (WRITE && c) {
-      long long o = out0 + base + wbase + incl - c;
-#pragma unroll
-      for (int q = 0; q < kPxPerThread; ++q) {
-        if (!(mask >> q & 1)) continue;
-        const int p = px + q, u = p % W, v = p / W;
-        // rgbd_to_point_cloud (AccumulatorSpace.py:77-85) then xyz_mm/1000 (:619) then *1000/acc_unit (:376)
-        const double z = __ddiv_rn(zraw[q], a.fp.depth_div);
-        double x = __ddiv_rn(__dmul_rn(__dsub_rn((double)u, cx), z), fx);
-        double y = __ddiv_rn(__dmul_rn(__dsub_rn((double)v, cy), z), fy);
-        pool.X[o] = __ddiv_rn(__dmul_rn(__ddiv_rn(x, a.fp.xyz_div), 1000.0), a.acc_unit);
-        pool.Y[o] = __ddiv_rn(__dmul_rn(__ddiv_rn(y, a.fp.xyz_div), 1000.0), a.acc_unit);
-        pool.Z[o] = __ddiv_rn(__dmul_rn(__ddiv_rn(z, a.fp.xyz_div), 1000.0), a.acc_unit);
-        double rd; int ri;
-        radius_to_voxel_f32(rad[q], (float)a.radius_scale, (float)a.acc_unit, rd, ri);
-        pool.Rd[o] = rd;
-        pool.Ri[o] = ri;
-        ++o;
-      }
+    for (int q = 0; q < kCompactThreads / 32; ++q) { const int t = s_warp[q]; if (q < warp) wbase += t; total += t; }
+    int o = base + wbase + incl - c;
+    while (w) {
+      const int b = __ffs((int)w) - 1;
+      w &= w - 1u;
+      out[o++] = wi * 32 + b;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) s_base = base + total;
+    base += total;
     __syncthreads();
   }
-  if (!WRITE && threadIdx.x == 0) cnt[item] = s_base;
+}
+
+// rgbd_to_point_cloud (AccumulatorSpace.py:77-85), xyz_mm/1000 (:619), *1000/acc_unit (:376) and the radius in voxels
+// (:388, :332) for the surviving pixels, one thread per point; reads pix[] (= pool.perm) and writes the pool.
+__global__ void __launch_bounds__(256) k_points_from_pixels(FrameArgs a, const ItemMeta* __restrict__ meta, Pool pool) {
+  const int item = blockIdx.x;
+  const ItemMeta m = meta[item];
+  if (m.n == 0) return;
+  const int frame = item / a.n_kpts;
+  const int W = a.fp.width, npx = a.fp.height * a.fp.width;
+  const long long frame_px0 = (long long)frame * npx, item_px0 = (long long)item * npx;
+  const double* Kp = a.K + (long long)frame * a.fp.k_stride;
+  const double fx = Kp[0], cx = Kp[2], fy = Kp[4], cy = Kp[5];
+  for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < m.n; q += gridDim.y * blockDim.x) {
+    const long long o = m.off + q;
+    const int p = pool.perm[o];
+    const int u = p % W, v = p / W;
+    const double z = __ddiv_rn(load_depth(a.depth, a.fp.depth_dtype, frame_px0 + p), a.fp.depth_div);
+    const double x = __ddiv_rn(__dmul_rn(__dsub_rn((double)u, cx), z), fx);
+    const double y = __ddiv_rn(__dmul_rn(__dsub_rn((double)v, cy), z), fy);
+    pool.X[o] = __ddiv_rn(__dmul_rn(__ddiv_rn(x, a.fp.xyz_div), 1000.0), a.acc_unit);
+    pool.Y[o] = __ddiv_rn(__dmul_rn(__ddiv_rn(y, a.fp.xyz_div), 1000.0), a.acc_unit);
+    pool.Z[o] = __ddiv_rn(__dmul_rn(__ddiv_rn(z, a.fp.xyz_div), 1000.0), a.acc_unit);
+    double rd; int ri;
+    radius_to_voxel_f32(a.radius[item_px0 + p], (float)a.radius_scale, (float)a.acc_unit, rd, ri);
+    pool.Rd[o] = rd;
+    pool.Ri[o] = ri;
+  }
 }
 
 // Exclusive scan of per-item counts into pool offsets (one block; n_items <= a few 10^4).
@@ -702,8 +732,7 @@ typedef unsigned long long f32x2_t;   // two floats in an aligned register pair:
 __device__ __forceinline__ f32x2_t pack2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ float lo2(f32x2_t a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return lo; }
+__device__ __forceinline__ float lo2(f32x2_t a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); (void)hi; return lo; }
 
 // Adds `bit` to `flags` if a candidate of the column needs the exact path.
 template <bool OWN, int NC, int M>
@@ -1334,6 +1363,7 @@ struct rcv_ctx {
   Unit* units;
   int* counters;  // [0] units queued, [1] queue cursor
   int* cnt;
+  unsigned* mask_bits; long long mask_words;   // K1 scratch: one survival bit per pixel of every item of a call (grown on demand)
   unsigned long long *best, *votes;
   PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
   cudaEvent_t evr[64][2]; long long ev_count;   // ring of (start, stop) events around the vote kernel
@@ -1375,7 +1405,7 @@ RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri); cudaFree(c->pool.perm);
   cudaFree(c->meta); cudaFree(c->units); cudaFree(c->counters); cudaFree(c->cnt); cudaFree(c->best); cudaFree(c->votes);
-  cudaFree(c->leaves); cudaFree(c->leaf_sums);
+  cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits);
   for (int s = 0; s < 2; ++s) { cudaFree(c->st_depth[s]); cudaFree(c->st_radius[s]); cudaFree(c->st_sem[s]); }
   cudaFree(c->st_K); cudaFree(c->st_maxr); cudaFree(c->st_centre); cudaFree(c->st_peak); cudaFree(c->st_votes);
   cudaFree(c->st_np); cudaFree(c->st_grid); cudaFree(c->st_status); cudaFree(c->st_horn_in);
@@ -1509,10 +1539,19 @@ RCV_EXPORT int rcv_vote_frames(rcv_ctx* c, int n_frames, int n_kpts, const void*
   const long long npx = (long long)fp->height * fp->width;
   const int vec_ok = (npx % 8 == 0) && (((uintptr_t)depth | (uintptr_t)radius | (uintptr_t)sem) % 16 == 0);
   FrameArgs fa{depth, radius, sem, K, max_radii, *fp, vp->acc_unit, vp->radius_scale, n_kpts, vec_ok};
-  k_frame_compact<false><<<n_items, kCompactThreads, 0, st>>>(fa, c->cnt, c->meta, c->pool);
+  const int words = (int)((npx + 255) / 256) * 8;   // whole warp-steps of 256 pixels
+  const long long need = (long long)n_items * words;
+  if (need > c->mask_words) {   // first call of this size only: the mask scratch depends on the image size, which rcv_create does not know
+    CK(c, cudaStreamSynchronize(st));
+    cudaFree(c->mask_bits); c->mask_bits = nullptr; c->mask_words = 0;
+    CK(c, cudaMalloc(&c->mask_bits, (size_t)need * 4));
+    c->mask_words = need;
+  }
+  k_frame_mask<<<n_items, kCompactThreads, 0, st>>>(fa, c->cnt, c->mask_bits, words);
   k_scan_items<<<1, 1024, 0, st>>>(c->cnt, n_items, c->pool.cap, c->meta);
-  k_frame_compact<true><<<n_items, kCompactThreads, 0, st>>>(fa, c->cnt, c->meta, c->pool);
-  c->launches += 3;
+  k_frame_emit<<<n_items, kCompactThreads, 0, st>>>(c->mask_bits, words, c->meta, c->pool.perm);
+  k_points_from_pixels<<<dim3(n_items, 4), 256, 0, st>>>(fa, c->meta, c->pool);
+  c->launches += 4;
   return run_items(c, n_items, vp, centre_mm, peak, votes, n_points, grid, nullptr, status, nullptr, 0, st);
 }
 
