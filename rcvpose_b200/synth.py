@@ -102,9 +102,10 @@ def frame_to_points(K, depth, radius):
     return xyz_mm / 1000, radius[dm.nonzero()]
 
 
-def torch_batch(n_frames, n_kpts=3, seed=0, device="cuda", K=linemod_K, chunk=128, sigma_dm=0.01, outlier_frac=0.02, h=H, w=W):
+def torch_batch(n_frames, n_kpts=3, seed=0, device="cuda", K=linemod_K, chunk=128, sigma_dm=0.01, outlier_frac=0.02, h=H, w=W,
+                obj_radius_mm=(40.0, 70.0)):
     """Config-3 shaped batch generated on the GPU: per frame an object sphere of radius
-    U(40,70) mm at x,y U(-150,150), z U(700,1100) mm; `n_kpts` keypoints at 1.5-2.5 object radii in
+    U(obj_radius_mm) = U(40,70) mm at x,y U(-150,150), z U(700,1100) mm; `n_kpts` keypoints at 1.5-2.5 object radii in
     dispersed directions; radius maps (decimetres, float32) with N(0, sigma) noise and a fraction of
     uniform outliers in [0, max radius]; depth uint16 millimetres (returned as an int16 view).
     Returns dict(depth (B,H,W) int16-view-of-uint16, radius (B,Kp,H,W) f32, kpts_mm (B,Kp,3) f64,
@@ -116,7 +117,7 @@ def torch_batch(n_frames, n_kpts=3, seed=0, device="cuda", K=linemod_K, chunk=12
     depth = torch.empty((n_frames, h, w), dtype=torch.int16, device=dev)
     radius = torch.empty((n_frames, n_kpts, h, w), dtype=torch.float32, device=dev)
     U = lambda *s: torch.rand(*s, generator=g, device=dev, dtype=torch.float64)  # noqa: E731
-    obj_r = 40.0 + 30.0 * U(n_frames)
+    obj_r = obj_radius_mm[0] + (obj_radius_mm[1] - obj_radius_mm[0]) * U(n_frames)
     centre = torch.stack([-150 + 300 * U(n_frames), -150 + 300 * U(n_frames), 700 + 400 * U(n_frames)], dim=1)
     base = torch.tensor([[1.0, 0.2, 0.1], [-0.3, 1.0, 0.2], [0.2, -0.4, 1.0], [-1.0, -0.5, 0.3]], dtype=torch.float64, device=dev)[:n_kpts]
     dirs = base[None] + 0.15 * torch.randn((n_frames, n_kpts, 3), generator=g, device=dev, dtype=torch.float64)
