@@ -207,6 +207,74 @@ def test_empty_and_degenerate_inputs(acc, ctx):
     assert int(out["status"][0, 0]) == api.RCV_ST_EMPTY_MASK
 
 
+def test_ragged_batch_capacity_and_error_codes():
+    """The boundary's error behaviour (include/rcvvote.h): data-dependent conditions are per-item status bits and never UB
+    (empty item inside a batch, D beyond max_grid, point pool or tile work list exhausted: the other items of the call
+    are still bit-exact); bad arguments and requests beyond the capacities fixed at rcv_create are call errors."""
+    from rcvpose_b200 import api
+    rng = np.random.default_rng(21)
+    sizes = [0, 5, 300, 1, 120]
+    clouds, radii = [], []
+    for n in sizes:
+        xyz = rng.normal(0, 0.02, size=(n, 3)) + np.array([0.0, 0.05, 0.7])
+        kp = np.array([0.07, 0.02, 0.66])
+        clouds.append(xyz)
+        radii.append((np.linalg.norm(xyz - kp, axis=1) * 10).astype(np.float32))
+    off = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64).cuda()
+    X = torch.from_numpy(np.concatenate(clouds)).cuda()
+    Rr = torch.from_numpy(np.concatenate(radii)).cuda()
+    want = [oracle.Accumulator_3D(c, r, return_info=True) if len(c) else None for c, r in zip(clouds, radii)]
+
+    def check(out, ok_items):
+        for b in ok_items:
+            w, info = want[b]
+            assert int(out["status"][b]) == 0 and int(out["grid"][b]) == info["D"] and int(out["votes"][b]) == info["votes"]
+            assert np.array_equal(out["centre_mm"][b].cpu().numpy(), w[0])
+
+    ctx = api.VoteContext(0, max_items=8, max_points_total=4096, max_grid=128)
+    out = ctx.vote_points(X, Rr, off)                                   # ragged batch with an empty item
+    torch.cuda.synchronize()
+    assert int(out["status"][0]) == api.RCV_ST_EMPTY_MASK
+    check(out, [1, 2, 3, 4])
+    # grid larger than the capacity of the context: that item only
+    small = api.VoteContext(0, max_items=8, max_points_total=4096, max_grid=max(want[1][1]["D"], want[3][1]["D"]))
+    out = small.vote_points(X, Rr, off)
+    torch.cuda.synchronize()
+    big = [b for b in (1, 2, 3, 4) if want[b][1]["D"] > small.max_grid]
+    assert big and all(int(out["status"][b]) & api.RCV_ST_D_EXCEEDS_CAP for b in big)
+    check(out, [b for b in (1, 2, 3, 4) if b not in big])
+    # tile work list too short: items that do not fit report it, earlier ones are unaffected
+    few = api.VoteContext(0, max_items=8, max_points_total=4096, max_grid=128, max_units=3)
+    out = few.vote_points(X, Rr, off)
+    torch.cuda.synchronize()
+    st = [int(v) for v in out["status"].cpu()]
+    assert any(v & api.RCV_ST_UNIT_OVERFLOW for v in st)
+    check(out, [b for b in (1, 2, 3, 4) if st[b] == 0])
+    # point pool exhausted by the frames entry point: overflowed items carry the status and no points
+    frames = [synth.config3_frame(f) for f in range(2)]
+    depth = torch.from_numpy(np.stack([f["depth"] for f in frames]).view(np.int16)).cuda()
+    radius = torch.from_numpy(np.stack([f["radius"] for f in frames])).cuda()
+    K = torch.from_numpy(synth.linemod_K).cuda()
+    full = api.VoteContext(0, max_items=8, max_points_total=1 << 16, max_grid=256).vote_frames(depth, radius, K, mask_flags=api.RCV_MASK_RADIUS_NONZERO)
+    n0 = int(full["n_points"][0, 0])
+    tight = api.VoteContext(0, max_items=8, max_points_total=n0 + 10, max_grid=256)
+    out = tight.vote_frames(depth, radius, K, mask_flags=api.RCV_MASK_RADIUS_NONZERO)
+    torch.cuda.synchronize()
+    assert int(out["status"][0, 0]) == 0 and np.array_equal(out["centre_mm"][0, 0].cpu().numpy(), full["centre_mm"][0, 0].cpu().numpy())
+    assert all(int(v) & api.RCV_ST_POINT_OVERFLOW for v in out["status"].flatten()[1:].cpu())
+    assert int(out["n_points"].flatten()[1:].sum()) == 0
+    # call errors
+    with pytest.raises(api.RcvError):
+        tight.vote_frames(depth.repeat(5, 1, 1), radius.repeat(5, 1, 1, 1), K, mask_flags=api.RCV_MASK_RADIUS_NONZERO)   # 30 items > max_items
+    with pytest.raises(api.RcvError):
+        ctx.vote_points(X, Rr, off, acc_unit=0.0)
+    with pytest.raises(api.RcvError):
+        ctx.vote_frames(depth, radius, K, mask_flags=api.RCV_MASK_SEM_GT)                                                   # sem rule without a sem map
+    out = ctx.vote_points(X, Rr, off)                                   # the context is still usable after errors
+    torch.cuda.synchronize()
+    check(out, [1, 2, 3, 4])
+
+
 def test_argmax_volume_first_max_in_c_order(ctx):
     rng = np.random.default_rng(2)
     for D in (5, 33, 86):
