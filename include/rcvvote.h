@@ -144,6 +144,16 @@ int rcv_horn_batch(rcv_ctx* ctx, const double* model, long long model_stride, co
 int rcv_horn_batch_host(rcv_ctx* ctx, const double* model, long long model_stride, const double* est, int n, int n_frames,
                         double* RT, void* stream);
 
+/* ---- ADD(-S) distance before ICP  -- AccumulatorSpace.py:664-702 (LM), 897-927 (LMO), 1119-1150 (YCB) -----------
+ * The step right after the path: the CAD points are transformed by the estimated pose and
+ * by the ground-truth pose (project(), :64-75: xyz @ R^T + t) and, for every ground-truth point, the distance to the
+ * NEAREST estimated point is taken (open3d compute_point_cloud_distance, :688/:692); the reference thresholds the
+ * MEAN of these distances, or their MINIMUM for the symmetric classes.  Brute-force float64 nearest neighbour.
+ *   model_mm [n_model][3] float64 (one CAD model shared by the frames), RT_est / RT_gt [n_frames][4][4] float64
+ *   row-major (rows 0..2 used; translations in the unit of model_mm), outputs mean_out / min_out [n_frames] float64. */
+int rcv_add_metric_batch(rcv_ctx* ctx, const double* model_mm, int n_model, const double* RT_est, const double* RT_gt, int n_frames,
+                         double* mean_out, double* min_out, void* stream);
+
 /* ---- conv8 of the radius-map producer  -- models/fcnresnet.py:118 (definition), :187-189 (use) -----------
  * out[b][n][p] = bias[n] + sum_k bf16(weight[n][k]) * up[b][k][p],  n = 0 (seg), 1 (radial), k = 0..31.
  * The 1x1 head as a tcgen05 tensor-core kernel (bf16 operands, fp32 accumulation in tensor memory).

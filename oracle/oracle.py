@@ -176,3 +176,14 @@ def lmshorn(P1, P2, n, A):
     out = np.empty((4, 4), dtype=np.float64)
     lib().orc_lmshorn(_p(P1), _p(P2), int(n), _p(out))
     A[...] = out
+
+
+def add_metric(model_mm, RT_est, RT_gt):
+    """ADD(-S) distance before ICP as the reference computes it (AccumulatorSpace.py:664-702): the CAD points under the
+    estimated and the ground-truth pose (project(), :64-75), then for every ground-truth point the distance to the nearest
+    estimated point (open3d compute_point_cloud_distance = exact nearest neighbour; a k-d tree here).  Returns (mean, min)."""
+    from scipy.spatial import cKDTree
+    est = np.dot(model_mm, RT_est[:3, :3].T) + RT_est[:3, 3:].T
+    gt = np.dot(model_mm, RT_gt[:3, :3].T) + RT_gt[:3, 3:].T
+    d, _ = cKDTree(est).query(gt, k=1)
+    return float(d.mean()), float(d.min())

@@ -16,7 +16,7 @@ RCV_ST_VOLUME_SKIPPED = 32
 
 EXPORTS = ["rcv_create", "rcv_destroy", "rcv_last_error", "rcv_abi_version", "rcv_backproject", "rcv_vote_points", "rcv_vote_frames",
            "rcv_vote_frames_host", "rcv_argmax_volume", "rcv_head_1x1", "rcv_horn_batch", "rcv_horn_batch_host", "rcv_launch_count",
-           "rcv_last_vote_kernel_ms", "rcv_vote_kernel_times", "rcv_ubench_smem_atomics"]
+           "rcv_last_vote_kernel_ms", "rcv_vote_kernel_times", "rcv_ubench_smem_atomics", "rcv_add_metric_batch"]
 
 
 class rcv_config(C.Structure):
@@ -73,6 +73,8 @@ def load():
     L.rcv_argmax_volume.argtypes = [vp, vp, C.c_int, ip, ip, vp]
     L.rcv_horn_batch.restype = C.c_int
     L.rcv_horn_batch.argtypes = [vp, vp, C.c_longlong, vp, C.c_int, C.c_int, vp, vp]
+    L.rcv_add_metric_batch.restype = C.c_int
+    L.rcv_add_metric_batch.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]
     L.rcv_horn_batch_host.restype = C.c_int
     L.rcv_horn_batch_host.argtypes = [vp, vp, C.c_longlong, vp, C.c_int, C.c_int, vp, vp]
     L.rcv_head_1x1.restype = C.c_int

@@ -209,6 +209,24 @@ class VoteContext:
             self._ck(self.lib.rcv_horn_batch(self.h, _ptr(model), stride, _ptr(est), n, B, _ptr(RT), _stream()))
         return RT
 
+    # ---- ADD(-S) distance before ICP (AccumulatorSpace.py:664-702) ----
+    def add_metric(self, model_mm, RT_est, RT_gt):
+        """model_mm (M,3), RT_est / RT_gt (B,4,4) float64 CUDA (translations in the unit of model_mm) -> (mean, min) (B,) float64:
+        mean and minimum over the ground-truth-transformed CAD points of the distance to the nearest estimate-transformed
+        CAD point.  The reference thresholds the mean, or the minimum for its symmetric classes (:688-695)."""
+        _check_cuda(model_mm, torch.float64, "model_mm")
+        _check_cuda(RT_est, torch.float64, "RT_est")
+        _check_cuda(RT_gt, torch.float64, "RT_gt")
+        B = RT_est.shape[0]
+        if RT_est.shape[1:] != (4, 4) or RT_gt.shape != RT_est.shape or model_mm.dim() != 2 or model_mm.shape[1] != 3:
+            raise RcvError("add_metric: model_mm (M,3), RT_est and RT_gt (B,4,4)")
+        mean = torch.empty(B, dtype=torch.float64, device=RT_est.device)
+        mn = torch.empty(B, dtype=torch.float64, device=RT_est.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_add_metric_batch(self.h, _ptr(model_mm), int(model_mm.shape[0]), _ptr(RT_est), _ptr(RT_gt), B, _ptr(mean),
+                                                   _ptr(mn), _stream()))
+        return mean, mn
+
     def head_1x1(self, up, weight, bias):
         """conv8 of the reference's producer (models/fcnresnet.py:118,187-189) on the tensor cores.
         up (B,32,H,W) bfloat16 NCHW, weight (2,32[,1,1]) and bias (2,) float32 -> out (B,2,H,W) float32:

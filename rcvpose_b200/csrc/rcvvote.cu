@@ -1326,6 +1326,69 @@ __global__ void k_horn(const double* __restrict__ model, long long model_stride,
 }
 
 // ------------------------------------------------------------------------------------------------
+// ADD(-S) distance before ICP (AccumulatorSpace.py:664-702): for every ground-truth-transformed CAD point the distance
+// to the nearest estimate-transformed CAD point, brute force in float64.  One CTA per (frame, tile of 256 ground-truth
+// points): a thread owns one ground-truth point, the estimated cloud streams through shared memory in tiles.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAddThreads = 256;
+__device__ __forceinline__ void rt_apply(const double* __restrict__ RT, double x, double y, double z, double& ox, double& oy, double& oz) {
+  // np.dot(xyz, R.T) + t (project(), :71): row . point, accumulated left to right
+  ox = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, RT[0]), __dmul_rn(y, RT[1])), __dmul_rn(z, RT[2])), RT[3]);
+  oy = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, RT[4]), __dmul_rn(y, RT[5])), __dmul_rn(z, RT[6])), RT[7]);
+  oz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, RT[8]), __dmul_rn(y, RT[9])), __dmul_rn(z, RT[10])), RT[11]);
+}
+__global__ void __launch_bounds__(kAddThreads) k_add_nn(const double* __restrict__ model, int n_model, const double* __restrict__ RT_est,
+                                                       const double* __restrict__ RT_gt, double* __restrict__ part_sum,
+                                                       double* __restrict__ part_min, int tiles) {
+  const int frame = blockIdx.y, tile = blockIdx.x;
+  __shared__ double s_e[3][kAddThreads];
+  __shared__ double s_rt[2][12];
+  __shared__ double s_red[2][kAddThreads / 32];
+  if (threadIdx.x < 12) { s_rt[0][threadIdx.x] = RT_est[16LL * frame + threadIdx.x]; s_rt[1][threadIdx.x] = RT_gt[16LL * frame + threadIdx.x]; }
+  __syncthreads();
+  const int g = tile * kAddThreads + threadIdx.x;
+  double gx = 0, gy = 0, gz = 0;
+  if (g < n_model) rt_apply(s_rt[1], model[3 * g], model[3 * g + 1], model[3 * g + 2], gx, gy, gz);
+  double best = INFINITY;
+  for (int e0 = 0; e0 < n_model; e0 += kAddThreads) {
+    const int e = e0 + threadIdx.x;
+    double ex = INFINITY, ey = INFINITY, ez = INFINITY;   // padding never wins the minimum
+    if (e < n_model) rt_apply(s_rt[0], model[3 * e], model[3 * e + 1], model[3 * e + 2], ex, ey, ez);
+    __syncthreads();
+    s_e[0][threadIdx.x] = ex; s_e[1][threadIdx.x] = ey; s_e[2][threadIdx.x] = ez;
+    __syncthreads();
+    const int cnt = min(kAddThreads, n_model - e0);
+#pragma unroll 4
+    for (int q = 0; q < cnt; ++q) {
+      const double dx = gx - s_e[0][q], dy = gy - s_e[1][q], dz = gz - s_e[2][q];
+      const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+      best = fmin(best, d2);
+    }
+  }
+  double dist = g < n_model ? sqrt(best) : 0.0, dmin = g < n_model ? dist : INFINITY;
+  // deterministic tile reduction: warp shuffles in a fixed pattern, then warp partials in order
+#pragma unroll
+  for (int m = 16; m; m >>= 1) { dist += __shfl_xor_sync(0xffffffffu, dist, m); dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, m)); }
+  if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = dist; s_red[1][threadIdx.x >> 5] = dmin; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0, mn = INFINITY;
+    for (int w = 0; w < kAddThreads / 32; ++w) { s += s_red[0][w]; mn = fmin(mn, s_red[1][w]); }
+    part_sum[(long long)frame * tiles + tile] = s;
+    part_min[(long long)frame * tiles + tile] = mn;
+  }
+}
+__global__ void k_add_finish(const double* __restrict__ part_sum, const double* __restrict__ part_min, int tiles, int n_model, int n_frames,
+                             double* __restrict__ mean_out, double* __restrict__ min_out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  double s = 0, mn = INFINITY;
+  for (int t = 0; t < tiles; ++t) { s += part_sum[(long long)f * tiles + t]; mn = fmin(mn, part_min[(long long)f * tiles + t]); }
+  mean_out[f] = s / (double)n_model;
+  min_out[f] = mn;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Roofline denominator: conflict-free shared-memory atomic rate of this GPU (one ATOMS per warp
 // instruction, 32 distinct banks), measured the same way as tools/ubench_atoms.cu.
 // ------------------------------------------------------------------------------------------------
@@ -1363,7 +1426,8 @@ struct rcv_ctx {
   Unit* units;
   int* counters;  // [0] units queued, [1] queue cursor
   int* cnt;
-  unsigned* mask_bits; long long mask_words;   // K1 scratch: one survival bit per pixel of every item of a call (grown on demand)
+  unsigned* mask_bits; long long mask_words;
+  double* add_part; long long add_part_cap;     // ADD metric scratch: per-(frame, tile) partial sums and minima   // K1 scratch: one survival bit per pixel of every item of a call (grown on demand)
   unsigned long long *best, *votes;
   PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
   cudaEvent_t evr[64][2]; long long ev_count;   // ring of (start, stop) events around the vote kernel
@@ -1405,7 +1469,7 @@ RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri); cudaFree(c->pool.perm);
   cudaFree(c->meta); cudaFree(c->units); cudaFree(c->counters); cudaFree(c->cnt); cudaFree(c->best); cudaFree(c->votes);
-  cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits);
+  cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits); cudaFree(c->add_part);
   for (int s = 0; s < 2; ++s) { cudaFree(c->st_depth[s]); cudaFree(c->st_radius[s]); cudaFree(c->st_sem[s]); }
   cudaFree(c->st_K); cudaFree(c->st_maxr); cudaFree(c->st_centre); cudaFree(c->st_peak); cudaFree(c->st_votes);
   cudaFree(c->st_np); cudaFree(c->st_grid); cudaFree(c->st_status); cudaFree(c->st_horn_in);
@@ -1675,6 +1739,30 @@ RCV_EXPORT int rcv_horn_batch(rcv_ctx* c, const double* model, long long model_s
   CK(c, cudaSetDevice(c->device));
   k_horn<<<(n_frames + 63) / 64, 64, 0, (cudaStream_t)stream>>>(model, model_stride, est, n, n_frames, RT);
   c->launches += 1;
+  CK(c, cudaGetLastError());
+  return RCV_OK;
+}
+
+RCV_EXPORT int rcv_add_metric_batch(rcv_ctx* c, const double* model_mm, int n_model, const double* RT_est, const double* RT_gt, int n_frames,
+                                    double* mean_out, double* min_out, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!model_mm || !RT_est || !RT_gt || !mean_out || !min_out || n_model <= 0 || n_frames <= 0)
+    FAIL(c, RCV_E_INVALID, "rcv_add_metric_batch: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(c, cudaSetDevice(c->device));
+  const int tiles = (n_model + kAddThreads - 1) / kAddThreads;
+  const long long need = 2LL * n_frames * tiles;
+  if (need > c->add_part_cap) {   // first call of this size only
+    CK(c, cudaStreamSynchronize(st));
+    cudaFree(c->add_part); c->add_part = nullptr; c->add_part_cap = 0;
+    CK(c, cudaMalloc(&c->add_part, (size_t)need * 8));
+    c->add_part_cap = need;
+  }
+  double* ps = c->add_part;
+  double* pm = c->add_part + (long long)n_frames * tiles;
+  k_add_nn<<<dim3(tiles, n_frames), kAddThreads, 0, st>>>(model_mm, n_model, RT_est, RT_gt, ps, pm, tiles);
+  k_add_finish<<<(n_frames + 127) / 128, 128, 0, st>>>(ps, pm, tiles, n_model, n_frames, mean_out, min_out);
+  c->launches += 2;
   CK(c, cudaGetLastError());
   return RCV_OK;
 }

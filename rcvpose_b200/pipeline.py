@@ -68,6 +68,15 @@ class VotingPipeline:
         out["RT"] = self.ctx.horn_batch(model_mm, out["centre_mm"])
         return out
 
+    def add_pass(self, cad_mm, RT_est, RT_gt, threshold_mm, symmetric=False):
+        """ADD(-S) bookkeeping of the reference's evaluator before ICP (AccumulatorSpace.py:687-695): per frame, does the mean
+        (or, for a symmetric class, the minimum) nearest-neighbour distance between the CAD points under the ground-truth and
+        under the estimated pose stay within `threshold_mm` (the reference uses add_threshold[class] * 1000)?  Returns
+        (passed (B,) bool, distance (B,) float64)."""
+        mean, mn = self.ctx.add_metric(cad_mm, RT_est, RT_gt)
+        d = mn if symmetric else mean
+        return d <= threshold_mm, d
+
     def step_gathered(self, depth, radius, K, model_mm, counts=None, **kw):
         out = self.step(depth, radius, K, model_mm, **kw)
         rows = gather_results(pack_results(out["centre_mm"], out["RT"], out["peak"], out["status"]), counts)

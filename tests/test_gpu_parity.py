@@ -313,6 +313,34 @@ def test_horn_batch_device(ctx, golden):
     np.testing.assert_allclose(RT0[0], golden["h0_RT"], rtol=1e-12, atol=1e-9)
 
 
+def test_add_metric_vs_kdtree(ctx):
+    """ADD(-S) before ICP (AccumulatorSpace.py:664-702): brute-force float64 nearest neighbour on the GPU against a k-d tree
+    on the host; 1e-9 relative (the nearest neighbour is exact on both sides, only the summation order differs)."""
+    rng = np.random.default_rng(31)
+    M, B = 1357, 6
+    u = rng.normal(size=(M, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    model = u * np.array([45.0, 30.0, 60.0]) * rng.uniform(0.7, 1.0, size=(M, 1))     # an ellipsoidal shell of CAD points, mm
+
+    def pose(rv, t):
+        th = np.linalg.norm(rv); k = rv / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+        RT = np.eye(4); RT[:3, :3] = R; RT[:3, 3] = t
+        return RT
+    RT_gt = np.stack([pose(rng.normal(size=3), rng.uniform(-200, 200, 3) + np.array([0, 0, 900.0])) for _ in range(B)])
+    RT_est = RT_gt.copy()
+    for b in range(B):                                   # frame 0: identical pose (distance 0); then growing errors
+        if b:
+            RT_est[b] = pose(rng.normal(size=3) * 0.01 * b, rng.normal(size=3) * 2.0 * b) @ RT_gt[b]
+    mean, mn = ctx.add_metric(torch.from_numpy(model).cuda(), torch.from_numpy(RT_est).cuda(), torch.from_numpy(RT_gt).cuda())
+    torch.cuda.synchronize()
+    for b in range(B):
+        wm, wn = oracle.add_metric(model, RT_est[b], RT_gt[b])
+        assert abs(float(mean[b]) - wm) <= 1e-9 * max(1.0, wm), (b, float(mean[b]), wm)
+        assert abs(float(mn[b]) - wn) <= 1e-9 * max(1.0, wn), (b, float(mn[b]), wn)
+    assert float(mean[0]) == 0.0 and float(mean[B - 1]) > float(mean[1]) > 0.0
+
+
 @pytest.mark.parametrize("shape", [(1, 480, 640), (3, 480, 640), (2, 24, 40), (1, 8, 24)])
 def test_head_1x1_tensor_core_vs_torch(ctx, shape):
     """K5 (conv8 of the producer, models/fcnresnet.py:118,187-189): tcgen05 kernel vs torch's fp32 conv of the same
