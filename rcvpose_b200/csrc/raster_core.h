@@ -104,8 +104,12 @@ RCV_HD bool exact_hit(double px, double py, double pz, int R, int i, int j, int 
 
 // A tile of the accumulator owned by one CTA: slices [i0,i0+ni) x rows [j0,j0+nj) x all k in [0,D).
 // Word offset of voxel (i,j,k) = ((i-i0)*nj + (j-j0))*Dp + k, Dp >= D odd (bank spreading).
+// A guarded tile also holds glo / ghi guard cells below 0 / above D - 1 along C (the tile pointer is shifted by glo cells,
+// Dp >= D + glo + ghi) and along B (j0 = -glo, nj = D + glo + ghi): votes of a sphere that overhangs the grid land in guard
+// cells, which are never read back, so no candidate of such a tile needs a bounds test (ring_noclip).
 struct Tile {
   int i0, ni, j0, nj, D, Dp;
+  int glo, ghi;
 };
 
 // Per-point constants (one lane).
@@ -653,7 +657,7 @@ RCV_HD int slab_thickness(int ni_max) {
 // (candidates lie within R + 1 of the nearest lattice point), so the per-candidate bounds test can be skipped.
 RCV_HD bool ring_noclip(const PointCtx& c, const Tile& t) {
   if (c.R <= 0) return true;   // draws nothing (padding lanes of a warp's last group)
-  return (c.ipz - c.R - 2 >= 0) && (c.ipz + c.R + 2 < t.D) && (c.ipy - c.R - 2 >= t.j0) && (c.ipy + c.R + 2 < t.j0 + t.nj);
+  return (c.ipz - c.R - 2 >= -t.glo) && (c.ipz + c.R + 2 < t.D + t.ghi) && (c.ipy - c.R - 2 >= t.j0) && (c.ipy + c.R + 2 < t.j0 + t.nj);
 }
 
 }  // namespace rcv

@@ -51,7 +51,7 @@ struct ItemMeta {
   int D, Dp, zb;  // grid side, padded row stride, zero boundary
   int ni, nj;     // tile shape (slices x rows); every tile spans all k
   int status;
-  int pad;
+  int guard;      // glo | ghi << 16: guard cells of a whole-slice tile below 0 / above D - 1 along the in-slice axes (0 for row-band tiles)
   double mean[3];
   double rmax;
 };
@@ -416,6 +416,7 @@ struct PreludeArgs {
 };
 
 constexpr int kPreludeThreads = 256;
+constexpr int kMaxGuard = 8;     // guard cells per side of a whole-slice tile; beyond that the item uses the clipped passes
 constexpr int kSortBins = 8192;   // bins of the (y voxel, R) counting sort that orders an item's points for k_vote
 
 __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
@@ -425,6 +426,7 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
   __shared__ int s_nleaf;
   __shared__ double s_mean[3];
   __shared__ double s_red[3][kPreludeThreads / 32];
+  __shared__ double s_red2[2][kPreludeThreads / 32];
   __shared__ int s_zb, s_ok, s_ubase;
   if (n <= 0) {
     if (threadIdx.x == 0) { if (!(m.status & RCV_ST_POINT_OVERFLOW)) m.status |= RCV_ST_EMPTY_MASK; a.meta[item] = m; }
@@ -473,19 +475,27 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
   const double mx = s_mean[0], my = s_mean[1], mz = s_mean[2];
   // recentre; global min / max over all three axes; max radius
   double vmin = INFINITY, vmax = -INFINITY, rmax = -INFINITY;
+  double elo = INFINITY, ehi = -INFINITY;   // extent of the drawn spheres (coordinate -+ integer radius), for the guard band
   for (int q = threadIdx.x; q < n; q += blockDim.x) {
     const double x = __dsub_rn(X[q], mx), y = __dsub_rn(Y[q], my), z = __dsub_rn(Z[q], mz);
     X[q] = x; Y[q] = y; Z[q] = z;
-    vmin = fmin(vmin, fmin(x, fmin(y, z)));
-    vmax = fmax(vmax, fmax(x, fmax(y, z)));
+    const double lo3 = fmin(x, fmin(y, z)), hi3 = fmax(x, fmax(y, z));
+    vmin = fmin(vmin, lo3);
+    vmax = fmax(vmax, hi3);
     rmax = fmax(rmax, Rd[q]);
+    const int ri = a.pool.Ri[m.off + q];
+    if (ri > 0) { elo = fmin(elo, lo3 - (double)ri); ehi = fmax(ehi, hi3 + (double)ri); }
   }
   vmin = warp_min_f64(vmin); vmax = warp_max_f64(vmax); rmax = warp_max_f64(rmax);
+  elo = warp_min_f64(elo); ehi = warp_max_f64(ehi);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { s_red[0][warp] = vmin; s_red[1][warp] = vmax; s_red[2][warp] = rmax; }
+  if (lane == 0) { s_red[0][warp] = vmin; s_red[1][warp] = vmax; s_red[2][warp] = rmax; s_red2[0][warp] = elo; s_red2[1][warp] = ehi; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < kPreludeThreads / 32; ++w) { vmin = fmin(vmin, s_red[0][w]); vmax = fmax(vmax, s_red[1][w]); rmax = fmax(rmax, s_red[2][w]); }
+    for (int w = 1; w < kPreludeThreads / 32; ++w) {
+      vmin = fmin(vmin, s_red[0][w]); vmax = fmax(vmax, s_red[1][w]); rmax = fmax(rmax, s_red[2][w]);
+      elo = fmin(elo, s_red2[0][w]); ehi = fmax(ehi, s_red2[1][w]);
+    }
     // zero_boundary = int(xyz_mm_min - radius_max) + 1   (int() truncates toward zero)
     const double zbd = __dsub_rn(vmin, rmax);
     int zb = (int)zbd + 1;  // values beyond int range are rejected below through D
@@ -503,15 +513,26 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
     m.D = D; m.zb = zb; m.rmax = rmax; m.mean[0] = mx; m.mean[1] = my; m.mean[2] = mz; m.status = status;
     int nunits = 0;
     if (ok) {
-      const int Dp = D | 1;  // odd row stride: consecutive rows start in different banks
+      // Guard band: how far the candidates of the item's spheres can leave [0, D) along the in-slice axes (they lie within
+      // R + 2 of the nearest lattice point, ring_noclip).  The reference sizes the grid so that spheres overhang by at most
+      // ~3 voxels; with the guard cells inside the tile no warp of the item needs the clipped passes.
+      // nearest lattice point within 0.5 of the (shifted) coordinate, candidates within R + 2 of it
+      const double shift = zb < 0 ? (double)zb : 0.0;
+      const double need_lo = 2.5 - (elo - shift), need_hi = (ehi - shift) + 2.5 - (double)(D - 1);
+      int glo = need_lo > 0.0 ? (need_lo < 1e6 ? (int)ceil(need_lo) : kMaxGuard + 1) : 0;
+      int ghi = need_hi > 0.0 ? (need_hi < 1e6 ? (int)ceil(need_hi) : kMaxGuard + 1) : 0;
+      if (glo > kMaxGuard || ghi > kMaxGuard) { glo = 0; ghi = 0; }   // YCBGEN-style grids without upper pad: clipped passes
+      int Dp = (D + glo + ghi) | 1;  // odd row stride: consecutive rows start in different banks
+      long long slice = (long long)(D + glo + ghi) * Dp;
+      if (slice > a.tile_words) { glo = 0; ghi = 0; Dp = D | 1; slice = (long long)D * Dp; }   // row-band tiles are not guarded
       m.Dp = Dp;
-      const long long slice = (long long)D * Dp;
+      m.guard = glo | (ghi << 16);
       if (slice <= a.tile_words) {
         int ni_max = (int)(a.tile_words / slice);
         if (ni_max > 32) ni_max = 32;   // the polar pass keeps one mask bit per slice of a tile
         if (ni_max > D) ni_max = D;
         m.ni = ni_max >= D ? D : slab_thickness(ni_max);   // a multiple of 3 or 4: the ring passes walk a slab in chunks
-        m.nj = D;
+        m.nj = D + glo + ghi;
         nunits = (D + m.ni - 1) / m.ni;
       } else {
         const int nj_max = a.tile_words / Dp;
@@ -590,12 +611,15 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
   }
   // tile work list
   m = a.meta[item];
-  const int tj = (m.D + m.nj - 1) / m.nj, ti = (m.D + m.ni - 1) / m.ni;
+  const int glo = m.guard & 0xffff, gspan = (m.guard & 0xffff) + (m.guard >> 16);
+  const bool whole = m.nj >= m.D;   // whole-slice tiles (guarded); otherwise row bands
+  const int tj = whole ? 1 : (m.D + m.nj - 1) / m.nj, ti = (m.D + m.ni - 1) / m.ni;
   for (int t = threadIdx.x; t < ti * tj; t += blockDim.x) {
     Unit u;
     u.item = item;
     u.i0 = (t / tj) * m.ni; u.ni = min(m.ni, m.D - u.i0);
-    u.j0 = (t % tj) * m.nj; u.nj = min(m.nj, m.D - u.j0);
+    if (whole) { u.j0 = -glo; u.nj = m.D + gspan; }
+    else { u.j0 = (t % tj) * m.nj; u.nj = min(m.nj, m.D - u.j0); }
     a.units[s_ubase + t] = u;
   }
 }
@@ -1070,8 +1094,6 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
   asm volatile("mov.u32 %0, %0;" : "+r"(tile_s));   // keep the shared-window base in a register (ptxas otherwise rematerialises it per use)
-  const SmemEmit emit{tile_s, 4 * (kTileWords + warp * 32 + lane)};
-  const SlowArcCall slowarc{tile_s};
   const int n_units = a.counters[0];
   for (;;) {
     __syncthreads();
@@ -1083,7 +1105,11 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
     const ItemMeta& m = a.meta[u.item];
     const int D = m.D, Dp = m.Dp, n = m.n;
     const long long off = m.off;
-    const Tile t{u.i0, u.ni, u.j0, u.nj, D, Dp};
+    const int glo = m.guard & 0xffff, ghi = m.guard >> 16;
+    const Tile t{u.i0, u.ni, u.j0, u.nj, D, Dp, glo, ghi};
+    // voxel (i, j, k) of the tile sits at word ((i - i0) * nj + (j - j0)) * Dp + k of the pointer shifted by the low guard
+    const SmemEmit emit{tile_s + 4u * (unsigned)glo, 4 * (kTileWords + warp * 32 + lane - glo)};
+    const SlowArcCall slowarc{tile_s + 4u * (unsigned)glo};
     const int words = u.ni * u.nj * Dp;
     {
       int4* t4 = reinterpret_cast<int4*>(tile);
@@ -1140,11 +1166,12 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
     // ---- peak of the tile (K3 fused) + vote tally + optional volume dump ----
     // tile row r = (A - i0) * nj + (B - j0) holds reference voxels (i, j, k) = (B, A, k)
     unsigned long long key = 0, sum = 0;
-    const int rows = u.ni * u.nj;
+    const int jr0 = u.j0 < 0 ? 0 : u.j0, njr = min(u.j0 + u.nj, D) - jr0;   // the real rows of a slice (guard rows are not read back)
+    const int rows = u.ni * njr;
     for (int r = warp; r < rows; r += kVoteWarps) {
-      const int ga = u.i0 + r / u.nj, gb = u.j0 + r % u.nj;
+      const int sa = r / njr, gb = jr0 + r - sa * njr, ga = u.i0 + sa;
       const unsigned lin0 = ((unsigned)gb * (unsigned)D + (unsigned)ga) * (unsigned)D;
-      const int* row = tile + r * Dp;
+      const int* row = tile + glo + (sa * u.nj + (gb - u.j0)) * Dp;
       for (int k = lane; k < D; k += 32) {
         const int v = row[k];
         const unsigned long long kk = pack_peak(v, lin0 + k);
