@@ -217,22 +217,37 @@ def run_ours(args):
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        hd = torch.empty(depth.shape, dtype=depth.dtype, pin_memory=True)
-        hr = torch.empty(radius.shape, dtype=radius.dtype, pin_memory=True)
-        hd.copy_(depth)
-        hr.copy_(radius)
+        # the e2e leg pins a host copy of the step's inputs on every rank; on a box whose RAM is shared by all ranks keep the
+        # pinned total under half of what is available (whole 256-frame chunks; the rate is per frame, the note says so)
+        Be = B
+        try:
+            import psutil
+            per_frame = H * W * (2 + 4 * KPTS)
+            fit = int(0.5 * psutil.virtual_memory().available / max(1, world) / per_frame)
+            if fit < B:
+                Be = max(256, fit // 256 * 256)
+        except Exception:
+            pass
+        if world > 1:
+            t_be = torch.tensor([Be], dtype=torch.int64, device=dev)
+            dist.all_reduce(t_be, op=dist.ReduceOp.MIN)
+            Be = int(t_be.item())
+        hd = torch.empty((Be,) + tuple(depth.shape[1:]), dtype=depth.dtype, pin_memory=True)
+        hr = torch.empty((Be,) + tuple(radius.shape[1:]), dtype=radius.dtype, pin_memory=True)
+        hd.copy_(depth[:Be])
+        hr.copy_(radius[:Be])
         hdn, hrn = hd.numpy().view(np.uint16), hr.numpy()
-        hmodel = model.cpu().numpy()
+        hmodel = model[:Be].cpu().numpy()
         res = {k: torch.empty(s, dtype=t, pin_memory=True).numpy() for k, s, t in
-               [("centre_mm", (B, KPTS, 3), torch.float64), ("peak", (B, KPTS), torch.int32), ("votes", (B, KPTS), torch.int64),
-                ("n_points", (B, KPTS), torch.int32), ("grid", (B, KPTS), torch.int32), ("status", (B, KPTS), torch.int32)]}
+               [("centre_mm", (Be, KPTS, 3), torch.float64), ("peak", (Be, KPTS), torch.int32), ("votes", (Be, KPTS), torch.int64),
+                ("n_points", (Be, KPTS), torch.int32), ("grid", (Be, KPTS), torch.int32), ("status", (Be, KPTS), torch.int32)]}
 
         def e2e_step():
             o = ctx.vote_frames_host(hdn, hrn, Knp, mask_flags=1, frames_per_chunk=256, out=res)
             return o, ctx.horn_batch_host(hmodel, o["centre_mm"])
 
         o, RT = e2e_step()                                  # warm-up (allocates staging)
-        assert np.array_equal(o["centre_mm"], out["centre_mm"].cpu().numpy()), "host and device entry points disagree"
+        assert np.array_equal(o["centre_mm"], out["centre_mm"][:Be].cpu().numpy()), "host and device entry points disagree"
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -245,7 +260,7 @@ def run_ours(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         h2d = hdn.nbytes + hrn.nbytes + 72 + hmodel.nbytes + o["centre_mm"].nbytes
         d2h = sum(v.nbytes for v in res.values()) + RT.nbytes
-        e2e = {"value": frames_global * args.e2e_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        e2e = {"value": Be * world * args.e2e_steps / float(dt.item()), "unit": UNIT, "frames_per_gpu_per_step": Be, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": args.e2e_steps, "api": "rcv_vote_frames_host + rcv_horn_batch_host (pinned host buffers, 256-frame chunks, copy/compute overlap)"}
         del hd, hr
 
