@@ -644,8 +644,9 @@ RCV_HD void slice_range(const PointCtx& c, const Tile& t, int& ia, int& ib) {
   if (c.R <= 0) { ia = 1; ib = 0; }
 }
 
-// Slices per chunk of the ring passes for a slab of ni slices: 3 or 4, whichever pads the slab less.
-RCV_HD int ring_chunk(int ni) { return (((ni + 2) / 3) * 3 < ((ni + 3) / 4) * 4) ? 3 : 4; }
+// Slices per chunk of the ring passes for a slab of ni slices: 3 or 4, whichever pads the slab less (thin slabs of large
+// grids: 1 or 2, the slab itself).
+RCV_HD int ring_chunk(int ni) { return ni <= 2 ? (ni < 1 ? 1 : ni) : ((((ni + 2) / 3) * 3 < ((ni + 3) / 4) * 4) ? 3 : 4); }
 // Largest slab thickness <= ni_max that is a multiple of 3 or 4 (no padding in the ring passes).
 RCV_HD int slab_thickness(int ni_max) {
   if (ni_max < 3) return ni_max;

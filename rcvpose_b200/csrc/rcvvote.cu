@@ -743,10 +743,14 @@ __device__ __forceinline__ void ring_pass(const PointCtx& c, const Tile& t, cons
   R2_SLICE_HEAD2 VOTE("q0", "d0") R2_EMIT_INWARD("au0", "%11") VOTE("q1", "d1") R2_EMIT_INWARD("au1", "%9")
 #define R2_TAIL(BIT) "@pa or.b32 %0, %0, " BIT ";\n\t}"
 #define R2_DECL2 ".reg .b32 au0, au1;\n\t"
+#define R2_BODY1(SL, VOTE) R2_DECL R2_DECL2 SL("%12", "%13", "%14", VOTE) R2_TAIL("%15")
+#define R2_BODY2(SL, VOTE) R2_DECL R2_DECL2 SL("%12", "%14", "%16", VOTE) SL("%13", "%15", "%17", VOTE) R2_TAIL("%18")
 #define R2_BODY3(SL, VOTE) R2_DECL R2_DECL2 SL("%12", "%15", "%18", VOTE) SL("%13", "%16", "%19", VOTE) SL("%14", "%17", "%20", VOTE) R2_TAIL("%21")
 #define R2_BODY4(SL, VOTE) \
   R2_DECL R2_DECL2 SL("%12", "%16", "%20", VOTE) SL("%13", "%17", "%21", VOTE) SL("%14", "%18", "%22", VOTE) SL("%15", "%19", "%23", VOTE) R2_TAIL("%24")
 #define R2_COMMON_IN "l"(duf2), "l"(mu2), "l"(hW2), "l"(cpm2), "l"(sfv2), "f"(hw_m), "f"(nhw_p), "r"(sink), "r"(sv), "f"(thr), "r"(nsv)
+#define R2_IN1 R2_COMMON_IN, "l"(a2[0]), "r"(K0[0]), "r"(K1[0]), "r"(bit)
+#define R2_IN2 R2_COMMON_IN, "l"(a2[0]), "l"(a2[1]), "r"(K0[0]), "r"(K0[1]), "r"(K1[0]), "r"(K1[1]), "r"(bit)
 #define R2_IN3 R2_COMMON_IN, "l"(a2[0]), "l"(a2[1]), "l"(a2[2]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), "r"(bit)
 #define R2_IN4 \
   R2_COMMON_IN, "l"(a2[0]), "l"(a2[1]), "l"(a2[2]), "l"(a2[3]), "r"(K0[0]), "r"(K0[1]), "r"(K0[2]), "r"(K0[3]), "r"(K1[0]), "r"(K1[1]), "r"(K1[2]), \
@@ -763,7 +767,23 @@ template <bool OWN, int NC, int M>
 __device__ __forceinline__ void ring2_asm(unsigned& flags, unsigned bit, f32x2_t duf2, f32x2_t mu2, f32x2_t hW2, f32x2_t cpm2, f32x2_t sfv2, float hw_m,
                                           float nhw_p, unsigned sink, unsigned sv, unsigned nsv, float thr, const f32x2_t (&a2)[NC],
                                           const unsigned (&K0)[NC], const unsigned (&K1)[NC]) {
-  if constexpr (NC == 3) {
+  if constexpr (NC == 1) {
+    if constexpr (M == 1) {
+      if constexpr (OWN) asm volatile(R2_BODY1(R2_SLICE1, R2_V_OWN) : "+r"(flags) : R2_IN1 : "memory");
+      else asm volatile(R2_BODY1(R2_SLICE1, R2_V_INT) : "+r"(flags) : R2_IN1 : "memory");
+    } else {
+      if constexpr (OWN) asm volatile(R2_BODY1(R2_SLICE2, R2_V_OWN) : "+r"(flags) : R2_IN1 : "memory");
+      else asm volatile(R2_BODY1(R2_SLICE2, R2_V_INT) : "+r"(flags) : R2_IN1 : "memory");
+    }
+  } else if constexpr (NC == 2) {
+    if constexpr (M == 1) {
+      if constexpr (OWN) asm volatile(R2_BODY2(R2_SLICE1, R2_V_OWN) : "+r"(flags) : R2_IN2 : "memory");
+      else asm volatile(R2_BODY2(R2_SLICE1, R2_V_INT) : "+r"(flags) : R2_IN2 : "memory");
+    } else {
+      if constexpr (OWN) asm volatile(R2_BODY2(R2_SLICE2, R2_V_OWN) : "+r"(flags) : R2_IN2 : "memory");
+      else asm volatile(R2_BODY2(R2_SLICE2, R2_V_INT) : "+r"(flags) : R2_IN2 : "memory");
+    }
+  } else if constexpr (NC == 3) {
     if constexpr (M == 1) {
       if constexpr (OWN) asm volatile(R2_BODY3(R2_SLICE1, R2_V_OWN) : "+r"(flags) : R2_IN3 : "memory");
       else asm volatile(R2_BODY3(R2_SLICE1, R2_V_INT) : "+r"(flags) : R2_IN3 : "memory");
@@ -852,9 +872,9 @@ __device__ __forceinline__ void ring_pass2(const PointCtx& c, const Tile& t, con
         float m0, m1;
         ring2_magic(PASS, u, t.Dp, m0, m1);
         ring2_slow_call(c.px, c.py, c.pz, c.R, PASS ? c.ipz : c.ipy, PASS ? c.ipy : c.ipz, u, i0c, (PASS ? 1 : 0) | (NC << 1) | (M << 4), c.hW,
-                        c.hw_m, c.hw_p, f_sub((float)u, fu), cp, cm, fv, m0, m1, sv, a4[0], a4[1], a4[2], NC > 3 ? a4[NC - 1] : a4[0],
-                        K0[0] - kback, K0[1] - kback, K0[2] - kback, NC > 3 ? K0[NC - 1] - kback : 0u, K1[0] - kback, K1[1] - kback,
-                        K1[2] - kback, NC > 3 ? K1[NC - 1] - kback : 0u);
+                        c.hw_m, c.hw_p, f_sub((float)u, fu), cp, cm, fv, m0, m1, sv, a4[0], a4[NC > 1 ? 1 : 0], a4[NC > 2 ? 2 : 0], a4[NC > 3 ? 3 : 0],
+                        K0[0] - kback, K0[NC > 1 ? 1 : 0] - kback, K0[NC > 2 ? 2 : 0] - kback, K0[NC > 3 ? 3 : 0] - kback, K1[0] - kback,
+                        K1[NC > 1 ? 1 : 0] - kback, K1[NC > 2 ? 2 : 0] - kback, K1[NC > 3 ? 3 : 0] - kback);
       } while (flags);
     }
     __syncwarp();   // lanes that took the exact path rejoin here (measured: they otherwise walk the rest of the pass alone)
@@ -1159,7 +1179,9 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
         const bool noclip = __all_sync(0xffffffffu, ring_noclip(c, t));
         SlowExactCall slow{pa, pb, pc, R};
         if (NC == 3) ring_chunk_work<3>(c, t, ia, ib, i0c, slice_bytes, noclip, slow, emit, slowarc);
-        else ring_chunk_work<4>(c, t, ia, ib, i0c, slice_bytes, noclip, slow, emit, slowarc);
+        else if (NC == 4) ring_chunk_work<4>(c, t, ia, ib, i0c, slice_bytes, noclip, slow, emit, slowarc);
+        else if (NC == 2) ring_chunk_work<2>(c, t, ia, ib, i0c, slice_bytes, noclip, slow, emit, slowarc);   // thin slabs of large grids
+        else ring_chunk_work<1>(c, t, ia, ib, i0c, slice_bytes, noclip, slow, emit, slowarc);
       }
     }
     __syncthreads();

@@ -176,7 +176,9 @@ int hostsim_render_v6(const double* p, const int* R, long n, int D, int Dp, int 
       mplus[l] = mminus[l] = 0u; smax[l] = 0.f; slo[l] = 3.0e38f;
     }
     if (wa > wb) continue;
-    if (ring_chunk(ni) == 3) ring_chunks<3>(c, ia, ib, t, wa, wb, mplus, mminus, smax, slo, emit, emit_slow, counters);
+    if (ring_chunk(ni) == 1) ring_chunks<1>(c, ia, ib, t, wa, wb, mplus, mminus, smax, slo, emit, emit_slow, counters);
+    else if (ring_chunk(ni) == 2) ring_chunks<2>(c, ia, ib, t, wa, wb, mplus, mminus, smax, slo, emit, emit_slow, counters);
+    else if (ring_chunk(ni) == 3) ring_chunks<3>(c, ia, ib, t, wa, wb, mplus, mminus, smax, slo, emit, emit_slow, counters);
     else ring_chunks<4>(c, ia, ib, t, wa, wb, mplus, mminus, smax, slo, emit, emit_slow, counters);
     // polar pass over the tile's polar slices
     int Hp = -1; bool anyp = false, anym = false;

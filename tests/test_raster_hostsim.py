@@ -91,7 +91,7 @@ def test_linemod_shaped_frame_matches_reference_volume(golden):
     assert st["votes"] == int(golden["c1_votes"])
 
 
-@pytest.mark.parametrize("slab", [1, 3, 4, 6, 7, 12, 32])
+@pytest.mark.parametrize("slab", [1, 2, 3, 4, 6, 7, 12, 32])
 def test_slab_thickness_and_chunking(slab):
     """The kernel walks a slab in chunks of 3 or 4 slices and draws the polar caps once per slab: every slab
     thickness must give the same volume (exercises chunk alignment, polar masks and the annulus row ranges)."""
