@@ -430,12 +430,16 @@ RCV_HD void ring2_slow_lane(bool pass, int nc, int M, int ipl, int ipc, int u, i
         const float fl = f_sub(cd.fl, (float)m);                 // exact: small integers
         const float d = m ? f_add(fl, sfv) : cd.d;
         if (!(fabsf(d) > thr)) continue;
-        if (m < M) {
-          const float q = m ? f_fma(d, d, hWg) : cd.q;
-          if ((fabsf(q) < hw_m) || !(q > -hw_p)) continue;       // decided by the fast path
+        const float q = m ? f_fma(d, d, hWg) : cd.q;
+        const bool sure = fabsf(q) < hw_m;
+        if (!(q > -hw_p) || q >= hw_p) continue;                 // surely below the inner or above the outer sphere: no vote
+        const unsigned addr = addr0 + (unsigned)(m * dir) * sv;
+        if (sure) {                                              // surely inside the shell
+          if (m == M) emit_slow((int)addr);                      // (m < M: the fast path has cast this vote already)
+          continue;
         }
-        const int cc = arc ? ipc - n + m : ipc + n - m;
-        if (slow(i, pass ? cc : lc, pass ? lc : cc)) emit_slow((int)(addr0 + (unsigned)(m * dir) * sv));
+        const int cc = arc ? ipc - n + m : ipc + n - m;          // within eps of a shell boundary: the reference's float64 sequence
+        if (slow(i, pass ? cc : lc, pass ? lc : cc)) emit_slow((int)addr);
       }
     }
   }
@@ -595,7 +599,7 @@ RCV_HD bool polar2_side(const PointCtx& c, const Tile& t, unsigned mask, bool pl
   return mask == full;
 }
 struct Polar2Cell {
-  float q, fl;
+  float q, fl, hWg;
   unsigned bits;
   bool wide, sure, vote, amb;
 };
@@ -605,6 +609,7 @@ RCV_HD void polar2_cell(const PointCtx& c, const Polar2Side& s, float ucf, float
   const float g = f_fma(-dc, dc, r2mdb2);
   const float zs = f_sqrt_fast(g);          // NaN outside the sphere's shadow: no vote, no exact path
   const float hWg = f_sub(c.hW, g);
+  o.hWg = hWg;
   const float tm = f_add(f_add(zs, s.cx), RCV_MAGIC);
   o.bits = (unsigned)f_bits(tm);
   o.fl = f_sub(tm, RCV_MAGIC);
@@ -627,10 +632,17 @@ RCV_HD void polar2_slow_cell(const PointCtx& c, const Polar2Side& s, float ucf, 
   if (!o.amb) return;
   const int n = (int)o.fl;
   const unsigned addr = o.bits * smul + K;
-  if (n >= s.nlo && n <= s.nhi_i && slow(c.ipx + s.sgn * n, jb, kc)) emit_slow((int)addr);
+  // the candidate itself: the float64 sequence only if its residual is within eps of a shell boundary (beyond hw_p it is
+  // surely outside the outer sphere)
+  if (o.q < c.hw_p && n >= s.nlo && n <= s.nhi_i && slow(c.ipx + s.sgn * n, jb, kc)) emit_slow((int)addr);
   if (o.q >= c.hw_m) {   // the candidate may lie outside the outer sphere: the voxel one step inwards can then be inside
     const int n2 = n - 1;
-    if (n2 >= s.nlo && n2 <= s.nhi_i && slow(c.ipx + s.sgn * n2, jb, kc)) emit_slow((int)(addr - smul));
+    if (n2 >= s.nlo && n2 <= s.nhi_i) {
+      const float d2 = f_add(f_sub(o.fl, 1.0f), s.sfx);          // (integer - 1) -+ fraction, one rounding
+      const float q2 = f_fma(d2, d2, o.hWg);
+      if (fabsf(q2) < c.hw_m) emit_slow((int)(addr - smul));     // surely inside the shell
+      else if ((q2 > -c.hw_p) && (q2 < c.hw_p) && slow(c.ipx + s.sgn * n2, jb, kc)) emit_slow((int)(addr - smul));
+    }
   }
 }
 
