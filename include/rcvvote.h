@@ -154,6 +154,33 @@ int rcv_horn_batch_host(rcv_ctx* ctx, const double* model, long long model_strid
 int rcv_add_metric_batch(rcv_ctx* ctx, const double* model_mm, int n_model, const double* RT_est, const double* RT_gt, int n_frames,
                          double* mean_out, double* min_out, void* stream);
 
+/* ---- scene cloud of a frame (the ICP target)  -- AccumulatorSpace.py:620-625 (LM), :863-868 (LMO), :1070-1075 (YCB) ----
+ * The reference appends, keypoint after keypoint, the masked cloud's points that were not seen before (`xyz_mm_icp`, an
+ * O(N^2) Python loop).  Every cloud of a frame is a back-projection of the same depth map, so the union is
+ * rgbd_to_point_cloud(K, depth * (mask_1 | ... | mask_Kp)) (:77-85), times `scale` (1 for LM/LMO whose clouds are in mm,
+ * 1000 for YCB's xyz_icp*1000, :1154).  Same inputs and mask rules as rcv_vote_frames.  Points come out frame after
+ * frame in row-major pixel order: xyz_out [offsets_out[f], offsets_out[f+1]) x 3 float64; offsets_out has n_frames + 1
+ * entries; a frame that does not fit xyz_capacity (points) gets an empty range and RCV_ST_POINT_OVERFLOW in status_out
+ * (may be NULL), an empty union RCV_ST_EMPTY_MASK. */
+int rcv_scene_clouds(rcv_ctx* ctx, int n_frames, int n_kpts, const void* depth, const float* radius, const float* sem,
+                     const double* K, const double* max_radii, const rcv_frame_params* fp, double scale, double* xyz_out,
+                     long long xyz_capacity, long long* offsets_out, int* status_out, void* stream);
+
+/* ---- point-to-point ICP refinement of the Horn pose  -- AccumulatorSpace.py:704-718 (LM), :929-950 (LMO), :1152-1180 (YCB) ----
+ * Replaces open3d 0.14.1 (rcvpose.yml:176; third-party, not in the reference tree)
+ *   registration_icp(source = CAD model, target = scene, max_correspondence_distance, init,
+ *                    TransformationEstimationPointToPoint(), ICPConvergenceCriteria(relative_fitness, relative_rmse, max_iteration))
+ * for n_frames frames at once (see csrc/refine.cu for the restated algorithm).  Exact brute-force float64 nearest neighbour.
+ *   model [n_model][3] float64 (shared by the frames), scene [*][3] float64 with frame f owning
+ *   [scene_offsets[f], scene_offsets[f+1]) (the layout rcv_scene_clouds writes), RT_init [n_frames][4][4] row-major,
+ *   max_dist [n_frames] (the reference passes the ADD(-S) distance before ICP), defaults of open3d: max_iter 30,
+ *   rel_fitness = rel_rmse = 1e-6.  Outputs: RT_out [n_frames][4][4] (reg.transformation), fitness_out / rmse_out
+ *   [n_frames] (reg.fitness, reg.inlier_rmse), iters_out [n_frames] (updates applied).  Stream-ordered; for
+ *   max_iter > 32 the call looks at a device counter every 32 iterations and stops once every frame has converged. */
+int rcv_icp_batch(rcv_ctx* ctx, const double* model, int n_model, const double* scene, const long long* scene_offsets,
+                  const double* RT_init, const double* max_dist, int n_frames, int max_iter, double rel_fitness, double rel_rmse,
+                  double* RT_out, double* fitness_out, double* rmse_out, int* iters_out, void* stream);
+
 /* ---- conv8 of the radius-map producer  -- models/fcnresnet.py:118 (definition), :187-189 (use) -----------
  * out[b][n][p] = bias[n] + sum_k bf16(weight[n][k]) * up[b][k][p],  n = 0 (seg), 1 (radial), k = 0..31.
  * The 1x1 head as a tcgen05 tensor-core kernel (bf16 operands, fp32 accumulation in tensor memory).

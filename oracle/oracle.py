@@ -187,3 +187,76 @@ def add_metric(model_mm, RT_est, RT_gt):
     gt = np.dot(model_mm, RT_gt[:3, :3].T) + RT_gt[:3, 3:].T
     d, _ = cKDTree(est).query(gt, k=1)
     return float(d.mean()), float(d.min())
+
+
+def scene_union(clouds):
+    """xyz_mm_icp (AccumulatorSpace.py:620-625, :863-868, :1070-1075): the first keypoint's cloud, then every point of the later
+    clouds that is not in the list yet, in order of first appearance (the reference's O(N^2) loop, restated with a set of rows)."""
+    out = [np.asarray(c, dtype=np.float64) for c in clouds[:1]]
+    seen = set(map(bytes, out[0])) if out else set()
+    for c in clouds[1:]:
+        keep = []
+        for row in np.asarray(c, dtype=np.float64):
+            b = bytes(row)
+            if b not in seen:
+                seen.add(b)
+                keep.append(row)
+        if keep:
+            out.append(np.array(keep))
+    return np.concatenate(out, axis=0) if out else np.zeros((0, 3))
+
+
+def umeyama_rigid(src, dst):
+    """Eigen::umeyama(src, dst, with_scaling=false) on (n,3) arrays -> 4x4: the rigid transform of
+    TransformationEstimationPointToPoint::ComputeTransformation (open3d 0.14.1).  Restated from Eigen/src/Geometry/Umeyama.h:
+    sigma = dst_demean * src_demean^T / n, SVD, S = diag(1, 1, sign(det U det V)), R = U S V^T, t = mean_dst - R mean_src."""
+    n = src.shape[0]
+    ms, md = src.mean(axis=0), dst.mean(axis=0)
+    sigma = (dst - md).T @ (src - ms) / n
+    U, _, Vt = np.linalg.svd(sigma)
+    S = np.ones(3)
+    if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+        S[2] = -1.0
+    R = U @ np.diag(S) @ Vt
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = md - R @ ms
+    return T
+
+
+def registration_icp(source, target, max_correspondence_distance, init, max_iteration=30, relative_fitness=1e-6, relative_rmse=1e-6):
+    """open3d.pipelines.registration.registration_icp(source, target, max_correspondence_distance, init,
+    TransformationEstimationPointToPoint(), ICPConvergenceCriteria(...)) as the reference calls it
+    (AccumulatorSpace.py:704-718, :929-950, :1152-1180).  open3d 0.14.1 (rcvpose.yml:176) is a third-party dependency that is
+    not in the reference tree nor in this image, so this is a restatement of its published algorithm
+    (cpp/open3d/pipelines/registration/Registration.cpp: RegistrationICP + GetRegistrationResultAndCorrespondences) and
+    parity for this row is UNPINNED (no open3d output to check against).  Returns dict(transformation, fitness, inlier_rmse,
+    iterations)."""
+    from scipy.spatial import cKDTree
+    source = np.asarray(source, dtype=np.float64)
+    target = np.asarray(target, dtype=np.float64)
+    tree = cKDTree(target) if len(target) else None
+
+    def evaluate(pcd):
+        if tree is None:
+            return 0.0, 0.0, np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+        d, j = tree.query(pcd, k=1)
+        keep = d * d < max_correspondence_distance * max_correspondence_distance    # SearchHybrid: strict
+        i = np.nonzero(keep)[0]
+        if len(i) == 0:
+            return 0.0, 0.0, i, j[i]
+        return len(i) / len(pcd), float(np.sqrt(np.sum(d[i] ** 2) / len(i))), i, j[i]
+
+    T = np.array(init, dtype=np.float64)
+    pcd = source @ T[:3, :3].T + T[:3, 3]
+    fit, rmse, ci, cj = evaluate(pcd)
+    it = 0
+    for it in range(1, max_iteration + 1):
+        upd = umeyama_rigid(pcd[ci], target[cj]) if len(ci) else np.eye(4)
+        T = upd @ T
+        pcd = pcd @ upd[:3, :3].T + upd[:3, 3]
+        bfit, brmse = fit, rmse
+        fit, rmse, ci, cj = evaluate(pcd)
+        if abs(bfit - fit) < relative_fitness and abs(brmse - rmse) < relative_rmse:
+            break
+    return dict(transformation=T, fitness=fit, inlier_rmse=rmse, iterations=it)

@@ -4,6 +4,8 @@ signatures, dtypes, units and return shapes -- executed on the B200 through libr
     rgbd_to_point_cloud(K, depth)     reference AccumulatorSpace.py:77-85
     Accumulator_3D(xyz, radial_list)  reference AccumulatorSpace.py:373-419
     linemod_K                         reference AccumulatorSpace.py:59-61
+    read_depth(path)                  reference AccumulatorSpace.py:482-490
+    estimate_6d_pose_lm(opts)         reference AccumulatorSpace.py:495-744 (batched: rcvpose_b200/evaluate.py)
 
 Putting this package's directory ahead of the reference on sys.path makes
 `estimate_6d_pose_*` (reference :495-1197) call these instead.  Inputs and outputs are NumPy
@@ -79,3 +81,13 @@ def vote_volume(xyz, radial_list, acc_unit=5, radius_scale=100, policy=api.RCV_P
     D = int(out["grid"].item())
     out = ctx.vote_points(x, rr, acc_unit=acc_unit, radius_scale=radius_scale, policy=policy, want_volume=True, volume_capacity=D ** 3)
     return out["volume_flat"][: D ** 3].reshape(D, D, D).cpu().numpy(), out
+
+
+def read_depth(path):
+    from . import formats
+    return formats.read_depth(path)
+
+
+def estimate_6d_pose_lm(opts):
+    from . import evaluate
+    return evaluate.estimate_6d_pose_lm(opts)

@@ -60,7 +60,7 @@ class VoteContext:
         if rc != 0:
             raise RcvError("rcv_create failed (%d): %s" % (rc, self.lib.rcv_last_error(None).decode()))
         self.h = h
-        self.max_items, self.max_grid = int(max_items), int(max_grid)
+        self.max_items, self.max_grid, self.max_points_total = int(max_items), int(max_grid), int(max_points_total)
 
     def close(self):
         if getattr(self, "h", None):
@@ -226,6 +226,53 @@ class VoteContext:
             self._ck(self.lib.rcv_add_metric_batch(self.h, _ptr(model_mm), int(model_mm.shape[0]), _ptr(RT_est), _ptr(RT_gt), B, _ptr(mean),
                                                    _ptr(mn), _stream()))
         return mean, mn
+
+    # ---- xyz_mm_icp: union of a frame's masked clouds (AccumulatorSpace.py:620-625) ----
+    def scene_clouds(self, depth, radius, K, sem=None, max_radii=None, mask_flags=MASK_LM_NPY, sem_threshold=0.8, depth_div=1.0, scale=1.0,
+                     capacity=None):
+        """Same maps and mask rules as vote_frames -> (xyz (N,3) float64 CUDA, offsets (B+1,) int64 CUDA, status (B,) int32 CUDA):
+        frame f's scene cloud is xyz[offsets[f]:offsets[f+1]] = rgbd_to_point_cloud(K, depth * (mask_1 | ... | mask_Kp)) * scale."""
+        _check_cuda(depth, None, "depth")
+        _check_cuda(radius, torch.float32, "radius")
+        _check_cuda(K, torch.float64, "K")
+        B, Kp, H, W = radius.shape
+        if tuple(depth.shape) != (B, H, W):
+            raise RcvError("depth must be (B,H,W) matching radius (B,Kp,H,W)")
+        if sem is not None:
+            _check_cuda(sem, torch.float32, "sem")
+        if max_radii is not None:
+            _check_cuda(max_radii, torch.float64, "max_radii")
+        dev = radius.device
+        cap = int(capacity if capacity is not None else min(self.max_points_total, B * H * W))
+        fp = _lib.rcv_frame_params(H, W, _DEPTH_DTYPES[depth.dtype], float(depth_div), 1000.0, int(mask_flags), float(sem_threshold),
+                                   9 if (K.dim() == 3 and K.shape[0] == B) else 0,
+                                   Kp if (max_radii is not None and max_radii.dim() == 2 and max_radii.shape[0] == B) else 0)
+        xyz = torch.empty((cap, 3), dtype=torch.float64, device=dev)
+        offsets = torch.empty(B + 1, dtype=torch.int64, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_scene_clouds(self.h, B, Kp, _ptr(depth), _ptr(radius), _ptr(sem), _ptr(K), _ptr(max_radii), C.byref(fp),
+                                               float(scale), _ptr(xyz), cap, _ptr(offsets), _ptr(status), _stream()))
+        return xyz, offsets, status
+
+    # ---- open3d registration_icp, point to point (AccumulatorSpace.py:704-718) ----
+    def icp(self, model, scene, scene_offsets, RT_init, max_dist, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6):
+        """model (M,3), scene (N,3), scene_offsets (B+1,) int64, RT_init (B,4,4), max_dist (B,) -- all CUDA, float64 unless noted ->
+        dict(RT (B,4,4), fitness (B,), rmse (B,), iters (B,) int32): open3d's reg.transformation / fitness / inlier_rmse."""
+        for t, n in ((model, "model"), (scene, "scene"), (RT_init, "RT_init"), (max_dist, "max_dist")):
+            _check_cuda(t, torch.float64, n)
+        _check_cuda(scene_offsets, torch.int64, "scene_offsets")
+        B = RT_init.shape[0]
+        if RT_init.shape[1:] != (4, 4) or max_dist.numel() != B or scene_offsets.numel() != B + 1 or model.dim() != 2 or model.shape[1] != 3:
+            raise RcvError("icp: model (M,3), scene (N,3), scene_offsets (B+1,), RT_init (B,4,4), max_dist (B,)")
+        dev = RT_init.device
+        out = dict(RT=torch.empty((B, 4, 4), dtype=torch.float64, device=dev), fitness=torch.empty(B, dtype=torch.float64, device=dev),
+                   rmse=torch.empty(B, dtype=torch.float64, device=dev), iters=torch.empty(B, dtype=torch.int32, device=dev))
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_icp_batch(self.h, _ptr(model), int(model.shape[0]), _ptr(scene), _ptr(scene_offsets), _ptr(RT_init),
+                                            _ptr(max_dist), B, int(max_iter), float(rel_fitness), float(rel_rmse), _ptr(out["RT"]),
+                                            _ptr(out["fitness"]), _ptr(out["rmse"]), _ptr(out["iters"]), _stream()))
+        return out
 
     def head_1x1(self, up, weight, bias):
         """conv8 of the reference's producer (models/fcnresnet.py:118,187-189) on the tensor cores.

@@ -22,6 +22,7 @@
 
 #include "../../include/rcvvote.h"
 #include "raster_core.h"
+#include "horn_core.h"
 
 #define RCV_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -344,6 +345,112 @@ __global__ void k_scan_items(const int* __restrict__ cnt, int n_items, long long
     if (o + m.n > cap) { m.status = RCV_ST_POINT_OVERFLOW; m.n = 0; m.off = 0; }
     o += cnt[b];
     meta[b] = m;
+  }
+}
+
+// ---- scene cloud of a frame: the union over its keypoints of the masked clouds ------------------------------------
+// The reference builds the ICP target `xyz_mm_icp` by appending, keypoint after keypoint, the points not seen before
+// (an O(N^2) Python loop, AccumulatorSpace.py:620-625, :863-868, :1070-1075).  All of a frame's clouds come from the same
+// depth map, so the union is the back-projection of the pixels that survive ANY keypoint's mask rule: one CTA per frame
+// ORs the survival bits of the keypoints; compaction and conversion reuse the K1 kernels' scheme.  The points come out in
+// row-major pixel order (the reference's order is first appearance by keypoint; ICP does not depend on the order).
+__global__ void __launch_bounds__(kCompactThreads) k_scene_mask(FrameArgs a, int* __restrict__ cnt, unsigned* __restrict__ bits, int words_per_item) {
+  const int frame = blockIdx.x;
+  const int npx = a.fp.height * a.fp.width;
+  const long long frame_px0 = (long long)frame * npx;
+  const bool vec_ok = a.vec_ok != 0;
+  unsigned* out = bits + (long long)frame * words_per_item;
+  const int lane = threadIdx.x & 31;
+  int n = 0;
+  for (int px = threadIdx.x * kPxPerThread; px < words_per_item * 32; px += kPxPerIter) {
+    double zraw[kPxPerThread];
+    float rad[kPxPerThread];
+    unsigned m = 0;
+    if (px < npx) {
+      for (int kp = 0; kp < a.n_kpts; ++kp) {
+        const double max_r = a.max_radii ? a.max_radii[(long long)frame * a.fp.max_radii_stride + kp] : 0.0;
+        m |= pixel_group_mask(a, frame_px0, ((long long)frame * a.n_kpts + kp) * npx, px, npx, vec_ok, max_r, zraw, rad);
+      }
+    }
+    n += __popc(m);
+    unsigned w = m << ((lane & 3) * 8);
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    if ((lane & 3) == 0) out[px >> 5] = w;
+  }
+  __shared__ int s_n[kCompactThreads / 32];
+  n = __reduce_add_sync(0xffffffffu, n);
+  if (lane == 0) s_n[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kCompactThreads / 32; ++w) t += s_n[w];
+    cnt[frame] = t;
+  }
+}
+
+// Exclusive scan of the per-frame counts into offsets[n_frames + 1]; frames that do not fit below `cap` get an empty range
+// and status RCV_ST_POINT_OVERFLOW (once one frame overflows all later ones do).
+__global__ void k_scene_scan(const int* __restrict__ cnt, int n_frames, long long cap, ItemMeta* meta, long long* __restrict__ offsets,
+                             int* __restrict__ status) {
+  __shared__ long long s_part[1024];
+  __shared__ unsigned long long s_limit;
+  const int per = (n_frames + blockDim.x - 1) / blockDim.x;
+  const int b0 = threadIdx.x * per, b1 = min(n_frames, b0 + per);
+  long long s = 0;
+  for (int b = b0; b < b1; ++b) s += cnt[b];
+  s_part[threadIdx.x] = s;
+  if (threadIdx.x == 0) s_limit = ~0ull;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    for (int t = 0; t < (int)blockDim.x; ++t) { long long v = s_part[t]; s_part[t] = run; run += v; }
+    if (run <= cap) s_limit = (unsigned long long)run;   // everything fits: the end offset is the total
+  }
+  __syncthreads();
+  long long o = s_part[threadIdx.x];
+  for (int b = b0; b < b1; ++b) {
+    if (o + cnt[b] > cap) atomicMin(&s_limit, (unsigned long long)o);
+    o += cnt[b];
+  }
+  __syncthreads();
+  const long long limit = (long long)s_limit;
+  o = s_part[threadIdx.x];
+  for (int b = b0; b < b1; ++b) {
+    ItemMeta m;
+    memset(&m, 0, sizeof(m));
+    const bool fits = o + cnt[b] <= cap;
+    m.off = fits ? o : limit;
+    m.n = fits ? cnt[b] : 0;
+    m.status = fits ? (cnt[b] ? RCV_ST_OK : RCV_ST_EMPTY_MASK) : RCV_ST_POINT_OVERFLOW;
+    meta[b] = m;
+    offsets[b] = m.off;
+    if (status) status[b] = m.status;
+    o += cnt[b];
+  }
+  if (threadIdx.x == 0) offsets[n_frames] = limit;
+}
+
+// rgbd_to_point_cloud (AccumulatorSpace.py:77-85) of the union pixels, times `scale` (the YCB evaluator's xyz_icp*1000, :1154)
+__global__ void __launch_bounds__(256) k_scene_points(FrameArgs a, const ItemMeta* __restrict__ meta, const int* __restrict__ pix, double scale,
+                                                     double* __restrict__ xyz) {
+  const int frame = blockIdx.x;
+  const ItemMeta m = meta[frame];
+  if (m.n == 0) return;
+  const int W = a.fp.width, npx = a.fp.height * a.fp.width;
+  const long long frame_px0 = (long long)frame * npx;
+  const double* Kp = a.K + (long long)frame * a.fp.k_stride;
+  const double fx = Kp[0], cx = Kp[2], fy = Kp[4], cy = Kp[5];
+  for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < m.n; q += gridDim.y * blockDim.x) {
+    const long long o = m.off + q;
+    const int p = pix[o];
+    const int u = p % W, v = p / W;
+    const double z = __ddiv_rn(load_depth(a.depth, a.fp.depth_dtype, frame_px0 + p), a.fp.depth_div);
+    const double x = __ddiv_rn(__dmul_rn(__dsub_rn((double)u, cx), z), fx);
+    const double y = __ddiv_rn(__dmul_rn(__dsub_rn((double)v, cy), z), fy);
+    xyz[3 * o + 0] = __dmul_rn(x, scale);
+    xyz[3 * o + 1] = __dmul_rn(y, scale);
+    xyz[3 * o + 2] = __dmul_rn(z, scale);
   }
 }
 
@@ -1293,12 +1400,6 @@ __global__ void k_argmax_unpack(const unsigned long long* best, int D, int* idx_
 // Quaternion method: eigenvector of the largest eigenvalue of the symmetric 4x4 N built from the
 // cross-covariance sums; cyclic Jacobi with the reference's sweep order, thresholds and 50-sweep cap.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void jac_rot(double (*a)[4], int i, int j, int k, int l, double s, double tau) {
-  const double g = a[i][j], h = a[k][l];
-  a[i][j] = g - s * (h + g * tau);
-  a[k][l] = h + s * (g - h * tau);
-}
-
 __global__ void k_horn(const double* __restrict__ model, long long model_stride, const double* __restrict__ est, int n, int n_frames,
                        double* __restrict__ RT) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1316,55 +1417,8 @@ __global__ void k_horn(const double* __restrict__ model, long long model_stride,
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) S[r][c] += a[r] * b[c];
   }
-  double A[4][4], V[4][4], d[4], bq[4], zq[4];
-  A[0][0] = S[0][0] + S[1][1] + S[2][2]; A[0][1] = S[1][2] - S[2][1]; A[0][2] = S[2][0] - S[0][2]; A[0][3] = S[0][1] - S[1][0];
-  A[1][0] = A[0][1]; A[1][1] = S[0][0] - S[1][1] - S[2][2]; A[1][2] = S[0][1] + S[1][0]; A[1][3] = S[2][0] + S[0][2];
-  A[2][0] = A[0][2]; A[2][1] = A[1][2]; A[2][2] = -S[0][0] + S[1][1] - S[2][2]; A[2][3] = S[1][2] + S[2][1];
-  A[3][0] = A[0][3]; A[3][1] = A[1][3]; A[3][2] = A[2][3]; A[3][3] = -S[0][0] - S[1][1] + S[2][2];
-  for (int p = 0; p < 4; ++p) {
-    for (int q = 0; q < 4; ++q) V[p][q] = 0.0;
-    V[p][p] = 1.0;
-    bq[p] = d[p] = A[p][p];
-    zq[p] = 0.0;
-  }
-  for (int sweep = 1; sweep <= 50; ++sweep) {
-    double sm = 0.0;
-    for (int p = 0; p < 3; ++p)
-      for (int q = 0; q < 4; ++q) sm += fabs(A[p][q]);  // util/horn.py:28-30 sums whole rows, diagonal included
-    if (sm == 0.0) break;
-    const double tresh = sweep < 4 ? 0.2 * sm / 16.0 : 0.0;
-    for (int p = 0; p < 3; ++p)
-      for (int q = p + 1; q < 4; ++q) {
-        const double g = 100.0 * fabs(A[p][q]);
-        if (sweep > 4 && fabs(d[p]) + g == fabs(d[p]) && fabs(d[q]) + g == fabs(d[q])) A[p][q] = 0.0;
-        else if (fabs(A[p][q]) > tresh) {
-          double h = d[q] - d[p], t;
-          if (fabs(h) + g == fabs(h)) t = A[p][q] / h;
-          else {
-            const double theta = 0.5 * h / A[p][q];
-            t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
-            if (theta < 0.0) t = -t;
-          }
-          const double c = 1.0 / sqrt(1 + t * t), s = t * c, tau = s / (1.0 + c);
-          h = t * A[p][q];
-          zq[p] -= h; zq[q] += h; d[p] -= h; d[q] += h;
-          A[p][q] = 0.0;
-          for (int j = 0; j < p; ++j) jac_rot(A, j, p, j, q, s, tau);
-          for (int j = p + 1; j < q; ++j) jac_rot(A, p, j, j, q, s, tau);
-          for (int j = q + 1; j < 4; ++j) jac_rot(A, p, j, q, j, s, tau);
-          for (int j = 0; j < 4; ++j) jac_rot(V, j, p, j, q, s, tau);
-        }
-      }
-    for (int p = 0; p < 4; ++p) { bq[p] += zq[p]; d[p] = bq[p]; zq[p] = 0.0; }
-  }
-  int me = 0;
-  for (int p = 1; p < 4; ++p)
-    if (d[p] > d[me]) me = p;
-  const double q0 = V[0][me], q1 = V[1][me], q2 = V[2][me], q3 = V[3][me];
   double R[3][3];
-  R[0][0] = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3; R[0][1] = 2 * (q1 * q2 - q0 * q3); R[0][2] = 2 * (q1 * q3 + q0 * q2);
-  R[1][0] = 2 * (q1 * q2 + q0 * q3); R[1][1] = q0 * q0 + q2 * q2 - q1 * q1 - q3 * q3; R[1][2] = 2 * (q2 * q3 - q0 * q1);
-  R[2][0] = 2 * (q1 * q3 - q0 * q2); R[2][1] = 2 * (q2 * q3 + q0 * q1); R[2][2] = q0 * q0 + q3 * q3 - q1 * q1 - q2 * q2;
+  horn_rotation_from_S(S, R);
   double* o = RT + (long long)f * 16;
   for (int r = 0; r < 3; ++r) {
     for (int c = 0; c < 3; ++c) o[4 * r + c] = R[r][c];
@@ -1476,6 +1530,7 @@ struct rcv_ctx {
   int* counters;  // [0] units queued, [1] queue cursor
   int* cnt;
   unsigned* mask_bits; long long mask_words;
+  double* icp_scratch; long long icp_cap;         // ICP scratch: per-frame state + per-(frame, tile) partial sums
   double* add_part; long long add_part_cap;     // ADD metric scratch: per-(frame, tile) partial sums and minima   // K1 scratch: one survival bit per pixel of every item of a call (grown on demand)
   unsigned long long *best, *votes;
   PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
@@ -1518,7 +1573,7 @@ RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri); cudaFree(c->pool.perm);
   cudaFree(c->meta); cudaFree(c->units); cudaFree(c->counters); cudaFree(c->cnt); cudaFree(c->best); cudaFree(c->votes);
-  cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits); cudaFree(c->add_part);
+  cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits); cudaFree(c->add_part); cudaFree(c->icp_scratch);
   for (int s = 0; s < 2; ++s) { cudaFree(c->st_depth[s]); cudaFree(c->st_radius[s]); cudaFree(c->st_sem[s]); }
   cudaFree(c->st_K); cudaFree(c->st_maxr); cudaFree(c->st_centre); cudaFree(c->st_peak); cudaFree(c->st_votes);
   cudaFree(c->st_np); cudaFree(c->st_grid); cudaFree(c->st_status); cudaFree(c->st_horn_in);
@@ -1813,6 +1868,62 @@ RCV_EXPORT int rcv_add_metric_batch(rcv_ctx* c, const double* model_mm, int n_mo
   k_add_finish<<<(n_frames + 127) / 128, 128, 0, st>>>(ps, pm, tiles, n_model, n_frames, mean_out, min_out);
   c->launches += 2;
   CK(c, cudaGetLastError());
+  return RCV_OK;
+}
+
+RCV_EXPORT int rcv_scene_clouds(rcv_ctx* c, int n_frames, int n_kpts, const void* depth, const float* radius, const float* sem,
+                                const double* K, const double* max_radii, const rcv_frame_params* fp, double scale, double* xyz_out,
+                                long long xyz_capacity, long long* offsets_out, int* status_out, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!depth || !radius || !K || !xyz_out || !offsets_out || xyz_capacity <= 0) FAIL(c, RCV_E_INVALID, "rcv_scene_clouds: bad argument");
+  int rc = check_frame_params(c, n_frames, n_kpts, fp, sem, max_radii);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(c, cudaSetDevice(c->device));
+  const long long npx = (long long)fp->height * fp->width;
+  const int vec_ok = (npx % 8 == 0) && (((uintptr_t)depth | (uintptr_t)radius | (uintptr_t)sem) % 16 == 0);
+  FrameArgs fa{depth, radius, sem, K, max_radii, *fp, 1.0, 1.0, n_kpts, vec_ok};
+  const int words = (int)((npx + 255) / 256) * 8;
+  const long long need = (long long)n_frames * words;
+  if (need > c->mask_words) {
+    CK(c, cudaStreamSynchronize(st));
+    cudaFree(c->mask_bits); c->mask_bits = nullptr; c->mask_words = 0;
+    CK(c, cudaMalloc(&c->mask_bits, (size_t)need * 4));
+    c->mask_words = need;
+  }
+  const long long cap = xyz_capacity < c->pool.cap ? xyz_capacity : c->pool.cap;   // the pixel list lives in the pool's index array
+  k_scene_mask<<<n_frames, kCompactThreads, 0, st>>>(fa, c->cnt, c->mask_bits, words);
+  k_scene_scan<<<1, 1024, 0, st>>>(c->cnt, n_frames, cap, c->meta, offsets_out, status_out);
+  k_frame_emit<<<n_frames, kCompactThreads, 0, st>>>(c->mask_bits, words, c->meta, c->pool.perm);
+  k_scene_points<<<dim3(n_frames, 4), 256, 0, st>>>(fa, c->meta, c->pool.perm, scale, xyz_out);
+  c->launches += 4;
+  CK(c, cudaGetLastError());
+  return RCV_OK;
+}
+
+extern "C" long long rcv_icp_scratch_doubles(int n_frames, int n_model);
+extern "C" int rcv_icp_launch(const double* model, int n_model, const double* scene, const long long* scene_off, const double* RT_init,
+                              const double* max_dist, int n_frames, int max_iter, double rel_fitness, double rel_rmse, double* scratch,
+                              double* RT_out, double* fitness_out, double* rmse_out, int* iters_out, void* stream, long long* launches);
+
+RCV_EXPORT int rcv_icp_batch(rcv_ctx* c, const double* model, int n_model, const double* scene, const long long* scene_offsets,
+                             const double* RT_init, const double* max_dist, int n_frames, int max_iter, double rel_fitness, double rel_rmse,
+                             double* RT_out, double* fitness_out, double* rmse_out, int* iters_out, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!model || !scene || !scene_offsets || !RT_init || !max_dist || !RT_out || !fitness_out || !rmse_out || !iters_out || n_model <= 0 ||
+      n_frames <= 0 || n_frames > 65535 || max_iter < 0)
+    FAIL(c, RCV_E_INVALID, "rcv_icp_batch: bad argument (n_frames in 1..65535, max_iter >= 0)");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(c, cudaSetDevice(c->device));
+  const long long need = rcv_icp_scratch_doubles(n_frames, n_model);
+  if (need > c->icp_cap) {   // first call of this size only
+    CK(c, cudaStreamSynchronize(st));
+    cudaFree(c->icp_scratch); c->icp_scratch = nullptr; c->icp_cap = 0;
+    CK(c, cudaMalloc(&c->icp_scratch, (size_t)need * 8));
+    c->icp_cap = need;
+  }
+  CK(c, (cudaError_t)rcv_icp_launch(model, n_model, scene, scene_offsets, RT_init, max_dist, n_frames, max_iter, rel_fitness, rel_rmse,
+                                    c->icp_scratch, RT_out, fitness_out, rmse_out, iters_out, stream, &c->launches));
   return RCV_OK;
 }
 

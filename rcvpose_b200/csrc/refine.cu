@@ -1,0 +1,211 @@
+// refine.cu -- point-to-point ICP refinement of the Horn pose on the GPU (SURVEY.md section 8f, N3 second half).
+//
+// What it replaces: the reference refines every pose with open3d (third-party, un-vendored, pinned to 0.14.1 by
+// rcvpose.yml:176; absent from /root/reference), AccumulatorSpace.py:704-718 (LM), :929-950 (LMO), :1152-1180 (YCB):
+//     reg = registration_icp(cad_model, scene, threshold, trans_init = RT,
+//                            TransformationEstimationPointToPoint(), ICPConvergenceCriteria())
+// with source = the CAD points (mm), target = the union of the keypoints' masked clouds (mm), threshold = the ADD(-S)
+// distance measured before ICP, default criteria (relative_fitness = relative_rmse = 1e-6, max_iteration = 30).
+// open3d's published algorithm (pipelines/registration/Registration.cpp: RegistrationICP,
+// GetRegistrationResultAndCorrespondences; TransformationEstimationPointToPoint::ComputeTransformation = Eigen::umeyama
+// without scaling), restated here:
+//     T = init; result = evaluate(T)
+//     repeat max_iteration times:
+//         update = rigid transform minimising sum |update * (T s_i) - t_c(i)|^2 over the correspondences of `result`
+//         T = update * T;  backup = result;  result = evaluate(T)
+//         stop when |backup.fitness - result.fitness| < relative_fitness and |backup.rmse - result.rmse| < relative_rmse
+//     evaluate(T): for every source point the nearest target point, kept when dist^2 < threshold^2 (strict, KDTreeFlann
+//         SearchHybrid); fitness = kept / n_source, inlier_rmse = sqrt(sum dist^2 / kept) (0 when nothing is kept)
+//
+// GPU form.  The nearest neighbour is an exact brute-force float64 search (no k-d tree: a frame's scene has a few thousand
+// points, and all frames of a batch run at once): k_icp_corr, one CTA per (frame, tile of 256 source points), the frame's
+// scene streamed through shared memory; each CTA leaves 17 partial sums (count, sum d^2, sum p, sum q, sum p q^T, taken
+// relative to a per-frame origin so that the covariance does not cancel).  k_icp_update, one thread per frame, reduces the
+// partials in tile order (deterministic), applies the convergence rule and composes the update; the rotation is Horn's
+// quaternion solution (horn_core.h), which equals the SVD solution of umeyama for non-degenerate correspondences.
+// The whole iteration runs stream-ordered with no host round trip: converged frames raise a flag and their CTAs exit.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "horn_core.h"
+
+namespace {
+
+constexpr int kIcpThreads = 256;
+constexpr int kIcpSums = 17;   // n, sum d2, p[3], q[3], pq[9]
+
+struct IcpState {     // one per frame, in the context's scratch
+  double T[12];       // current transformation (rows 0..2 of the 4x4)
+  double origin[3];   // translation of the initial pose: sums are taken relative to it
+  double prev_fitness, prev_rmse;
+  int done, iters;
+};
+
+__global__ void k_icp_init(const double* __restrict__ RT_init, int n_frames, IcpState* __restrict__ st) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  IcpState s;
+  for (int i = 0; i < 12; ++i) s.T[i] = RT_init[16LL * f + i];
+  s.origin[0] = s.T[3]; s.origin[1] = s.T[7]; s.origin[2] = s.T[11];
+  s.prev_fitness = 0.0; s.prev_rmse = 0.0; s.done = 0; s.iters = 0;
+  st[f] = s;
+}
+
+__global__ void __launch_bounds__(kIcpThreads) k_icp_corr(const double* __restrict__ model, int n_model, const double* __restrict__ scene,
+                                                         const long long* __restrict__ scene_off, const double* __restrict__ max_dist,
+                                                         const IcpState* __restrict__ st, double* __restrict__ partials, int tiles) {
+  const int frame = blockIdx.y, tile = blockIdx.x;
+  if (st[frame].done) return;
+  __shared__ double s_q[3][kIcpThreads];
+  __shared__ double s_T[15];
+  __shared__ double s_red[kIcpSums][kIcpThreads / 32];
+  if (threadIdx.x < 12) s_T[threadIdx.x] = st[frame].T[threadIdx.x];
+  if (threadIdx.x < 3) s_T[12 + threadIdx.x] = st[frame].origin[threadIdx.x];
+  __syncthreads();
+  const int g = tile * kIcpThreads + threadIdx.x;
+  double px = 0, py = 0, pz = 0;
+  if (g < n_model) {
+    const double x = model[3 * g], y = model[3 * g + 1], z = model[3 * g + 2];
+    px = s_T[0] * x + s_T[1] * y + s_T[2] * z + s_T[3];
+    py = s_T[4] * x + s_T[5] * y + s_T[6] * z + s_T[7];
+    pz = s_T[8] * x + s_T[9] * y + s_T[10] * z + s_T[11];
+  }
+  const long long q0 = scene_off[frame], q1 = scene_off[frame + 1];
+  double best = INFINITY;
+  long long bi = -1;
+  for (long long e0 = q0; e0 < q1; e0 += kIcpThreads) {
+    const long long e = e0 + threadIdx.x;
+    double ex = INFINITY, ey = INFINITY, ez = INFINITY;   // padding never wins the minimum
+    if (e < q1) { ex = scene[3 * e]; ey = scene[3 * e + 1]; ez = scene[3 * e + 2]; }
+    __syncthreads();
+    s_q[0][threadIdx.x] = ex; s_q[1][threadIdx.x] = ey; s_q[2][threadIdx.x] = ez;
+    __syncthreads();
+    const int cnt = (int)((q1 - e0) < kIcpThreads ? (q1 - e0) : kIcpThreads);
+#pragma unroll 4
+    for (int q = 0; q < cnt; ++q) {
+      const double dx = px - s_q[0][q], dy = py - s_q[1][q], dz = pz - s_q[2][q];
+      const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+      if (d2 < best) { best = d2; bi = e0 + q; }     // first nearest point in scene order wins a tie
+    }
+  }
+  const double md = max_dist[frame];
+  const bool ok = g < n_model && bi >= 0 && best < md * md;     // strict, like SearchHybrid's lower_bound on radius^2
+  double v[kIcpSums];
+#pragma unroll
+  for (int i = 0; i < kIcpSums; ++i) v[i] = 0.0;
+  if (ok) {
+    const double a[3] = {px - s_T[12], py - s_T[13], pz - s_T[14]};
+    const double b[3] = {scene[3 * bi] - s_T[12], scene[3 * bi + 1] - s_T[13], scene[3 * bi + 2] - s_T[14]};
+    v[0] = 1.0; v[1] = best;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      v[2 + r] = a[r]; v[5 + r] = b[r];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[8 + 3 * r + c] = a[r] * b[c];
+    }
+  }
+  // deterministic tile reduction: warp shuffles in a fixed pattern, then the warp partials in order
+#pragma unroll
+  for (int i = 0; i < kIcpSums; ++i) {
+#pragma unroll
+    for (int m = 16; m; m >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], m);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < kIcpSums; ++i) s_red[i][threadIdx.x >> 5] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < kIcpSums) {
+    double s = 0.0;
+    for (int w = 0; w < kIcpThreads / 32; ++w) s += s_red[threadIdx.x][w];
+    partials[((long long)frame * tiles + tile) * kIcpSums + threadIdx.x] = s;
+  }
+}
+
+// Evaluation k of the open3d loop has just been reduced into `partials` (k = 0: the evaluation of the initial pose).
+__global__ void k_icp_update(const double* __restrict__ partials, int tiles, int n_model, int n_frames, int k, int max_iter, double rel_fitness,
+                             double rel_rmse, IcpState* __restrict__ st, double* __restrict__ RT_out, double* __restrict__ fitness_out,
+                             double* __restrict__ rmse_out, int* __restrict__ iters_out, int* __restrict__ n_done) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  IcpState s = st[f];
+  if (s.done) return;
+  double v[kIcpSums];
+  for (int i = 0; i < kIcpSums; ++i) v[i] = 0.0;
+  for (int t = 0; t < tiles; ++t)
+    for (int i = 0; i < kIcpSums; ++i) v[i] += partials[((long long)f * tiles + t) * kIcpSums + i];
+  const double n = v[0];
+  const double fitness = n / (double)n_model;
+  const double rmse = n > 0.0 ? sqrt(v[1] / n) : 0.0;
+  // the result open3d would return if the loop ended here
+  double* o = RT_out + 16LL * f;
+  for (int i = 0; i < 12; ++i) o[i] = s.T[i];
+  o[12] = o[13] = o[14] = 0.0; o[15] = 1.0;
+  fitness_out[f] = fitness; rmse_out[f] = rmse; iters_out[f] = k;
+  s.iters = k;
+  if (k >= 1 && fabs(s.prev_fitness - fitness) < rel_fitness && fabs(s.prev_rmse - rmse) < rel_rmse) s.done = 1;
+  if (k >= max_iter) s.done = 1;
+  if (s.done) atomicAdd(n_done, 1);
+  if (!s.done) {
+    s.prev_fitness = fitness; s.prev_rmse = rmse;
+    if (n > 0.0) {   // no correspondences: ComputeTransformation returns the identity
+      double mp[3], mq[3], S[3][3], R[3][3];
+      for (int r = 0; r < 3; ++r) { mp[r] = v[2 + r] / n; mq[r] = v[5 + r] / n; }
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) S[r][c] = v[8 + 3 * r + c] - n * mp[r] * mq[c];
+      rcv::horn_rotation_from_S(S, R);
+      // update: x -> R (x - cp) + cq with cp = origin + mp, cq = origin + mq;  T <- update * T
+      double tu[3];
+      for (int r = 0; r < 3; ++r) {
+        const double cp0 = s.origin[0] + mp[0], cp1 = s.origin[1] + mp[1], cp2 = s.origin[2] + mp[2];
+        tu[r] = (s.origin[r] + mq[r]) - (R[r][0] * cp0 + R[r][1] * cp1 + R[r][2] * cp2);
+      }
+      double Tn[12];
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) Tn[4 * r + c] = R[r][0] * s.T[c] + R[r][1] * s.T[4 + c] + R[r][2] * s.T[8 + c];
+        Tn[4 * r + 3] = R[r][0] * s.T[3] + R[r][1] * s.T[7] + R[r][2] * s.T[11] + tu[r];
+      }
+      for (int i = 0; i < 12; ++i) s.T[i] = Tn[i];
+    }
+  }
+  st[f] = s;
+}
+
+}  // namespace
+
+// Scratch (in doubles) the launch needs for n_frames frames of an n_model-point source.
+extern "C" long long rcv_icp_scratch_doubles(int n_frames, int n_model) {
+  const long long tiles = (n_model + kIcpThreads - 1) / kIcpThreads;
+  return (long long)n_frames * ((long long)(sizeof(IcpState) + 7) / 8 + tiles * kIcpSums) + 1;   // + the converged-frames counter
+}
+
+extern "C" int rcv_icp_launch(const double* model, int n_model, const double* scene, const long long* scene_off, const double* RT_init,
+                              const double* max_dist, int n_frames, int max_iter, double rel_fitness, double rel_rmse, double* scratch,
+                              double* RT_out, double* fitness_out, double* rmse_out, int* iters_out, void* stream, long long* launches) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int tiles = (n_model + kIcpThreads - 1) / kIcpThreads;
+  IcpState* st = reinterpret_cast<IcpState*>(scratch);
+  double* partials = scratch + (long long)n_frames * ((long long)(sizeof(IcpState) + 7) / 8);
+  int* n_done = reinterpret_cast<int*>(partials + (long long)n_frames * tiles * kIcpSums);
+  cudaMemsetAsync(n_done, 0, sizeof(int), s);
+  k_icp_init<<<(n_frames + 127) / 128, 128, 0, s>>>(RT_init, n_frames, st);
+  *launches += 1;
+  for (int k = 0; k <= max_iter; ++k) {
+    k_icp_corr<<<dim3(tiles, n_frames), kIcpThreads, 0, s>>>(model, n_model, scene, scene_off, max_dist, st, partials, tiles);
+    k_icp_update<<<(n_frames + 63) / 64, 64, 0, s>>>(partials, tiles, n_model, n_frames, k, max_iter, rel_fitness, rel_rmse, st, RT_out,
+                                                     fitness_out, rmse_out, iters_out, n_done);
+    *launches += 2;
+    // open3d's default is 30 iterations: the whole loop is enqueued without a host round trip.  Longer loops (the YCB
+    // evaluator asks for max_iteration = 2,000,000, i.e. "until converged") look at the converged-frames counter every
+    // 32 iterations and stop enqueuing once every frame has finished.
+    if (k % 32 == 31 && k < max_iter) {
+      int h = 0;
+      cudaError_t e = cudaMemcpyAsync(&h, n_done, sizeof(int), cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) return (int)e;
+      if (h >= n_frames) break;
+    }
+  }
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,219 @@
+"""Batched evaluator: the caller of the voting path with the step after it (N3) and the LINEMOD
+directory layout in front of it (N4).
+
+Replaces the body of the reference's `estimate_6d_pose_lm` (AccumulatorSpace.py:495-744), which walks the test images one
+by one and, per image, runs mask rule -> rgbd_to_point_cloud -> Accumulator_3D for three keypoints (:578-656), lmshorn
+(:660-662), the ADD(-S) distance of the CAD model before ICP (:664-702), open3d's point-to-point ICP against the union of
+the masked clouds (:620-625, :704-718) and the ADD(-S) distance after it (:723-731).  Here a batch of frames goes through
+the same stages as device-resident arrays, every stage one call into librcvvote.so (include/rcvvote.h):
+
+    rcv_vote_frames -> rcv_horn_batch -> rcv_add_metric_batch -> rcv_scene_clouds -> rcv_icp_batch -> rcv_add_metric_batch
+
+Nothing is computed on the CPU except file reading and the pass / fail counters.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import api, formats
+
+# ---- data of the reference's evaluator (AccumulatorSpace.py:18, :43, :45-58, :59-61) ----
+lm_cls_names = ['ape', 'benchvise', 'cam', 'can', 'cat', 'duck', 'driller', 'eggbox', 'glue', 'holepuncher', 'iron', 'lamp', 'phone']
+lm_syms = ['eggbox', 'glue']
+add_threshold = {   # 10 % of the model diameter, metres
+    'eggbox': 0.019735770122546523, 'ape': 0.01421240983190395, 'cat': 0.018594838977253875, 'cam': 0.02222763033276377,
+    'duck': 0.015569664208967385, 'glue': 0.01930723067998101, 'can': 0.028415044264086586, 'driller': 0.031877906042,
+    'holepuncher': 0.019606109985, 'benchvise': .033091264970068, 'iron': .03172344425531, 'lamp': .03165980764376,
+    'phone': .02543407135792}
+linemod_K = np.array([[572.4114, 0., 325.2611], [0., 573.57043, 242.04899], [0., 0., 1.]])
+
+
+def max_radii_dm(cad_m, keypoints_m, n_kpts=3):
+    """Largest distance from keypoint k to a CAD point, in decimetres (AccumulatorSpace.py:539-545)."""
+    out = np.zeros(n_kpts)
+    for i in range(n_kpts):
+        d = ((cad_m[:, 0] - keypoints_m[i + 1, 0]) ** 2 + (cad_m[:, 1] - keypoints_m[i + 1, 1]) ** 2
+             + (cad_m[:, 2] - keypoints_m[i + 1, 2]) ** 2) ** 0.5
+        out[i] = d.max() * 10
+    return out
+
+
+def _to_device(a, dev, dtype=None):
+    if a is None:
+        return None
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    t = t.to(dev)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+class FrameEvaluator:
+    """Device-side stage chain for batches of frames of ONE object class (one CAD model, one keypoint set)."""
+
+    def __init__(self, cad_mm, kpts_mm, symmetric, threshold_mm, device=0, frames_per_batch=64, image=(480, 640), n_kpts=3, max_grid=256,
+                 icp=True, icp_max_iter=30):
+        self.dev = torch.device("cuda", device)
+        self.B, self.n_kpts, self.image = int(frames_per_batch), int(n_kpts), tuple(image)
+        self.ctx = api.VoteContext(device, max_items=self.B * n_kpts, max_points_total=self.B * n_kpts * image[0] * image[1], max_grid=max_grid)
+        self.cad_mm = torch.as_tensor(np.ascontiguousarray(cad_mm, dtype=np.float64), device=self.dev)
+        self.kpts_mm = torch.as_tensor(np.ascontiguousarray(kpts_mm, dtype=np.float64), device=self.dev)
+        self.symmetric, self.threshold_mm = bool(symmetric), float(threshold_mm)
+        self.icp, self.icp_max_iter = bool(icp), int(icp_max_iter)
+
+    def run(self, depth, radius, K, RT_gt_mm, max_radii=None, sem=None, mask_flags=api.MASK_LM_NPY, sem_threshold=0.8, depth_div=1.0,
+            scene_scale=1.0, centres_override=None, **vote_kw):
+        """depth (B,H,W), radius (B,Kp,H,W) float32 [, sem (B,Kp,H,W) float32], K (3,3) or (B,3,3), RT_gt_mm (B,3,4) or (B,4,4)
+        (translation in mm) -- NumPy or torch, host or device.  Returns a dict of HOST arrays: centre_mm (B,Kp,3), RT (B,4,4),
+        dist_before (B,), RT_icp (B,4,4), dist_after (B,), passed_before / passed_after (B,) bool, status (B,Kp), n_points (B,Kp),
+        icp_fitness / icp_rmse / icp_iters, scene_points (B,)."""
+        dev, ctx = self.dev, self.ctx
+        to = lambda a, dt=None: _to_device(a, dev, dt)  # noqa: E731
+        depth, radius, sem = to(depth), to(radius, torch.float32), to(sem, torch.float32)
+        K, max_radii = to(K, torch.float64), to(max_radii, torch.float64)
+        B = radius.shape[0]
+        gt = torch.zeros((B, 4, 4), dtype=torch.float64, device=dev)
+        g = to(RT_gt_mm, torch.float64)
+        gt[:, :g.shape[1], :] = g
+        gt[:, 3, 3] = 1.0
+        out = ctx.vote_frames(depth, radius, K, sem=sem, max_radii=max_radii, mask_flags=mask_flags, sem_threshold=sem_threshold,
+                              depth_div=depth_div, **vote_kw)
+        centres = out["centre_mm"]
+        if centres_override is not None:   # frames voted outside the fused path (float64 radius maps), see LinemodEvaluator
+            idx, val = centres_override
+            centres[idx[0].to(dev), idx[1].to(dev)] = to(val, torch.float64)
+        RT = ctx.horn_batch(self.kpts_mm, centres)
+        mean, mn = ctx.add_metric(self.cad_mm, RT, gt)
+        before = mn if self.symmetric else mean
+        res = dict(centre_mm=centres, RT=RT, dist_before=before, passed_before=before <= self.threshold_mm, status=out["status"],
+                   n_points=out["n_points"], peak=out["peak"], grid=out["grid"])
+        if self.icp:
+            scene, offs, _ = ctx.scene_clouds(depth, radius, K, sem=sem, max_radii=max_radii, mask_flags=mask_flags, sem_threshold=sem_threshold,
+                                              depth_div=depth_div, scale=scene_scale)
+            reg = ctx.icp(self.cad_mm, scene, offs, RT, before.contiguous(), max_iter=self.icp_max_iter)
+            mean2, mn2 = ctx.add_metric(self.cad_mm, reg["RT"], gt)
+            after = mn2 if self.symmetric else mean2
+            res.update(RT_icp=reg["RT"], dist_after=after, passed_after=after <= self.threshold_mm, icp_fitness=reg["fitness"],
+                       icp_rmse=reg["rmse"], icp_iters=reg["iters"], scene_points=offs[1:] - offs[:-1])
+        return {k: v.cpu().numpy() for k, v in res.items()}
+
+
+class LinemodClass:
+    """One class of the reference's LINEMOD layout (AccumulatorSpace.py:500-551, :566, :599, :612):
+        <root>/LINEMOD/<cls>/{<cls>.ply, Outside9.npy, Split/val.txt, JPEGImages/<stem>.jpg, pose/pose<N>.npy}
+        <root>/LINEMOD_ORIG/<cls>/data/depth<N>.dpt
+        <root>/LINEMOD_ORIG/estRadialMap/<cls>/Out_pt<k>_dm/<stem>.npy        (k = 1..3, decimetres)"""
+
+    def __init__(self, root_dataset, class_name):
+        self.name = class_name
+        self.pv = root_dataset + "LINEMOD/" + class_name + "/"
+        self.orig = root_dataset + "LINEMOD_ORIG/" + class_name + "/"
+        self.est = os.path.join(root_dataset + "LINEMOD_ORIG/", "estRadialMap", class_name)
+        self.cad_m = formats.read_ply_points(self.pv + class_name + ".ply")
+        self.keypoints_m = formats.load_keypoints(self.pv + "Outside9.npy")
+        self.max_radii_dm = max_radii_dm(self.cad_m, self.keypoints_m)
+        test = set(formats.read_split(self.pv + "Split/val.txt"))
+        self.stems = sorted(os.path.splitext(f)[0] for f in os.listdir(self.pv + "JPEGImages/")
+                            if f.endswith(".jpg") and os.path.splitext(f)[0] in test)
+
+    def image_path(self, stem):
+        return self.pv + "JPEGImages/" + stem + ".jpg"
+
+    def depth(self, stem):
+        return formats.read_depth(self.orig + "data/depth" + str(int(stem)) + ".dpt")
+
+    def pose_mm(self, stem):
+        rt = formats.load_pose(self.pv + "pose/pose" + str(int(stem)) + ".npy").copy()
+        rt[:, 3] = rt[:, 3] * 1000
+        return rt
+
+    def radial_est(self, stem, k):
+        return np.load(os.path.join(self.est, "Out_pt" + str(k) + "_dm", stem + ".npy"))
+
+
+def evaluate_lm_class(root_dataset, class_name, using_ckpts=False, producer=None, device=0, frames_per_batch=64, icp=True, verbose=True):
+    """One class of estimate_6d_pose_lm.  `producer(class_name, k, image_path) -> (sem, radial)` supplies the (H,W) float32 maps of
+    keypoint k = 1..3 when using_ckpts (the reference's FCResBackbone + DenseFCNResNet152 stay PyTorch code outside this package).
+    Returns dict(n, add_before, add_after, frames=[...], per-frame arrays)."""
+    from . import AccumulatorSpace as shim
+    cls = LinemodClass(root_dataset, class_name)
+    sym = class_name in lm_syms
+    if using_ckpts and producer is None:
+        raise ValueError("using_ckpts needs a producer(class_name, k, image_path) -> (sem, radial): the radius-map network is not part of rcvpose_b200")
+    ev = None
+    acc = {}
+    for b0 in range(0, len(cls.stems), frames_per_batch):
+        stems = cls.stems[b0:b0 + frames_per_batch]
+        depth = np.stack([cls.depth(s) for s in stems])
+        H, W = depth.shape[1:]
+        radius = np.empty((len(stems), 3, H, W), np.float32)
+        sem = np.empty_like(radius) if using_ckpts else None
+        override_idx, override_val = [], []
+        for i, s in enumerate(stems):
+            for k in range(1, 4):
+                if using_ckpts:
+                    sm, rd = producer(class_name, k, cls.image_path(s))
+                    sem[i, k - 1], radius[i, k - 1] = sm, rd
+                    continue
+                rd = cls.radial_est(s, k)
+                if rd.dtype == np.float32:
+                    radius[i, k - 1] = rd
+                    continue
+                # A map that is not float32 keeps its dtype through the reference's radius arithmetic (r*100/5), which
+                # the fused float32 path would not reproduce: vote this (frame, keypoint) through the exact drop-in surface
+                # (Accumulator_3D with the radii as they are, :612-628) and hand the fused path a float32 map with the same mask.
+                rd = np.where(rd <= cls.max_radii_dm[k - 1], rd, 0)
+                dm = depth[i] * np.where(rd != 0, 1, 0)
+                xyz_mm = shim.rgbd_to_point_cloud(linemod_K, dm)
+                override_idx.append((i, k - 1))
+                override_val.append(shim.Accumulator_3D(xyz_mm / 1000, rd[dm.nonzero()])[0])
+                radius[i, k - 1] = np.where(rd != 0, np.float32(1e-3), np.float32(0))
+        if ev is None:
+            ev = FrameEvaluator(cls.cad_m * 1000, cls.keypoints_m[1:4, :] * 1000, sym, add_threshold[class_name] * 1000, device=device,
+                                frames_per_batch=frames_per_batch, image=(H, W), icp=icp)
+        gt = np.stack([cls.pose_mm(s) for s in stems])
+        ov = None
+        if override_idx:
+            ii = np.array(override_idx)
+            ov = ((torch.as_tensor(ii[:, 0]), torch.as_tensor(ii[:, 1])), np.array(override_val))
+        res = ev.run(depth, radius, linemod_K, gt, max_radii=cls.max_radii_dm, sem=sem,
+                     mask_flags=api.MASK_LM_CKPT if using_ckpts else api.MASK_LM_NPY, centres_override=ov)
+        st = res["status"].copy()
+        if override_idx:
+            st[ii[:, 0], ii[:, 1]] = 0
+        bad = (st & api.RCV_ST_EMPTY_MASK) != 0
+        if bad.any():   # the reference dies in Accumulator_3D on an empty cloud (ValueError from .min())
+            i, k = np.argwhere(bad)[0]
+            raise ValueError("zero-size array to reduction operation minimum which has no identity (frame %s, keypoint %d: empty mask)" % (stems[i], k + 1))
+        if st.any():
+            raise api.RcvError("voting failed with status %s" % np.unique(st))
+        for k, v in res.items():
+            acc.setdefault(k, []).append(v)
+        if verbose:
+            n = sum(len(a) for a in acc["passed_before"])
+            print("Current ADD\\(s\\) of " + class_name + " before ICP: ", np.concatenate(acc["passed_before"]).sum() / n)
+            if icp:
+                print("Currnet ADD\\(s\\) of " + class_name + " after ICP: ", np.concatenate(acc["passed_after"]).sum() / n)
+    out = {k: np.concatenate(v) for k, v in acc.items()}
+    n = len(cls.stems)
+    out.update(frames=list(cls.stems), n=n, add_before=float(out["passed_before"].sum() / n) if n else float("nan"),
+               add_after=float(out["passed_after"].sum() / n) if (n and icp) else float("nan"))
+    if verbose:
+        tag = "ADDs" if sym else "ADD"
+        print(tag + " of " + class_name + " before ICP: ", out["add_before"])
+        print(tag + " of " + class_name + " after ICP: ", out["add_after"])
+    return out
+
+
+def estimate_6d_pose_lm(opts):
+    """Drop-in for AccumulatorSpace.estimate_6d_pose_lm(opts) (:495-744): opts.root_dataset, opts.using_ckpts [, opts.producer,
+    opts.classes, opts.device, opts.frames_per_batch].  Prints the reference's summary lines and, unlike the reference (which
+    returns None), returns {class_name: result dict}."""
+    results = {}
+    for class_name in getattr(opts, "classes", None) or lm_cls_names:
+        print("Evaluation on ", class_name)
+        results[class_name] = evaluate_lm_class(opts.root_dataset, class_name, using_ckpts=bool(getattr(opts, "using_ckpts", False)),
+                                                producer=getattr(opts, "producer", None), device=getattr(opts, "device", 0),
+                                                frames_per_batch=getattr(opts, "frames_per_batch", 64))
+    return results

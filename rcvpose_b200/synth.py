@@ -89,6 +89,52 @@ def config3_frame(f, n_kpts=3, K=linemod_K):
                 centre_mm=centre)
 
 
+def write_lm_dataset(root, class_name, n_frames, seed=0, obj_radius_mm=55.0, n_cad=1500, radius_dtype=np.float32, split_extra=2):
+    """Lays out a synthetic class in the reference's LINEMOD directory structure (AccumulatorSpace.py:500-551, :566, :599, :612;
+    see rcvpose_b200.evaluate.LinemodClass): a sphere-shaped object (CAD = points on the sphere, metres), `Outside9.npy`
+    keypoints, and per frame a random pose, the rendered `.dpt` depth and three estimated radius maps (decimetres, noisy, 2 %
+    outliers).  `split_extra` more images exist on disk than `Split/val.txt` lists.  Returns the list of test stems."""
+    import os
+    from . import formats
+    rng = np.random.default_rng(seed)
+    pv, orig = root + "LINEMOD/" + class_name + "/", root + "LINEMOD_ORIG/" + class_name + "/"
+    for d in (pv + "JPEGImages", pv + "pose", pv + "Split", orig + "data"):
+        os.makedirs(d, exist_ok=True)
+    u = rng.normal(size=(n_cad, 3))
+    cad_m = u / np.linalg.norm(u, axis=1, keepdims=True) * (obj_radius_mm / 1000)
+    formats.write_ply_points(pv + class_name + ".ply", cad_m)
+    cad_m = formats.read_ply_points(pv + class_name + ".ply")     # float32 on disk
+    dirs = np.array([[0, 0, 0], [1.0, 0.2, 0.1], [-0.3, 1.0, 0.2], [0.2, -0.4, 1.0], [-1.0, -0.5, 0.3], [0.5, 0.5, -1.0], [1, 1, 1], [-1, 1, -1],
+                     [1, -1, -1]], dtype=np.float64)
+    dirs[1:] /= np.linalg.norm(dirs[1:], axis=1, keepdims=True)
+    kp_m = dirs * (obj_radius_mm / 1000) * 1.8
+    np.save(pv + "Outside9.npy", kp_m)
+    max_r = [float(np.linalg.norm(cad_m - kp_m[k], axis=1).max() * 10) for k in (1, 2, 3)]
+    stems = []
+    for f in range(n_frames + split_extra):
+        stem = "%06d" % (f * 7 + 3)
+        open(pv + "JPEGImages/" + stem + ".jpg", "wb").close()
+        if f >= n_frames:
+            continue
+        stems.append(stem)
+        rv = rng.normal(size=3); th = np.linalg.norm(rv); k = rv / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+        t_m = np.array([rng.uniform(-0.15, 0.15), rng.uniform(-0.15, 0.15), rng.uniform(0.7, 1.1)])
+        np.save(pv + "pose/pose" + str(int(stem)) + ".npy", np.concatenate([R, t_m[:, None]], axis=1))
+        depth = sphere_depth(linemod_K, t_m * 1000, obj_radius_mm)
+        formats.write_depth_dpt(orig + "data/depth" + str(int(stem)) + ".dpt", depth)
+        for k in (1, 2, 3):
+            d = root + "LINEMOD_ORIG/estRadialMap/" + class_name + "/Out_pt" + str(k) + "_dm/"
+            os.makedirs(d, exist_ok=True)
+            kpt_mm = (R @ kp_m[k] + t_m) * 1000
+            r = radius_map_dm(linemod_K, depth, kpt_mm, rng, 0.01, 0.02, max_r[k - 1] * 1.2)   # some outliers exceed max_radii
+            np.save(d + stem + ".npy", r.astype(radius_dtype))
+    with open(pv + "Split/val.txt", "w") as fh:
+        fh.write("".join(s + "\n" for s in stems))
+    return stems
+
+
 def frame_to_points(K, depth, radius):
     """The reference caller's glue (AccumulatorSpace.py:612-619, npy branch): masked depth ->
     xyz in metres (N,3) float64 + radial list (N,) in the map's dtype."""
