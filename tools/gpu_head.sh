@@ -1,9 +1,11 @@
 #!/bin/bash
-# Head kernel check: parity test + bandwidth sweep.  Usage: tools/gpu_head.sh
+# Head kernel check: parity test + bandwidth sweep.  Usage: tools/gpu_head.sh [tag]
+TAG=${1:-head}
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py -k head -x -q 2>&1 | tail -3 | tee gpurun_out/head_pytest.txt
-for cfg in "21 16" "24 3" "22 8"; do set -- $cfg
-RCV_HEAD_CFG=$1 RCV_HEAD_CTAS=$2 timeout 300 python - <<'PY' 2>&1 | tee -a gpurun_out/head_bw.txt
+timeout 300 python -m pytest tests/test_gpu_parity.py -k head -x -q 2>&1 | tail -3 | tee gpurun_out/${TAG}_pytest.txt
+rm -f gpurun_out/${TAG}_bw.txt
+for cfg in "21 16" "21 8" "22 8" "24 3" "32 4" "34 2" "31 8"; do set -- $cfg
+RCV_HEAD_CFG=$1 RCV_HEAD_CTAS=$2 timeout 300 python - <<'PY' 2>&1 | tee -a gpurun_out/${TAG}_bw.txt
 import torch, json, os
 from rcvpose_b200 import api
 ctx = api.VoteContext(0, max_items=4, max_points_total=1024, max_grid=64)
