@@ -190,6 +190,20 @@ int rcv_icp_batch(rcv_ctx* ctx, const double* model, int n_model, const double* 
 int rcv_head_1x1(rcv_ctx* ctx, const void* up_bf16, const float* weight, const float* bias, float* out, int n_images, long long hw,
                  void* stream);
 
+/* ---- fused producer head + voting  -- models/fcnresnet.py:118,187-189 + AccumulatorSpace.py:603-656 ----
+ * conv8 of the n_kpts radius-map networks -> the evaluator's mask rule -> back-projection -> Accumulator_3D, for n_frames frames:
+ * rcv_head_1x1 followed by rcv_vote_frames (sem = the head's seg plane), except that the head's epilogue applies the mask rule
+ * itself: the seg plane never reaches HBM, the radius plane is written once and only gathered at the surviving pixels, and
+ * no kernel streams the maps a second time.  Results are bit-identical to the two-call sequence.
+ *   up     [n_frames][n_kpts][32][H*W] bfloat16: conv7 + BN + ReLU output of keypoint network k for frame f
+ *   weight [n_kpts][2][32] float32, bias [n_kpts][2] float32: conv8 of each network (n_kpts <= 8)
+ *   depth, K, max_radii, fp, vp and the outputs as in rcv_vote_frames (fp->mask_flags usually RCV_MASK_MAX_RADIUS | RCV_MASK_SEM_GT)
+ *   radius_out: optional [n_frames][n_kpts][H*W] float32 to receive the radius planes (NULL: context scratch) */
+int rcv_head_vote_frames(rcv_ctx* ctx, int n_frames, int n_kpts, const void* up_bf16, const float* weight, const float* bias,
+                         const void* depth, const double* K, const double* max_radii, const rcv_frame_params* fp,
+                         const rcv_vote_params* vp, double* centre_mm, int* peak, long long* votes, int* n_points, int* grid, int* status,
+                         float* radius_out, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (the bench's gpu_launches claim). */
 long long rcv_launch_count(const rcv_ctx* ctx);

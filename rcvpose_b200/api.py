@@ -291,6 +291,40 @@ class VoteContext:
             self._ck(self.lib.rcv_head_1x1(self.h, _ptr(up), _ptr(weight), _ptr(bias), _ptr(out), B, H * W, _stream()))
         return out
 
+    # ---- conv8 -> mask rule -> voting, fused (models/fcnresnet.py:187-189 + AccumulatorSpace.py:603-656) ----
+    def head_vote_frames(self, up, weight, bias, depth, K, max_radii=None, mask_flags=MASK_LM_CKPT, sem_threshold=0.8, depth_div=1.0,
+                         xyz_div=1000.0, acc_unit=5.0, radius_scale=100.0, policy=RCV_POLICY_LM, want_radius=False):
+        """up (B,Kp,32,H,W) bfloat16, weight (Kp,2,32[,1,1]), bias (Kp,2), depth (B,H,W), K (3,3)/(B,3,3) float64 -- CUDA.  Same outputs as
+        vote_frames (bit-identical to head_1x1 + vote_frames with sem = the head's seg plane); out["radius"] (B,Kp,H,W) if want_radius."""
+        if isinstance(up, torch.Tensor):
+            up = up.contiguous()
+        _check_cuda(up, torch.bfloat16, "up")
+        _check_cuda(depth, None, "depth")
+        _check_cuda(K, torch.float64, "K")
+        B, Kp, Cin, H, W = up.shape
+        if Cin != 32 or tuple(depth.shape) != (B, H, W):
+            raise RcvError("head_vote_frames: up (B,Kp,32,H,W), depth (B,H,W)")
+        dev = up.device
+        weight = weight.reshape(Kp, 2, 32).to(device=dev, dtype=torch.float32).contiguous()
+        bias = bias.reshape(Kp, 2).to(device=dev, dtype=torch.float32).contiguous()
+        if max_radii is not None:
+            _check_cuda(max_radii, torch.float64, "max_radii")
+        fp = _lib.rcv_frame_params(H, W, _DEPTH_DTYPES[depth.dtype], float(depth_div), float(xyz_div), int(mask_flags), float(sem_threshold),
+                                   9 if (K.dim() == 3 and K.shape[0] == B) else 0,
+                                   Kp if (max_radii is not None and max_radii.dim() == 2 and max_radii.shape[0] == B) else 0)
+        vp = _lib.rcv_vote_params(float(acc_unit), float(radius_scale), int(policy), RCV_F32)
+        out = dict(centre_mm=torch.empty((B, Kp, 3), dtype=torch.float64, device=dev), peak=torch.empty((B, Kp), dtype=torch.int32, device=dev),
+                   votes=torch.empty((B, Kp), dtype=torch.int64, device=dev), n_points=torch.empty((B, Kp), dtype=torch.int32, device=dev),
+                   grid=torch.empty((B, Kp), dtype=torch.int32, device=dev), status=torch.empty((B, Kp), dtype=torch.int32, device=dev))
+        rad = torch.empty((B, Kp, H, W), dtype=torch.float32, device=dev) if want_radius else None
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_head_vote_frames(self.h, B, Kp, _ptr(up), _ptr(weight), _ptr(bias), _ptr(depth), _ptr(K), _ptr(max_radii),
+                                                   C.byref(fp), C.byref(vp), _ptr(out["centre_mm"]), _ptr(out["peak"]), _ptr(out["votes"]),
+                                                   _ptr(out["n_points"]), _ptr(out["grid"]), _ptr(out["status"]), _ptr(rad), _stream()))
+        if rad is not None:
+            out["radius"] = rad
+        return out
+
     def horn_batch_host(self, model, est):
         model = np.ascontiguousarray(model, dtype=np.float64)
         est = np.ascontiguousarray(est, dtype=np.float64)

@@ -16,6 +16,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "../../include/rcvvote.h"
+
 #ifndef RCV_HEAD_QMAP
 #define RCV_HEAD_QMAP 1   // quarter-warp = the 8 channels of one pixel group (conflict-free shared-memory side)
 #endif
@@ -35,7 +37,19 @@ constexpr int kC = 32;                      // input channels = 2 x UMMA K
 constexpr int kN = 16;                      // UMMA N (2 real outputs)
 constexpr int kATile = kC * kTileM * 2;     // 8192 bytes
 constexpr int kBTile = kN * kC * 2;         // 1024 bytes
-template <int kStages, int kTpi> constexpr int smem_bytes() { return kStages * kTpi * kATile + kBTile + 64; }
+constexpr int kMaxKp = 8;                   // fused mode: weight tiles of up to 8 keypoint networks live in shared memory
+
+// Fused mode: "image" b is the item (frame, keypoint) = (b / n_kpts, b % n_kpts); the epilogue applies the
+// evaluator's mask rule (AccumulatorSpace.py:603-605, :837-840, :1049-1053) to the seg / radius values it has just read from
+// tensor memory, writes one survival bit per pixel + the item's count (the outputs of k_frame_mask, rcvvote.cu) and the
+// radius plane; the seg plane never reaches HBM and nothing reads the maps back.
+struct FusedArgs {
+  const void* depth; int depth_dtype; int n_kpts;
+  const double* max_radii; int max_radii_stride; int flags; float sem_threshold;
+  unsigned* bits; int words_per_item; int* cnt;
+};
+
+template <int kStages, int kTpi, bool kFused = false> constexpr int smem_bytes() { return kStages * kTpi * kATile + (kFused ? kMaxKp : 1) * kBTile + 64; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -50,22 +64,24 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((
 // One iteration of a CTA handles a group of kTpi consecutive 128-pixel tiles of one image (one ring stage), so the
 // serial chain  copy-wait -> barrier -> MMA -> commit -> mbarrier -> tcgen05.ld -> store  is paid once per
 // kTpi * 8 KB of input.
-template <int kStages, int kTpi>
+template <int kStages, int kTpi, bool kFused>
 __global__ void __launch_bounds__(kThreads) k_head1x1(const __nv_bfloat16* __restrict__ up, const float* __restrict__ w, const float* __restrict__ bias,
-                                                     float* __restrict__ out, long long HW, int groups_per_image, long long n_groups) {
+                                                     float* __restrict__ out, long long HW, int groups_per_image, long long n_groups, FusedArgs fz) {
   constexpr int kTmemCols = kTpi * kN < 32 ? 32 : kTpi * kN;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kTpi * kATile;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + kBTile);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(sB + kBTile + 16);
+  constexpr int kWTiles = kFused ? kMaxKp : 1;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + kWTiles * kBTile);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(sB + kWTiles * kBTile + 16);
   const int tid = threadIdx.x, warp = tid >> 5;
 
   // weights -> canonical K-major no-swizzle tile: (n % 8) * 16 + (n / 8) * 512 + (k % 8) * 2 + (k / 8) * 128
-  for (int e = tid; e < kN * kC; e += kThreads) {
-    const int n = e / kC, k = e % kC;
-    const float v = n < 2 ? w[n * kC + k] : 0.f;
-    *reinterpret_cast<__nv_bfloat16*>(sB + (n % 8) * 16 + (n / 8) * 512 + (k % 8) * 2 + (k / 8) * 128) = __float2bfloat16_rn(v);
+  const int n_wtiles = kFused ? fz.n_kpts : 1;   // fused: one weight tile per keypoint network
+  for (int e = tid; e < n_wtiles * kN * kC; e += kThreads) {
+    const int t = e / (kN * kC), n = (e / kC) % kN, k = e % kC;
+    const float v = n < 2 ? w[t * 2 * kC + n * kC + k] : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(sB + t * kBTile + (n % 8) * 16 + (n / 8) * 512 + (k % 8) * 2 + (k / 8) * 128) = __float2bfloat16_rn(v);
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tslot)), "r"(kTmemCols) : "memory");
@@ -80,7 +96,7 @@ __global__ void __launch_bounds__(kThreads) k_head1x1(const __nv_bfloat16* __res
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tslot;
-  const float bias0 = bias[0], bias1 = bias[1];
+  float bias0 = bias[0], bias1 = bias[1];
 
   const long long step = gridDim.x;
   auto issue = [&](long long grp, int stage) {
@@ -168,7 +184,8 @@ __global__ void __launch_bounds__(kThreads) k_head1x1(const __nv_bfloat16* __res
 #endif
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a0 = smem_u32(sA + (it % kStages) * kTpi * kATile), b0 = smem_u32(sB);
+      const uint32_t a0 = smem_u32(sA + (it % kStages) * kTpi * kATile);
+      const uint32_t b0 = smem_u32(sB) + (kFused ? (uint32_t)((grp / groups_per_image) % fz.n_kpts) * kBTile : 0u);
 #pragma unroll
       for (int tl = 0; tl < kTpi; ++tl)
 #pragma unroll
@@ -198,14 +215,47 @@ __global__ void __launch_bounds__(kThreads) k_head1x1(const __nv_bfloat16* __res
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     const long long b = grp / groups_per_image;
     const long long pix0 = (grp - b * groups_per_image) * (kTpi * kTileM) + tid;
-    float* o = out + b * 2 * HW;
+    if constexpr (!kFused) {
+      float* o = out + b * 2 * HW;
 #pragma unroll
-    for (int tl = 0; tl < kTpi; ++tl) {
-      const long long pix = pix0 + tl * kTileM;
-      if (pix < HW) {
-        o[pix] = __uint_as_float(r[tl][0]) + bias0;
-        o[HW + pix] = __uint_as_float(r[tl][1]) + bias1;
+      for (int tl = 0; tl < kTpi; ++tl) {
+        const long long pix = pix0 + tl * kTileM;
+        if (pix < HW) {
+          o[pix] = __uint_as_float(r[tl][0]) + bias0;
+          o[HW + pix] = __uint_as_float(r[tl][1]) + bias1;
+        }
       }
+    } else {
+      const int kp = (int)(b % fz.n_kpts);
+      const long long frame = b / fz.n_kpts;
+      bias0 = bias[2 * kp]; bias1 = bias[2 * kp + 1];
+      const double max_r = fz.max_radii ? fz.max_radii[frame * fz.max_radii_stride + kp] : 0.0;
+      float* o = out + b * HW;                      // radius plane only
+      unsigned* bits = fz.bits + b * (long long)fz.words_per_item;
+      int n = 0;
+#pragma unroll
+      for (int tl = 0; tl < kTpi; ++tl) {
+        const long long pix = pix0 + tl * kTileM;
+        bool ok = false;
+        if (pix < HW) {
+          const float sv = __uint_as_float(r[tl][0]) + bias0, rad = __uint_as_float(r[tl][1]) + bias1;
+          o[pix] = rad;
+          const long long di = frame * HW + pix;
+          const double z = fz.depth_dtype == RCV_U16 ? (double)((const unsigned short*)fz.depth)[di]
+                           : fz.depth_dtype == RCV_F32 ? (double)((const float*)fz.depth)[di] : ((const double*)fz.depth)[di];
+          ok = z != 0.0;
+          if (fz.flags & RCV_MASK_MAX_RADIUS) ok = ok && ((double)rad <= max_r);
+          if (fz.flags & RCV_MASK_RADIUS_NONZERO) ok = ok && (rad != 0.f);
+          if (fz.flags & RCV_MASK_RADIUS_POSITIVE) ok = ok && (rad > 0.f);
+          if (fz.flags & RCV_MASK_SEM_GT) ok = ok && (sv > fz.sem_threshold);
+          if (fz.flags & RCV_MASK_SEM_GE) ok = ok && (sv >= fz.sem_threshold);
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, ok);    // a warp owns 32 consecutive pixels: one word of the bit mask
+        const long long wi = (pix - (tid & 31)) >> 5;
+        if ((tid & 31) == 0 && wi < fz.words_per_item) bits[wi] = word;
+        n += __popc(word);
+      }
+      if ((tid & 31) == 0 && n) atomicAdd(fz.cnt + b, n);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();   // TMEM and the stage buffer are free again
@@ -217,13 +267,14 @@ __global__ void __launch_bounds__(kThreads) k_head1x1(const __nv_bfloat16* __res
 
 }  // namespace rcv_head
 
-template <int kStages, int kTpi>
+template <int kStages, int kTpi, bool kFused = false>
 static int launch(const void* up_bf16, const float* weight, const float* bias, float* out, int n_images, long long hw, int sms, int ctas_per_sm,
-                  void* stream) {
+                  void* stream, rcv_head::FusedArgs fz = rcv_head::FusedArgs{}) {
   using namespace rcv_head;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_head1x1<kStages, kTpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kStages, kTpi>());
+    cudaError_t e = cudaFuncSetAttribute(k_head1x1<kStages, kTpi, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes<kStages, kTpi, kFused>());
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -231,8 +282,8 @@ static int launch(const void* up_bf16, const float* weight, const float* bias, f
   const long long n_groups = (long long)n_images * groups_per_image;
   long long grid = (long long)sms * ctas_per_sm;
   if (grid > n_groups) grid = n_groups;
-  k_head1x1<kStages, kTpi><<<(int)grid, kThreads, smem_bytes<kStages, kTpi>(), (cudaStream_t)stream>>>((const __nv_bfloat16*)up_bf16, weight, bias, out,
-                                                                                                    hw, groups_per_image, n_groups);
+  k_head1x1<kStages, kTpi, kFused><<<(int)grid, kThreads, smem_bytes<kStages, kTpi, kFused>(), (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)up_bf16, weight, bias, out, hw, groups_per_image, n_groups, fz);
   return (int)cudaGetLastError();
 }
 
@@ -254,4 +305,14 @@ extern "C" int rcv_head1x1_launch(const void* up_bf16, const float* weight, cons
     case 28: return launch<2, 8>(up_bf16, weight, bias, out, n_images, hw, sms, ctas, stream);
     default: return launch<2, 4>(up_bf16, weight, bias, out, n_images, hw, sms, ctas, stream);
   }
+}
+
+// Fused head + mask rule (rcvvote.cu: rcv_head_vote_frames).  up [n_items][32][hw], weight [n_kpts][2][32], bias [n_kpts][2];
+// writes radius_out [n_items][hw], bits [n_items][words_per_item] and adds the survivors to cnt [n_items] (zeroed by the caller).
+extern "C" int rcv_head1x1_fused_launch(const void* up_bf16, const float* weight, const float* bias, float* radius_out, int n_items, long long hw,
+                                        int sms, const void* depth, int depth_dtype, int n_kpts, const double* max_radii, int max_radii_stride,
+                                        int flags, float sem_threshold, unsigned* bits, int words_per_item, int* cnt, void* stream) {
+  if (n_kpts < 1 || n_kpts > rcv_head::kMaxKp) return (int)cudaErrorInvalidValue;
+  rcv_head::FusedArgs fz{depth, depth_dtype, n_kpts, max_radii, max_radii_stride, flags, sem_threshold, bits, words_per_item, cnt};
+  return launch<2, 4, true>(up_bf16, weight, bias, radius_out, n_items, hw, sms, 3, stream, fz);   // 512-pixel groups: whole 256-pixel mask steps
 }

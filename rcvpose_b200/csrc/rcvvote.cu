@@ -1530,6 +1530,7 @@ struct rcv_ctx {
   int* counters;  // [0] units queued, [1] queue cursor
   int* cnt;
   unsigned* mask_bits; long long mask_words;
+  float* head_radius; long long head_radius_cap;   // fused head: radius planes of the items of a call
   double* icp_scratch; long long icp_cap;         // ICP scratch: per-frame state + per-(frame, tile) partial sums
   double* add_part; long long add_part_cap;     // ADD metric scratch: per-(frame, tile) partial sums and minima   // K1 scratch: one survival bit per pixel of every item of a call (grown on demand)
   unsigned long long *best, *votes;
@@ -1573,7 +1574,7 @@ RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri); cudaFree(c->pool.perm);
   cudaFree(c->meta); cudaFree(c->units); cudaFree(c->counters); cudaFree(c->cnt); cudaFree(c->best); cudaFree(c->votes);
-  cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits); cudaFree(c->add_part); cudaFree(c->icp_scratch);
+  cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits); cudaFree(c->add_part); cudaFree(c->icp_scratch); cudaFree(c->head_radius);
   for (int s = 0; s < 2; ++s) { cudaFree(c->st_depth[s]); cudaFree(c->st_radius[s]); cudaFree(c->st_sem[s]); }
   cudaFree(c->st_K); cudaFree(c->st_maxr); cudaFree(c->st_centre); cudaFree(c->st_peak); cudaFree(c->st_votes);
   cudaFree(c->st_np); cudaFree(c->st_grid); cudaFree(c->st_status); cudaFree(c->st_horn_in);
@@ -1962,6 +1963,55 @@ RCV_EXPORT int rcv_head_1x1(rcv_ctx* c, const void* up_bf16, const float* weight
   if (rc != 0) FAIL(c, RCV_E_CUDA, "rcv_head_1x1: launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   c->launches += 1;
   return RCV_OK;
+}
+
+extern "C" int rcv_head1x1_fused_launch(const void* up_bf16, const float* weight, const float* bias, float* radius_out, int n_items, long long hw,
+                                        int sms, const void* depth, int depth_dtype, int n_kpts, const double* max_radii, int max_radii_stride,
+                                        int flags, float sem_threshold, unsigned* bits, int words_per_item, int* cnt, void* stream);
+
+RCV_EXPORT int rcv_head_vote_frames(rcv_ctx* c, int n_frames, int n_kpts, const void* up_bf16, const float* weight, const float* bias,
+                                    const void* depth, const double* K, const double* max_radii, const rcv_frame_params* fp,
+                                    const rcv_vote_params* vp, double* centre_mm, int* peak, long long* votes, int* n_points, int* grid, int* status,
+                                    float* radius_out, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!up_bf16 || !weight || !bias || !depth || !K || !centre_mm || !status) FAIL(c, RCV_E_INVALID, "rcv_head_vote_frames: null pointer");
+  int rc = check_vote_params(c, vp);
+  if (rc) return rc;
+  rc = check_frame_params(c, n_frames, n_kpts, fp, (const float*)up_bf16 /* the seg values come from the head */, max_radii);
+  if (rc) return rc;
+  const long long npx = (long long)fp->height * fp->width;
+  if (n_kpts > 8 || npx % 8 != 0 || ((uintptr_t)up_bf16 & 15)) FAIL(c, RCV_E_INVALID, "rcv_head_vote_frames: n_kpts <= 8, H*W %% 8 == 0, up 16-byte aligned");
+  if (vp->radius_dtype != RCV_F32) FAIL(c, RCV_E_INVALID, "rcv_head_vote_frames: the head's radius maps are float32");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(c, cudaSetDevice(c->device));
+  const int n_items = n_frames * n_kpts;
+  const int words = (int)((npx + 255) / 256) * 8;
+  const long long need = (long long)n_items * words;
+  if (need > c->mask_words) {
+    CK(c, cudaStreamSynchronize(st));
+    cudaFree(c->mask_bits); c->mask_bits = nullptr; c->mask_words = 0;
+    CK(c, cudaMalloc(&c->mask_bits, (size_t)need * 4));
+    c->mask_words = need;
+  }
+  float* rad = radius_out;
+  if (!rad) {   // context-owned radius planes (the vote only gathers them at the surviving pixels)
+    if ((long long)n_items * npx > c->head_radius_cap) {
+      CK(c, cudaStreamSynchronize(st));
+      cudaFree(c->head_radius); c->head_radius = nullptr; c->head_radius_cap = 0;
+      CK(c, cudaMalloc(&c->head_radius, (size_t)n_items * npx * 4));
+      c->head_radius_cap = (long long)n_items * npx;
+    }
+    rad = c->head_radius;
+  }
+  CK(c, cudaMemsetAsync(c->cnt, 0, 4 * (size_t)n_items, st));
+  CK(c, (cudaError_t)rcv_head1x1_fused_launch(up_bf16, weight, bias, rad, n_items, npx, c->sms, depth, fp->depth_dtype, n_kpts, max_radii,
+                                              fp->max_radii_stride, fp->mask_flags, fp->sem_threshold, c->mask_bits, words, c->cnt, stream));
+  FrameArgs fa{depth, rad, nullptr, K, max_radii, *fp, vp->acc_unit, vp->radius_scale, n_kpts, 0};
+  k_scan_items<<<1, 1024, 0, st>>>(c->cnt, n_items, c->pool.cap, c->meta);
+  k_frame_emit<<<n_items, kCompactThreads, 0, st>>>(c->mask_bits, words, c->meta, c->pool.perm);
+  k_points_from_pixels<<<dim3(n_items, 4), 256, 0, st>>>(fa, c->meta, c->pool);
+  c->launches += 4;
+  return run_items(c, n_items, vp, centre_mm, peak, votes, n_points, grid, nullptr, status, nullptr, 0, st);
 }
 
 RCV_EXPORT int rcv_vote_kernel_times(rcv_ctx* c, float* ms_out, int n) {

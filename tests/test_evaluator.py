@@ -317,3 +317,47 @@ def test_evaluator_empty_mask_raises_like_the_reference(tmp_path):
     with pytest.raises(ValueError) as ei:       # Accumulator_3D on an empty cloud: ValueError from .min()
         A.estimate_6d_pose_lm(types.SimpleNamespace(root_dataset=root, using_ckpts=False, classes=["duck"]))
     assert "zero-size array" in str(ei.value) and stems[1] in str(ei.value)
+
+
+@pytest.mark.gpu
+def test_fused_head_vote_frames_bit_identical_to_two_calls(ctx):
+    """conv8 -> mask rule -> voting in one entry point (the head's epilogue writes the survival bits; the seg plane
+    never reaches HBM) against rcv_head_1x1 followed by rcv_vote_frames on the maps it produced: every output bit-identical,
+    the survivors equal to the mask rule evaluated in NumPy on those maps, and one item checked against the oracle."""
+    from rcvpose_b200 import api
+    frames = [synth.config3_frame(f) for f in (31, 32, 33)]
+    B, Kp, H, W = 3, 3, 480, 640
+    g = torch.Generator(device="cuda").manual_seed(7)
+    up = torch.relu(torch.randn((B, Kp, 32, H, W), generator=g, device="cuda")) * 0.5
+    depth_np = np.stack([f["depth"] for f in frames])
+    rad_np = np.stack([f["radius"] for f in frames])
+    up[:, :, 0] = torch.from_numpy(rad_np).cuda()                                                # channel 0 carries the radius (dm)
+    inside = torch.from_numpy((depth_np != 0).astype(np.float32)).cuda()[:, None].expand(B, Kp, H, W)
+    up[:, :, 1] = inside * (0.75 + 0.2 * torch.rand((B, Kp, H, W), generator=g, device="cuda"))   # channel 1: seg score around the 0.8 threshold
+    up = up.to(torch.bfloat16).contiguous()
+    weight = torch.randn((Kp, 2, 32), generator=g, device="cuda") * 2e-4
+    weight[:, 0, 1] = 1.0
+    weight[:, 1, 0] = 1.0
+    bias = torch.randn((Kp, 2), generator=g, device="cuda") * 1e-3
+    depth = torch.from_numpy(depth_np.view(np.int16)).cuda()
+    K = torch.from_numpy(frames[0]["K"]).cuda()
+    mr = torch.from_numpy(np.stack([f["max_radii_dm"] for f in frames])).cuda()
+    fused = ctx.head_vote_frames(up, weight, bias, depth, K, max_radii=mr, mask_flags=api.MASK_LM_CKPT, want_radius=True)
+    maps = torch.stack([ctx.head_1x1(up[:, k].contiguous(), weight[k], bias[k]) for k in range(Kp)], dim=1)    # (B,Kp,2,H,W)
+    sem, radius = maps[:, :, 0].contiguous(), maps[:, :, 1].contiguous()
+    two = ctx.vote_frames(depth, radius, K, sem=sem, max_radii=mr, mask_flags=api.MASK_LM_CKPT)
+    torch.cuda.synchronize()
+    assert torch.equal(fused["radius"], radius)
+    for k in ("centre_mm", "peak", "votes", "n_points", "grid", "status"):
+        assert torch.equal(fused[k], two[k]), k
+    assert int(fused["status"].abs().sum()) == 0 and int(fused["votes"].min()) > 0
+    sem_np, radius_np = sem.cpu().numpy(), radius.cpu().numpy()
+    m = (depth_np[:, None] != 0) & (sem_np > np.float32(0.8)) & (radius_np.astype(np.float64) <= mr.cpu().numpy()[:, :, None, None])
+    assert np.array_equal(fused["n_points"].cpu().numpy(), m.sum(axis=(2, 3)))
+    assert 0.2 < m[0, 0].sum() / (depth_np[0] != 0).sum() < 0.8            # the seg threshold really cuts
+    xyz_mm = oracle.rgbd_to_point_cloud(frames[1]["K"], depth_np[1] * m[1, 2])
+    want = oracle.Accumulator_3D(xyz_mm / 1000, radius_np[1, 2][(depth_np[1] * m[1, 2]).nonzero()])
+    assert np.array_equal(fused["centre_mm"][1, 2].cpu().numpy(), want[0])
+    # a second context-scratch call (no radius_out) gives the same results
+    again = ctx.head_vote_frames(up, weight, bias, depth, K, max_radii=mr, mask_flags=api.MASK_LM_CKPT)
+    assert torch.equal(again["centre_mm"], fused["centre_mm"]) and torch.equal(again["votes"], fused["votes"])
