@@ -6,6 +6,7 @@ signatures, dtypes, units and return shapes -- executed on the B200 through libr
     linemod_K                         reference AccumulatorSpace.py:59-61
     read_depth(path)                  reference AccumulatorSpace.py:482-490
     estimate_6d_pose_lm(opts)         reference AccumulatorSpace.py:495-744 (batched: rcvpose_b200/evaluate.py)
+    estimate_6d_pose_lmo(opts)        reference AccumulatorSpace.py:741-983 (batched: rcvpose_b200/evaluate.py)
 
 Putting this package's directory ahead of the reference on sys.path makes
 `estimate_6d_pose_*` (reference :495-1197) call these instead.  Inputs and outputs are NumPy
@@ -91,3 +92,8 @@ def read_depth(path):
 def estimate_6d_pose_lm(opts):
     from . import evaluate
     return evaluate.estimate_6d_pose_lm(opts)
+
+
+def estimate_6d_pose_lmo(opts):
+    from . import evaluate
+    return evaluate.estimate_6d_pose_lmo(opts)

@@ -18,7 +18,8 @@ import torch
 
 from . import api, formats
 
-# ---- data of the reference's evaluator (AccumulatorSpace.py:18, :43, :45-58, :59-61) ----
+# ---- data of the reference's evaluator (AccumulatorSpace.py:18-19, :43, :45-58, :59-61) ----
+lmo_cls_names = ['ape', 'can', 'cat', 'duck', 'driller', 'eggbox', 'glue', 'holepuncher']
 lm_cls_names = ['ape', 'benchvise', 'cam', 'can', 'cat', 'duck', 'driller', 'eggbox', 'glue', 'holepuncher', 'iron', 'lamp', 'phone']
 lm_syms = ['eggbox', 'glue']
 add_threshold = {   # 10 % of the model diameter, metres
@@ -63,7 +64,7 @@ class FrameEvaluator:
         self.icp, self.icp_max_iter = bool(icp), int(icp_max_iter)
 
     def run(self, depth, radius, K, RT_gt_mm, max_radii=None, sem=None, mask_flags=api.MASK_LM_NPY, sem_threshold=0.8, depth_div=1.0,
-            scene_scale=1.0, centres_override=None, **vote_kw):
+            scene_scale=1.0, centres_override=None, icp_rel_fitness=1e-6, icp_rel_rmse=1e-6, zero_empty_centres=False, **vote_kw):
         """depth (B,H,W), radius (B,Kp,H,W) float32 [, sem (B,Kp,H,W) float32], K (3,3) or (B,3,3), RT_gt_mm (B,3,4) or (B,4,4)
         (translation in mm) -- NumPy or torch, host or device.  Returns a dict of HOST arrays: centre_mm (B,Kp,3), RT (B,4,4),
         dist_before (B,), RT_icp (B,4,4), dist_after (B,), passed_before / passed_after (B,) bool, status (B,Kp), n_points (B,Kp),
@@ -80,6 +81,8 @@ class FrameEvaluator:
         out = ctx.vote_frames(depth, radius, K, sem=sem, max_radii=max_radii, mask_flags=mask_flags, sem_threshold=sem_threshold,
                               depth_div=depth_div, **vote_kw)
         centres = out["centre_mm"]
+        if zero_empty_centres:   # the LMO evaluator leaves the row of a keypoint without pixels at zero (AccumulatorSpace.py:795, :858)
+            centres[(out["status"] & api.RCV_ST_EMPTY_MASK) != 0] = 0.0
         if centres_override is not None:   # frames voted outside the fused path (float64 radius maps), see LinemodEvaluator
             idx, val = centres_override
             centres[idx[0].to(dev), idx[1].to(dev)] = to(val, torch.float64)
@@ -91,7 +94,8 @@ class FrameEvaluator:
         if self.icp:
             scene, offs, _ = ctx.scene_clouds(depth, radius, K, sem=sem, max_radii=max_radii, mask_flags=mask_flags, sem_threshold=sem_threshold,
                                               depth_div=depth_div, scale=scene_scale)
-            reg = ctx.icp(self.cad_mm, scene, offs, RT, before.contiguous(), max_iter=self.icp_max_iter)
+            reg = ctx.icp(self.cad_mm, scene, offs, RT, before.contiguous(), max_iter=self.icp_max_iter, rel_fitness=icp_rel_fitness,
+                          rel_rmse=icp_rel_rmse)
             mean2, mn2 = ctx.add_metric(self.cad_mm, reg["RT"], gt)
             after = mn2 if self.symmetric else mean2
             res.update(RT_icp=reg["RT"], dist_after=after, passed_after=after <= self.threshold_mm, icp_fitness=reg["fitness"],
@@ -216,4 +220,145 @@ def estimate_6d_pose_lm(opts):
         results[class_name] = evaluate_lm_class(opts.root_dataset, class_name, using_ckpts=bool(getattr(opts, "using_ckpts", False)),
                                                 producer=getattr(opts, "producer", None), device=getattr(opts, "device", 0),
                                                 frames_per_batch=getattr(opts, "frames_per_batch", 64))
+    return results
+
+
+# ------------------------------------------------------------------------------------------------
+# Occlusion LINEMOD (AccumulatorSpace.py:741-983)
+# ------------------------------------------------------------------------------------------------
+class LmoClass:
+    """One class of the reference's Occlusion-LINEMOD layout (AccumulatorSpace.py:746, :769-785, :809-850):
+        <root>/LINEMOD/<cls>/{<cls>.ply, Outside9.npy}
+        <root>/OCCLUSION_LINEMOD/RGB-D/rgb_noseg/color_<NNNNN>.png, RGB-D/depth_noseg/depth_<NNNNN>.png   (depth in mm)
+        <root>/OCCLUSION_LINEMOD/blender_poses/<cls>/pose<N>.npy
+        <root>/OCCLUSION_LINEMOD/estRadialMap/<cls>/Out_pt<k>_dm/_<NNNNN>.npy
+    `entries` is every directory entry of rgb_noseg (the reference's counter advances for each one, :962); `stems` are the
+    frames that are evaluated: .png images whose pose and (npy branch) three radius maps exist (:809-817)."""
+
+    def __init__(self, root_dataset, class_name, using_ckpts=False):
+        self.name = class_name
+        self.root = root_dataset + "OCCLUSION_LINEMOD/"
+        pv = root_dataset + "LINEMOD/" + class_name + "/"
+        self.cad_m = formats.read_ply_points(pv + class_name + ".ply")
+        self.keypoints_m = formats.load_keypoints(pv + "Outside9.npy")
+        self.max_radii_dm = max_radii_dm(self.cad_m, self.keypoints_m)
+        self.entries = sorted(os.listdir(self.root + "RGB-D/rgb_noseg/"))
+        self.stems = []
+        for f in self.entries:
+            if not f.endswith(".png"):
+                continue
+            stem = os.path.splitext(f)[0]
+            ok = os.path.isfile(self.pose_path(stem))
+            if not using_ckpts:
+                ok = ok and all(os.path.isfile(self.radial_path(stem, k)) for k in (1, 2, 3))
+            if ok:
+                self.stems.append(stem)
+
+    @staticmethod
+    def index(stem):
+        return int(stem[6:])                       # "color_00076" -> 76
+
+    def image_path(self, stem):
+        return self.root + "RGB-D/rgb_noseg/" + stem + ".png"
+
+    def pose_path(self, stem):
+        return self.root + "blender_poses/" + self.name + "/pose" + str(self.index(stem)) + ".npy"
+
+    def radial_path(self, stem, k):
+        return os.path.join(self.root, "estRadialMap", self.name, "Out_pt" + str(k) + "_dm", "_" + str(self.index(stem)).zfill(5) + ".npy")
+
+    def depth(self, stem):
+        return np.array(formats.read_depth(self.root + "RGB-D/depth_noseg/depth_" + stem[6:].zfill(5) + ".png"), dtype=np.float64)
+
+    def pose_mm(self, stem):
+        rt = formats.load_pose(self.pose_path(stem)).copy()
+        rt[:, 3] = rt[:, 3] * 1000
+        return rt
+
+
+def evaluate_lmo_class(root_dataset, class_name, using_ckpts=False, producer=None, device=0, frames_per_batch=64, icp=True, verbose=True):
+    """One class of estimate_6d_pose_lmo (AccumulatorSpace.py:741-983).  Differences from the LINEMOD evaluator, all the
+    reference's: float64 depth images in mm (:833), mask rule `radial > 0` (npy, :849-851) or `sem >= 0.5` (ckpt, :837-840), a
+    keypoint whose thresholded radius map is all zero is skipped and its row stays 0 (:858, :795), ICP runs with
+    relative_fitness = relative_rmse = add_threshold * 1000 (:939-941), and the ADD(-S) ratios are taken over EVERY entry of the
+    image directory, evaluated or not (:962)."""
+    from . import AccumulatorSpace as shim
+    cls = LmoClass(root_dataset, class_name, using_ckpts)
+    sym = class_name in lm_syms
+    thr = add_threshold[class_name] * 1000
+    if using_ckpts and producer is None:
+        raise ValueError("using_ckpts needs a producer(class_name, k, image_path) -> (sem, radial): the radius-map network is not part of rcvpose_b200")
+    ev, acc = None, {}
+    for b0 in range(0, len(cls.stems), frames_per_batch):
+        stems = cls.stems[b0:b0 + frames_per_batch]
+        depth = np.stack([cls.depth(s) for s in stems])
+        H, W = depth.shape[1:]
+        radius = np.empty((len(stems), 3, H, W), np.float32)
+        sem = np.empty_like(radius) if using_ckpts else None
+        zero_map = np.zeros((len(stems), 3), bool)
+        override_idx, override_val = [], []
+        for i, s in enumerate(stems):
+            for k in range(1, 4):
+                if using_ckpts:
+                    sm, rd = producer(class_name, k, cls.image_path(s))
+                    sem[i, k - 1], radius[i, k - 1] = sm, rd
+                    m = (np.asarray(sm) >= 0.5) & (np.asarray(rd) <= cls.max_radii_dm[k - 1])
+                    zero_map[i, k - 1] = (np.asarray(rd) * m).max() == 0
+                    continue
+                rd = np.load(cls.radial_path(s, k))
+                rd = np.where(rd <= cls.max_radii_dm[k - 1], rd, 0)
+                zero_map[i, k - 1] = rd.max() == 0
+                if rd.dtype == np.float32:
+                    radius[i, k - 1] = rd
+                    continue
+                # not float32: exact drop-in surface for this (frame, keypoint), as in evaluate_lm_class
+                radius[i, k - 1] = np.where(rd > 0, np.float32(1e-3), np.float32(0))
+                if not zero_map[i, k - 1]:
+                    dm = depth[i] * np.where(rd > 0, 1, 0)
+                    xyz_mm = shim.rgbd_to_point_cloud(linemod_K, dm)
+                    override_idx.append((i, k - 1))
+                    override_val.append(shim.Accumulator_3D(xyz_mm / 1000, rd[dm.nonzero()])[0])
+        if ev is None:
+            ev = FrameEvaluator(cls.cad_m * 1000, cls.keypoints_m[1:4, :] * 1000, sym, thr, device=device, frames_per_batch=frames_per_batch,
+                                image=(H, W), icp=icp)
+        gt = np.stack([cls.pose_mm(s) for s in stems])
+        ov = None
+        if override_idx:
+            ii = np.array(override_idx)
+            ov = ((torch.as_tensor(ii[:, 0]), torch.as_tensor(ii[:, 1])), np.array(override_val))
+        res = ev.run(depth, radius, linemod_K, gt, max_radii=cls.max_radii_dm, sem=sem, sem_threshold=0.5,
+                     mask_flags=api.MASK_LMO_CKPT if using_ckpts else api.MASK_LMO_NPY, centres_override=ov, icp_rel_fitness=thr,
+                     icp_rel_rmse=thr, zero_empty_centres=True)
+        st = res["status"].copy()
+        if override_idx:
+            st[ii[:, 0], ii[:, 1]] = 0
+        empty = (st & api.RCV_ST_EMPTY_MASK) != 0
+        if (empty & ~zero_map).any():   # radii survive but no depth under them: the reference calls Accumulator_3D on an empty cloud
+            i, k = np.argwhere(empty & ~zero_map)[0]
+            raise ValueError("zero-size array to reduction operation minimum which has no identity (frame %s, keypoint %d: empty cloud)" % (stems[i], k + 1))
+        if (st & ~api.RCV_ST_EMPTY_MASK).any():
+            raise api.RcvError("voting failed with status %s" % np.unique(st))
+        for k, v in res.items():
+            acc.setdefault(k, []).append(v)
+    n = len(cls.entries)
+    out = {k: np.concatenate(v) for k, v in acc.items()}
+    nb = int(out["passed_before"].sum()) if acc else 0
+    na = int(out["passed_after"].sum()) if (acc and icp) else 0
+    out.update(frames=list(cls.stems), n=n, evaluated=len(cls.stems), add_before=nb / n if n else float("nan"),
+               add_after=(na / n if icp else float("nan")) if n else float("nan"))
+    if verbose:
+        tag = "ADDs" if sym else "ADD"
+        print(tag + " of " + class_name + " before ICP: ", out["add_before"])
+        print(tag + " of " + class_name + " after ICP: ", out["add_after"])
+    return out
+
+
+def estimate_6d_pose_lmo(opts):
+    """Drop-in for AccumulatorSpace.estimate_6d_pose_lmo(opts) (:741-983); returns {class_name: result dict}."""
+    results = {}
+    for class_name in getattr(opts, "classes", None) or lmo_cls_names:
+        print(class_name)
+        results[class_name] = evaluate_lmo_class(opts.root_dataset, class_name, using_ckpts=bool(getattr(opts, "using_ckpts", False)),
+                                                 producer=getattr(opts, "producer", None), device=getattr(opts, "device", 0),
+                                                 frames_per_batch=getattr(opts, "frames_per_batch", 64))
     return results

@@ -135,6 +135,55 @@ def write_lm_dataset(root, class_name, n_frames, seed=0, obj_radius_mm=55.0, n_c
     return stems
 
 
+def write_lmo_dataset(root, class_name, n_frames, seed=0, obj_radius_mm=55.0, n_cad=1500, radius_dtype=np.float32):
+    """Synthetic class in the reference's Occlusion-LINEMOD layout (AccumulatorSpace.py:746-850; rcvpose_b200.evaluate.LmoClass).
+    Besides n_frames complete frames the image directory holds one frame without a pose, one without the third radius map and a
+    stray non-image file (all three are counted but not evaluated, :962); in the second complete frame the radius map of
+    keypoint 2 is all zero (the reference skips that keypoint, :858).  Returns the stems of the complete frames."""
+    import os
+    from PIL import Image
+    from . import formats
+    rng = np.random.default_rng(seed)
+    pv, occ = root + "LINEMOD/" + class_name + "/", root + "OCCLUSION_LINEMOD/"
+    for d in (pv, occ + "RGB-D/rgb_noseg", occ + "RGB-D/depth_noseg", occ + "blender_poses/" + class_name):
+        os.makedirs(d, exist_ok=True)
+    u = rng.normal(size=(n_cad, 3))
+    formats.write_ply_points(pv + class_name + ".ply", u / np.linalg.norm(u, axis=1, keepdims=True) * (obj_radius_mm / 1000))
+    cad_m = formats.read_ply_points(pv + class_name + ".ply")
+    dirs = np.array([[0, 0, 0], [1.0, 0.2, 0.1], [-0.3, 1.0, 0.2], [0.2, -0.4, 1.0], [-1.0, -0.5, 0.3], [0.5, 0.5, -1.0], [1, 1, 1], [-1, 1, -1],
+                     [1, -1, -1]], dtype=np.float64)
+    dirs[1:] /= np.linalg.norm(dirs[1:], axis=1, keepdims=True)
+    kp_m = dirs * (obj_radius_mm / 1000) * 1.8
+    np.save(pv + "Outside9.npy", kp_m)
+    max_r = [float(np.linalg.norm(cad_m - kp_m[k], axis=1).max() * 10) for k in (1, 2, 3)]
+    stems = []
+    for f in range(n_frames + 2):
+        idx = f * 5 + 2
+        stem = "color_%05d" % idx
+        open(occ + "RGB-D/rgb_noseg/" + stem + ".png", "wb").close()
+        rv = rng.normal(size=3); th = np.linalg.norm(rv); k = rv / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+        t_m = np.array([rng.uniform(-0.15, 0.15), rng.uniform(-0.15, 0.15), rng.uniform(0.7, 1.1)])
+        if f != n_frames:                                  # frame n_frames has no pose
+            np.save(occ + "blender_poses/" + class_name + "/pose" + str(idx) + ".npy", np.concatenate([R, t_m[:, None]], axis=1))
+        depth = sphere_depth(linemod_K, t_m * 1000, obj_radius_mm)
+        Image.fromarray(depth).save(occ + "RGB-D/depth_noseg/depth_%05d.png" % idx)
+        for k in (1, 2, 3):
+            if f == n_frames + 1 and k == 3:               # frame n_frames + 1 lacks the third map
+                continue
+            d = occ + "estRadialMap/" + class_name + "/Out_pt" + str(k) + "_dm/"
+            os.makedirs(d, exist_ok=True)
+            r = radius_map_dm(linemod_K, depth, (R @ kp_m[k] + t_m) * 1000, rng, 0.01, 0.02, max_r[k - 1] * 1.2)
+            if f == 1 and k == 2:
+                r = r * 0 + 9.0e3 * (depth != 0)           # everything beyond max_radii: the thresholded map is all zero
+            np.save(d + "_%05d.npy" % idx, r.astype(radius_dtype))
+        if f < n_frames:
+            stems.append(stem)
+    open(occ + "RGB-D/rgb_noseg/Thumbs.db", "wb").close()
+    return stems
+
+
 def frame_to_points(K, depth, radius):
     """The reference caller's glue (AccumulatorSpace.py:612-619, npy branch): masked depth ->
     xyz in metres (N,3) float64 + radial list (N,) in the map's dtype."""

@@ -361,3 +361,73 @@ def test_fused_head_vote_frames_bit_identical_to_two_calls(ctx):
     # a second context-scratch call (no radius_out) gives the same results
     again = ctx.head_vote_frames(up, weight, bias, depth, K, max_radii=mr, mask_flags=api.MASK_LM_CKPT)
     assert torch.equal(again["centre_mm"], fused["centre_mm"]) and torch.equal(again["votes"], fused["votes"])
+
+
+def test_lmo_layout_counts_every_directory_entry(tmp_path):
+    from rcvpose_b200 import evaluate
+    root = str(tmp_path) + "/"
+    stems = synth.write_lmo_dataset(root, "duck", 3, seed=4)
+    cls = evaluate.LmoClass(root, "duck")
+    assert cls.stems == stems and len(cls.entries) == 6          # 3 complete + no pose + no third map + a stray file (:962 counts all)
+    assert cls.index("color_00076") == 76
+    d = cls.depth(stems[0])
+    assert d.dtype == np.float64 and d.shape == (480, 640) and (d != 0).sum() > 1000     # :833
+    assert len(evaluate.LmoClass(root, "duck", using_ckpts=True).stems) == 4              # the ckpt branch only needs the pose (:809-811)
+
+
+def _reference_loop_lmo(root, class_name, sym, thr):
+    """estimate_6d_pose_lmo's per-image loop (AccumulatorSpace.py:786-962, npy branch) on the oracle's functions."""
+    from rcvpose_b200 import evaluate
+    cls = evaluate.LmoClass(root, class_name)
+    K = evaluate.linemod_K
+    out = []
+    for stem in cls.stems:
+        depth_map1 = cls.depth(stem)
+        est = np.zeros((3, 3))
+        clouds = []
+        for k in (1, 2, 3):
+            r = np.load(cls.radial_path(stem, k))
+            r = np.where(r <= cls.max_radii_dm[k - 1], r, 0)
+            sem = np.where(r > 0, 1, 0)
+            dm = depth_map1 * sem
+            if r.max() != 0:
+                xyz_mm = oracle.rgbd_to_point_cloud(K, dm)
+                est[k - 1] = oracle.Accumulator_3D(xyz_mm / 1000, r[dm.nonzero()])[0]
+                clouds.append(xyz_mm)
+        RT = np.zeros((4, 4))
+        oracle.lmshorn(cls.keypoints_m[1:4] * 1000, est, 3, RT)
+        gt = np.eye(4)
+        gt[:3] = cls.pose_mm(stem)
+        mean, mn = oracle.add_metric(cls.cad_m * 1000, RT, gt)
+        before = mn if sym else mean
+        reg = oracle.registration_icp(cls.cad_m * 1000, oracle.scene_union(clouds), before, RT, relative_fitness=thr, relative_rmse=thr)
+        mean2, mn2 = oracle.add_metric(cls.cad_m * 1000, reg["transformation"], gt)
+        after = mn2 if sym else mean2
+        out.append(dict(centres=est, RT=RT, before=before, after=after, RT_icp=reg["transformation"], iters=reg["iterations"],
+                        pb=before <= thr, pa=after <= thr))
+    return cls, out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_estimate_6d_pose_lmo_vs_reference_loop(tmp_path, dtype):
+    """The Occlusion-LINEMOD drop-in (float64 depth images, `radial > 0` rule, skipped all-zero keypoint with its row left at 0,
+    ICP criteria add_threshold*1000, ratios over every directory entry) against the reference's per-image loop on the oracle."""
+    from rcvpose_b200 import AccumulatorSpace as A, evaluate
+    root = str(tmp_path) + "/"
+    synth.write_lmo_dataset(root, "can", 3, seed=6, radius_dtype=dtype)
+    res = A.estimate_6d_pose_lmo(types.SimpleNamespace(root_dataset=root, using_ckpts=False, classes=["can"], frames_per_batch=2))["can"]
+    thr = evaluate.add_threshold["can"] * 1000
+    cls, want = _reference_loop_lmo(root, "can", False, thr)
+    assert res["frames"] == cls.stems and res["n"] == 6 and res["evaluated"] == 3
+    assert np.array_equal(res["centre_mm"][1, 1], np.zeros(3)) and np.array_equal(want[1]["centres"][1], np.zeros(3))
+    for i, w in enumerate(want):
+        assert np.array_equal(res["centre_mm"][i], w["centres"]), (i, res["centre_mm"][i], w["centres"])
+        np.testing.assert_allclose(res["RT"][i], w["RT"], rtol=0, atol=1e-9)
+        assert abs(res["dist_before"][i] - w["before"]) <= 1e-9 * max(1.0, w["before"])
+        assert res["icp_iters"][i] == w["iters"] <= 2                  # criteria of ~28 mm: the first or second update already "converges"
+        np.testing.assert_allclose(res["RT_icp"][i], w["RT_icp"], rtol=0, atol=1e-6)
+        assert abs(res["dist_after"][i] - w["after"]) <= 1e-6 * max(1.0, w["after"])
+        assert bool(res["passed_before"][i]) == bool(w["pb"]) and bool(res["passed_after"][i]) == bool(w["pa"])
+    assert res["add_before"] == sum(w["pb"] for w in want) / 6 and res["add_after"] == sum(w["pa"] for w in want) / 6
+    assert res["passed_before"][0] and not res["passed_before"][1]     # a keypoint at the origin ruins the pose of frame 1
