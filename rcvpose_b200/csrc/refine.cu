@@ -18,7 +18,7 @@
 //         SearchHybrid); fitness = kept / n_source, inlier_rmse = sqrt(sum dist^2 / kept) (0 when nothing is kept)
 //
 // GPU form.  The nearest neighbour is an exact brute-force float64 search (no k-d tree: a frame's scene has a few thousand
-// points, and all frames of a batch run at once): k_icp_corr, one CTA per (frame, tile of 256 source points), the frame's
+// points, and all frames of a batch run at once): k_icp_corr, one CTA per (frame, tile of 256 source points, two per thread), the frame's
 // scene streamed through shared memory; each CTA leaves 17 partial sums (count, sum d^2, sum p, sum q, sum p q^T, taken
 // relative to a per-frame origin so that the covariance does not cancel).  k_icp_update, one thread per frame, reduces the
 // partials in tile order (deterministic), applies the convergence rule and composes the update; the rotation is Horn's
@@ -32,7 +32,12 @@
 
 namespace {
 
-constexpr int kIcpThreads = 256;
+constexpr int kIcpThreads = 128;
+#ifndef RCV_ICP_PTS
+#define RCV_ICP_PTS 2
+#endif
+constexpr int kIcpPts = RCV_ICP_PTS;          // source points per thread
+constexpr int kIcpTile = kIcpThreads * kIcpPts; // source points per CTA = scene points per shared-memory tile
 constexpr int kIcpSums = 17;   // n, sum d2, p[3], q[3], pq[9]
 
 struct IcpState {     // one per frame, in the context's scratch
@@ -57,52 +62,79 @@ __global__ void __launch_bounds__(kIcpThreads) k_icp_corr(const double* __restri
                                                          const IcpState* __restrict__ st, double* __restrict__ partials, int tiles) {
   const int frame = blockIdx.y, tile = blockIdx.x;
   if (st[frame].done) return;
-  __shared__ double s_q[3][kIcpThreads];
+  __shared__ double s_q[4][kIcpTile];
   __shared__ double s_T[15];
   __shared__ double s_red[kIcpSums][kIcpThreads / 32];
   if (threadIdx.x < 12) s_T[threadIdx.x] = st[frame].T[threadIdx.x];
   if (threadIdx.x < 3) s_T[12 + threadIdx.x] = st[frame].origin[threadIdx.x];
   __syncthreads();
-  const int g = tile * kIcpThreads + threadIdx.x;
-  double px = 0, py = 0, pz = 0;
-  if (g < n_model) {
-    const double x = model[3 * g], y = model[3 * g + 1], z = model[3 * g + 2];
-    px = s_T[0] * x + s_T[1] * y + s_T[2] * z + s_T[3];
-    py = s_T[4] * x + s_T[5] * y + s_T[6] * z + s_T[7];
-    pz = s_T[8] * x + s_T[9] * y + s_T[10] * z + s_T[11];
+  // a thread owns kIcpPts source points, so that every scene point read from shared memory serves kIcpPts pairs
+  double px[kIcpPts], py[kIcpPts], pz[kIcpPts], rx[kIcpPts], ry[kIcpPts], rz[kIcpPts], best[kIcpPts];
+  int bi[kIcpPts];     // index of the nearest scene point so far, relative to the frame's first
+#pragma unroll
+  for (int j = 0; j < kIcpPts; ++j) {
+    const int g = tile * kIcpTile + j * kIcpThreads + threadIdx.x;
+    px[j] = py[j] = pz[j] = 0.0;
+    if (g < n_model) {
+      const double x = model[3 * g], y = model[3 * g + 1], z = model[3 * g + 2];
+      px[j] = s_T[0] * x + s_T[1] * y + s_T[2] * z + s_T[3];
+      py[j] = s_T[4] * x + s_T[5] * y + s_T[6] * z + s_T[7];
+      pz[j] = s_T[8] * x + s_T[9] * y + s_T[10] * z + s_T[11];
+    }
+    // argmin_q |p - q|^2 = argmin_q (|q|^2 / 2 - p . q): three DFMA and one compare per pair instead of seven float64
+    // operations (the kernel is bound by the float64 pipe).  Coordinates are taken relative to the frame's origin (|.| ~ the
+    // object size), so the cancellation costs ~1e-12 mm^2; the distance of the winner is then recomputed directly.
+    rx[j] = px[j] - s_T[12]; ry[j] = py[j] - s_T[13]; rz[j] = pz[j] - s_T[14];
+    best[j] = INFINITY; bi[j] = -1;
   }
   const long long q0 = scene_off[frame], q1 = scene_off[frame + 1];
-  double best = INFINITY;
-  long long bi = -1;
-  for (long long e0 = q0; e0 < q1; e0 += kIcpThreads) {
-    const long long e = e0 + threadIdx.x;
-    double ex = INFINITY, ey = INFINITY, ez = INFINITY;   // padding never wins the minimum
-    if (e < q1) { ex = scene[3 * e]; ey = scene[3 * e + 1]; ez = scene[3 * e + 2]; }
+  for (long long e0 = q0; e0 < q1; e0 += kIcpTile) {
     __syncthreads();
-    s_q[0][threadIdx.x] = ex; s_q[1][threadIdx.x] = ey; s_q[2][threadIdx.x] = ez;
+#pragma unroll
+    for (int j = 0; j < kIcpPts; ++j) {
+      const int si = j * kIcpThreads + threadIdx.x;
+      const long long e = e0 + si;
+      double ex = 0.0, ey = 0.0, ez = 0.0, eh = INFINITY;   // padding never wins the minimum
+      if (e < q1) {
+        ex = scene[3 * e] - s_T[12]; ey = scene[3 * e + 1] - s_T[13]; ez = scene[3 * e + 2] - s_T[14];
+        eh = 0.5 * (ex * ex + ey * ey + ez * ez);
+      }
+      s_q[0][si] = ex; s_q[1][si] = ey; s_q[2][si] = ez; s_q[3][si] = eh;
+    }
     __syncthreads();
-    const int cnt = (int)((q1 - e0) < kIcpThreads ? (q1 - e0) : kIcpThreads);
+    const int cnt = (int)((q1 - e0) < kIcpTile ? (q1 - e0) : kIcpTile);
+    const int rel0 = (int)(e0 - q0);
 #pragma unroll 4
     for (int q = 0; q < cnt; ++q) {
-      const double dx = px - s_q[0][q], dy = py - s_q[1][q], dz = pz - s_q[2][q];
-      const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-      if (d2 < best) { best = d2; bi = e0 + q; }     // first nearest point in scene order wins a tie
+      const double qx = s_q[0][q], qy = s_q[1][q], qz = s_q[2][q], qh = s_q[3][q];
+#pragma unroll
+      for (int j = 0; j < kIcpPts; ++j) {
+        const double sc = fma(-rz[j], qz, fma(-ry[j], qy, fma(-rx[j], qx, qh)));
+        if (sc < best[j]) { best[j] = sc; bi[j] = rel0 + q; }     // first nearest point in scene order wins a tie
+      }
     }
   }
   const double md = max_dist[frame];
-  const bool ok = g < n_model && bi >= 0 && best < md * md;     // strict, like SearchHybrid's lower_bound on radius^2
   double v[kIcpSums];
 #pragma unroll
   for (int i = 0; i < kIcpSums; ++i) v[i] = 0.0;
-  if (ok) {
-    const double a[3] = {px - s_T[12], py - s_T[13], pz - s_T[14]};
-    const double b[3] = {scene[3 * bi] - s_T[12], scene[3 * bi + 1] - s_T[13], scene[3 * bi + 2] - s_T[14]};
-    v[0] = 1.0; v[1] = best;
+#pragma unroll
+  for (int j = 0; j < kIcpPts; ++j) {
+    const int g = tile * kIcpTile + j * kIcpThreads + threadIdx.x;
+    if (g >= n_model || bi[j] < 0) continue;
+    const double* sp = scene + 3 * (q0 + bi[j]);
+    const double sx = sp[0], sy = sp[1], sz = sp[2];
+    const double dx = px[j] - sx, dy = py[j] - sy, dz = pz[j] - sz;
+    const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    if (!(d2 < md * md)) continue;     // strict, like SearchHybrid's lower_bound on radius^2
+    const double a[3] = {rx[j], ry[j], rz[j]};
+    const double b[3] = {sx - s_T[12], sy - s_T[13], sz - s_T[14]};
+    v[0] += 1.0; v[1] += d2;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      v[2 + r] = a[r]; v[5 + r] = b[r];
+      v[2 + r] += a[r]; v[5 + r] += b[r];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[8 + 3 * r + c] = a[r] * b[c];
+      for (int c = 0; c < 3; ++c) v[8 + 3 * r + c] += a[r] * b[c];
     }
   }
   // deterministic tile reduction: warp shuffles in a fixed pattern, then the warp partials in order
@@ -176,7 +208,7 @@ __global__ void k_icp_update(const double* __restrict__ partials, int tiles, int
 
 // Scratch (in doubles) the launch needs for n_frames frames of an n_model-point source.
 extern "C" long long rcv_icp_scratch_doubles(int n_frames, int n_model) {
-  const long long tiles = (n_model + kIcpThreads - 1) / kIcpThreads;
+  const long long tiles = (n_model + kIcpTile - 1) / kIcpTile;
   return (long long)n_frames * ((long long)(sizeof(IcpState) + 7) / 8 + tiles * kIcpSums) + 1;   // + the converged-frames counter
 }
 
@@ -184,7 +216,7 @@ extern "C" int rcv_icp_launch(const double* model, int n_model, const double* sc
                               const double* max_dist, int n_frames, int max_iter, double rel_fitness, double rel_rmse, double* scratch,
                               double* RT_out, double* fitness_out, double* rmse_out, int* iters_out, void* stream, long long* launches) {
   cudaStream_t s = (cudaStream_t)stream;
-  const int tiles = (n_model + kIcpThreads - 1) / kIcpThreads;
+  const int tiles = (n_model + kIcpTile - 1) / kIcpTile;
   IcpState* st = reinterpret_cast<IcpState*>(scratch);
   double* partials = scratch + (long long)n_frames * ((long long)(sizeof(IcpState) + 7) / 8);
   int* n_done = reinterpret_cast<int*>(partials + (long long)n_frames * tiles * kIcpSums);

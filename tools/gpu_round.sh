@@ -5,8 +5,8 @@ TAG=${1:-r01}
 mkdir -p gpurun_out
 if [ "$2" != "skip-tests" ]; then
   timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/${TAG}_pytest.txt
-  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 99 python -m pytest tests/test_gpu_parity.py -x -q \
-    -k "config1 or random_clouds or frames_api or mask_rules or large_grid" > gpurun_out/${TAG}_memcheck.log 2>&1
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 99 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
+    -k "config1 or random_clouds or frames_api or mask_rules or large_grid or icp_vs_oracle or scene_clouds or fused or lmo_vs" tests/test_evaluator.py > gpurun_out/${TAG}_memcheck.log 2>&1
   echo "memcheck rc=$?" | tee -a gpurun_out/${TAG}_memcheck.log; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/${TAG}_memcheck.log | tail -3
 fi
 timeout 900 python bench.py 2> gpurun_out/${TAG}_bench.err | tee gpurun_out/${TAG}_bench.json
@@ -21,4 +21,8 @@ timeout 300 python tools/head_bw.py | tee gpurun_out/${TAG}_head_bw.json
 RCV_HEAD_IMAGES=48 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_head -s 3 -c 1 -f -o gpurun_out/${TAG}_head \
   python tools/head_bw.py > gpurun_out/${TAG}_ncu_head.log 2>&1
 tail -3 gpurun_out/${TAG}_ncu_head.log
+timeout 300 python tools/evaluator_bw.py 2>/dev/null | tee gpurun_out/${TAG}_evaluator_bw.json
+for v in icp4 icp1; do
+  if [ -f build/librcvvote_$v.so ]; then RCV_LIB_PATH=$PWD/build/librcvvote_$v.so timeout 300 python tools/evaluator_bw.py 2>/dev/null | sed "s/^{/{\"variant\": \"$v\", /" | tee -a gpurun_out/${TAG}_evaluator_bw.json; fi
+done
 ls -la gpurun_out/ | tail -20
