@@ -21,17 +21,6 @@
 
 #include "../../include/rcvvote.h"
 
-#ifndef RCV_HEAD_QMAP
-#define RCV_HEAD_QMAP 1   // quarter-warp = the 8 channels of one pixel group (conflict-free shared-memory side)
-#endif
-#ifndef RCV_HEAD_CA
-#define RCV_HEAD_CA 0     // cp.async.ca (through L1) instead of .cg (L2 only)
-#endif
-
-#ifndef RCV_HEAD_LDG
-#define RCV_HEAD_LDG 0    // 1: ld.global.nc.v4 -> registers -> st.shared.v4 (software-pipelined) instead of cp.async
-#endif
-
 namespace rcv_head {
 
 constexpr int kThreads = 128;
@@ -165,76 +154,28 @@ __global__ void __launch_bounds__(kThreads) k_head1x1(const __nv_bfloat16* __res
         // is conflict-free; the four quarters take 4 consecutive pixel groups (64 contiguous bytes per channel in global
         // memory).  The first version gave consecutive lanes consecutive pixel groups of ONE channel: 128-byte stride in
         // shared memory, every lane on the same four banks, 8x the wavefronts -- 16 B/clk/SM, the 3.87 TB/s plateau.
-#if RCV_HEAD_QMAP
         const int chunk = tid + j * kThreads, lane = chunk & 31, wi = chunk >> 5;
         const int k = (wi / (4 * kTpi)) * 8 + (lane & 7), mg = (wi % (4 * kTpi)) * 4 + (lane >> 3);
-#else
-        const int chunk = tid + j * kThreads, k = chunk / (16 * kTpi), mg = chunk % (16 * kTpi);
-#endif
         const long long pix = m0 + mg * 8;
         const bool valid = pix < HW;
         const __nv_bfloat16* src = src0 + (long long)k * HW + (valid ? pix : 0);
         const uint32_t dst = dst0 + (mg >> 4) * kATile + (mg & 15) * 128 + (k & 7) * 16 + (k >> 3) * 2048;
-#if RCV_HEAD_CA
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
-#else
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
-#endif
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   const long long grp0 = blockIdx.x;
-#if RCV_HEAD_LDG
-  constexpr int kChunksPerThread = kTpi * (kC * kTileM / 8) / kThreads;
-  uint4 regs[kChunksPerThread];
-  auto ldg = [&](long long grp) {
-    if (grp < n_groups) {
-      const long long b = grp / groups_per_image;
-      const long long m0 = (grp - b * groups_per_image) * (kTpi * kTileM);
-      const __nv_bfloat16* src0 = up + b * kC * HW;
-#pragma unroll
-      for (int j = 0; j < kChunksPerThread; ++j) {
-        const int chunk = tid + j * kThreads, lane = chunk & 31, wi = chunk >> 5;
-        const int k = (wi / (4 * kTpi)) * 8 + (lane & 7), mg = (wi % (4 * kTpi)) * 4 + (lane >> 3);
-        const long long pix = m0 + mg * 8;
-        regs[j] = make_uint4(0u, 0u, 0u, 0u);
-        if (pix < HW)
-          asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(regs[j].x), "=r"(regs[j].y), "=r"(regs[j].z), "=r"(regs[j].w) : "l"(src0 + (long long)k * HW + pix));
-      }
-    }
-  };
-  auto sts = [&](int stage) {
-    const uint32_t dst0 = smem_u32(sA + stage * kTpi * kATile);
-#pragma unroll
-    for (int j = 0; j < kChunksPerThread; ++j) {
-      const int chunk = tid + j * kThreads, lane = chunk & 31, wi = chunk >> 5;
-      const int k = (wi / (4 * kTpi)) * 8 + (lane & 7), mg = (wi % (4 * kTpi)) * 4 + (lane >> 3);
-      const uint32_t dst = dst0 + (mg >> 4) * kATile + (mg & 15) * 128 + (k & 7) * 16 + (k >> 3) * 2048;
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(regs[j].x), "r"(regs[j].y), "r"(regs[j].z), "r"(regs[j].w) : "memory");
-    }
-  };
-  ldg(grp0);
-#else
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) issue(grp0 + s * step, s);
-#endif
   uint32_t phase = 0;
   int it = 0;
   for (long long grp = grp0; grp < n_groups; grp += step, ++it) {
-#if RCV_HEAD_LDG
-    sts(it % kStages);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    ldg(grp + step);     // in flight during the MMA and the epilogue of this group
-#else
     issue(grp + (kStages - 1) * step, (it + kStages - 1) % kStages);
     asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-#endif
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a0 = smem_u32(sA + (it % kStages) * kTpi * kATile);
