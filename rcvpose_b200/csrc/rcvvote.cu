@@ -1681,11 +1681,11 @@ RCV_EXPORT int rcv_vote_points(rcv_ctx* c, const double* xyz, const void* radii,
   return run_items(c, n_items, vp, centre_mm, peak, votes, nullptr, grid, zero_boundary, status, volume_out, volume_capacity, st);
 }
 
-static int check_frame_params(rcv_ctx* c, int n_frames, int n_kpts, const rcv_frame_params* fp, const float* sem, const double* max_radii) {
+static int check_frame_params(rcv_ctx* c, int n_frames, int n_kpts, const rcv_frame_params* fp, bool has_sem, const double* max_radii) {
   if (!fp || fp->height <= 0 || fp->width <= 0) FAIL(c, RCV_E_INVALID, "frame params: bad image size");
   if (fp->depth_dtype != RCV_U16 && fp->depth_dtype != RCV_F32 && fp->depth_dtype != RCV_F64) FAIL(c, RCV_E_INVALID, "frame params: bad depth dtype");
   if (!(fp->depth_div > 0) || !(fp->xyz_div > 0)) FAIL(c, RCV_E_INVALID, "frame params: depth_div and xyz_div must be positive");
-  if ((fp->mask_flags & (RCV_MASK_SEM_GT | RCV_MASK_SEM_GE)) && !sem) FAIL(c, RCV_E_INVALID, "frame params: sem rule without a sem map");
+  if ((fp->mask_flags & (RCV_MASK_SEM_GT | RCV_MASK_SEM_GE)) && !has_sem) FAIL(c, RCV_E_INVALID, "frame params: sem rule without a sem map");
   if ((fp->mask_flags & RCV_MASK_MAX_RADIUS) && !max_radii) FAIL(c, RCV_E_INVALID, "frame params: max-radius rule without max_radii");
   if (n_frames <= 0 || n_kpts <= 0 || (long long)n_frames * n_kpts > c->cfg.max_items)
     FAIL(c, RCV_E_CAPACITY, "n_frames*n_kpts = %lld exceeds max_items %d", (long long)n_frames * n_kpts, c->cfg.max_items);
@@ -1699,7 +1699,7 @@ RCV_EXPORT int rcv_vote_frames(rcv_ctx* c, int n_frames, int n_kpts, const void*
   if (!depth || !radius || !K || !centre_mm || !status) FAIL(c, RCV_E_INVALID, "rcv_vote_frames: null pointer");
   int rc = check_vote_params(c, vp);
   if (rc) return rc;
-  rc = check_frame_params(c, n_frames, n_kpts, fp, sem, max_radii);
+  rc = check_frame_params(c, n_frames, n_kpts, fp, sem != nullptr, max_radii);
   if (rc) return rc;
   if (vp->radius_dtype != RCV_F32) FAIL(c, RCV_E_INVALID, "rcv_vote_frames: radius maps are float32");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1763,7 +1763,7 @@ RCV_EXPORT int rcv_vote_frames_host(rcv_ctx* c, int n_frames, int n_kpts, const 
   if (frames_per_chunk <= 0) frames_per_chunk = 256;
   if ((long long)frames_per_chunk * n_kpts > c->cfg.max_items) frames_per_chunk = c->cfg.max_items / (n_kpts > 0 ? n_kpts : 1);
   if (frames_per_chunk > n_frames) frames_per_chunk = n_frames;
-  rc = check_frame_params(c, frames_per_chunk, n_kpts, fp, sem, max_radii);
+  rc = check_frame_params(c, frames_per_chunk, n_kpts, fp, sem != nullptr, max_radii);
   if (rc) return rc;
   CK(c, cudaSetDevice(c->device));
   const long long px = (long long)fp->height * fp->width;
@@ -1877,7 +1877,7 @@ RCV_EXPORT int rcv_scene_clouds(rcv_ctx* c, int n_frames, int n_kpts, const void
                                 long long xyz_capacity, long long* offsets_out, int* status_out, void* stream) {
   if (!c) return RCV_E_INVALID;
   if (!depth || !radius || !K || !xyz_out || !offsets_out || xyz_capacity <= 0) FAIL(c, RCV_E_INVALID, "rcv_scene_clouds: bad argument");
-  int rc = check_frame_params(c, n_frames, n_kpts, fp, sem, max_radii);
+  int rc = check_frame_params(c, n_frames, n_kpts, fp, sem != nullptr, max_radii);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   CK(c, cudaSetDevice(c->device));
@@ -1977,7 +1977,7 @@ RCV_EXPORT int rcv_head_vote_frames(rcv_ctx* c, int n_frames, int n_kpts, const 
   if (!up_bf16 || !weight || !bias || !depth || !K || !centre_mm || !status) FAIL(c, RCV_E_INVALID, "rcv_head_vote_frames: null pointer");
   int rc = check_vote_params(c, vp);
   if (rc) return rc;
-  rc = check_frame_params(c, n_frames, n_kpts, fp, (const float*)up_bf16 /* the seg values come from the head */, max_radii);
+  rc = check_frame_params(c, n_frames, n_kpts, fp, true /* the seg values come from the head */, max_radii);
   if (rc) return rc;
   const long long npx = (long long)fp->height * fp->width;
   if (n_kpts > 8 || npx % 8 != 0 || ((uintptr_t)up_bf16 & 15)) FAIL(c, RCV_E_INVALID, "rcv_head_vote_frames: n_kpts <= 8, H*W %% 8 == 0, up 16-byte aligned");

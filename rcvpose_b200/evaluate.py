@@ -40,6 +40,41 @@ def max_radii_dm(cad_m, keypoints_m, n_kpts=3):
     return out
 
 
+def _world():
+    """(rank, world) of the evaluation: one process per GPU under torchrun, else (0, 1)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_frames(stems):
+    """Frames are independent: rank r evaluates a contiguous range of the class's frames."""
+    from .pipeline import shard_range
+    rank, world = _world()
+    lo, hi = shard_range(len(stems), rank, world)
+    return stems[lo:hi]
+
+
+def reduce_counts(values):
+    """Sum of small integer counters over the ranks (the only communication of a sharded evaluation): one all_reduce of
+    len(values) int64, on the GPU over NCCL or on the host over gloo."""
+    import torch.distributed as dist
+    rank, world = _world()
+    if world == 1:
+        return [int(v) for v in values]
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [int(v) for v in t.tolist()]
+
+
+def _default_device(opts):
+    """opts.device if given, else the process's GPU under torchrun (LOCAL_RANK), else 0."""
+    d = getattr(opts, "device", None)
+    return int(d) if d is not None else int(os.environ.get("LOCAL_RANK", "0"))
+
+
 def _to_device(a, dev, dtype=None):
     if a is None:
         return None
@@ -147,8 +182,10 @@ def evaluate_lm_class(root_dataset, class_name, using_ckpts=False, producer=None
         raise ValueError("using_ckpts needs a producer(class_name, k, image_path) -> (sem, radial): the radius-map network is not part of rcvpose_b200")
     ev = None
     acc = {}
-    for b0 in range(0, len(cls.stems), frames_per_batch):
-        stems = cls.stems[b0:b0 + frames_per_batch]
+    my_stems = shard_frames(cls.stems)        # under torchrun every rank takes a contiguous range of the frames
+    verbose = verbose and _world()[0] == 0
+    for b0 in range(0, len(my_stems), frames_per_batch):
+        stems = my_stems[b0:b0 + frames_per_batch]
         depth = np.stack([cls.depth(s) for s in stems])
         H, W = depth.shape[1:]
         radius = np.empty((len(stems), 3, H, W), np.float32)
@@ -200,9 +237,10 @@ def evaluate_lm_class(root_dataset, class_name, using_ckpts=False, producer=None
             if icp:
                 print("Currnet ADD\\(s\\) of " + class_name + " after ICP: ", np.concatenate(acc["passed_after"]).sum() / n)
     out = {k: np.concatenate(v) for k, v in acc.items()}
+    nb, na = reduce_counts([out["passed_before"].sum() if acc else 0, out["passed_after"].sum() if (acc and icp) else 0])
     n = len(cls.stems)
-    out.update(frames=list(cls.stems), n=n, add_before=float(out["passed_before"].sum() / n) if n else float("nan"),
-               add_after=float(out["passed_after"].sum() / n) if (n and icp) else float("nan"))
+    out.update(frames=list(my_stems), n=n, add_before=float(nb / n) if n else float("nan"),
+               add_after=float(na / n) if (n and icp) else float("nan"))
     if verbose:
         tag = "ADDs" if sym else "ADD"
         print(tag + " of " + class_name + " before ICP: ", out["add_before"])
@@ -218,7 +256,7 @@ def estimate_6d_pose_lm(opts):
     for class_name in getattr(opts, "classes", None) or lm_cls_names:
         print("Evaluation on ", class_name)
         results[class_name] = evaluate_lm_class(opts.root_dataset, class_name, using_ckpts=bool(getattr(opts, "using_ckpts", False)),
-                                                producer=getattr(opts, "producer", None), device=getattr(opts, "device", 0),
+                                                producer=getattr(opts, "producer", None), device=_default_device(opts),
                                                 frames_per_batch=getattr(opts, "frames_per_batch", 64))
     return results
 
@@ -289,8 +327,10 @@ def evaluate_lmo_class(root_dataset, class_name, using_ckpts=False, producer=Non
     if using_ckpts and producer is None:
         raise ValueError("using_ckpts needs a producer(class_name, k, image_path) -> (sem, radial): the radius-map network is not part of rcvpose_b200")
     ev, acc = None, {}
-    for b0 in range(0, len(cls.stems), frames_per_batch):
-        stems = cls.stems[b0:b0 + frames_per_batch]
+    my_stems = shard_frames(cls.stems)
+    verbose = verbose and _world()[0] == 0
+    for b0 in range(0, len(my_stems), frames_per_batch):
+        stems = my_stems[b0:b0 + frames_per_batch]
         depth = np.stack([cls.depth(s) for s in stems])
         H, W = depth.shape[1:]
         radius = np.empty((len(stems), 3, H, W), np.float32)
@@ -342,9 +382,8 @@ def evaluate_lmo_class(root_dataset, class_name, using_ckpts=False, producer=Non
             acc.setdefault(k, []).append(v)
     n = len(cls.entries)
     out = {k: np.concatenate(v) for k, v in acc.items()}
-    nb = int(out["passed_before"].sum()) if acc else 0
-    na = int(out["passed_after"].sum()) if (acc and icp) else 0
-    out.update(frames=list(cls.stems), n=n, evaluated=len(cls.stems), add_before=nb / n if n else float("nan"),
+    nb, na = reduce_counts([out["passed_before"].sum() if acc else 0, out["passed_after"].sum() if (acc and icp) else 0])
+    out.update(frames=list(my_stems), n=n, evaluated=len(cls.stems), add_before=nb / n if n else float("nan"),
                add_after=(na / n if icp else float("nan")) if n else float("nan"))
     if verbose:
         tag = "ADDs" if sym else "ADD"
@@ -359,6 +398,6 @@ def estimate_6d_pose_lmo(opts):
     for class_name in getattr(opts, "classes", None) or lmo_cls_names:
         print(class_name)
         results[class_name] = evaluate_lmo_class(opts.root_dataset, class_name, using_ckpts=bool(getattr(opts, "using_ckpts", False)),
-                                                 producer=getattr(opts, "producer", None), device=getattr(opts, "device", 0),
+                                                 producer=getattr(opts, "producer", None), device=_default_device(opts),
                                                  frames_per_batch=getattr(opts, "frames_per_batch", 64))
     return results

@@ -431,3 +431,48 @@ def test_estimate_6d_pose_lmo_vs_reference_loop(tmp_path, dtype):
         assert bool(res["passed_before"][i]) == bool(w["pb"]) and bool(res["passed_after"][i]) == bool(w["pa"])
     assert res["add_before"] == sum(w["pb"] for w in want) / 6 and res["add_after"] == sum(w["pa"] for w in want) / 6
     assert res["passed_before"][0] and not res["passed_before"][1]     # a keypoint at the origin ruins the pose of frame 1
+
+
+def _gloo_eval_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from rcvpose_b200 import evaluate
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        stems = ["%06d" % i for i in range(7)]
+        mine = evaluate.shard_frames(stems)
+        counts = evaluate.reduce_counts([len(mine), rank + 1, 10 * rank])
+        q.put((rank, mine, counts))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_evaluation_world2_gloo():
+    """N > 1 evaluation on CPU: two ranks take contiguous frame ranges that partition the class, and the pass counters are
+    summed with one small all_reduce (the evaluators' only communication)."""
+    import socket
+    import torch.multiprocessing as mp
+    from rcvpose_b200 import evaluate
+    assert evaluate.shard_frames(["a", "b", "c"]) == ["a", "b", "c"] and evaluate.reduce_counts([3, 4]) == [3, 4]     # single process
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_eval_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] + res[1][1] == ["%06d" % i for i in range(7)] and abs(len(res[0][1]) - len(res[1][1])) == 1
+    assert res[0][2] == res[1][2] == [7, 3, 10]
+
+
+def test_evaluator_needs_a_producer_for_the_checkpoint_branch(tmp_path):
+    from rcvpose_b200 import evaluate
+    root = str(tmp_path) + "/"
+    synth.write_lm_dataset(root, "ape", 1)
+    with pytest.raises(ValueError) as ei:       # checked before any GPU work: the network is not part of the package
+        evaluate.evaluate_lm_class(root, "ape", using_ckpts=True)
+    assert "producer" in str(ei.value)
