@@ -137,8 +137,8 @@ def write_lm_dataset(root, class_name, n_frames, seed=0, obj_radius_mm=55.0, n_c
 
 def write_lmo_dataset(root, class_name, n_frames, seed=0, obj_radius_mm=55.0, n_cad=1500, radius_dtype=np.float32):
     """Synthetic class in the reference's Occlusion-LINEMOD layout (AccumulatorSpace.py:746-850; rcvpose_b200.evaluate.LmoClass).
-    Besides n_frames complete frames the image directory holds one frame without a pose, one without the third radius map and a
-    stray non-image file (all three are counted but not evaluated, :962); in the second complete frame the radius map of
+    Besides n_frames complete frames the image directory holds one frame without a pose and one without the third radius map
+    (both are counted but not evaluated, :962; a non-image entry would crash the reference at :896); in the second complete frame the radius map of
     keypoint 2 is all zero (the reference skips that keypoint, :858).  Returns the stems of the complete frames."""
     import os
     from PIL import Image
@@ -180,7 +180,6 @@ def write_lmo_dataset(root, class_name, n_frames, seed=0, obj_radius_mm=55.0, n_
             np.save(d + "_%05d.npy" % idx, r.astype(radius_dtype))
         if f < n_frames:
             stems.append(stem)
-    open(occ + "RGB-D/rgb_noseg/Thumbs.db", "wb").close()
     return stems
 
 
