@@ -580,3 +580,90 @@ def test_estimate_6d_pose_lmo_vs_real_reference_golden(tmp_path, eval_golden):
         assert res["scene_points"][i] == eval_golden["lmo_can_scene_points"][j]
     rb, ra = eval_golden["lmo_can_ratios"]
     assert res["add_before"] == rb and res["add_after"] == ra
+
+
+# ------------------------------------------------------------------------------------------------
+# host logic of the evaluators with the device stage chain replaced by a recorder (CPU)
+# ------------------------------------------------------------------------------------------------
+class _FakeEvaluator:
+    calls = []
+
+    def __init__(self, cad_mm, kpts_mm, symmetric, threshold_mm, **kw):
+        self.cad_mm, self.kpts_mm, self.symmetric, self.threshold_mm, self.kw = cad_mm, kpts_mm, symmetric, threshold_mm, kw
+
+    def run(self, depth, radius, K, gt, **kw):
+        from rcvpose_b200 import api
+        B = radius.shape[0]
+        _FakeEvaluator.calls.append(dict(depth=depth, radius=radius, K=K, gt=gt, ev=self, **kw))
+        status = np.zeros((B, 3), np.int32)
+        if getattr(_FakeEvaluator, "empty_at", None) is not None and len(_FakeEvaluator.calls) == 1:
+            status[_FakeEvaluator.empty_at] = api.RCV_ST_EMPTY_MASK
+        before = np.arange(B, dtype=np.float64) + 10.0 * len(_FakeEvaluator.calls)
+        return dict(centre_mm=np.zeros((B, 3, 3)), RT=np.tile(np.eye(4), (B, 1, 1)), dist_before=before, passed_before=before < 21.0,
+                    status=status, n_points=np.ones((B, 3), np.int32), peak=np.ones((B, 3), np.int32), grid=np.ones((B, 3), np.int32),
+                    RT_icp=np.tile(np.eye(4), (B, 1, 1)), dist_after=before / 2, passed_after=before / 2 < 21.0,
+                    icp_fitness=np.ones(B), icp_rmse=np.zeros(B), icp_iters=np.ones(B, np.int32), scene_points=np.ones(B, np.int64))
+
+
+def test_lm_evaluator_host_logic_checkpoint_branch_and_batching(tmp_path, monkeypatch, capsys):
+    """The checkpoint branch (AccumulatorSpace.py:594-610) and the batching, with the device chain replaced by a recorder:
+    the producer is asked for every (frame, keypoint) in order, its maps reach the chain with the sem > 0.8 + max-radius rule,
+    poses are converted to mm, batches respect frames_per_batch, counters and the reference's print-out add up."""
+    from rcvpose_b200 import api, evaluate
+    root = str(tmp_path) + "/"
+    stems = synth.write_lm_dataset(root, "lamp", 5, seed=2)
+    monkeypatch.setattr(evaluate, "FrameEvaluator", _FakeEvaluator)
+    _FakeEvaluator.calls, _FakeEvaluator.empty_at = [], None
+    asked = []
+
+    def producer(cls, k, path):
+        asked.append((cls, k, os.path.basename(path)))
+        return np.full((480, 640), 0.9, np.float32), np.full((480, 640), float(k), np.float32)
+    res = evaluate.evaluate_lm_class(root, "lamp", using_ckpts=True, producer=producer, frames_per_batch=2)
+    assert asked == [("lamp", k, s + ".jpg") for s in sorted(stems) for k in (1, 2, 3)]
+    assert [c["radius"].shape[0] for c in _FakeEvaluator.calls] == [2, 2, 1]
+    c0 = _FakeEvaluator.calls[0]
+    assert c0["mask_flags"] == api.MASK_LM_CKPT and c0["sem"].shape == (2, 3, 480, 640) and float(c0["sem"][0, 0, 0, 0]) == np.float32(0.9)
+    assert np.array_equal(c0["radius"][1, 2], np.full((480, 640), 3.0, np.float32)) and c0["depth"].dtype == np.uint16
+    raw = np.load(root + "LINEMOD/lamp/pose/pose%d.npy" % int(sorted(stems)[0]))
+    assert np.array_equal(c0["gt"][0][:, 3], raw[:, 3] * 1000) and np.array_equal(c0["gt"][0][:, :3], raw[:, :3])
+    ev = c0["ev"]
+    assert ev.symmetric is False and ev.threshold_mm == evaluate.add_threshold["lamp"] * 1000
+    assert np.allclose(ev.kpts_mm, np.load(root + "LINEMOD/lamp/Outside9.npy")[1:4] * 1000) and ev.cad_mm.shape == (1500, 3)
+    # before = [10, 11 | 20, 21 | 30]: 3 of 5 pass; after = before / 2: all pass
+    assert res["n"] == 5 and res["add_before"] == 3 / 5 and res["add_after"] == 1.0 and res["frames"] == sorted(stems)
+    out = capsys.readouterr().out
+    assert "ADD of lamp before ICP:  0.6" in out and "ADD of lamp after ICP:  1.0" in out
+
+
+def test_lm_evaluator_host_logic_empty_mask_is_the_reference_error(tmp_path, monkeypatch):
+    from rcvpose_b200 import evaluate
+    root = str(tmp_path) + "/"
+    stems = synth.write_lm_dataset(root, "iron", 2, seed=3)
+    monkeypatch.setattr(evaluate, "FrameEvaluator", _FakeEvaluator)
+    _FakeEvaluator.calls, _FakeEvaluator.empty_at = [], (1, 2)
+    with pytest.raises(ValueError) as ei:
+        evaluate.evaluate_lm_class(root, "iron", frames_per_batch=2, verbose=False)
+    assert sorted(stems)[1] in str(ei.value) and "keypoint 3" in str(ei.value)
+    _FakeEvaluator.empty_at = None
+
+
+def test_lmo_evaluator_host_logic_zero_maps_and_counters(tmp_path, monkeypatch):
+    """LMO host logic with the recorder: all-zero thresholded maps are tolerated (the keypoint is skipped, :858), an empty cloud
+    under surviving radii is the reference's ValueError, ICP criteria are add_threshold * 1000 (:939-941), ratios are over every
+    directory entry (:962)."""
+    from rcvpose_b200 import api, evaluate
+    root = str(tmp_path) + "/"
+    stems = synth.write_lmo_dataset(root, "glue", 3, seed=8)
+    monkeypatch.setattr(evaluate, "FrameEvaluator", _FakeEvaluator)
+    _FakeEvaluator.calls, _FakeEvaluator.empty_at = [], (1, 1)            # frame 1 / keypoint 2 has the all-zero map: tolerated
+    res = evaluate.evaluate_lmo_class(root, "glue", frames_per_batch=8, verbose=False)
+    c0 = _FakeEvaluator.calls[0]
+    thr = evaluate.add_threshold["glue"] * 1000
+    assert c0["mask_flags"] == api.MASK_LMO_NPY and c0["icp_rel_fitness"] == thr and c0["icp_rel_rmse"] == thr and c0["zero_empty_centres"]
+    assert c0["depth"].dtype == np.float64 and c0["ev"].symmetric is True
+    assert res["n"] == 5 and res["evaluated"] == 3 and res["frames"] == stems and res["add_before"] == 3 / 5
+    _FakeEvaluator.calls, _FakeEvaluator.empty_at = [], (0, 0)            # radii survive there: the reference would call Accumulator_3D on nothing
+    with pytest.raises(ValueError):
+        evaluate.evaluate_lmo_class(root, "glue", frames_per_batch=8, verbose=False)
+    _FakeEvaluator.empty_at = None
