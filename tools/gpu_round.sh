@@ -1,5 +1,6 @@
 #!/bin/bash
-# One GPU session: tests, memcheck, bench, reference arm, ncu launch list, ncu full capture of the vote kernel and the head.
+# One GPU session: tests, memcheck, bench, reference arm, ncu launch list, ncu full capture of the vote kernel, the head and the ICP
+# search kernel, evaluator stage-chain timing.
 # Usage: tools/gpu_round.sh <tag> [skip-tests]
 TAG=${1:-r01}
 mkdir -p gpurun_out
@@ -22,6 +23,8 @@ RCV_HEAD_IMAGES=48 timeout 600 ncu --set full --clock-control none --import-sour
   python tools/head_bw.py > gpurun_out/${TAG}_ncu_head.log 2>&1
 tail -3 gpurun_out/${TAG}_ncu_head.log
 timeout 300 python tools/evaluator_bw.py 2>/dev/null | tee gpurun_out/${TAG}_evaluator_bw.json
+RCV_EVAL_FRAMES=64 RCV_EVAL_REPS=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_icp_corr -s 2 -c 1 -f -o gpurun_out/${TAG}_icp \
+  python tools/evaluator_bw.py > gpurun_out/${TAG}_ncu_icp.log 2>&1
 for v in icp4 icp1; do
   if [ -f build/librcvvote_$v.so ]; then RCV_LIB_PATH=$PWD/build/librcvvote_$v.so timeout 300 python tools/evaluator_bw.py 2>/dev/null | sed "s/^{/{\"variant\": \"$v\", /" | tee -a gpurun_out/${TAG}_evaluator_bw.json; fi
 done
