@@ -135,6 +135,33 @@ def write_lm_dataset(root, class_name, n_frames, seed=0, obj_radius_mm=55.0, n_c
     return stems
 
 
+def write_lm_ckpt_maps(root, class_name, stems, seed=0):
+    """Stand-ins for the outputs of the three keypoint networks on a class written by write_lm_dataset (the reference's checkpoint
+    branch, AccumulatorSpace.py:594-610): per (keypoint k, frame) a seg score map (0.95 on most of the object, 0.6 on the rest of
+    it, 0.1 elsewhere -- never above the 0.8 threshold where depth is 0, which would trip the reference's list mis-alignment,
+    SURVEY 8a a-2) and a radius map that, like a network's, has values everywhere (the estimated radii on the object, noise off it).
+    Files: <root>ckpt_maps/<cls>/pt<k>/<stem>_sem.npy, _radial.npy (float32)."""
+    import os
+    from . import formats
+    rng = np.random.default_rng(seed)
+    for stem in stems:
+        depth = formats.read_depth(root + "LINEMOD_ORIG/" + class_name + "/data/depth" + str(int(stem)) + ".dpt")
+        for k in (1, 2, 3):
+            d = root + "ckpt_maps/" + class_name + "/pt" + str(k) + "/"
+            os.makedirs(d, exist_ok=True)
+            est = np.load(os.path.join(root + "LINEMOD_ORIG/", "estRadialMap", class_name, "Out_pt" + str(k) + "_dm", stem + ".npy")).astype(np.float32)
+            obj = depth != 0
+            sem = np.where(obj, np.where(rng.random(depth.shape) < 0.85, 0.95, 0.6), 0.1).astype(np.float32)
+            radial = np.where(obj, est, rng.uniform(0.0, 3.0, size=depth.shape)).astype(np.float32)
+            np.save(d + stem + "_sem.npy", sem)
+            np.save(d + stem + "_radial.npy", radial)
+
+
+def load_lm_ckpt_maps(root, class_name, k, stem):
+    d = root + "ckpt_maps/" + class_name + "/pt" + str(k) + "/"
+    return np.load(d + stem + "_sem.npy"), np.load(d + stem + "_radial.npy")
+
+
 def write_lmo_dataset(root, class_name, n_frames, seed=0, obj_radius_mm=55.0, n_cad=1500, radius_dtype=np.float32):
     """Synthetic class in the reference's Occlusion-LINEMOD layout (AccumulatorSpace.py:746-850; rcvpose_b200.evaluate.LmoClass).
     Besides n_frames complete frames the image directory holds one frame without a pose and one without the third radius map

@@ -11,6 +11,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "pending_gpu: GPU test written after a round's GPU budget was spent -- not yet run on a GPU; "
+                                       "run with -m pending_gpu (tools/gpu_round.sh does) and promote to `gpu` once green")
 
 
 @pytest.fixture(scope="session")

@@ -35,6 +35,7 @@ from rcvpose_b200 import formats, synth  # noqa: E402
 
 LM_CLASSES = [("ape", 3, 11, np.float32), ("eggbox", 2, 12, np.float32)]      # (class, frames, seed, radius map dtype)
 LMO_CLASSES = [("can", 3, 6, np.float32)]
+LM_CKPT_CLASSES = [("cat", 3, 13)]                                              # checkpoint branch: (class, frames, seed)
 
 
 class _Cloud:
@@ -116,6 +117,28 @@ class _RecHorn(_Horn):
 A.Accumulator_3D, A.read_depth, A.HornPoseFitting = _rec_acc3d, _rec_read_depth, _RecHorn
 
 
+# ---- checkpoint branch: the networks are replaced by map files (synth.write_lm_ckpt_maps); the reference's own code decides what
+# to do with the maps (AccumulatorSpace.py:594-610) ----
+class _FakeNet:
+    count = 0
+
+    def __init__(self, *a):
+        _FakeNet.count += 1
+        self.k = (_FakeNet.count - 1) % 3 + 1          # the reference builds the three keypoint networks in order (:518-527)
+
+    def parameters(self):
+        import torch
+        return [torch.nn.Parameter(torch.zeros(1))]
+
+    def eval(self):
+        return self
+
+
+def _fake_backbone(model, input_img_path, normalized_depth):
+    stem = os.path.splitext(os.path.basename(input_img_path))[0]
+    return synth.load_lm_ckpt_maps(RECORD["root"], RECORD["cls"], model.k, stem)
+
+
 def run(fn, opts):
     for k in ("centres", "n_points", "depth_paths", "RT", "est_kpts", "distances", "icp"):
         RECORD[k] = []
@@ -174,6 +197,35 @@ def main():
         out[tag + "_ratios"] = np.array(final_ratios(text, cls))
         out[tag + "_seed"] = np.array([n_frames, seed])
         print(tag, out[tag + "_ratios"], out[tag + "_icp_iters"], out[tag + "_est_kpts"][:, :, 0])
+    # ---- LINEMOD, checkpoint branch ----
+    A.DenseFCNResNet152 = _FakeNet
+    A.utils.load_checkpoint = lambda model, optim, path: (model, optim, 0, 0)
+    A.FCResBackbone = _fake_backbone
+    for cls, n_frames, seed in LM_CKPT_CLASSES:
+        root = tempfile.mkdtemp() + "/"
+        stems = synth.write_lm_dataset(root, cls, n_frames, seed=seed)
+        synth.write_lm_ckpt_maps(root, cls, stems, seed=seed)
+        os.makedirs(root + "ckpts")
+        for k in (1, 2, 3):
+            open(root + "ckpts/" + cls + "_pt" + str(k) + ".pth.tar", "wb").close()
+        A.lm_cls_names = [cls]
+        _FakeNet.count = 0
+        RECORD["root"], RECORD["cls"] = root, cls
+        text = run(A.estimate_6d_pose_lm, types.SimpleNamespace(root_dataset=root, model_dir=root + "ckpts/", using_ckpts=True, demo_mode=False))
+        stems_run = ["%06d" % int(re.search(r"depth(\d+)\.dpt$", p).group(1)) for p in RECORD["depth_paths"][::3]]
+        order = np.argsort(stems_run)
+        tag = "lmckpt_" + cls
+        out[tag + "_stems"] = np.array(stems_run)[order]
+        out[tag + "_centres"] = np.array(RECORD["centres"]).reshape(n_frames, 3, 3)[order]
+        out[tag + "_n_points"] = np.array(RECORD["n_points"]).reshape(n_frames, 3)[order]
+        out[tag + "_RT"] = np.array(RECORD["RT"])[order]
+        d = np.array(RECORD["distances"])
+        d = d.reshape(n_frames, len(d) // n_frames, 2)[order]
+        out[tag + "_dist_before"] = d[:, 0, 0]
+        out[tag + "_scene_points"] = np.array([r[4] for r in RECORD["icp"]])[order]
+        out[tag + "_ratios"] = np.array(final_ratios(text, cls))
+        out[tag + "_seed"] = np.array([n_frames, seed])
+        print(tag, out[tag + "_stems"], out[tag + "_ratios"], out[tag + "_n_points"], out[tag + "_dist_before"])
     np.savez_compressed(os.path.join(HERE, "evaluator_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "evaluator_golden.npz"))
 

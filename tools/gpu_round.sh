@@ -6,6 +6,7 @@ TAG=${1:-r01}
 mkdir -p gpurun_out
 if [ "$2" != "skip-tests" ]; then
   timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/${TAG}_pytest.txt
+  timeout 600 python -m pytest tests -m pending_gpu -q 2>&1 | tail -8 | tee gpurun_out/${TAG}_pytest_pending.txt   # promote to `gpu` once green
   timeout 900 compute-sanitizer --tool memcheck --error-exitcode 99 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
     -k "config1 or random_clouds or frames_api or mask_rules or large_grid or icp_vs_oracle or scene_clouds or fused or lmo_vs" tests/test_evaluator.py > gpurun_out/${TAG}_memcheck.log 2>&1
   echo "memcheck rc=$?" | tee -a gpurun_out/${TAG}_memcheck.log; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/${TAG}_memcheck.log | tail -3
