@@ -1,0 +1,109 @@
+"""The PyTorch input stage (rcvpose_b200/producer.py, BASELINE configs[1]): the trunk of the reference's DenseFCNResNet152 up to
+conv7, with the reference's parameter names, against the reference model's own outputs (tests/golden/make_golden_producer.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from rcvpose_b200 import producer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+
+@pytest.fixture(scope="module")
+def seeded():
+    from make_golden_producer_helpers import seeded_trunk
+    return seeded_trunk()
+
+
+def test_trunk_matches_the_reference_model_outputs(seeded):
+    """Same state_dict, same input: seg / radial maps of the reference's network (golden, computed by the reference model itself)
+    against RadiusTrunk + conv8 in PyTorch fp32: 1e-5 relative (the same convolutions; only the kernel selection may differ)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "producer_golden.npz"))
+    net, x = seeded
+    assert abs(float(x.double().sum()) - float(g["x_checksum"])) < 1e-9
+    keys = "\n".join("%s %s" % (k, tuple(v.shape)) for k, v in net.state_dict().items())
+    assert keys == str(g["keys"]), "parameter names / shapes differ from the reference's DenseFCNResNet152: checkpoints would not load"
+    with torch.no_grad():
+        seg, rad = net.forward_reference(x.clone())
+    for got, want in ((seg.numpy(), g["seg"]), (rad.numpy(), g["radial"])):
+        assert got.shape == want.shape == (2, 1, 64, 96)
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    w, b = net.head()
+    with torch.no_grad():
+        up = net(x.clone())
+    assert up.shape == (2, 32, 64, 96) and float(up.min()) >= 0.0            # conv7 + BN + ReLU: what the head kernel consumes
+    manual = torch.einsum("nk,bkhw->bnhw", w, up) + b[None, :, None, None]
+    assert torch.allclose(manual[:, :1], seg, atol=1e-6) and torch.allclose(manual[:, 1:], rad, atol=1e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="the reference tree exists in the build container only")
+def test_trunk_is_state_dict_compatible_with_the_reference(seeded):
+    sys.path.insert(0, "/root/reference")
+    from models.fcnresnet import DenseFCNResNet152
+    net, x = seeded
+    ref = DenseFCNResNet152(3, 2).eval()
+    ref.load_state_dict(net.state_dict(), strict=True)          # a reference checkpoint loads the other way round just the same
+    net2 = producer.RadiusTrunk().eval()
+    net2.load_state_dict(ref.state_dict(), strict=True)
+    with torch.no_grad():
+        s_ref, r_ref = ref(x.clone())
+        s, r = net2.forward_reference(x.clone())
+    assert torch.equal(s, s_ref) and torch.equal(r, r_ref)
+
+
+def test_normalise_rgb_is_the_reference_preprocessing():
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(5, 7, 3)).astype(np.uint8)
+    t = producer.normalise_rgb(img)
+    want = np.array(img, dtype=np.float64)          # AccumulatorSpace.py:143-147
+    want /= 255.
+    want -= np.array([0.485, 0.456, 0.406])
+    want /= np.array([0.229, 0.224, 0.225])
+    assert t.shape == (1, 3, 5, 7) and t.dtype == torch.float32
+    assert np.array_equal(t[0].numpy(), want.transpose(2, 0, 1).astype(np.float32))
+    assert producer.normalise_rgb(np.stack([img, img])).shape == (2, 3, 5, 7)
+
+
+_pending = [pytest.mark.pending_gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+
+
+def _pending_gpu(fn):
+    for m in _pending:
+        fn = m(fn)
+    return fn
+
+
+@_pending_gpu
+def test_producer_stage_feeds_the_fused_head_vote():
+    """BASELINE configs[1] plumbing on the GPU: three bf16 trunks -> conv7 activations -> rcv_head_vote_frames, bit-identical to
+    rcv_head_1x1 + rcv_vote_frames on the same activations; the bf16 activations agree with the fp32 trunk to bf16 accuracy."""
+    from rcvpose_b200 import api, synth
+    ctx = api.VoteContext(0, max_items=16, max_points_total=1 << 22, max_grid=400)
+    torch.manual_seed(5)
+    trunks = [producer.RadiusTrunk() for _ in range(3)]
+    stage = producer.ProducerStage(trunks, ctx)
+    frames = [synth.config3_frame(f) for f in (41, 42)]
+    rgb = torch.rand((2, 3, 480, 640))
+    depth = torch.from_numpy(np.stack([f["depth"] for f in frames]).view(np.int16)).cuda()
+    K = torch.from_numpy(frames[0]["K"]).cuda()
+    mr = torch.full((3,), 1.0e9, dtype=torch.float64, device="cuda")
+    up = stage.activations(rgb)
+    assert up.shape == (2, 3, 32, 480, 640) and up.dtype == torch.bfloat16 and up.is_contiguous() and bool(torch.isfinite(up.float()).all())
+    fused = ctx.head_vote_frames(up, stage.weight, stage.bias, depth, K, max_radii=mr, mask_flags=api.RCV_MASK_MAX_RADIUS | api.RCV_MASK_RADIUS_POSITIVE,
+                                 want_radius=True)
+    maps = torch.stack([ctx.head_1x1(up[:, k].contiguous(), stage.weight[k], stage.bias[k]) for k in range(3)], dim=1)
+    two = ctx.vote_frames(depth, maps[:, :, 1].contiguous(), K, max_radii=mr, mask_flags=api.RCV_MASK_MAX_RADIUS | api.RCV_MASK_RADIUS_POSITIVE)
+    torch.cuda.synchronize()
+    assert torch.equal(fused["radius"], maps[:, :, 1])
+    for k in ("centre_mm", "peak", "votes", "n_points", "grid", "status"):
+        assert torch.equal(fused[k], two[k]), k
+    out = stage.vote(rgb, depth, K, mr, mask_flags=api.RCV_MASK_MAX_RADIUS | api.RCV_MASK_RADIUS_POSITIVE)
+    assert torch.equal(out["n_points"], fused["n_points"])
+    with torch.no_grad():
+        up32 = trunks[0].float()(rgb.cuda()[:1])
+    err = (up[:1, 0].float() - up32).abs().max().item()
+    assert err <= 0.1 * max(1.0, up32.abs().max().item()), err
