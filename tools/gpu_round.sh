@@ -29,4 +29,5 @@ RCV_EVAL_FRAMES=64 RCV_EVAL_REPS=1 timeout 300 ncu --set full --clock-control no
 for v in icp4 icp1; do
   if [ -f build/librcvvote_$v.so ]; then RCV_LIB_PATH=$PWD/build/librcvvote_$v.so timeout 300 python tools/evaluator_bw.py 2>/dev/null | sed "s/^{/{\"variant\": \"$v\", /" | tee -a gpurun_out/${TAG}_evaluator_bw.json; fi
 done
+timeout 300 python tools/config2_bench.py 2>gpurun_out/${TAG}_config2.err | tee gpurun_out/${TAG}_config2.json; tail -2 gpurun_out/${TAG}_config2.err
 ls -la gpurun_out/ | tail -20
