@@ -4,6 +4,8 @@
     read_ply_points(path)     replaces o3d.io.read_point_cloud(...).points (AccumulatorSpace.py:505, :533)
     read_split(path)          the `Split/val.txt` list (AccumulatorSpace.py:502-503)
     load_keypoints / load_pose  `Outside9.npy` (:535) and `pose/pose<N>.npy` (:566)
+    read_xyz_points(path)     YCB-Video `models/<cls>/points.xyz` (AccumulatorSpace.py:988; 3DRadius_ycb.py)
+    load_ycb_meta(path)       YCB-Video `<seq>/<frame>-meta.mat`: intrinsics, factor_depth, poses, class indices (:1015-1016, :1050-1057)
 
 The writers exist so that tests and tools can lay out a synthetic dataset in the reference's directory structure.
 """
@@ -129,3 +131,34 @@ def load_pose(path):
     if rt.shape != (3, 4):
         raise ValueError("%s: expected a (3,4) pose, got %s" % (path, rt.shape))
     return np.asarray(rt, dtype=np.float64)
+
+
+def read_xyz_points(path):
+    """`points.xyz`: one "x y z" line per CAD point, metres -> (N,3) float64 (what o3d.io.read_point_cloud gives the YCB evaluator,
+    AccumulatorSpace.py:988-990)."""
+    pts = np.loadtxt(path, dtype=np.float64, ndmin=2)
+    if pts.shape[1] < 3:
+        raise ValueError("%s: expected at least 3 columns, got %d" % (path, pts.shape[1]))
+    return np.ascontiguousarray(pts[:, :3])
+
+
+def load_ycb_meta(path):
+    """YCB-Video `-meta.mat` (scipy.io.loadmat, AccumulatorSpace.py:1015): dict(intrinsic_matrix (3,3) float64, factor_depth float,
+    cls_indexes (M,) int, poses (M,3,4) float64 -- object-major, translation in metres).  `pose_of(meta, class_id)` picks one object
+    (:1016)."""
+    import scipy.io
+    m = scipy.io.loadmat(path)
+    for k in ("intrinsic_matrix", "factor_depth", "cls_indexes", "poses"):
+        if k not in m:
+            raise ValueError("%s: no %r in the meta file" % (path, k))
+    poses = np.asarray(m["poses"], dtype=np.float64)
+    if poses.ndim == 2:
+        poses = poses[:, :, None]
+    return dict(intrinsic_matrix=np.asarray(m["intrinsic_matrix"], dtype=np.float64).reshape(3, 3), factor_depth=float(np.ravel(m["factor_depth"])[0]),
+                cls_indexes=np.ravel(m["cls_indexes"]).astype(np.int64), poses=np.ascontiguousarray(poses.transpose(2, 0, 1)))
+
+
+def pose_of(meta, class_id):
+    """(3,4) ground-truth pose of object `class_id` in a frame's meta, or None if the object is not in the frame."""
+    hit = np.nonzero(meta["cls_indexes"] == class_id)[0]
+    return meta["poses"][hit[0]] if len(hit) else None

@@ -737,3 +737,25 @@ def test_estimate_6d_pose_lm_checkpoint_branch_vs_real_reference_golden(tmp_path
     np.testing.assert_allclose(res["RT"], g["lmckpt_cat_RT"], rtol=0, atol=1e-9)
     np.testing.assert_allclose(res["dist_before"], g["lmckpt_cat_dist_before"], rtol=1e-9, atol=0)
     assert np.array_equal(res["scene_points"], g["lmckpt_cat_scene_points"]) and res["add_before"] == g["lmckpt_cat_ratios"][0]
+
+
+def test_ycb_format_readers(tmp_path):
+    """N4, YCB-Video side: points.xyz and the -meta.mat fields the evaluator reads (AccumulatorSpace.py:988, :1015-1016, :1050-1057)."""
+    import scipy.io
+    rng = np.random.default_rng(4)
+    pts = rng.normal(size=(25, 3)) * 0.05
+    p = str(tmp_path / "points.xyz")
+    np.savetxt(p, pts, fmt="%.9f")
+    got = formats.read_xyz_points(p)
+    assert got.shape == (25, 3) and np.allclose(got, pts, atol=1e-9)
+    poses = rng.normal(size=(3, 4, 2))
+    K = np.array([[1066.778, 0, 312.9869], [0, 1067.487, 241.3109], [0, 0, 1]])
+    q = str(tmp_path / "000001-meta.mat")
+    scipy.io.savemat(q, dict(intrinsic_matrix=K, factor_depth=np.array([[10000]], dtype=np.uint16), cls_indexes=np.array([[5], [12]], dtype=np.uint8),
+                             poses=poses, center=np.zeros((2, 2))))
+    meta = formats.load_ycb_meta(q)
+    assert np.array_equal(meta["intrinsic_matrix"], K) and meta["factor_depth"] == 10000.0 and list(meta["cls_indexes"]) == [5, 12]
+    assert meta["poses"].shape == (2, 3, 4) and np.array_equal(formats.pose_of(meta, 12), poses[:, :, 1]) and formats.pose_of(meta, 7) is None
+    scipy.io.savemat(q, dict(intrinsic_matrix=K))
+    with pytest.raises(ValueError):
+        formats.load_ycb_meta(q)
