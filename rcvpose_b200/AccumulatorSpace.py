@@ -17,7 +17,17 @@ the CUDA library or a GPU the functions raise.
 import numpy as np
 import torch
 
-from . import api
+try:
+    from . import api
+except ImportError:
+    # Zero-change drop-in: this directory was put on sys.path, so the module was imported
+    # top-level as `AccumulatorSpace` (reference train.py:12, AccumulatorSpace.py:2) and has no parent package.
+    import os as _os
+    import sys as _sys
+    _root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    if _root not in _sys.path:
+        _sys.path.append(_root)
+    from rcvpose_b200 import api
 
 linemod_K = np.array([[572.4114, 0., 325.2611],
                       [0., 573.57043, 242.04899],
@@ -85,15 +95,15 @@ def vote_volume(xyz, radial_list, acc_unit=5, radius_scale=100, policy=api.RCV_P
 
 
 def read_depth(path):
-    from . import formats
+    from rcvpose_b200 import formats
     return formats.read_depth(path)
 
 
 def estimate_6d_pose_lm(opts):
-    from . import evaluate
+    from rcvpose_b200 import evaluate
     return evaluate.estimate_6d_pose_lm(opts)
 
 
 def estimate_6d_pose_lmo(opts):
-    from . import evaluate
+    from rcvpose_b200 import evaluate
     return evaluate.estimate_6d_pose_lmo(opts)

@@ -1,8 +1,17 @@
 """Drop-in for the reference's util/horn.py (HornPoseFitting.lmshorn, :75-181) on the GPU."""
 import numpy as np
 
-from .. import api
-from ..AccumulatorSpace import _ctx
+try:
+    from ..AccumulatorSpace import _ctx
+except ImportError:
+    # Zero-change drop-in: rcvpose_b200/ itself is on sys.path, so this is the top-level package `util`
+    # (reference AccumulatorSpace.py:2, `from util.horn import HornPoseFitting`).
+    import os as _os
+    import sys as _sys
+    _root = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+    if _root not in _sys.path:
+        _sys.path.append(_root)
+    from rcvpose_b200.AccumulatorSpace import _ctx
 
 
 class HornPoseFitting:

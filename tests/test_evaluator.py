@@ -546,7 +546,7 @@ def test_oracle_loop_matches_the_real_reference_evaluator_lmo(tmp_path, eval_gol
     assert rb == sum(w["pb"] for w in want) / len(cls.entries) and ra == sum(w["pa"] for w in want) / len(cls.entries)
 
 
-_pending = [pytest.mark.pending_gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+_pending = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
 
 
 def _pending_gpu(fn):

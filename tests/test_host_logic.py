@@ -127,3 +127,62 @@ def test_gather_results_world2_gloo(n_frames):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+_DROPIN_SNIPPET = r"""
+import sys
+sys.path.insert(0, {pkg!r})            # INTEGRATION.md section 1, verbatim: the package DIRECTORY goes first on sys.path
+import AccumulatorSpace                  # reference train.py:12 / AccumulatorSpace.py imported by name
+from AccumulatorSpace import estimate_6d_pose_lm, estimate_6d_pose_lmo, rgbd_to_point_cloud, Accumulator_3D, linemod_K, read_depth
+from util.horn import HornPoseFitting    # reference AccumulatorSpace.py:2
+assert AccumulatorSpace.__file__.startswith({pkg!r}), AccumulatorSpace.__file__
+assert callable(HornPoseFitting().lmshorn) and linemod_K.shape == (3, 3)
+{body}
+print("DROPIN_OK")
+"""
+
+
+def _run_dropin(body=""):
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "rcvpose_b200")
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    res = subprocess.run([sys.executable, "-c", _DROPIN_SNIPPET.format(pkg=pkg, body=body)], cwd="/tmp", env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0 and "DROPIN_OK" in res.stdout, res.stdout + res.stderr
+
+
+def test_sys_path_dropin_imports_like_the_reference():
+    """with rcvpose_b200/ first on sys.path the reference's own import lines resolve to the shims
+    (no parent package: the shims must not depend on relative imports)."""
+    _run_dropin()
+
+
+@pytest.mark.gpu
+def test_sys_path_dropin_runs_the_reference_shaped_loop():
+    """The reference's per-image body (AccumulatorSpace.py:606-662: cloud, /1000, Accumulator_3D per keypoint, lmshorn) through the
+    top-level shims, against the oracle."""
+    body = r'''
+import numpy as np
+sys.path.append({root!r})
+from oracle import oracle
+from rcvpose_b200 import synth
+fr = synth.config3_frame(3)
+K = fr["K"]; est = np.zeros((3, 3)); want = np.zeros((3, 3))
+for k in range(3):
+    radial_est = np.where(fr["radius"][k] <= fr["max_radii_dm"][k], fr["radius"][k], 0)     # :612-616, npy branch
+    depth_map = fr["depth"] * (radial_est != 0)
+    xyz_mm = rgbd_to_point_cloud(K, depth_map)
+    assert np.array_equal(xyz_mm, oracle.rgbd_to_point_cloud(K, depth_map))
+    radial_list = radial_est[depth_map.nonzero()]
+    xyz = xyz_mm / 1000
+    est[k] = Accumulator_3D(xyz, radial_list)[0]
+    want[k] = oracle.Accumulator_3D(xyz, radial_list)[0]
+assert np.array_equal(est, want), (est, want)
+P1 = fr["kpts_mm"]
+RT = np.zeros((4, 4)); RTo = np.zeros((4, 4))
+HornPoseFitting().lmshorn(P1, est, 3, RT)
+oracle.lmshorn(P1, want, 3, RTo)
+assert np.allclose(RT, RTo, atol=1e-9), (RT, RTo)
+'''.format(root=ROOT)
+    _run_dropin(body)

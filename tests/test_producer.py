@@ -68,7 +68,7 @@ def test_normalise_rgb_is_the_reference_preprocessing():
     assert producer.normalise_rgb(np.stack([img, img])).shape == (2, 3, 5, 7)
 
 
-_pending = [pytest.mark.pending_gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+_pending = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
 
 
 def _pending_gpu(fn):
