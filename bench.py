@@ -76,14 +76,28 @@ def cpu_items(frames):
     return items
 
 
-def cpu_run(items):
-    """Accumulator_3D (brute-force N*D^3 loop, OpenMP over slices) + lmshorn per frame; returns seconds, votes."""
+def host_threads():
+    """Threads for the CPU arm: every core this process may run on.  torch.distributed.run exports OMP_NUM_THREADS=1 to
+    its workers, which would silently make the reference arm single-threaded, so the count is passed explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+CPU_PORT = ("oracle port of the reference's fast_for (float64 shell test per voxel, OpenMP over x-slices) with exact per-slice / per-row "
+            "culls -- 0.8x the time of the real numba fast_for on the same 8 cores (tools/cpu_calibrate.py, profiles/r02_cpu_calibration.json), "
+            "so the ratio to it is conservative -- + lmshorn")
+
+
+def cpu_run(items, threads=0):
+    """Accumulator_3D (the reference's shell-test loop, OpenMP over slices) + lmshorn per frame; returns seconds, votes."""
     from oracle import oracle
     t0 = time.perf_counter()
     votes = 0
     centres = []
     for xyz, rl in items:
-        c, info = oracle.Accumulator_3D(xyz, rl, method="brute", return_info=True)
+        c, info = oracle.Accumulator_3D(xyz, rl, method="brute", return_info=True, threads=threads)
         votes += info["votes"]
         centres.append(c[0])
     A = np.zeros((4, 4))
@@ -94,26 +108,31 @@ def cpu_run(items):
 
 
 def run_reference(args):
+    """The CPU arm.  Under torchrun only rank 0 works (the other ranks exit at once), with ALL host cores: the value is the
+    whole box's CPU throughput whatever --gpus says."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle
     from rcvpose_b200 import synth
-    threads = oracle.num_threads()
+    threads = host_threads()
     nf = args.ref_frames
     pools = [cpu_items([synth.config3_frame(10_000 + s * nf + f) for f in range(nf)]) for s in range(min(4, args.steps + args.warmup))]
     for w in range(args.warmup):
-        cpu_run(pools[w % len(pools)][:KPTS])
+        cpu_run(pools[w % len(pools)][:KPTS], threads)
     tot, votes = 0.0, 0
     for s in range(args.steps):
-        dt, v, _ = cpu_run(pools[s % len(pools)])
+        dt, v, _ = cpu_run(pools[s % len(pools)], threads)
         tot += dt
         votes += v
     value = args.steps * nf / tot
-    sample = "%d frames x %d keypoints per step, oracle port of fast_for (N*D^3 brute force) + lmshorn, %d OpenMP threads" % (nf, KPTS, threads)
+    sample = "%d frames x %d keypoints per step (%d frames timed in all, on rank 0 only), %d OpenMP threads: %s" % (
+        nf, KPTS, nf * args.steps, threads, CPU_PORT)
+    cfg = config(args.frames, args.gpus)
+    cfg["reference_arm"] = "CPU only: %d frames per step on the host cores of the box; global_frames describes the GPU arm's step" % nf
+    cfg["frames_timed_per_step"] = nf
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args.frames, args.gpus),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "gvotes_per_s": votes / tot / 1e9,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -268,18 +287,17 @@ def run_ours(args):
     cpu = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import oracle
         nf = min(args.cpu_frames, B)
         frames = [dict(K=Knp, depth=depth[f].cpu().numpy().view(np.uint16), radius=radius[f].cpu().numpy()) for f in range(nf)]
         items = cpu_items(frames)
-        cpu_run(items[:1])                                  # warm-up (library load, thread pool)
-        dt, v, centres = cpu_run(items)
+        threads = host_threads()
+        cpu_run(items[:1], threads)                         # warm-up (library load, thread pool)
+        dt, v, centres = cpu_run(items, threads)
         got = out["centre_mm"][:nf].cpu().numpy().reshape(-1, 3)
         gv = int(out["votes"][:nf].sum().item())
         parity = {"frames": nf, "centres_bit_equal": bool(np.array_equal(got, centres)), "votes_equal": bool(gv == v)}
-        cpu = {"value": nf / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "gvotes_per_s": v / dt / 1e9,
-               "sample": "%d frames x %d keypoints of this workload (%.1f s): oracle port of the reference's fast_for brute force "
-                         "(N*D^3 shell tests, OpenMP over slices) + lmshorn" % (nf, KPTS, dt)}
+        cpu = {"value": nf / dt, "unit": UNIT, "cores": threads, "kind": "port", "gvotes_per_s": v / dt / 1e9,
+               "sample": "%d frames x %d keypoints of this workload (%.1f s): %s" % (nf, KPTS, dt, CPU_PORT)}
 
     if rank == 0:
         peaks = {}

@@ -43,6 +43,8 @@ def lib():
         L.orc_prelude.argtypes = [vp, C.c_long, vp, C.c_int, C.c_double, C.c_double, C.c_int, vp, vp, vp, ip, ip, dp]
         L.orc_fast_for.restype = None
         L.orc_fast_for.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_int]
+        L.orc_fast_for_full.restype = None
+        L.orc_fast_for_full.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_int]
         L.orc_fast_for_literal.restype = None
         L.orc_fast_for_literal.argtypes = [vp, vp, C.c_long, C.c_int, vp]
         L.orc_scatter.restype = None
@@ -115,6 +117,8 @@ def fast_for(p, R, D, threads=0, method="brute"):
     vol = np.zeros((D, D, D), dtype=np.int32)
     if method == "brute":
         lib().orc_fast_for(_p(p), _p(R), p.shape[0], D, _p(vol), threads)
+    elif method == "full":
+        lib().orc_fast_for_full(_p(p), _p(R), p.shape[0], D, _p(vol), threads)
     elif method == "literal":
         lib().orc_fast_for_literal(_p(p), _p(R), p.shape[0], D, _p(vol))
     elif method == "scatter":
@@ -155,7 +159,7 @@ def Accumulator_3D(xyz, radial_list, acc_unit=5.0, radius_scale=100.0, policy=PO
     if return_volume:
         pre = prelude(xyz, r, acc_unit, radius_scale, policy)
         vol = np.zeros((pre["D"],) * 3, dtype=np.int32)
-    rc = lib().orc_accumulator_3d(_p(xyz), n, _p(r), is32, acc_unit, radius_scale, policy, int(method == "brute"), threads,
+    rc = lib().orc_accumulator_3d(_p(xyz), n, _p(r), is32, acc_unit, radius_scale, policy, {"brute": 1, "full": 2}.get(method, 0), threads,
                                   _p(c), C.byref(D), C.byref(zb), C.byref(pk), C.byref(votes),
                                   _p(vol) if vol is not None else None)
     if rc == 2:

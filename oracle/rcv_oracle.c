@@ -185,6 +185,36 @@ ORC_API void orc_fast_for(const double *p, const int *R, long n, int D, int32_t 
     }
 }
 
+/* The reference's loop with NO culls -- every one of the N * D^3 (point, voxel) shell tests the numba kernel performs
+ * (AccumulatorSpace.py:329-339) -- parallel over i-slices instead of the reference's racy prange over points (same
+ * work, disjoint voxels per thread, deterministic).  This is what bench.py times as the CPU reference arm. */
+ORC_API void orc_fast_for_full(const double *p, const int *R, long n, int D, int32_t *vol, int threads)
+{
+    const double factor = sqrt(3.0) / 4.0;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < D; ++i) {
+        for (long c = 0; c < n; ++c) {
+            const double x = p[3 * c], y = p[3 * c + 1], z = p[3 * c + 2];
+            const double radius = (double)R[c];
+            const double dx = (double)i - x, dx2 = dx * dx;
+            for (int j = 0; j < D; ++j) {
+                const double dy = (double)j - y;
+                const double dxy2 = dx2 + dy * dy;
+                int32_t *row = vol + ((long)i * D + j) * D;
+                for (int k = 0; k < D; ++k) {
+                    const double dz = (double)k - z;
+                    const double distance = sqrt(dxy2 + dz * dz);
+                    const double t = radius - distance;
+                    if (t < factor && t > 0.0) row[k] += 1;
+                }
+            }
+        }
+    }
+}
+
 /* The literal triple loop with no culls, for validating the culled version above. */
 ORC_API void orc_fast_for_literal(const double *p, const int *R, long n, int D, int32_t *vol)
 {
@@ -392,7 +422,8 @@ ORC_API void orc_lmshorn(const double *P1in, const double *P2in, int n, double *
 /* ------------------------------------------------------------------------------------------
  * Accumulator_3D end to end -- AccumulatorSpace.py:373-419 -- for timing the CPU baseline and
  * for one-call parity.  vol_out may be NULL (a scratch volume is allocated).  brute=1 uses the
- * reference's N*D^3 loop (the honest CPU baseline), brute=0 the exact scatter renderer.
+ * reference's N*D^3 loop with per-slice / per-row culls, brute=2 the same loop with no culls (every N*D^3 test, the CPU
+ * reference arm of bench.py), brute=0 the exact scatter renderer.
  * Returns 0 ok, 1 empty input, 2 non-positive D.
  * ---------------------------------------------------------------------------------------- */
 ORC_API int orc_accumulator_3d(const double *xyz, long n, const void *radii, int radius_is_f32, double acc_unit,
@@ -409,7 +440,8 @@ ORC_API int orc_accumulator_3d(const double *xyz, long n, const void *radii, int
     long total = (long)D * D * D;
     int32_t *vol = vol_out ? vol_out : (int32_t *)malloc(sizeof(int32_t) * total);
     memset(vol, 0, sizeof(int32_t) * total);
-    if (brute) orc_fast_for(p, R, n, D, vol, threads);
+    if (brute == 2) orc_fast_for_full(p, R, n, D, vol, threads);
+    else if (brute) orc_fast_for(p, R, n, D, vol, threads);
     else orc_scatter(p, R, n, D, vol);
     int idx[3];
     int32_t mx;

@@ -64,7 +64,6 @@ RCV_HD int d_rint(double a) { return __double2int_rn(a); }
 // Host build (tests only).  g_sqrt_perturb lets the fuzz tests emulate the <=2-ulp error of the
 // device's MUFU.SQRT so the exactness argument is exercised, not just IEEE sqrtf.
 static int g_sqrt_perturb = 0;
-static uint32_t g_sqrt_rng = 12345u;
 RCV_HD float f_add(float a, float b) { return a + b; }
 RCV_HD float f_sub(float a, float b) { return a - b; }
 RCV_HD float f_mul(float a, float b) { return a * b; }
@@ -74,8 +73,9 @@ RCV_HD float f_from_bits(int x) { float f; memcpy(&f, &x, 4); return f; }
 RCV_HD float f_sqrt_fast(float x) {
   float r = sqrtf(x);   // NaN for x < 0, like the device instruction
   if (g_sqrt_perturb && r > 0.f) {
-    g_sqrt_rng = g_sqrt_rng * 1664525u + 1013904223u;
-    r = f_from_bits(f_bits(r) + (int)((g_sqrt_rng >> 16) % 5u) - 2);
+    // deterministic in the argument (a fast path and the rare path that re-derives it must see the same value, as on the device)
+    uint32_t h = (uint32_t)f_bits(x) * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    r = f_from_bits(f_bits(r) + (int)(h % 5u) - 2);
   }
   return r;
 }

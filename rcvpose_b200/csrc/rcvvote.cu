@@ -22,6 +22,7 @@
 
 #include "../../include/rcvvote.h"
 #include "raster_core.h"
+#include "runs_core.h"
 #include "horn_core.h"
 
 #define RCV_EXPORT extern "C" __attribute__((visibility("default")))
@@ -53,6 +54,7 @@ struct ItemMeta {
   int ni, nj;     // tile shape (slices x rows); every tile spans all k
   int status;
   int guard;      // glo | ghi << 16: guard cells of a whole-slice tile below 0 / above D - 1 along the in-slice axes (0 for row-band tiles)
+  int clip;       // gen 2: 1 if run boundaries can leave the tile (row bands, or spheres overhang a grid whose guard band was refused)
   double mean[3];
   double rmax;
 };
@@ -65,6 +67,7 @@ struct Pool {
   double *X, *Y, *Z, *Rd;  // voxel-unit coordinates (recentred in place by the prelude), radius in voxels
   int* Ri;                 // np.around(radius) -- AccumulatorSpace.py:332
   int* perm;               // per item: its points ordered by (y voxel, R) so that the 32 points of a warp of k_vote draw alike
+  int4* rec;               // per point IN VOTE ORDER: the float32 record of the run rasteriser (RunPoint, 2 x int4)
   long long cap;
 };
 
@@ -518,7 +521,7 @@ __device__ double pw_leaf_sum(const double* __restrict__ a, int n) {
 }
 
 struct PreludeArgs {
-  Pool pool; ItemMeta* meta; Unit* units; int* counters; int max_units; int max_grid; int policy; int tile_words;
+  Pool pool; ItemMeta* meta; Unit* units; int* counters; int max_units; int max_grid; int policy; int tile_words; int gen;
   PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
 };
 
@@ -629,20 +632,25 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
       int glo = need_lo > 0.0 ? (need_lo < 1e6 ? (int)ceil(need_lo) : kMaxGuard + 1) : 0;
       int ghi = need_hi > 0.0 ? (need_hi < 1e6 ? (int)ceil(need_hi) : kMaxGuard + 1) : 0;
       if (glo > kMaxGuard || ghi > kMaxGuard) { glo = 0; ghi = 0; }   // YCBGEN-style grids without upper pad: clipped passes
-      int Dp = (D + glo + ghi) | 1;  // odd row stride: consecutive rows start in different banks
-      long long slice = (long long)(D + glo + ghi) * Dp;
-      if (slice > a.tile_words) { glo = 0; ghi = 0; Dp = D | 1; slice = (long long)D * Dp; }   // row-band tiles are not guarded
+      // odd row stride: consecutive rows start in different banks.  The run rasteriser (gen 2) keeps one spare cell above the
+      // upper guard: the -1 that closes a run ending at the last cell lands there.
+      // gen 2 also keeps TWO planes per slice (run starts, run ends: only `add 1` merges lanes that hit the same address).
+      const int spare = a.gen >= 2 ? 1 : 0, planes = a.gen >= 2 ? 2 : 1;
+      int Dp = (D + glo + ghi + spare) | 1;
+      long long slice = (long long)planes * (D + glo + ghi) * Dp;
+      if (slice > a.tile_words) { glo = 0; ghi = 0; Dp = (D + spare) | 1; slice = (long long)planes * D * Dp; }   // row-band tiles are not guarded
       m.Dp = Dp;
       m.guard = glo | (ghi << 16);
+      m.clip = (slice > a.tile_words || ((need_lo > 0.0 || need_hi > 0.0) && glo == 0 && ghi == 0)) ? 1 : 0;
       if (slice <= a.tile_words) {
         int ni_max = (int)(a.tile_words / slice);
-        if (ni_max > 32) ni_max = 32;   // the polar pass keeps one mask bit per slice of a tile
+        if (ni_max > 32) ni_max = 32;   // (gen 1: the polar pass keeps one mask bit per slice of a tile)
         if (ni_max > D) ni_max = D;
         m.ni = ni_max >= D ? D : slab_thickness(ni_max);   // a multiple of 3 or 4: the ring passes walk a slab in chunks
         m.nj = D + glo + ghi;
         nunits = (D + m.ni - 1) / m.ni;
       } else {
-        const int nj_max = a.tile_words / Dp;
+        const int nj_max = a.tile_words / (planes * Dp);
         const int nt = (D + nj_max - 1) / nj_max;
         m.ni = 1; m.nj = (D + nt - 1) / nt;
         nunits = D * ((D + m.nj - 1) / m.nj);
@@ -714,6 +722,13 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
       const int ya = __double2int_rn(Y[q]), r = max(Ri[q], 0);
       const int pos = atomicAdd(&s_hist[((ya - amin) >> ash) * nRq + ((r - rmin) >> sh)], 1);
       perm[pos] = q;
+      if (a.gen >= 2) {   // internal axes (A,B,C) = reference (y,x,z)
+        RunPoint rp;
+        run_point_setup(rp, Y[q], X[q], Z[q], Ri[q]);
+        int4* rec = a.pool.rec + 2 * (m.off + pos);
+        rec[0] = make_int4(rp.ipa, rp.ipb, rp.ipc, rp.R);
+        rec[1] = make_int4(__float_as_int(rp.fa), __float_as_int(rp.fb), __float_as_int(rp.fc), __float_as_int(rp.W));
+      }
     }
   }
   // tile work list
@@ -1321,6 +1336,252 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2, second generation -- the run-length vote kernel (runs_core.h).
+// Same persistent structure (one CTA per SM, (item, tile) units from a global queue, the tile never leaves shared
+// memory), but the tile is a DIFFERENCE ARRAY along C (reference z): a lane (= one point) walks the columns
+// u = -H..H of its sphere and records, per column and slice, the two runs of shell voxels as marks at their ends (a
+// plane of run starts, a plane of run ends) -- four atomics per (column, slice) whatever the run lengths; when every
+// point has been drawn, one prefix sum per row of (starts - ends) gives the counts, fused with the peak search and the
+// vote tally.
+// ------------------------------------------------------------------------------------------------
+#ifndef RCV_RUNS_THREADS
+#define RCV_RUNS_THREADS 512
+#endif
+constexpr int kRunsThreads = RCV_RUNS_THREADS;
+constexpr int kRunsWarps = kRunsThreads / 32;
+constexpr int kRunsTileWords = kSmemBytes / 4 - 192;    // 192 words left for static shared variables
+
+// Only `add 1` (ATOMS.POPC.INC) merges the lanes of a warp that hit the same address; every other shared-memory atomic
+// (add of a register or of -1, inc, dec) replays once per duplicate lane (tools/ubench_atoms2.cu,
+// profiles/r02c_ubench_atoms2.jsonl: 282 G warp-instr/s against 9 G with 32 equal addresses).  Adjacent pixels share
+// most of their run boundaries, so the difference array is kept as two planes of plain counters -- run starts and run
+// ends -- and every mark is an `add 1`.
+
+// The rare path of one (lane, column): exact decisions for the voxels next to flagged run boundaries, for every slice
+// of the chunk.  Everything is re-derived from the point record (the same arithmetic as the fast path); the float64
+// coordinates are fetched here.  (A,B,C) = reference (y,x,z): exact_hit() wants the reference order.
+struct RunSlowCtx {
+  const double *X, *Y, *Z;   // pool (item base already added)
+  const int* perm;           // vote order -> pool index (item base already added)
+};
+template <bool CLIP>
+__device__ __noinline__ void runs_slow_column(RunPoint c, int pidx, RunSlowCtx sc, int u, int uc, int i0c, int nsl, int Dp, unsigned K0, unsigned slice_bytes,
+                                              unsigned plane_bytes, int clo, int chi) {
+  RunLane L;
+  run_lane_setup(c, L);
+  RunCol C;
+  run_col_setup(c, u, uc, Dp, C);
+  const unsigned base = (unsigned)RCV_MAGIC_BITS + (unsigned)(uc * Dp);
+  const int q = sc.perm[pidx];
+  const double px = sc.X[q], py = sc.Y[q], pz = sc.Z[q];
+  const int row = c.ipb + u;
+  for (int s = 0; s < nsl; ++s) {
+    const int i = i0c + s;
+    const f2 aa = run_slice_consts(c, L, i, true);
+    const unsigned K = K0 + (unsigned)s * slice_bytes;
+    auto exact = [&](int m) { return exact_hit_call(px, py, pz, c.R, row, i, c.ipc + m); };
+    auto fix = [&](unsigned nbits, int delta) {   // voxel m joins (delta = +1) or leaves (-1) the set: a run [m, m+1) added to / taken from the planes
+      int b0 = (int)nbits, b1 = (int)nbits + 1;
+      if (CLIP) { b0 = min(max(b0, (int)base + clo), (int)base + chi); b1 = min(max(b1, (int)base + clo), (int)base + chi); }
+      smem_inc((unsigned)b0 * 4u + K + (delta > 0 ? 0u : plane_bytes));
+      smem_inc((unsigned)b1 * 4u + K + (delta > 0 ? plane_bytes : 0u));
+    };
+    run_slow_slice(L, C, aa, base, exact, fix);
+  }
+}
+
+// One chunk of NC slices for a warp whose 32 lanes each own one point.
+//   K0 = shared-window address constant of the chunk's first slice for this lane:
+//        tile_s + 4 * (glo + ((i0c - i0) * nj + (ipb - j0)) * Dp + ipc - MAGIC_BITS)   (mod 2^32), so that the cell of
+//        boundary bits b (= MAGIC_BITS + uc * Dp + lattice offset) is  b * 4 + K0 + s * slice_bytes.
+template <int NC, bool CLIP>
+__device__ __forceinline__ void runs_chunk(const RunPoint& c, const RunLane& L, const Tile& t, int i0c, int nsl, unsigned K0, unsigned slice_bytes,
+                                           unsigned plane_bytes, int pidx, const RunSlowCtx& sc) {
+  f2 aa[NC];
+  float amax = -1.f;
+#pragma unroll
+  for (int s = 0; s < NC; ++s) {
+    aa[s] = run_slice_consts(c, L, i0c + s, s < nsl);
+    amax = fmaxf(amax, f2_lo(aa[s]));
+  }
+  const int Hl = run_half_width(amax);
+  // the lane's own column range [ulo, uhi] (inside the tile's rows when CLIP); empty: ulo > uhi
+  int ulo = -Hl, uhi = Hl;
+  if (CLIP) { ulo = max(ulo, t.j0 - c.ipb); uhi = min(uhi, t.j0 + t.nj - 1 - c.ipb); }
+  if (Hl < 0) { ulo = 1; uhi = 0; }
+  const int wlo = __reduce_min_sync(0xffffffffu, ulo <= uhi ? ulo : 0x7fffffff), whi = __reduce_max_sync(0xffffffffu, ulo <= uhi ? uhi : -0x7fffffff);
+  if (wlo > whi) return;
+  // a lane without columns parks on a row that is certainly inside the tile
+  const int upark = CLIP ? min(max(0, t.j0 - c.ipb), t.j0 + t.nj - 1 - c.ipb) : 0;
+  if (ulo > uhi) { ulo = upark; uhi = upark; }
+  // starts go to plane 0, ends to plane 1; a slice of the chunk beyond the tile (its columns are all empty) re-uses the
+  // last real slice's cells, where its four marks cancel
+  unsigned K[NC], KE[NC];
+#pragma unroll
+  for (int s = 0; s < NC; ++s) { K[s] = K0 + (unsigned)min(s, nsl - 1) * slice_bytes; KE[s] = K[s] + plane_bytes; }
+  // clip bounds of the boundary bits relative to `base` (CLIP): lattice offsets [-glo - ipc, D + ghi - ipc]
+  const int clo = -t.glo - c.ipc, chi = t.D + t.ghi - c.ipc;
+  const float Dpf = (float)t.Dp;
+#pragma unroll 1
+  for (int u0 = wlo; u0 <= whi; u0 += 32) {
+    unsigned flags = 0;
+    const int ue = min(u0 + 31, whi);
+    float uf = (float)u0;
+#pragma unroll 1
+    for (int u = u0; u <= ue; ++u, uf += 1.0f) {
+      const int uc = min(max(u, ulo), uhi);                      // beyond its own range the lane parks on its edge row
+      const bool off_range = uc != u;
+      float du = f_sub(uf, c.fb);
+      if (off_range) du = 1.0e18f;                               // ... and the parked column is empty (g'' = -huge)
+      RunCol C;
+      C.du = f2_dup(du); C.ndu = f2_dup(-du);
+      C.mu = f2_dup(f_fma((float)uc, Dpf, RCV_MAGIC));            // exact: integers below 2^24
+      int acc = 0;
+#pragma unroll
+      for (int s = 0; s < NC; ++s) {
+        RunOut o;
+        run_slice(L, C, aa[s], o);
+        int b1 = (int)o.b1, b2 = (int)o.b2, b3 = (int)o.b3, b4 = (int)o.b4;
+        if (CLIP) {
+          const int base = RCV_MAGIC_BITS + uc * t.Dp, lo = base + clo, hi = base + chi;
+          b1 = min(max(b1, lo), hi); b2 = min(max(b2, lo), hi); b3 = min(max(b3, lo), hi); b4 = min(max(b4, lo), hi);
+        }
+        smem_inc((unsigned)b1 * 4u + K[s]);
+        smem_inc((unsigned)b2 * 4u + KE[s]);
+        smem_inc((unsigned)b3 * 4u + K[s]);
+        smem_inc((unsigned)b4 * 4u + KE[s]);
+        acc |= run_flag_bits(o);
+      }
+      if (acc < 0) flags |= 1u << (u - u0);
+    }
+    if (__any_sync(0xffffffffu, flags != 0u)) {
+      while (flags) {
+        const int j = __ffs((int)flags) - 1;
+        flags &= flags - 1u;
+        const int u = u0 + j;
+        runs_slow_column<CLIP>(c, pidx, sc, u, u, i0c, nsl, t.Dp, K0, slice_bytes, plane_bytes, clo, chi);   // a flagged column is never a parked one
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
+  extern __shared__ __align__(16) int smem[];
+  int* tile = smem;
+  __shared__ int s_unit, s_next;
+  __shared__ unsigned long long s_key[kRunsWarps], s_sum[kRunsWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
+  asm volatile("mov.u32 %0, %0;" : "+r"(tile_s));
+  const int n_units = a.counters[0];
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) { s_unit = atomicAdd(&a.counters[1], 1); s_next = 0; }
+    __syncthreads();
+    const int ui = s_unit;
+    if (ui >= n_units) break;
+    const Unit u = a.units[ui];
+    const ItemMeta& m = a.meta[u.item];
+    const int D = m.D, Dp = m.Dp, n = m.n;
+    const long long off = m.off;
+    const int glo = m.guard & 0xffff, ghi = m.guard >> 16;
+    const Tile t{u.i0, u.ni, u.j0, u.nj, D, Dp, glo, ghi};
+    // whole-slice tiles whose guard band holds every sphere of the item need no clipping (the prelude sized the guards);
+    // row bands and unguarded grids (guard = 0 although spheres overhang) take the clipped variant
+    const bool clip = m.clip != 0;
+    const int plane_words = (u.ni * u.nj * Dp + 3) & ~3;   // plane 0: run starts, plane 1: run ends
+    {
+      int4* t4 = reinterpret_cast<int4*>(tile);
+      const int n4 = plane_words >> 1;
+      for (int w = threadIdx.x; w < n4; w += kRunsThreads) t4[w] = make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    // ---- scatter: a work item is (chunk of NC slices, group of 32 consecutive points of the vote order) ----
+    const unsigned slice_bytes = (unsigned)(u.nj * Dp * 4), plane_bytes = (unsigned)plane_words * 4u;
+    const int NC = ring_chunk(u.ni);
+    const int ngroups = (n + 31) >> 5, nchunks = (u.ni + NC - 1) / NC, nwork = ngroups * nchunks;
+    const RunSlowCtx sc{a.pool.X + off, a.pool.Y + off, a.pool.Z + off, a.pool.perm + off};
+    for (;;) {
+      int w = 0;
+      if (lane == 0) w = atomicAdd(&s_next, 1);
+      w = __shfl_sync(0xffffffffu, w, 0);
+      if (w >= nwork) break;
+      const int ch = w / ngroups, cur = (w - ch * ngroups) << 5;
+      const int i0c = u.i0 + ch * NC, nsl = min(NC, u.i0 + u.ni - i0c);
+      RunPoint c;
+      c.ipa = 0; c.ipb = 0; c.ipc = 0; c.R = 0; c.fa = 0.f; c.fb = 0.f; c.fc = 0.f; c.W = 0.f;
+      if (cur + lane < n) {
+        const int4* rec = a.pool.rec + 2 * (off + cur + lane);
+        const int4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+        c.ipa = r0.x; c.ipb = r0.y; c.ipc = r0.z; c.R = r0.w;
+        c.fa = __int_as_float(r1.x); c.fb = __int_as_float(r1.y); c.fc = __int_as_float(r1.z); c.W = __int_as_float(r1.w);
+      }
+      // does any sphere of the group reach the chunk's slices?
+      const bool here = c.R > 0 && (c.ipa + c.R + 1 >= i0c) && (c.ipa - c.R - 1 <= i0c + nsl - 1);
+      if (!__any_sync(0xffffffffu, here)) continue;
+      if (!here) c.R = 0;
+      RunLane L;
+      run_lane_setup(c, L);
+      const unsigned K0 = tile_s + 4u * (unsigned)(glo + ((i0c - u.i0) * u.nj + (c.ipb - u.j0)) * Dp + c.ipc - RCV_MAGIC_BITS);
+      const int pidx = cur + lane;
+      if (!clip) {
+        if (NC == 4) runs_chunk<4, false>(c, L, t, i0c, nsl, K0, slice_bytes, plane_bytes, pidx, sc);
+        else if (NC == 3) runs_chunk<3, false>(c, L, t, i0c, nsl, K0, slice_bytes, plane_bytes, pidx, sc);
+        else if (NC == 2) runs_chunk<2, false>(c, L, t, i0c, nsl, K0, slice_bytes, plane_bytes, pidx, sc);
+        else runs_chunk<1, false>(c, L, t, i0c, nsl, K0, slice_bytes, plane_bytes, pidx, sc);
+      } else {
+        if (NC >= 3) { runs_chunk<2, true>(c, L, t, i0c, min(nsl, 2), K0, slice_bytes, plane_bytes, pidx, sc); if (nsl > 2) runs_chunk<2, true>(c, L, t, i0c + 2, nsl - 2, K0 + 2u * slice_bytes, slice_bytes, plane_bytes, pidx, sc); }
+        else if (NC == 2) runs_chunk<2, true>(c, L, t, i0c, nsl, K0, slice_bytes, plane_bytes, pidx, sc);
+        else runs_chunk<1, true>(c, L, t, i0c, nsl, K0, slice_bytes, plane_bytes, pidx, sc);
+      }
+    }
+    __syncthreads();
+    // ---- prefix sum per row (differences -> counts) fused with the peak of the tile (K3) and the vote tally ----
+    // tile row r = (A - i0) * nj + (B - j0) holds reference voxels (i, j, k) = (B, A, k); cell k sits at word glo + k
+    unsigned long long key = 0, sum = 0;
+    const int jr0 = u.j0 < 0 ? 0 : u.j0, njr = min(u.j0 + u.nj, D) - jr0;   // the real rows of a slice (guard rows are not read back)
+    const int rows = u.ni * njr;
+    const bool dump = a.volume && (long long)D * D * D <= a.volume_cap;
+    for (int r = threadIdx.x; r < rows; r += kRunsThreads) {
+      const int sa = r / njr, gb = jr0 + r - sa * njr, ga = u.i0 + sa;
+      const unsigned lin0 = ((unsigned)gb * (unsigned)D + (unsigned)ga) * (unsigned)D;
+      int* row = tile + (sa * u.nj + (gb - u.j0)) * Dp;
+      const int* rowe = row + plane_words;
+      int run = 0;
+      for (int k = 0; k < glo; ++k) run += row[k] - rowe[k];
+      int best = -1, bestk = 0;
+      row += glo; rowe += glo;
+      for (int k = 0; k < D; ++k) {
+        run += row[k] - rowe[k];
+        sum += (unsigned)run;
+        if (run > best) { best = run; bestk = k; }
+        if (dump) row[k] = run;
+      }
+      const unsigned long long kk = pack_peak(best, lin0 + (unsigned)bestk);
+      key = kk > key ? kk : key;
+    }
+    if (dump) {   // parity / debug: the counts go to HBM, coalesced
+      __syncthreads();
+      for (int r = warp; r < rows; r += kRunsWarps) {
+        const int sa = r / njr, gb = jr0 + r - sa * njr, ga = u.i0 + sa;
+        const unsigned lin0 = ((unsigned)gb * (unsigned)D + (unsigned)ga) * (unsigned)D;
+        const int* row = tile + glo + (sa * u.nj + (gb - u.j0)) * Dp;
+        for (int k = lane; k < D; k += 32) a.volume[(long long)lin0 + k] = row[k];
+      }
+    }
+    key = warp_max_u64(key); sum = warp_sum_u64(sum);
+    if (lane == 0) { s_key[warp] = key; s_sum[warp] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kRunsWarps; ++w) { key = s_key[w] > key ? s_key[w] : key; sum += s_sum[w]; }
+      atomicMax(&a.best[u.item], key);
+      if (sum) atomicAdd(&a.votes[u.item], sum);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // F -- peak -> millimetres (AccumulatorSpace.py:409-415); scatter of per-item outputs
 // ------------------------------------------------------------------------------------------------
 struct FinalArgs {
@@ -1523,6 +1784,7 @@ __global__ void __launch_bounds__(1024, 1) k_ubench_atoms(int iters, unsigned* o
 // ================================================================================================
 struct rcv_ctx {
   int device, sms;
+  int gen;   // vote kernel generation: 2 = run-length difference arrays (k_vote_runs), 1 = per-candidate rasteriser (k_vote, RCV_VOTE_GEN=1)
   rcv_config cfg;
   Pool pool;
   ItemMeta* meta;
@@ -1572,7 +1834,7 @@ RCV_EXPORT long long rcv_launch_count(const rcv_ctx* ctx) { return ctx ? ctx->la
 RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri); cudaFree(c->pool.perm);
+  cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri); cudaFree(c->pool.perm); cudaFree(c->pool.rec);
   cudaFree(c->meta); cudaFree(c->units); cudaFree(c->counters); cudaFree(c->cnt); cudaFree(c->best); cudaFree(c->votes);
   cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits); cudaFree(c->add_part); cudaFree(c->icp_scratch); cudaFree(c->head_radius);
   for (int s = 0; s < 2; ++s) { cudaFree(c->st_depth[s]); cudaFree(c->st_radius[s]); cudaFree(c->st_sem[s]); }
@@ -1606,6 +1868,7 @@ RCV_EXPORT int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out) {
   rcv_ctx* c = (rcv_ctx*)calloc(1, sizeof(rcv_ctx));
   if (!c) return RCV_E_INVALID;
   c->device = device; c->cfg = *cfg; c->sms = prop.multiProcessorCount;
+  { const char* g = getenv("RCV_VOTE_GEN"); c->gen = (g && atoi(g) == 1) ? 1 : 2; }
   if (c->cfg.max_units <= 0) {
     // worst case per item: D slices x ceil(D / rows-per-tile) tiles
     const long long per_item = (long long)cfg->max_grid * ((cfg->max_grid * (long long)(cfg->max_grid | 1)) / kTileWords + 1);
@@ -1620,6 +1883,7 @@ RCV_EXPORT int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out) {
   c->pool.cap = cap;
   CKC(cudaMalloc(&c->pool.X, cap * 8)); CKC(cudaMalloc(&c->pool.Y, cap * 8)); CKC(cudaMalloc(&c->pool.Z, cap * 8));
   CKC(cudaMalloc(&c->pool.Rd, cap * 8)); CKC(cudaMalloc(&c->pool.Ri, cap * 4)); CKC(cudaMalloc(&c->pool.perm, cap * 4));
+  CKC(cudaMalloc(&c->pool.rec, cap * 32));
   CKC(cudaMalloc(&c->meta, sizeof(ItemMeta) * (size_t)cfg->max_items));
   CKC(cudaMalloc(&c->units, sizeof(Unit) * (size_t)c->cfg.max_units));
   CKC(cudaMalloc(&c->counters, 64 + 4096));
@@ -1630,6 +1894,7 @@ RCV_EXPORT int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out) {
   for (int e = 0; e < 64; ++e) { CKC(cudaEventCreate(&c->evr[e][0])); CKC(cudaEventCreate(&c->evr[e][1])); }
   CKC(cudaFuncSetAttribute(k_ubench_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
   CKC(cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (kTileWords + kDummyWords) * 4));
+  CKC(cudaFuncSetAttribute(k_vote_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, kRunsTileWords * 4));
 #undef CKC
   return RCV_OK;
 }
@@ -1640,13 +1905,14 @@ static int run_items(rcv_ctx* c, int n_items, const rcv_vote_params* vp, double*
   CK(c, cudaMemsetAsync(c->counters, 0, 64, st));
   CK(c, cudaMemsetAsync(c->best, 0, 8 * (size_t)n_items, st));
   CK(c, cudaMemsetAsync(c->votes, 0, 8 * (size_t)n_items, st));
-  PreludeArgs pa{c->pool, c->meta, c->units, c->counters, c->cfg.max_units, c->cfg.max_grid, vp->grid_policy, kTileWords,
-                 c->leaves, c->leaf_sums, c->leaf_cap};
+  PreludeArgs pa{c->pool, c->meta, c->units, c->counters, c->cfg.max_units, c->cfg.max_grid, vp->grid_policy,
+                 c->gen >= 2 ? kRunsTileWords : kTileWords, c->gen, c->leaves, c->leaf_sums, c->leaf_cap};
   k_prelude<<<n_items, kPreludeThreads, 0, st>>>(pa);
   VoteArgs va{c->pool, c->meta, c->units, c->counters, c->best, c->votes, volume, volume_cap};
   const int slot = (int)(c->ev_count % 64);
   CK(c, cudaEventRecord(c->evr[slot][0], st));
-  k_vote<<<c->sms, kVoteThreads, (kTileWords + kDummyWords) * 4, st>>>(va);
+  if (c->gen >= 2) k_vote_runs<<<c->sms, kRunsThreads, kRunsTileWords * 4, st>>>(va);
+  else k_vote<<<c->sms, kVoteThreads, (kTileWords + kDummyWords) * 4, st>>>(va);
   CK(c, cudaEventRecord(c->evr[slot][1], st));
   c->ev_count += 1;
   FinalArgs fa{c->meta, c->best, c->votes, n_items, vp->acc_unit, vp->grid_policy, volume != nullptr, volume_cap,
