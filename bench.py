@@ -86,7 +86,7 @@ def host_threads():
 
 
 CPU_PORT = ("oracle port of the reference's fast_for (float64 shell test per voxel, OpenMP over x-slices) with exact per-slice / per-row "
-            "culls -- 0.8x the time of the real numba fast_for on the same 8 cores (tools/cpu_calibrate.py, profiles/r02_cpu_calibration.json), "
+            "culls -- ~0.6x the time of the real numba fast_for on the same 8 cores (tools/cpu_calibrate.py, profiles/r02_cpu_calibration.json), "
             "so the ratio to it is conservative -- + lmshorn")
 
 

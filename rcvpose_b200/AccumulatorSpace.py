@@ -7,6 +7,7 @@ signatures, dtypes, units and return shapes -- executed on the B200 through libr
     read_depth(path)                  reference AccumulatorSpace.py:482-490
     estimate_6d_pose_lm(opts)         reference AccumulatorSpace.py:495-744 (batched: rcvpose_b200/evaluate.py)
     estimate_6d_pose_lmo(opts)        reference AccumulatorSpace.py:741-983 (batched: rcvpose_b200/evaluate.py)
+    estimate_6d_pose_ycb(opts)        reference AccumulatorSpace.py:976-1197, repaired (batched: rcvpose_b200/evaluate.py)
 
 Putting this package's directory ahead of the reference on sys.path makes
 `estimate_6d_pose_*` (reference :495-1197) call these instead.  Inputs and outputs are NumPy
@@ -107,3 +108,8 @@ def estimate_6d_pose_lm(opts):
 def estimate_6d_pose_lmo(opts):
     from rcvpose_b200 import evaluate
     return evaluate.estimate_6d_pose_lmo(opts)
+
+
+def estimate_6d_pose_ycb(opts):
+    from rcvpose_b200 import evaluate
+    return evaluate.estimate_6d_pose_ycb(opts)

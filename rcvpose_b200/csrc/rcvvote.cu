@@ -1349,7 +1349,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
 #endif
 constexpr int kRunsThreads = RCV_RUNS_THREADS;
 constexpr int kRunsWarps = kRunsThreads / 32;
-constexpr int kRunsTileWords = kSmemBytes / 4 - 192;    // 192 words left for static shared variables
+constexpr int kRunsTileWords = kSmemBytes / 4 - 192 - 2 * 64 * (RCV_RUNS_THREADS / 32);    // static shared variables: 192 words + the per-warp queues of deferred exact decisions
 
 // Only `add 1` (ATOMS.POPC.INC) merges the lanes of a warp that hit the same address; every other shared-memory atomic
 // (add of a register or of -1, inc, dec) replays once per duplicate lane (tools/ubench_atoms2.cu,
@@ -1390,53 +1390,95 @@ __device__ __noinline__ void runs_slow_column(RunPoint c, int pidx, RunSlowCtx s
   }
 }
 
-// One chunk of NC slices for a warp whose 32 lanes each own one point.
-//   K0 = shared-window address constant of the chunk's first slice for this lane:
-//        tile_s + 4 * (glo + ((i0c - i0) * nj + (ipb - j0)) * Dp + ipc - MAGIC_BITS)   (mod 2^32), so that the cell of
-//        boundary bits b (= MAGIC_BITS + uc * Dp + lattice offset) is  b * 4 + K0 + s * slice_bytes.
-template <int NC, bool CLIP>
-__device__ __forceinline__ void runs_chunk(const RunPoint& c, const RunLane& L, const Tile& t, int i0c, int nsl, unsigned K0, unsigned slice_bytes,
-                                           unsigned plane_bytes, int pidx, const RunSlowCtx& sc) {
-  f2 aa[NC];
-  float amax = -1.f;
-#pragma unroll
-  for (int s = 0; s < NC; ++s) {
-    aa[s] = run_slice_consts(c, L, i0c + s, s < nsl);
-    amax = fmaxf(amax, f2_lo(aa[s]));
+// ---- deferred exact decisions -----------------------------------------------------------------------------------
+// A flagged (point, column) is not decided where it is found -- one lane would walk the float64 path while 31 wait --
+// but queued per warp; the queue is drained 32 items at a time (every lane takes one) and at the end of the tile.  An item
+// carries what the rare path needs to re-derive the column: the point's index in vote order, the column, the chunk.
+constexpr int kRunsQueue = 64;
+struct RunTile {               // per-tile constants of the rare path
+  Tile t;
+  unsigned tile_s, slice_bytes, plane_bytes;
+  const int4* rec;             // point records of the item (item base already added)
+  RunSlowCtx sc;
+  bool clip;
+};
+__device__ __forceinline__ unsigned run_K0(const RunTile& rt, const RunPoint& c, int i0c) {
+  return rt.tile_s + 4u * (unsigned)(rt.t.glo + ((i0c - rt.t.i0) * rt.t.nj + (c.ipb - rt.t.j0)) * rt.t.Dp + c.ipc - RCV_MAGIC_BITS);
+}
+__device__ __forceinline__ RunPoint run_load_point(const int4* rec, int pidx) {
+  const int4 r0 = __ldg(rec + 2 * pidx), r1 = __ldg(rec + 2 * pidx + 1);
+  RunPoint c;
+  c.ipa = r0.x; c.ipb = r0.y; c.ipc = r0.z; c.R = r0.w;
+  c.fa = __int_as_float(r1.x); c.fb = __int_as_float(r1.y); c.fc = __int_as_float(r1.z); c.W = __int_as_float(r1.w);
+  return c;
+}
+__device__ __noinline__ void runs_slow_item(const RunTile& rt, unsigned long long item) {
+  const int pidx = (int)(unsigned)(item & 0xffffffffu);
+  const unsigned hi = (unsigned)(item >> 32);
+  const int u = (int)(hi & 0xfffu) - 2048, nsl = (int)((hi >> 12) & 0xfu), i0c = (int)(hi >> 16);
+  const RunPoint c = run_load_point(rt.rec, pidx);
+  const int clo = -rt.t.glo - c.ipc, chi = rt.t.D + rt.t.ghi - c.ipc;
+  if (rt.clip) runs_slow_column<true>(c, pidx, rt.sc, u, u, i0c, nsl, rt.t.Dp, run_K0(rt, c, i0c), rt.slice_bytes, rt.plane_bytes, clo, chi);
+  else runs_slow_column<false>(c, pidx, rt.sc, u, u, i0c, nsl, rt.t.Dp, run_K0(rt, c, i0c), rt.slice_bytes, rt.plane_bytes, clo, chi);
+}
+// Drains the warp's queue: whole batches of 32 items, or everything when `all`.  Called by all 32 lanes.
+__device__ __forceinline__ void runs_drain(const RunTile& rt, unsigned long long* q, int* qn, bool all) {
+  __syncwarp();
+  int n = min(*qn, kRunsQueue);
+  const int lane = threadIdx.x & 31;
+  while (n >= 32 || (all && n > 0)) {
+    const int take = min(n, 32);
+    if (lane < take) runs_slow_item(rt, q[n - take + lane]);
+    n -= take;
+    __syncwarp();
   }
-  const int Hl = run_half_width(amax);
-  // the lane's own column range [ulo, uhi] (inside the tile's rows when CLIP); empty: ulo > uhi
-  int ulo = -Hl, uhi = Hl;
-  if (CLIP) { ulo = max(ulo, t.j0 - c.ipb); uhi = min(uhi, t.j0 + t.nj - 1 - c.ipb); }
-  if (Hl < 0) { ulo = 1; uhi = 0; }
-  const int wlo = __reduce_min_sync(0xffffffffu, ulo <= uhi ? ulo : 0x7fffffff), whi = __reduce_max_sync(0xffffffffu, ulo <= uhi ? uhi : -0x7fffffff);
-  if (wlo > whi) return;
-  // a lane without columns parks on a row that is certainly inside the tile
-  const int upark = CLIP ? min(max(0, t.j0 - c.ipb), t.j0 + t.nj - 1 - c.ipb) : 0;
-  if (ulo > uhi) { ulo = upark; uhi = upark; }
-  // starts go to plane 0, ends to plane 1; a slice of the chunk beyond the tile (its columns are all empty) re-uses the
-  // last real slice's cells, where its four marks cancel
-  unsigned K[NC], KE[NC];
-#pragma unroll
-  for (int s = 0; s < NC; ++s) { K[s] = K0 + (unsigned)min(s, nsl - 1) * slice_bytes; KE[s] = K[s] + plane_bytes; }
-  // clip bounds of the boundary bits relative to `base` (CLIP): lattice offsets [-glo - ipc, D + ghi - ipc]
-  const int clo = -t.glo - c.ipc, chi = t.D + t.ghi - c.ipc;
+  if (lane == 0) *qn = n;
+  __syncwarp();
+}
+// Pushes the flagged columns of a block of 32 (bit j of `flags` = column u0 + j) of this lane's point.
+__device__ __forceinline__ void runs_push(const RunTile& rt, unsigned long long* q, int* qn, unsigned flags, int pidx, int u0, int i0c, int nsl) {
+  while (flags) {
+    const int j = __ffs((int)flags) - 1;
+    flags &= flags - 1u;
+    const unsigned long long item = (unsigned long long)(unsigned)pidx |
+                                    ((unsigned long long)((unsigned)(u0 + j + 2048) | ((unsigned)nsl << 12) | ((unsigned)i0c << 16)) << 32);
+    const int slot = atomicAdd(qn, 1);
+    if (slot < kRunsQueue) q[slot] = item;
+    else runs_slow_item(rt, item);          // queue full (a pathological block): decide at once
+  }
+}
+
+// A stretch [ua, ub] of columns of one chunk of NC slices, 32 lanes = 32 points.  PARK: some lane's own column range
+// [ulo, uhi] does not cover the stretch; beyond its range a lane parks on its edge row and the column is empty.
+//   K0 = shared-window address constant of the chunk's first slice for this lane (run_K0): the cell of boundary bits b
+//        (= MAGIC_BITS + uc * Dp + lattice offset) is  b * 4 + K0 + s * slice_bytes.
+template <int NC, bool CLIP, bool PARK>
+__device__ __forceinline__ void runs_columns(const RunPoint& c, const RunLane& L, const RunTile& rt, const f2 (&aa)[NC], const unsigned (&K)[NC],
+                                             const unsigned (&KE)[NC], int ua, int ub, int ulo, int uhi, int pidx, int i0c, int nsl,
+                                             unsigned long long* q, int* qn) {
+  const Tile& t = rt.t;
+  const int clo = -t.glo - c.ipc, chi = t.D + t.ghi - c.ipc;   // clip bounds of the boundary bits relative to `base` (CLIP)
   const float Dpf = (float)t.Dp;
 #pragma unroll 1
-  for (int u0 = wlo; u0 <= whi; u0 += 32) {
+  for (int u0 = ua; u0 <= ub; u0 += 32) {
     unsigned flags = 0;
-    const int ue = min(u0 + 31, whi);
+    const int ue = min(u0 + 31, ub);
     float uf = (float)u0;
+    unsigned bit = 1u;
 #pragma unroll 1
-    for (int u = u0; u <= ue; ++u, uf += 1.0f) {
-      const int uc = min(max(u, ulo), uhi);                      // beyond its own range the lane parks on its edge row
-      const bool off_range = uc != u;
+    for (int u = u0; u <= ue; ++u, uf += 1.0f, bit <<= 1) {
       float du = f_sub(uf, c.fb);
-      if (off_range) du = 1.0e18f;                               // ... and the parked column is empty (g'' = -huge)
       RunCol C;
+      int uc = u;
+      if (PARK) {
+        uc = min(max(u, ulo), uhi);                              // beyond its own range the lane parks on its edge row
+        if (uc != u) du = 1.0e18f;                               // ... and the parked column is empty (g'' = -huge)
+        C.mu = f2_dup(f_fma((float)uc, Dpf, RCV_MAGIC));          // exact: integers below 2^24
+      } else {
+        C.mu = f2_dup(f_fma(uf, Dpf, RCV_MAGIC));
+      }
       C.du = f2_dup(du); C.ndu = f2_dup(-du);
-      C.mu = f2_dup(f_fma((float)uc, Dpf, RCV_MAGIC));            // exact: integers below 2^24
-      int acc = 0;
+      unsigned amb = 0u;
 #pragma unroll
       for (int s = 0; s < NC; ++s) {
         RunOut o;
@@ -1450,19 +1492,53 @@ __device__ __forceinline__ void runs_chunk(const RunPoint& c, const RunLane& L, 
         smem_inc((unsigned)b2 * 4u + KE[s]);
         smem_inc((unsigned)b3 * 4u + K[s]);
         smem_inc((unsigned)b4 * 4u + KE[s]);
-        acc |= run_flag_bits(o);
+        run_flag_acc(amb, o);
       }
-      if (acc < 0) flags |= 1u << (u - u0);
+      if (amb) flags |= bit;
     }
     if (__any_sync(0xffffffffu, flags != 0u)) {
-      while (flags) {
-        const int j = __ffs((int)flags) - 1;
-        flags &= flags - 1u;
-        const int u = u0 + j;
-        runs_slow_column<CLIP>(c, pidx, sc, u, u, i0c, nsl, t.Dp, K0, slice_bytes, plane_bytes, clo, chi);   // a flagged column is never a parked one
-      }
-      __syncwarp();
+      runs_push(rt, q, qn, flags, pidx, u0, i0c, nsl);            // (a flagged column is never a parked one)
+      runs_drain(rt, q, qn, false);
     }
+  }
+}
+
+// One chunk of NC slices for a warp whose 32 lanes each own one point.
+template <int NC, bool CLIP>
+__device__ __forceinline__ void runs_chunk(const RunPoint& c, const RunLane& L, const RunTile& rt, int i0c, int nsl, int pidx, unsigned long long* q, int* qn) {
+  const Tile& t = rt.t;
+  f2 aa[NC];
+  float amax = -1.f;
+#pragma unroll
+  for (int s = 0; s < NC; ++s) {
+    aa[s] = run_slice_consts(c, L, i0c + s, s < nsl);
+    amax = fmaxf(amax, f2_lo(aa[s]));
+  }
+  const int Hl = run_half_width(amax);
+  // the lane's own column range [ulo, uhi] (inside the tile's rows when CLIP); empty: ulo > uhi
+  int ulo = -Hl, uhi = Hl;
+  if (CLIP) { ulo = max(ulo, t.j0 - c.ipb); uhi = min(uhi, t.j0 + t.nj - 1 - c.ipb); }
+  if (Hl < 0) { ulo = 1; uhi = 0; }
+  const bool some = ulo <= uhi;
+  const int wlo = __reduce_min_sync(0xffffffffu, some ? ulo : 0x7fffffff), whi = __reduce_max_sync(0xffffffffu, some ? uhi : -0x7fffffff);
+  if (wlo > whi) return;
+  // the stretch every lane covers with its own range: there the column body needs no parking logic
+  int mlo = __reduce_max_sync(0xffffffffu, some ? ulo : 0x7fffffff), mhi = __reduce_min_sync(0xffffffffu, some ? uhi : -0x7fffffff);
+  // a lane without columns parks on a row that is certainly inside the tile
+  const int upark = CLIP ? min(max(0, t.j0 - c.ipb), t.j0 + t.nj - 1 - c.ipb) : 0;
+  if (!some) { ulo = upark; uhi = upark; }
+  // starts go to plane 0, ends to plane 1; a slice of the chunk beyond the tile (its columns are all empty) re-uses the
+  // last real slice's cells, where its four marks cancel
+  const unsigned K0 = run_K0(rt, c, i0c);
+  unsigned K[NC], KE[NC];
+#pragma unroll
+  for (int s = 0; s < NC; ++s) { K[s] = K0 + (unsigned)min(s, nsl - 1) * rt.slice_bytes; KE[s] = K[s] + rt.plane_bytes; }
+  if (CLIP || mlo > mhi) {
+    runs_columns<NC, CLIP, true>(c, L, rt, aa, K, KE, wlo, whi, ulo, uhi, pidx, i0c, nsl, q, qn);
+  } else {
+    if (wlo < mlo) runs_columns<NC, CLIP, true>(c, L, rt, aa, K, KE, wlo, mlo - 1, ulo, uhi, pidx, i0c, nsl, q, qn);
+    runs_columns<NC, CLIP, false>(c, L, rt, aa, K, KE, mlo, mhi, ulo, uhi, pidx, i0c, nsl, q, qn);
+    if (mhi < whi) runs_columns<NC, CLIP, true>(c, L, rt, aa, K, KE, mhi + 1, whi, ulo, uhi, pidx, i0c, nsl, q, qn);
   }
 }
 
@@ -1471,10 +1547,13 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
   int* tile = smem;
   __shared__ int s_unit, s_next;
   __shared__ unsigned long long s_key[kRunsWarps], s_sum[kRunsWarps];
+  __shared__ unsigned long long s_q[kRunsWarps][kRunsQueue];
+  __shared__ int s_qn[kRunsWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
   asm volatile("mov.u32 %0, %0;" : "+r"(tile_s));
   const int n_units = a.counters[0];
+  if (lane == 0) s_qn[warp] = 0;
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) { s_unit = atomicAdd(&a.counters[1], 1); s_next = 0; }
@@ -1502,6 +1581,9 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
     const int NC = ring_chunk(u.ni);
     const int ngroups = (n + 31) >> 5, nchunks = (u.ni + NC - 1) / NC, nwork = ngroups * nchunks;
     const RunSlowCtx sc{a.pool.X + off, a.pool.Y + off, a.pool.Z + off, a.pool.perm + off};
+    const RunTile rt{t, tile_s, slice_bytes, plane_bytes, a.pool.rec + 2 * off, sc, clip};
+    unsigned long long* q = s_q[warp];
+    int* qn = &s_qn[warp];
     for (;;) {
       int w = 0;
       if (lane == 0) w = atomicAdd(&s_next, 1);
@@ -1511,31 +1593,26 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
       const int i0c = u.i0 + ch * NC, nsl = min(NC, u.i0 + u.ni - i0c);
       RunPoint c;
       c.ipa = 0; c.ipb = 0; c.ipc = 0; c.R = 0; c.fa = 0.f; c.fb = 0.f; c.fc = 0.f; c.W = 0.f;
-      if (cur + lane < n) {
-        const int4* rec = a.pool.rec + 2 * (off + cur + lane);
-        const int4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
-        c.ipa = r0.x; c.ipb = r0.y; c.ipc = r0.z; c.R = r0.w;
-        c.fa = __int_as_float(r1.x); c.fb = __int_as_float(r1.y); c.fc = __int_as_float(r1.z); c.W = __int_as_float(r1.w);
-      }
+      if (cur + lane < n) c = run_load_point(rt.rec, cur + lane);
       // does any sphere of the group reach the chunk's slices?
       const bool here = c.R > 0 && (c.ipa + c.R + 1 >= i0c) && (c.ipa - c.R - 1 <= i0c + nsl - 1);
       if (!__any_sync(0xffffffffu, here)) continue;
       if (!here) c.R = 0;
       RunLane L;
       run_lane_setup(c, L);
-      const unsigned K0 = tile_s + 4u * (unsigned)(glo + ((i0c - u.i0) * u.nj + (c.ipb - u.j0)) * Dp + c.ipc - RCV_MAGIC_BITS);
       const int pidx = cur + lane;
       if (!clip) {
-        if (NC == 4) runs_chunk<4, false>(c, L, t, i0c, nsl, K0, slice_bytes, plane_bytes, pidx, sc);
-        else if (NC == 3) runs_chunk<3, false>(c, L, t, i0c, nsl, K0, slice_bytes, plane_bytes, pidx, sc);
-        else if (NC == 2) runs_chunk<2, false>(c, L, t, i0c, nsl, K0, slice_bytes, plane_bytes, pidx, sc);
-        else runs_chunk<1, false>(c, L, t, i0c, nsl, K0, slice_bytes, plane_bytes, pidx, sc);
+        if (NC == 4) runs_chunk<4, false>(c, L, rt, i0c, nsl, pidx, q, qn);
+        else if (NC == 3) runs_chunk<3, false>(c, L, rt, i0c, nsl, pidx, q, qn);
+        else if (NC == 2) runs_chunk<2, false>(c, L, rt, i0c, nsl, pidx, q, qn);
+        else runs_chunk<1, false>(c, L, rt, i0c, nsl, pidx, q, qn);
       } else {
-        if (NC >= 3) { runs_chunk<2, true>(c, L, t, i0c, min(nsl, 2), K0, slice_bytes, plane_bytes, pidx, sc); if (nsl > 2) runs_chunk<2, true>(c, L, t, i0c + 2, nsl - 2, K0 + 2u * slice_bytes, slice_bytes, plane_bytes, pidx, sc); }
-        else if (NC == 2) runs_chunk<2, true>(c, L, t, i0c, nsl, K0, slice_bytes, plane_bytes, pidx, sc);
-        else runs_chunk<1, true>(c, L, t, i0c, nsl, K0, slice_bytes, plane_bytes, pidx, sc);
+        if (NC >= 3) { runs_chunk<2, true>(c, L, rt, i0c, min(nsl, 2), pidx, q, qn); if (nsl > 2) runs_chunk<2, true>(c, L, rt, i0c + 2, nsl - 2, pidx, q, qn); }
+        else if (NC == 2) runs_chunk<2, true>(c, L, rt, i0c, nsl, pidx, q, qn);
+        else runs_chunk<1, true>(c, L, rt, i0c, nsl, pidx, q, qn);
       }
     }
+    runs_drain(rt, q, qn, true);     // the exact decisions still queued belong to this tile
     __syncthreads();
     // ---- prefix sum per row (differences -> counts) fused with the peak of the tile (K3) and the vote tally ----
     // tile row r = (A - i0) * nj + (B - j0) holds reference voxels (i, j, k) = (B, A, k); cell k sits at word glo + k

@@ -62,6 +62,18 @@ RCV_HD float f_sqrt_run(float x) {
 #endif
 }
 
+// reciprocal square root for the run boundaries (MUFU.RSQ, relative error below 2^-22): NaN for a negative argument,
+// +inf for zero; s' = g * rsqrt(g)
+RCV_HD float f_rsqrt_run(float x) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  if (!(x >= 0.f)) return f_from_bits(0x7fffffff);
+  const float s = f_sqrt_fast(x);            // (perturbed by +-2 ulp under g_sqrt_perturb, like the device instruction's error)
+  return s > 0.f ? 1.0f / s : f_from_bits(0x7f800000);
+#endif
+}
+
 // ---- per point ----------------------------------------------------------------------------------------------------
 // Internal axes (A,B,C): A = slice axis of the tile (slabs of A-slices), B = row axis, C = the run axis (fastest).
 struct RunPoint {
@@ -87,10 +99,9 @@ RCV_HD void run_point_setup(RunPoint& c, double pa, double pb, double pc, int R)
 // biased g'' >= g_exact and gi'' >= gi_exact always (a NEGATIVE g'' / gi'' then proves the disc empty) and
 // |g'' - g_exact|, |gi'' - gi_exact| <= 2.75 E0.  A boundary computed as x' = fl(c -+ s'), s' = sqrt.approx(g''), is within
 // 2.75 E0 / s' + (R + 2) 2^-21 of the exact transition; multiplied by s' <= R + 2:  dist(x', Z) * s' <= 3.75 E0 must be
-// flagged.  epsh = 4 E0.
+// flagged (3.875 E0 with the rsqrt-and-multiply form of s', relative error 1.25 * 2^-22).  epsh = 4.5 E0.
 struct RunLane {
   f2 cc;      // (c, c), c = fc + 0.5: the +0.5 turns round-to-nearest into "first integer at or above"
-  f2 nq25;    // (-0.25, -0.25)
   f2 nepsh;   // (-epsh, -epsh)
   float E0;
 };
@@ -98,8 +109,7 @@ RCV_HD float run_E0(int R) { const float rp2 = (float)(R + 2); return f_mul(f_mu
 RCV_HD void run_lane_setup(const RunPoint& c, RunLane& L) {
   L.E0 = run_E0(c.R);
   L.cc = f2_dup(f_add(c.fc, 0.5f));
-  L.nq25 = f2_dup(-0.25f);
-  L.nepsh = f2_dup(-f_mul(L.E0, 4.0f));
+  L.nepsh = f2_dup(-f_mul(L.E0, 4.5f));
 }
 // Slice constants of A-slice i: (a'', aW'') = biased outer radius^2 of the ring in that slice and the same minus W.
 // A slice the sphere does not reach (or a lane that draws nothing) gets a negative pair: every column is then empty.
@@ -124,51 +134,66 @@ RCV_HD void run_col_setup(const RunPoint& c, int u, int uc, int Dp, RunCol& C) {
   C.mu = f2_dup(f_add(RCV_MAGIC, (float)(uc * Dp)));   // exact: |uc * Dp| < 2^22
 }
 // Boundaries as raw float bits of x + 0.5 + mu (an integer-valued float in [2^23, 2^24): bits = MAGIC_BITS + uc*Dp + b):
-//   lower run [b1, b2), upper run [b3, b4); the difference array gets +1 at b1 and b3, -1 at b2 and b4.
-// zU = (z4, z3), zL = (z1, z2): a NEGATIVE z (sign bit) flags the boundary: an integer may lie between the float32
-// transition and the exact one.  A column outside the sphere gives b1 = b2 = b3 = b4 and NaN (positive) z.
+//   lower run [b1, b2), upper run [b3, b4); starts b1 and b3, ends b2 and b4.
+// dL = (d1, d2), dU = (d4, d3): d = b - (x + 0.5) in [-0.5, 0.5], so the transition lies 0.5 - |d| from the nearest integer.
+// thr = (thr_outer, thr_inner): a boundary is FLAGGED -- an integer may lie between its float32 transition and the exact
+// one -- iff |d| >= thr, thr = 0.5 - epsh / s'  (dist * s' <= epsh, error budget above).  NaN thr (empty disc): never.
 struct RunOut {
   unsigned b1, b2, b3, b4;
-  f2 zU, zL, dU, dL;
+  f2 thr, dU, dL;
 };
 RCV_HD void run_slice(const RunLane& L, const RunCol& C, f2 aa, RunOut& o) {
   const f2 gg = f2_fma(C.ndu, C.du, aa);                               // (g'', gi''), one rounding each
-  const float so = f_sqrt_run(f2_lo(gg)), si = f_sqrt_run(f2_hi(gg));  // NaN (positive) for a negative argument
-  const f2 sn = f2_make(so, si);
-  const f2 sc = f2_make(f_max0(so), f_max0(si));                       // NaN -> 0: the run collapses
+  const f2 rr = f2_make(f_rsqrt_run(f2_lo(gg)), f_rsqrt_run(f2_hi(gg)));   // 1 / sqrt: NaN for a negative argument, +inf for 0
+  const f2 sn = f2_fma(gg, rr, f2_dup(0.f));                           // s' = g'' / sqrt(g''): NaN for g'' <= 0
+  const f2 sc = f2_make(f_max0(f2_lo(sn)), f_max0(f2_hi(sn)));         // NaN -> 0: the run collapses
   const f2 xU = f2_add(L.cc, sc), xL = f2_sub(L.cc, sc);               // transitions + 0.5: (x4, x3), (x1, x2)
   const f2 tU = f2_add(xU, C.mu), tL = f2_add(xL, C.mu);               // rounded to integers by the magic number
   o.b4 = (unsigned)f_bits(f2_lo(tU)); o.b3 = (unsigned)f_bits(f2_hi(tU));
   o.b1 = (unsigned)f_bits(f2_lo(tL)); o.b2 = (unsigned)f_bits(f2_hi(tL));
-  o.dU = f2_sub(f2_sub(tU, C.mu), xU); o.dL = f2_sub(f2_sub(tL, C.mu), xL);   // b - (x + 0.5), in [-0.5, 0.5]
-  // distance of the transition to the nearest integer: dist = 0.5 - |d|;  w = 0.25 - d^2 = dist (1 - dist) <= dist.
-  // flagged  <=>  z = w * s' - epsh < 0, formed as (d^2 - 0.25) * (-s') - epsh; NaN (never negative) when the disc is empty
-  const f2 sneg = f2_sub(f2_dup(0.f), sn);
-  o.zU = f2_fma(f2_fma(o.dU, o.dU, L.nq25), sneg, L.nepsh);
-  o.zL = f2_fma(f2_fma(o.dL, o.dL, L.nq25), sneg, L.nepsh);
+  o.dU = f2_sub(f2_sub(tU, C.mu), xU); o.dL = f2_sub(f2_sub(tL, C.mu), xL);
+  o.thr = f2_fma(L.nepsh, rr, f2_dup(0.5f));                           // 0.5 - epsh / s'
 }
-RCV_HD bool run_neg(float z) { return z < 0.f; }                        // false for NaN
-RCV_HD bool run_flagged(const RunOut& o) { return run_neg(f2_lo(o.zU)) || run_neg(f2_hi(o.zU)) || run_neg(f2_lo(o.zL)) || run_neg(f2_hi(o.zL)); }
-// device fast path: OR of the four sign bits (the NaN of an empty column is the canonical positive one; -0 cannot occur)
-RCV_HD int run_flag_bits(const RunOut& o) { return f_bits(f2_lo(o.zU)) | f_bits(f2_hi(o.zU)) | f_bits(f2_lo(o.zL)) | f_bits(f2_hi(o.zL)); }
+RCV_HD bool run_amb(float d, float thr) { return fabsf(d) >= thr; }     // false for a NaN threshold
+RCV_HD bool run_flagged(const RunOut& o) {
+  // (bitwise |: no short-circuit branches in the hot loop)
+  return run_amb(f2_lo(o.dL), f2_lo(o.thr)) | run_amb(f2_hi(o.dL), f2_hi(o.thr)) | run_amb(f2_hi(o.dU), f2_hi(o.thr)) |
+         run_amb(f2_lo(o.dU), f2_lo(o.thr));
+}
+
+// acc |= flagged(o), as one predicate chain on the device (four FSETP with the |d| modifier, no materialised booleans)
+RCV_HD void run_flag_acc(unsigned& acc, const RunOut& o) {
+#if defined(__CUDA_ARCH__)
+  asm("{\n\t.reg .pred p;\n\t.reg .f32 a;\n\t"
+      "setp.ne.u32 p, %0, 0;\n\t"
+      "abs.f32 a, %1;\n\tsetp.ge.or.f32 p, a, %5, p;\n\t"
+      "abs.f32 a, %2;\n\tsetp.ge.or.f32 p, a, %6, p;\n\t"
+      "abs.f32 a, %3;\n\tsetp.ge.or.f32 p, a, %6, p;\n\t"
+      "abs.f32 a, %4;\n\tsetp.ge.or.f32 p, a, %5, p;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "+r"(acc) : "f"(f2_lo(o.dL)), "f"(f2_hi(o.dL)), "f"(f2_hi(o.dU)), "f"(f2_lo(o.dU)), "f"(f2_lo(o.thr)), "f"(f2_hi(o.thr)));
+#else
+  if (run_flagged(o)) acc = 1u;
+#endif
+}
 
 // ---- the rare path: exact decision of the voxels next to flagged boundaries ----------------------------------------------
 // Re-derives the column with the same arithmetic (fast and slow path must agree on b1..b4), and for each flagged boundary
-// takes the integer m nearest to the float32 transition: the only voxel whose side of the boundary is in doubt.  Its
-// count in the difference array (from b1..b4) is compared with exact(m) and the array corrected.
+// takes the integer m nearest to the float32 transition: the only voxel whose side of that boundary can be in doubt.
+// Its count in the difference array (from b1..b4) is compared with exact(m) and the array corrected.
 //   base = MAGIC_BITS + uc * Dp (what the boundaries' bits are relative to),  exact(n) = reference predicate of the voxel
-//   n lattice steps from the point's nearest lattice point along C,  fix(nbits, delta): add delta at the cell whose bits
-//   are nbits and -delta at the next one.
+//   n lattice steps from the point's nearest lattice point along C,  fix(nbits, delta): voxel `nbits` joins (delta = +1)
+//   or leaves (-1) the set.
 template <class Exact, class Fix>
 RCV_HD int run_slow_slice(const RunLane& L, const RunCol& C, f2 aa, unsigned base, Exact& exact, Fix& fix) {
   RunOut o;
   run_slice(L, C, aa, o);
-  const float z[4] = {f2_lo(o.zL), f2_hi(o.zL), f2_hi(o.zU), f2_lo(o.zU)};   // boundaries 1..4
-  const float d[4] = {f2_lo(o.dL), f2_hi(o.dL), f2_hi(o.dU), f2_lo(o.dU)};
+  const float d[4] = {f2_lo(o.dL), f2_hi(o.dL), f2_hi(o.dU), f2_lo(o.dU)};       // boundaries 1..4: outer, inner, inner, outer
+  const float thr[4] = {f2_lo(o.thr), f2_hi(o.thr), f2_hi(o.thr), f2_lo(o.thr)};
   const int b[4] = {(int)(o.b1 - base), (int)(o.b2 - base), (int)(o.b3 - base), (int)(o.b4 - base)};
   int done[4], nd = 0, nfix = 0;
   for (int e = 0; e < 4; ++e) {
-    if (!run_neg(z[e])) continue;
+    if (!run_amb(d[e], thr[e])) continue;
     const int m = d[e] > 0.f ? b[e] - 1 : b[e];     // transition x = b - 0.5 - d: nearest integer is b - 1 for d > 0, else b
     bool seen = false;
     for (int q = 0; q < nd; ++q) seen = seen || (done[q] == m);

@@ -99,7 +99,8 @@ class FrameEvaluator:
         self.icp, self.icp_max_iter = bool(icp), int(icp_max_iter)
 
     def run(self, depth, radius, K, RT_gt_mm, max_radii=None, sem=None, mask_flags=api.MASK_LM_NPY, sem_threshold=0.8, depth_div=1.0,
-            scene_scale=1.0, centres_override=None, icp_rel_fitness=1e-6, icp_rel_rmse=1e-6, zero_empty_centres=False, **vote_kw):
+            scene_scale=1.0, centres_override=None, icp_rel_fitness=1e-6, icp_rel_rmse=1e-6, zero_empty_centres=False,
+            icp_threshold_mean=False, **vote_kw):
         """depth (B,H,W), radius (B,Kp,H,W) float32 [, sem (B,Kp,H,W) float32], K (3,3) or (B,3,3), RT_gt_mm (B,3,4) or (B,4,4)
         (translation in mm) -- NumPy or torch, host or device.  Returns a dict of HOST arrays: centre_mm (B,Kp,3), RT (B,4,4),
         dist_before (B,), RT_icp (B,4,4), dist_after (B,), passed_before / passed_after (B,) bool, status (B,Kp), n_points (B,Kp),
@@ -125,12 +126,13 @@ class FrameEvaluator:
         mean, mn = ctx.add_metric(self.cad_mm, RT, gt)
         before = mn if self.symmetric else mean
         res = dict(centre_mm=centres, RT=RT, dist_before=before, passed_before=before <= self.threshold_mm, status=out["status"],
-                   n_points=out["n_points"], peak=out["peak"], grid=out["grid"])
+                   n_points=out["n_points"], peak=out["peak"], grid=out["grid"], mean_before=mean)
         if self.icp:
             scene, offs, _ = ctx.scene_clouds(depth, radius, K, sem=sem, max_radii=max_radii, mask_flags=mask_flags, sem_threshold=sem_threshold,
                                               depth_div=depth_div, scale=scene_scale)
-            reg = ctx.icp(self.cad_mm, scene, offs, RT, before.contiguous(), max_iter=self.icp_max_iter, rel_fitness=icp_rel_fitness,
-                          rel_rmse=icp_rel_rmse)
+            # correspondence threshold: the ADD(-S) figure of the class (LM / LMO, :706-707, :929) or always the mean distance (YCB, :1151)
+            thr = (mean if icp_threshold_mean else before).contiguous()
+            reg = ctx.icp(self.cad_mm, scene, offs, RT, thr, max_iter=self.icp_max_iter, rel_fitness=icp_rel_fitness, rel_rmse=icp_rel_rmse)
             mean2, mn2 = ctx.add_metric(self.cad_mm, reg["RT"], gt)
             after = mn2 if self.symmetric else mean2
             res.update(RT_icp=reg["RT"], dist_after=after, passed_after=after <= self.threshold_mm, icp_fitness=reg["fitness"],
@@ -400,4 +402,173 @@ def estimate_6d_pose_lmo(opts):
         results[class_name] = evaluate_lmo_class(opts.root_dataset, class_name, using_ckpts=bool(getattr(opts, "using_ckpts", False)),
                                                  producer=getattr(opts, "producer", None), device=_default_device(opts),
                                                  frames_per_batch=getattr(opts, "frames_per_batch", 64))
+    return results
+
+
+# ------------------------------------------------------------------------------------------------
+# YCB-Video (AccumulatorSpace.py:976-1197)
+# ------------------------------------------------------------------------------------------------
+ycb_cls_names = {1: '002_master_chef_can', 2: '003_cracker_box', 3: '004_sugar_box', 4: '005_tomato_soup_can', 5: '006_mustard_bottle',
+                 6: '007_tuna_fish_can', 7: '008_pudding_box', 8: '009_gelatin_box', 9: '010_potted_meat_can', 10: '011_banana',
+                 11: '019_pitcher_base', 12: '021_bleach_cleanser', 13: '024_bowl', 14: '025_mug', 15: '035_power_drill',
+                 16: '036_wood_block', 17: '037_scissors', 18: '040_large_marker', 19: '051_large_clamp', 20: '052_extra_large_clamp',
+                 21: '061_foam_brick'}                                   # :21-41
+ycb_syms = ['024_bowl', '036_wood_block', '051_large_clamp', '052_extra_large_clamp', '061_foam_brick']   # :44
+ycb_auc_thresholds_m = [0, 0.02, 0.04, 0.06, 0.08, 0.1]                  # :978
+
+
+def obb_diagonal(points):
+    """Diagonal of the oriented bounding box open3d 0.14 builds from a point set (`get_oriented_bounding_box().extent`, :1118-1119):
+    axes = eigenvectors of the covariance of the points, extent = the points' range along each axis.  (Restated from open3d's
+    published algorithm -- open3d is not available here, so this figure is not pinned against it.)"""
+    p = np.asarray(points, dtype=np.float64)
+    c = p - p.mean(0)
+    _, vec = np.linalg.eigh(c.T @ c / len(p))
+    q = c @ vec
+    ext = q.max(0) - q.min(0)
+    return float(np.sqrt((ext ** 2).sum()))
+
+
+def trapezoid_auc(x, y):
+    """sklearn.metrics.auc(x, y) for increasing x (:1194-1195): the trapezoidal rule."""
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    return float(((x[1:] - x[:-1]) * (y[1:] + y[:-1]) / 2).sum())
+
+
+class YcbClass:
+    """One class of the layout estimate_6d_pose_ycb reads (:981-990, :1012-1016, :1044-1050):
+        <root>/Split/<cls>/val.txt                      frame names "<cycle>_<idx>"
+        <root>/models/<cls>/{points.xyz, Outside9.npy}  CAD points and keypoints, metres
+        <root>/<cls>.hdf5, group JPEGImages             the class's frames; only the key names are used by the reference (:1011-1012)
+        <root>/data/<cycle>/<idx>.mat                   poses (3,4,M) metres, cls_indexes, factor_depth, intrinsic_matrix (:1015)
+        <root>/data/<cycle>/<idx>-color.png, <idx>-depth.png
+    The frame list is `val.txt` intersected with the HDF5 keys when h5py is importable, otherwise with the frames whose files
+    exist under data/ (h5py is not installed in this image); both in sorted order, the order h5py iterates keys in.
+    `<idx>-meta.mat`, the name the YCB-Video distribution uses, is accepted as well."""
+
+    def __init__(self, root_dataset, class_id):
+        self.id, self.name = int(class_id), ycb_cls_names[int(class_id)]
+        self.root = root_dataset
+        self.cad_m = formats.read_xyz_points(root_dataset + "models/" + self.name + "/points.xyz")
+        self.keypoints_m = formats.load_keypoints(root_dataset + "models/" + self.name + "/Outside9.npy")
+        test = formats.read_split(root_dataset + "Split/" + self.name + "/val.txt")
+        keys = None
+        h5 = root_dataset + "/" + self.name + ".hdf5"
+        if os.path.isfile(h5):
+            try:
+                import h5py
+                with h5py.File(h5, "r") as f:
+                    keys = set(f["JPEGImages/"].keys())
+            except ImportError:
+                keys = None
+        self.stems = sorted(s for s in set(test) if s and (keys is None or s in keys) and os.path.isfile(self.meta_path(s)))
+
+    def _base(self, stem):
+        cycle, idx = stem.split("_")
+        return self.root + "data/" + cycle + "/" + idx
+
+    def meta_path(self, stem):
+        b = self._base(stem)
+        return b + ".mat" if os.path.isfile(b + ".mat") else b + "-meta.mat"
+
+    def image_path(self, stem):
+        return self._base(stem) + "-color.png"
+
+    def meta(self, stem):
+        return formats.load_ycb_meta(self.meta_path(stem))
+
+    def depth_raw(self, stem):
+        return np.asarray(formats.read_depth(self._base(stem) + "-depth.png"))
+
+
+def evaluate_ycb_class(root_dataset, class_id, producer, device=0, frames_per_batch=32, icp=True, verbose=True, horn_keypoints=(1, 4),
+                       max_grid=384):
+    """One class of estimate_6d_pose_ycb (AccumulatorSpace.py:976-1197) as the reference INTENDS it.  The function cannot run as
+    written; what is repaired here, and how:
+      * `keypoint_count` is read before it is assigned (:1003) and indexes a 3-element list with 1..3 (:1044) and a (3,3) array
+        with 1..3 (:1094): network k, keypoint k and row k - 1 belong together, as in the LINEMOD evaluator (:520-530, :654);
+      * `RTGT = poses[:, :, np.where(cls_indexes == class_id)]` (:1016) indexes with a tuple of arrays: the pose of the object
+        whose cls_index is class_id is meant (formats.pose_of);
+      * Horn is given `keypoints[0:3]` (:1115) against estimates of keypoints 1..3: `horn_keypoints` selects the model rows,
+        default (1, 4) = the keypoints that were voted for (pass (0, 3) for the literal rows);
+      * the summary lines sit outside the class loop (:1194-1197) and the AUC counters are never reset: here they are per class.
+    Kept as the reference has them: mask = sem > 0.8 only (:1049), depth / factor_depth in metres straight into
+    rgbd_to_point_cloud with the frame's own intrinsic matrix (:1050-1057), Accumulator_3D on metres and decimetres (:1067),
+    threshold = 1 % of the OBB diagonal (:1118-1119, :1141), ADD-S (minimum distance) for ycb_syms, ICP with
+    max_correspondence_distance = the MEAN distance for every class and max_iteration = 2000000 (:1151-1158), AUC over
+    [0, 0.1] m in steps of 0.02 divided by 0.1 (:1143-1150, :1194-1195).  Surviving pixel = sem > 0.8 and depth != 0 for both lists
+    (the reference's two lists mis-align when the mask covers a depth hole).
+    `producer(class_name, k, image_path) -> (sem, radial)` supplies the maps of keypoint k = 1..3 (decimetres)."""
+    cls = YcbClass(root_dataset, class_id)
+    sym = cls.name in ycb_syms
+    if producer is None:
+        raise ValueError("the YCB evaluator has only a checkpoint branch: it needs a producer(class_name, k, image_path) -> (sem, radial)")
+    thr_mm = obb_diagonal(cls.cad_m) * 0.01 * 1000
+    k0, k1 = horn_keypoints
+    ev, acc = None, {}
+    my_stems = shard_frames(cls.stems)
+    verbose = verbose and _world()[0] == 0
+    for b0 in range(0, len(my_stems), frames_per_batch):
+        stems = my_stems[b0:b0 + frames_per_batch]
+        metas = [cls.meta(s) for s in stems]
+        factor = metas[0]["factor_depth"]
+        if any(m["factor_depth"] != factor for m in metas):
+            raise ValueError("frames of one batch must share factor_depth (got %s)" % sorted({m["factor_depth"] for m in metas}))
+        depth = np.stack([cls.depth_raw(s) for s in stems])
+        H, W = depth.shape[1:]
+        radius = np.empty((len(stems), 3, H, W), np.float32)
+        sem = np.empty_like(radius)
+        gt = np.zeros((len(stems), 3, 4))
+        for i, s in enumerate(stems):
+            rt = formats.pose_of(metas[i], cls.id)
+            if rt is None:
+                raise ValueError("frame %s does not contain object %d (%s)" % (s, cls.id, cls.name))
+            gt[i] = rt
+            gt[i, :, 3] *= 1000
+            for k in range(1, 4):
+                sem[i, k - 1], radius[i, k - 1] = producer(cls.name, k, cls.image_path(s))
+        if ev is None:
+            ev = FrameEvaluator(cls.cad_m * 1000, cls.keypoints_m[k0:k1, :] * 1000, sym, thr_mm, device=device, frames_per_batch=frames_per_batch,
+                                image=(H, W), icp=icp, icp_max_iter=2000000, max_grid=max_grid)
+        Ks = np.stack([m["intrinsic_matrix"] for m in metas])
+        d = depth.view(np.int16) if depth.dtype == np.uint16 else depth.astype(np.float64)
+        res = ev.run(d, radius, Ks, gt, sem=sem, mask_flags=api.MASK_YCB, sem_threshold=0.8, depth_div=factor, xyz_div=1.0, scene_scale=1000.0,
+                     icp_threshold_mean=True)
+        st = res["status"]
+        if ((st & api.RCV_ST_EMPTY_MASK) != 0).any():
+            i, k = np.argwhere((st & api.RCV_ST_EMPTY_MASK) != 0)[0]
+            raise ValueError("zero-size array to reduction operation minimum which has no identity (frame %s, keypoint %d: empty mask)" % (stems[i], k + 1))
+        if st.any():
+            raise api.RcvError("voting failed with status %s" % np.unique(st))
+        for k, v in res.items():
+            acc.setdefault(k, []).append(v)
+    out = {k: np.concatenate(v) for k, v in acc.items()}
+    n = len(cls.stems)
+    thr = np.array(ycb_auc_thresholds_m) * 1000
+    counts = [out["passed_before"].sum() if acc else 0, out["passed_after"].sum() if (acc and icp) else 0]
+    counts += [(out["dist_before"] <= t).sum() if acc else 0 for t in thr]
+    counts += [(out["dist_after"] <= t).sum() if (acc and icp) else 0 for t in thr]
+    counts = reduce_counts(counts)
+    nan = float("nan")
+    out.update(frames=list(my_stems), n=n, threshold_mm=thr_mm, add_before=counts[0] / n if n else nan, add_after=(counts[1] / n if icp else nan) if n else nan,
+               auc_before=trapezoid_auc(ycb_auc_thresholds_m, np.array(counts[2:8]) / n) / 0.1 if n else nan,
+               auc_after=(trapezoid_auc(ycb_auc_thresholds_m, np.array(counts[8:14]) / n) / 0.1 if icp else nan) if n else nan)
+    if verbose:
+        print('ADD\\(s\\) AUC of ' + cls.name + ' before ICP: ', out["auc_before"])
+        print('ADD\\(s\\) AUC of ' + cls.name + ' after ICP: ', out["auc_after"])
+        print('ADD\\(s\\) of ' + cls.name + ' before ICP: ', out["add_before"])
+        print('ADD\\(s\\) of ' + cls.name + ' after ICP: ', out["add_after"])
+    return out
+
+
+def estimate_6d_pose_ycb(opts):
+    """Drop-in for AccumulatorSpace.estimate_6d_pose_ycb(opts) (:976-1197), repaired as evaluate_ycb_class documents:
+    opts.root_dataset, opts.producer [, opts.classes (ids), opts.device, opts.frames_per_batch, opts.horn_keypoints].
+    Returns {class_name: result dict}."""
+    results = {}
+    for class_id in getattr(opts, "classes", None) or list(ycb_cls_names):
+        print(ycb_cls_names[class_id])
+        results[ycb_cls_names[class_id]] = evaluate_ycb_class(opts.root_dataset, class_id, getattr(opts, "producer", None), device=_default_device(opts),
+                                                              frames_per_batch=getattr(opts, "frames_per_batch", 32),
+                                                              horn_keypoints=getattr(opts, "horn_keypoints", (1, 4)))
     return results

@@ -269,3 +269,90 @@ def torch_batch(n_frames, n_kpts=3, seed=0, device="cuda", K=linemod_K, chunk=12
             r = torch.where(out, mr[:, None, None] * torch.rand(d.shape, generator=g, device=dev, dtype=torch.float64), r)
             radius[f0:f1, k] = torch.where(hit, r, torch.zeros_like(r)).to(torch.float32)
     return dict(depth=depth, radius=radius, kpts_mm=kpts, centre_mm=centre, model_mm=model.contiguous())
+
+
+# ------------------------------------------------------------------------------------------------
+# YCB-Video-shaped class in the layout the reference's estimate_6d_pose_ycb reads (AccumulatorSpace.py:981-1057)
+# ------------------------------------------------------------------------------------------------
+def write_ycb_dataset(root, class_id, class_name, n_frames, seed=0, obj_radius_mm=55.0, n_cad=1200, cycle="0048", split_extra=1):
+    """<root>/Split/<cls>/val.txt ("<cycle>_<idx>" per line), models/<cls>/{points.xyz, Outside9.npy}, and per frame
+    data/<cycle>/<idx>.mat (the path the reference hands scipy.io.loadmat, :1015: poses (3,4,M) in metres, cls_indexes (M,1),
+    factor_depth, intrinsic_matrix), <idx>-depth.png (uint16, depth * factor_depth) and <idx>-color.png.  Every frame holds the
+    class's object (a sphere, like write_lm_dataset) and one more object of another class, so that the depth image is non-zero
+    off the object and cls_indexes has to be searched.  Returns the frame names listed in val.txt."""
+    import os
+    import scipy.io
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    md = root + "models/" + class_name + "/"
+    for d in (md, root + "Split/" + class_name, root + "data/" + cycle):
+        os.makedirs(d, exist_ok=True)
+    u = rng.normal(size=(n_cad, 3))
+    cad_m = u / np.linalg.norm(u, axis=1, keepdims=True) * (obj_radius_mm / 1000) * np.array([1.0, 0.8, 0.6])   # an ellipsoid cloud: the OBB is not a cube
+    np.savetxt(md + "points.xyz", cad_m, fmt="%.8f")
+    dirs = np.array([[0, 0, 0], [1.0, 0.2, 0.1], [-0.3, 1.0, 0.2], [0.2, -0.4, 1.0], [-1.0, -0.5, 0.3], [0.5, 0.5, -1.0], [1, 1, 1], [-1, 1, -1],
+                     [1, -1, -1]], dtype=np.float64)
+    dirs[1:] /= np.linalg.norm(dirs[1:], axis=1, keepdims=True)
+    kp_m = dirs * (obj_radius_mm / 1000) * 1.8
+    np.save(md + "Outside9.npy", kp_m)
+    names = []
+    other_id = 1 if class_id != 1 else 2
+    for f in range(n_frames + split_extra):
+        idx = "%06d" % (f * 5 + 1)
+        name = cycle + "_" + idx
+        rv = rng.normal(size=3); th = np.linalg.norm(rv); k = rv / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+        t_m = np.array([rng.uniform(-0.08, 0.02), rng.uniform(-0.06, 0.06), rng.uniform(0.85, 1.1)])
+        t2_m = t_m + np.array([0.2, 0.02, 0.05])                                     # the other object, to the right
+        Kf = ycb_K.copy()
+        Kf[0, 2] += f                                                                # intrinsics are per frame (:1057)
+        d1 = sphere_depth(Kf, t_m * 1000, obj_radius_mm).astype(np.float64)
+        d2 = sphere_depth(Kf, t2_m * 1000, 40.0).astype(np.float64)
+        depth_mm = np.where(d1 > 0, d1, d2)
+        factor = 10000.0
+        Image.fromarray(np.round(depth_mm * (factor / 1000)).astype(np.uint16)).save(root + "data/" + cycle + "/" + idx + "-depth.png")
+        Image.fromarray(np.zeros((H, W, 3), np.uint8)).save(root + "data/" + cycle + "/" + idx + "-color.png")
+        poses = np.stack([np.concatenate([np.eye(3), t2_m[:, None]], axis=1), np.concatenate([R, t_m[:, None]], axis=1)], axis=2)
+        scipy.io.savemat(root + "data/" + cycle + "/" + idx + ".mat",
+                         dict(poses=poses, cls_indexes=np.array([[other_id], [class_id]], dtype=np.uint8), factor_depth=np.array([[factor]]),
+                              intrinsic_matrix=Kf))
+        if f < n_frames:
+            names.append(name)
+    with open(root + "Split/" + class_name + "/val.txt", "w") as fh:
+        fh.write("".join(s + "\n" for s in names))
+    return names
+
+
+def write_ycb_ckpt_maps(root, class_id, class_name, names, seed=0):
+    """Stand-ins for the three keypoint networks' outputs on a class written by write_ycb_dataset: per (keypoint k = 1..3, frame) a
+    seg score map (0.95 on ~40 % of the object's pixels, 0.6 on the rest of it, 0.1 elsewhere -- including the OTHER object, where
+    depth is non-zero) and a radius map in decimetres with values everywhere.  <root>ckpt_maps/<cls>/pt<k>/<name>_sem.npy, _radial.npy."""
+    import os
+    import scipy.io
+    from PIL import Image
+    rng = np.random.default_rng(seed + 1)
+    kp_m = np.load(root + "models/" + class_name + "/Outside9.npy")
+    for name in names:
+        cycle, idx = name.split("_")
+        meta = scipy.io.loadmat(root + "data/" + cycle + "/" + idx + ".mat")
+        Kf = meta["intrinsic_matrix"]
+        j = int(np.nonzero(np.ravel(meta["cls_indexes"]) == class_id)[0][0])
+        RT = meta["poses"][:, :, j]
+        depth_m = np.array(Image.open(root + "data/" + cycle + "/" + idx + "-depth.png")).astype(np.float64) / float(meta["factor_depth"][0, 0])
+        obj = sphere_depth(Kf, RT[:, 3] * 1000, 1.0e-3 + float(np.linalg.norm(np.load(root + "models/" + class_name + "/Outside9.npy")[1]) / 1.8 * 1000)) > 0
+        obj &= depth_m > 0
+        for k in (1, 2, 3):
+            d = root + "ckpt_maps/" + class_name + "/pt" + str(k) + "/"
+            os.makedirs(d, exist_ok=True)
+            kpt_mm = (RT[:, :3] @ kp_m[k] + RT[:, 3]) * 1000
+            est = radius_map_dm(Kf, np.where(obj, depth_m * 1000, 0.0), kpt_mm, rng, 0.01, 0.02, None)
+            sem = np.where(obj, np.where(rng.random(obj.shape) < 0.4, 0.95, 0.6), 0.1).astype(np.float32)
+            radial = np.where(obj, est, rng.uniform(0.0, 3.0, size=obj.shape)).astype(np.float32)
+            np.save(d + name + "_sem.npy", sem)
+            np.save(d + name + "_radial.npy", radial)
+
+
+def load_ycb_ckpt_maps(root, class_name, k, name):
+    d = root + "ckpt_maps/" + class_name + "/pt" + str(k) + "/"
+    return np.load(d + name + "_sem.npy"), np.load(d + name + "_radial.npy")

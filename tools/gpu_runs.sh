@@ -4,7 +4,7 @@ TAG=${1:-r02b}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest.txt
 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu 2> gpurun_out/${TAG}_bench.err | tee gpurun_out/${TAG}_bench.json
-for v in t1024 t768; do
+for v in t768; do
   if [ -f build/librcvvote_$v.so ]; then RCV_LIB_PATH=$PWD/build/librcvvote_$v.so timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e 2>/dev/null | sed "s/^{/{\"variant\": \"$v\", /" | tee -a gpurun_out/${TAG}_bench_variants.json; fi
 done
 RCV_VOTE_GEN=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e 2>/dev/null | sed "s/^{/{\"variant\": \"gen1\", /" | tee -a gpurun_out/${TAG}_bench_variants.json
