@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RCV_ABI_VERSION 1
+#define RCV_ABI_VERSION 2
 
 /* call status */
 #define RCV_OK 0
@@ -67,6 +67,11 @@ typedef struct rcv_config {
   long long max_points_total;  /* pool for compacted points summed over the items of one call */
   int max_grid;                /* largest accumulator side D accepted */
   int max_units;               /* tile work-list capacity (0 = derive from max_items/max_grid) */
+  /* Scratch that depends on sizes only a call knows.  Given here, rcv_create allocates it and no entry point allocates on the
+   * hot call; left 0, the first call of a (larger) size allocates it after a stream synchronisation. */
+  long long image_pixels;      /* H*W of the frames entry points: survival-bit scratch for max_items items (0 = on first use) */
+  int max_model_points;        /* CAD points of rcv_add_metric_batch / rcv_icp_batch, for up to max_items frames (0 = on first use) */
+  int head_items;              /* items whose radius planes rcv_head_vote_frames keeps in the context (0 = on first use) */
 } rcv_config;
 
 /* Parameters of Accumulator_3D that the reference hard-codes (AccumulatorSpace.py:374,388). */
@@ -126,7 +131,9 @@ int rcv_vote_frames(rcv_ctx* ctx, int n_frames, int n_kpts, const void* depth, c
 
 /* Same, HOST buffers in and out: copies inputs host->device and results device->host on `stream`,
  * in chunks that overlap transfer with voting, and synchronises before returning.  For full
- * bandwidth the host buffers should be page-locked (cudaHostAlloc / torch pin_memory). */
+ * bandwidth the host buffers should be page-locked (cudaHostAlloc / torch pin_memory).
+ * Only the rows between the first and the last non-zero depth row of each frame are copied (every mask rule needs
+ * depth != 0, so the rest cannot contribute; results are bit-identical); rcv_last_h2d_bytes() reports what was moved. */
 int rcv_vote_frames_host(rcv_ctx* ctx, int n_frames, int n_kpts, const void* depth, const float* radius, const float* sem,
                          const double* K, const double* max_radii, const rcv_frame_params* fp, const rcv_vote_params* vp,
                          double* centre_mm, int* peak, long long* votes, int* n_points, int* grid, int* status,
@@ -207,6 +214,8 @@ int rcv_head_vote_frames(rcv_ctx* ctx, int n_frames, int n_kpts, const void* up_
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (the bench's gpu_launches claim). */
 long long rcv_launch_count(const rcv_ctx* ctx);
+/* bytes the last rcv_vote_frames_host call copied host -> device (images are cropped to their non-zero depth rows) */
+long long rcv_last_h2d_bytes(const rcv_ctx* ctx);
 /* Device time of the vote kernel in the most recent rcv_vote_* call, in ms (CUDA events on `stream`);
  * blocks until that call has finished.  Returns a negative value if no call was made. */
 float rcv_last_vote_kernel_ms(rcv_ctx* ctx);

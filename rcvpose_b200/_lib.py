@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RCV_LIB_PATH", os.path.join(HERE, "librcvvote.so"))   # override: kernel-variant experiments only
 
-RCV_ABI_VERSION = 1
+RCV_ABI_VERSION = 2
 RCV_OK = 0
 RCV_F32, RCV_F64, RCV_U16 = 0, 1, 2
 RCV_POLICY_LM, RCV_POLICY_YCBGEN = 0, 1
@@ -15,13 +15,13 @@ RCV_ST_OK, RCV_ST_EMPTY_MASK, RCV_ST_BAD_GRID, RCV_ST_D_EXCEEDS_CAP, RCV_ST_POIN
 RCV_ST_VOLUME_SKIPPED = 32
 
 EXPORTS = ["rcv_create", "rcv_destroy", "rcv_last_error", "rcv_abi_version", "rcv_backproject", "rcv_vote_points", "rcv_vote_frames",
-           "rcv_vote_frames_host", "rcv_argmax_volume", "rcv_head_1x1", "rcv_horn_batch", "rcv_horn_batch_host", "rcv_launch_count",
+           "rcv_vote_frames_host", "rcv_argmax_volume", "rcv_head_1x1", "rcv_horn_batch", "rcv_horn_batch_host", "rcv_launch_count", "rcv_last_h2d_bytes",
            "rcv_last_vote_kernel_ms", "rcv_vote_kernel_times", "rcv_ubench_smem_atomics", "rcv_add_metric_batch", "rcv_scene_clouds", "rcv_icp_batch", "rcv_head_vote_frames"]
 
 
 class rcv_config(C.Structure):
     _fields_ = [("abi_version", C.c_int), ("max_items", C.c_int), ("max_points_total", C.c_longlong), ("max_grid", C.c_int),
-                ("max_units", C.c_int)]
+                ("max_units", C.c_int), ("image_pixels", C.c_longlong), ("max_model_points", C.c_int), ("head_items", C.c_int)]
 
 
 class rcv_vote_params(C.Structure):
@@ -89,6 +89,8 @@ def load():
                                        vp, ip, llp, ip, ip, ip, vp, vp]
     L.rcv_launch_count.restype = C.c_longlong
     L.rcv_launch_count.argtypes = [vp]
+    L.rcv_last_h2d_bytes.restype = C.c_longlong
+    L.rcv_last_h2d_bytes.argtypes = [vp]
     L.rcv_last_vote_kernel_ms.restype = C.c_float
     L.rcv_last_vote_kernel_ms.argtypes = [vp]
     L.rcv_vote_kernel_times.restype = C.c_int

@@ -49,12 +49,16 @@ class VoteContext:
     """One context per (device, stream); not re-entrant.  Capacities are fixed here (no allocation
     on the hot calls)."""
 
-    def __init__(self, device=0, max_items=64, max_points_total=1 << 22, max_grid=256, max_units=0):
+    def __init__(self, device=0, max_items=64, max_points_total=1 << 22, max_grid=256, max_units=0, image=None, max_model_points=0,
+                 head_items=0):
         if not torch.cuda.is_available():
             raise RcvError("no CUDA device: rcvpose_b200 has no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device("cuda", device if isinstance(device, int) else device.index or 0)
-        cfg = _lib.rcv_config(_lib.RCV_ABI_VERSION, int(max_items), int(max_points_total), int(max_grid), int(max_units))
+        # image = (H, W) of the frames entry points, max_model_points = CAD size of the ADD / ICP entry points, head_items = items of
+        # the fused head: given here, their scratch is allocated now and never on a hot call
+        cfg = _lib.rcv_config(_lib.RCV_ABI_VERSION, int(max_items), int(max_points_total), int(max_grid), int(max_units),
+                              int(image[0]) * int(image[1]) if image else 0, int(max_model_points), int(head_items))
         h = C.c_void_p()
         rc = self.lib.rcv_create(self.device.index, C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -80,6 +84,11 @@ class VoteContext:
     @property
     def launches(self):
         return int(self.lib.rcv_launch_count(self.h))
+
+    @property
+    def last_h2d_bytes(self):
+        """Bytes the last vote_frames_host call moved host -> device (after cropping the images to their non-zero depth rows)."""
+        return int(self.lib.rcv_last_h2d_bytes(self.h))
 
     def last_vote_kernel_ms(self):
         return float(self.lib.rcv_last_vote_kernel_ms(self.h))

@@ -521,13 +521,22 @@ __device__ double pw_leaf_sum(const double* __restrict__ a, int n) {
 }
 
 struct PreludeArgs {
-  Pool pool; ItemMeta* meta; Unit* units; int* counters; int max_units; int max_grid; int policy; int tile_words; int gen;
+  Pool pool; ItemMeta* meta; Unit* units; int* counters; int max_units; int max_grid; int policy; int tile_words; int gen; int dp_mod;
   PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
 };
 
 constexpr int kPreludeThreads = 256;
 constexpr int kMaxGuard = 8;     // guard cells per side of a whole-slice tile; beyond that the item uses the clipped passes
 constexpr int kSortBins = 8192;   // bins of the (y voxel, R) counting sort that orders an item's points for k_vote
+
+// Row stride of a tile: odd, so that consecutive rows start in different banks; dp_mod >= 0 (experiments) asks for a given
+// residue modulo 32.
+__device__ __forceinline__ int row_stride(int need, int dp_mod) {
+  if (dp_mod < 0) return need | 1;
+  int dp = need;
+  while ((dp & 31) != (dp_mod & 31)) ++dp;
+  return dp;
+}
 
 __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
   const int item = blockIdx.x;
@@ -636,9 +645,9 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
       // upper guard: the -1 that closes a run ending at the last cell lands there.
       // gen 2 also keeps TWO planes per slice (run starts, run ends: only `add 1` merges lanes that hit the same address).
       const int spare = a.gen >= 2 ? 1 : 0, planes = a.gen >= 2 ? 2 : 1;
-      int Dp = (D + glo + ghi + spare) | 1;
+      int Dp = row_stride(D + glo + ghi + spare, a.dp_mod);
       long long slice = (long long)planes * (D + glo + ghi) * Dp;
-      if (slice > a.tile_words) { glo = 0; ghi = 0; Dp = (D + spare) | 1; slice = (long long)planes * D * Dp; }   // row-band tiles are not guarded
+      if (slice > a.tile_words) { glo = 0; ghi = 0; Dp = row_stride(D + spare, a.dp_mod); slice = (long long)planes * D * Dp; }   // row-band tiles are not guarded
       m.Dp = Dp;
       m.guard = glo | (ghi << 16);
       m.clip = (slice > a.tile_words || ((need_lo > 0.0 || need_hi > 0.0) && glo == 0 && ghi == 0)) ? 1 : 0;
@@ -1448,8 +1457,30 @@ __device__ __forceinline__ void runs_push(const RunTile& rt, unsigned long long*
   }
 }
 
+// One column of the chunk for this lane: the four marks per slice; returns 1 if a boundary of the column is flagged.
+template <int NC, bool CLIP>
+__device__ __forceinline__ unsigned runs_one_column(const RunLane& L, const RunCol& C, const f2 (&aa)[NC], const unsigned (&K)[NC], const unsigned (&KE)[NC],
+                                                    int lo, int hi) {
+  unsigned amb = 0u;
+#pragma unroll
+  for (int s = 0; s < NC; ++s) {
+    RunOut o;
+    run_slice(L, C, aa[s], o);
+    int b1 = (int)o.b1, b2 = (int)o.b2, b3 = (int)o.b3, b4 = (int)o.b4;
+    if (CLIP) { b1 = min(max(b1, lo), hi); b2 = min(max(b2, lo), hi); b3 = min(max(b3, lo), hi); b4 = min(max(b4, lo), hi); }
+    smem_inc((unsigned)b1 * 4u + K[s]);
+    smem_inc((unsigned)b2 * 4u + KE[s]);
+    smem_inc((unsigned)b3 * 4u + K[s]);
+    smem_inc((unsigned)b4 * 4u + KE[s]);
+    run_flag_acc(amb, o);
+  }
+  return amb;
+}
+
 // A stretch [ua, ub] of columns of one chunk of NC slices, 32 lanes = 32 points.  PARK: some lane's own column range
 // [ulo, uhi] does not cover the stretch; beyond its range a lane parks on its edge row and the column is empty.
+// Without PARK (every lane draws every column of the stretch) columns go two at a time when NC <= 2: twice the
+// independent dependency chains per warp and half the loop overhead.
 //   K0 = shared-window address constant of the chunk's first slice for this lane (run_K0): the cell of boundary bits b
 //        (= MAGIC_BITS + uc * Dp + lattice offset) is  b * 4 + K0 + s * slice_bytes.
 template <int NC, bool CLIP, bool PARK>
@@ -1459,14 +1490,29 @@ __device__ __forceinline__ void runs_columns(const RunPoint& c, const RunLane& L
   const Tile& t = rt.t;
   const int clo = -t.glo - c.ipc, chi = t.D + t.ghi - c.ipc;   // clip bounds of the boundary bits relative to `base` (CLIP)
   const float Dpf = (float)t.Dp;
+  constexpr bool PAIRS = !PARK && !CLIP && NC <= 2;
 #pragma unroll 1
   for (int u0 = ua; u0 <= ub; u0 += 32) {
     unsigned flags = 0;
     const int ue = min(u0 + 31, ub);
     float uf = (float)u0;
     unsigned bit = 1u;
+    int u = u0;
+    if (PAIRS) {
 #pragma unroll 1
-    for (int u = u0; u <= ue; ++u, uf += 1.0f, bit <<= 1) {
+      for (; u < ue; u += 2, uf += 2.0f, bit <<= 2) {
+        RunCol C0, C1;
+        const float du0 = f_sub(uf, c.fb), uf1 = f_add(uf, 1.0f), du1 = f_sub(uf1, c.fb);
+        C0.mu = f2_dup(f_fma(uf, Dpf, RCV_MAGIC)); C0.du = f2_dup(du0); C0.ndu = f2_dup(-du0);
+        C1.mu = f2_dup(f_fma(uf1, Dpf, RCV_MAGIC)); C1.du = f2_dup(du1); C1.ndu = f2_dup(-du1);
+        const unsigned a0 = runs_one_column<NC, false>(L, C0, aa, K, KE, 0, 0);
+        const unsigned a1 = runs_one_column<NC, false>(L, C1, aa, K, KE, 0, 0);
+        if (a0) flags |= bit;
+        if (a1) flags |= bit << 1;
+      }
+    }
+#pragma unroll 1
+    for (; u <= ue; ++u, uf += 1.0f, bit <<= 1) {
       float du = f_sub(uf, c.fb);
       RunCol C;
       int uc = u;
@@ -1478,23 +1524,8 @@ __device__ __forceinline__ void runs_columns(const RunPoint& c, const RunLane& L
         C.mu = f2_dup(f_fma(uf, Dpf, RCV_MAGIC));
       }
       C.du = f2_dup(du); C.ndu = f2_dup(-du);
-      unsigned amb = 0u;
-#pragma unroll
-      for (int s = 0; s < NC; ++s) {
-        RunOut o;
-        run_slice(L, C, aa[s], o);
-        int b1 = (int)o.b1, b2 = (int)o.b2, b3 = (int)o.b3, b4 = (int)o.b4;
-        if (CLIP) {
-          const int base = RCV_MAGIC_BITS + uc * t.Dp, lo = base + clo, hi = base + chi;
-          b1 = min(max(b1, lo), hi); b2 = min(max(b2, lo), hi); b3 = min(max(b3, lo), hi); b4 = min(max(b4, lo), hi);
-        }
-        smem_inc((unsigned)b1 * 4u + K[s]);
-        smem_inc((unsigned)b2 * 4u + KE[s]);
-        smem_inc((unsigned)b3 * 4u + K[s]);
-        smem_inc((unsigned)b4 * 4u + KE[s]);
-        run_flag_acc(amb, o);
-      }
-      if (amb) flags |= bit;
+      const int base = RCV_MAGIC_BITS + uc * t.Dp;
+      if (runs_one_column<NC, CLIP>(L, C, aa, K, KE, base + clo, base + chi)) flags |= bit;
     }
     if (__any_sync(0xffffffffu, flags != 0u)) {
       runs_push(rt, q, qn, flags, pidx, u0, i0c, nsl);            // (a flagged column is never a parked one)
@@ -1861,6 +1892,7 @@ __global__ void __launch_bounds__(1024, 1) k_ubench_atoms(int iters, unsigned* o
 // ================================================================================================
 struct rcv_ctx {
   int device, sms;
+  int dp_mod;   // experiments: residue of the tile row stride modulo 32 (RCV_DP_MOD), -1 = any odd stride
   int gen;   // vote kernel generation: 2 = run-length difference arrays (k_vote_runs), 1 = per-candidate rasteriser (k_vote, RCV_VOTE_GEN=1)
   rcv_config cfg;
   Pool pool;
@@ -1875,9 +1907,11 @@ struct rcv_ctx {
   unsigned long long *best, *votes;
   PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
   cudaEvent_t evr[64][2]; long long ev_count;   // ring of (start, stop) events around the vote kernel
+  cudaEvent_t ev_ubench[2];                     // rcv_ubench_smem_atomics
   long long launches;
   // staging for the _host entry points
-  cudaStream_t s_in, s_run; cudaEvent_t ev_in[2], ev_done[2], ev_user;
+  cudaStream_t s_in, s_in2, s_run; cudaEvent_t ev_in[2], ev_in2[2], ev_done[2], ev_user;
+  long long h2d_bytes;   // bytes the last rcv_vote_frames_host call copied to the device (after row-range cropping)
   void* st_depth[2]; float* st_radius[2]; float* st_sem[2]; double* st_K; double* st_maxr;
   double* st_centre; int* st_peak; long long* st_votes; int* st_np; int* st_grid; int* st_status;
   long long st_frames, st_kpts, st_px, st_depth_bytes; int st_has_sem; long long st_total_items;
@@ -1886,6 +1920,7 @@ struct rcv_ctx {
 };
 
 static char g_create_err[512] = "";
+extern "C" long long rcv_icp_scratch_doubles(int n_frames, int n_model);   // refine.cu
 
 #define CK(ctx, call)                                                                                         \
   do {                                                                                                        \
@@ -1908,6 +1943,8 @@ RCV_EXPORT const char* rcv_last_error(const rcv_ctx* ctx) { return ctx ? ctx->er
 
 RCV_EXPORT long long rcv_launch_count(const rcv_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+RCV_EXPORT long long rcv_last_h2d_bytes(const rcv_ctx* ctx) { return ctx ? ctx->h2d_bytes : 0; }
+
 RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -1919,8 +1956,11 @@ RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
   cudaFree(c->st_np); cudaFree(c->st_grid); cudaFree(c->st_status); cudaFree(c->st_horn_in);
   for (int e = 0; e < 64; ++e) { if (c->evr[e][0]) cudaEventDestroy(c->evr[e][0]); if (c->evr[e][1]) cudaEventDestroy(c->evr[e][1]); }
   if (c->ev_user) cudaEventDestroy(c->ev_user);
+  for (int q = 0; q < 2; ++q) if (c->ev_ubench[q]) cudaEventDestroy(c->ev_ubench[q]);
   for (int s = 0; s < 2; ++s) { if (c->ev_in[s]) cudaEventDestroy(c->ev_in[s]); if (c->ev_done[s]) cudaEventDestroy(c->ev_done[s]); }
   if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_in2) cudaStreamDestroy(c->s_in2);
+  for (int q = 0; q < 2; ++q) if (c->ev_in2[q]) cudaEventDestroy(c->ev_in2[q]);
   if (c->s_run) cudaStreamDestroy(c->s_run);
   free(c);
 }
@@ -1946,6 +1986,7 @@ RCV_EXPORT int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out) {
   if (!c) return RCV_E_INVALID;
   c->device = device; c->cfg = *cfg; c->sms = prop.multiProcessorCount;
   { const char* g = getenv("RCV_VOTE_GEN"); c->gen = (g && atoi(g) == 1) ? 1 : 2; }
+  { const char* g = getenv("RCV_DP_MOD"); c->dp_mod = g ? atoi(g) : -1; }
   if (c->cfg.max_units <= 0) {
     // worst case per item: D slices x ceil(D / rows-per-tile) tiles
     const long long per_item = (long long)cfg->max_grid * ((cfg->max_grid * (long long)(cfg->max_grid | 1)) / kTileWords + 1);
@@ -1969,6 +2010,22 @@ RCV_EXPORT int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out) {
   c->leaf_cap = cap / 56 + 2LL * cfg->max_items + 8;
   CKC(cudaMalloc(&c->leaves, sizeof(PwLeaf) * (size_t)c->leaf_cap)); CKC(cudaMalloc(&c->leaf_sums, 24 * (size_t)c->leaf_cap));
   for (int e = 0; e < 64; ++e) { CKC(cudaEventCreate(&c->evr[e][0])); CKC(cudaEventCreate(&c->evr[e][1])); }
+  CKC(cudaEventCreate(&c->ev_ubench[0])); CKC(cudaEventCreate(&c->ev_ubench[1]));
+  // scratch whose size depends on the image / model: allocated here when the configuration names the sizes (no allocation on a hot call)
+  if (cfg->image_pixels > 0) {
+    c->mask_words = (long long)cfg->max_items * ((cfg->image_pixels + 255) / 256) * 8;
+    CKC(cudaMalloc(&c->mask_bits, (size_t)c->mask_words * 4));
+    if (cfg->head_items > 0) {
+      c->head_radius_cap = (long long)cfg->head_items * cfg->image_pixels;
+      CKC(cudaMalloc(&c->head_radius, (size_t)c->head_radius_cap * 4));
+    }
+  }
+  if (cfg->max_model_points > 0) {
+    c->add_part_cap = 2LL * cfg->max_items * ((cfg->max_model_points + kAddThreads - 1) / kAddThreads);
+    CKC(cudaMalloc(&c->add_part, (size_t)c->add_part_cap * 8));
+    c->icp_cap = rcv_icp_scratch_doubles(cfg->max_items, cfg->max_model_points);
+    CKC(cudaMalloc(&c->icp_scratch, (size_t)c->icp_cap * 8));
+  }
   CKC(cudaFuncSetAttribute(k_ubench_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
   CKC(cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (kTileWords + kDummyWords) * 4));
   CKC(cudaFuncSetAttribute(k_vote_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, kRunsTileWords * 4));
@@ -1983,7 +2040,7 @@ static int run_items(rcv_ctx* c, int n_items, const rcv_vote_params* vp, double*
   CK(c, cudaMemsetAsync(c->best, 0, 8 * (size_t)n_items, st));
   CK(c, cudaMemsetAsync(c->votes, 0, 8 * (size_t)n_items, st));
   PreludeArgs pa{c->pool, c->meta, c->units, c->counters, c->cfg.max_units, c->cfg.max_grid, vp->grid_policy,
-                 c->gen >= 2 ? kRunsTileWords : kTileWords, c->gen, c->leaves, c->leaf_sums, c->leaf_cap};
+                 c->gen >= 2 ? kRunsTileWords : kTileWords, c->gen, c->dp_mod, c->leaves, c->leaf_sums, c->leaf_cap};
   k_prelude<<<n_items, kPreludeThreads, 0, st>>>(pa);
   VoteArgs va{c->pool, c->meta, c->units, c->counters, c->best, c->votes, volume, volume_cap};
   const int slot = (int)(c->ev_count % 64);
@@ -2053,7 +2110,7 @@ RCV_EXPORT int rcv_vote_frames(rcv_ctx* c, int n_frames, int n_kpts, const void*
   FrameArgs fa{depth, radius, sem, K, max_radii, *fp, vp->acc_unit, vp->radius_scale, n_kpts, vec_ok};
   const int words = (int)((npx + 255) / 256) * 8;   // whole warp-steps of 256 pixels
   const long long need = (long long)n_items * words;
-  if (need > c->mask_words) {   // first call of this size only: the mask scratch depends on the image size, which rcv_create does not know
+  if (need > c->mask_words) {   // only when rcv_config.image_pixels was left 0 or is exceeded: first call of this size
     CK(c, cudaStreamSynchronize(st));
     cudaFree(c->mask_bits); c->mask_bits = nullptr; c->mask_words = 0;
     CK(c, cudaMalloc(&c->mask_bits, (size_t)need * 4));
@@ -2065,6 +2122,23 @@ RCV_EXPORT int rcv_vote_frames(rcv_ctx* c, int n_frames, int n_kpts, const void*
   k_points_from_pixels<<<dim3(n_items, 4), 256, 0, st>>>(fa, c->meta, c->pool);
   c->launches += 4;
   return run_items(c, n_items, vp, centre_mm, peak, votes, n_points, grid, nullptr, status, nullptr, 0, st);
+}
+
+// true iff the `n` bytes at p are all zero (a depth row: u16 / f32 / f64 zeros are all-zero bytes; -0.0 counts as non-zero,
+// which only costs the copy of that row)
+static bool row_is_zero(const char* p, long long n) {
+  long long i = 0;
+  for (; i < n && ((uintptr_t)(p + i) & 7); ++i) if (p[i]) return false;
+  const unsigned long long* w = (const unsigned long long*)(p + i);
+  const long long nw = (n - i) / 8;
+  unsigned long long acc = 0;
+  for (long long q = 0; q < nw; q += 16) {            // a cache line or two at a time, early exit
+    const long long e = q + 16 < nw ? q + 16 : nw;
+    for (long long j = q; j < e; ++j) acc |= w[j];
+    if (acc) return false;
+  }
+  for (i += nw * 8; i < n; ++i) if (p[i]) return false;
+  return true;
 }
 
 static int ensure_staging(rcv_ctx* c, int frames, int kpts, long long px, long long depth_bytes, int has_sem, long long total_items) {
@@ -2088,6 +2162,8 @@ static int ensure_staging(rcv_ctx* c, int frames, int kpts, long long px, long l
   CK(c, cudaMalloc(&c->st_grid, (size_t)total_items * 4)); CK(c, cudaMalloc(&c->st_status, (size_t)total_items * 4));
   if (!c->s_in) {
     CK(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)); CK(c, cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking));
+    CK(c, cudaStreamCreateWithFlags(&c->s_in2, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q) CK(c, cudaEventCreateWithFlags(&c->ev_in2[q], cudaEventDisableTiming));
     for (int s = 0; s < 2; ++s) { CK(c, cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming)); CK(c, cudaEventCreateWithFlags(&c->ev_done[s], cudaEventDisableTiming)); }
     CK(c, cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
   }
@@ -2117,20 +2193,43 @@ RCV_EXPORT int rcv_vote_frames_host(rcv_ctx* c, int n_frames, int n_kpts, const 
   cudaStream_t user = (cudaStream_t)stream;
   CK(c, cudaEventRecord(c->ev_user, user));
   CK(c, cudaStreamWaitEvent(c->s_in, c->ev_user, 0));
+  CK(c, cudaStreamWaitEvent(c->s_in2, c->ev_user, 0));
   CK(c, cudaStreamWaitEvent(c->s_run, c->ev_user, 0));
   const long long nK = fp->k_stride ? n_frames : 1, nM = fp->max_radii_stride ? n_frames : 1;
+  c->h2d_bytes = (nK * 9 + (max_radii ? nM * n_kpts : 0)) * 8;
   CK(c, cudaMemcpyAsync(c->st_K, K, (size_t)(nK * 9 * 8), cudaMemcpyHostToDevice, c->s_in));
   if (max_radii) CK(c, cudaMemcpyAsync(c->st_maxr, max_radii, (size_t)(nM * n_kpts * 8), cudaMemcpyHostToDevice, c->s_in));
   int chunk = 0;
   for (int f0 = 0; f0 < n_frames; f0 += frames_per_chunk, ++chunk) {
     const int nf = n_frames - f0 < frames_per_chunk ? n_frames - f0 : frames_per_chunk;
     const int s = chunk & 1;
-    if (chunk >= 2) CK(c, cudaStreamWaitEvent(c->s_in, c->ev_done[s], 0));  // slot reuse: previous occupant finished voting
-    CK(c, cudaMemcpyAsync(c->st_depth[s], (const char*)depth + (size_t)(f0 * px * dbytes), (size_t)(nf * px * dbytes), cudaMemcpyHostToDevice, c->s_in));
-    CK(c, cudaMemcpyAsync(c->st_radius[s], radius + (size_t)f0 * n_kpts * px, (size_t)(nf * n_kpts * px * 4), cudaMemcpyHostToDevice, c->s_in));
-    if (sem) CK(c, cudaMemcpyAsync(c->st_sem[s], sem + (size_t)f0 * n_kpts * px, (size_t)(nf * n_kpts * px * 4), cudaMemcpyHostToDevice, c->s_in));
+    if (chunk >= 2) { CK(c, cudaStreamWaitEvent(c->s_in, c->ev_done[s], 0)); CK(c, cudaStreamWaitEvent(c->s_in2, c->ev_done[s], 0)); }  // slot reuse: previous occupant finished voting
+    // Row-range cropping.  Every mask rule keeps a pixel only where depth != 0, so the rows above the first and
+    // below the last non-zero depth row of a frame cannot contribute: only rows [r0, r1) of the depth image and of each radius /
+    // seg plane cross the bus; the depth slot is cleared first, and whatever the other planes still hold outside the range sits
+    // under zero depth.  Results are bit-identical to copying whole images; a dense depth image costs one row of scanning.
+    CK(c, cudaMemsetAsync(c->st_depth[s], 0, (size_t)(nf * px * dbytes), c->s_in));
+    const long long row_b = (long long)fp->width * dbytes;
+    for (int f = 0; f < nf; ++f) {
+      const char* dsrc = (const char*)depth + (size_t)((f0 + f) * px * dbytes);
+      int r0 = 0, r1 = fp->height;
+      while (r0 < r1 && row_is_zero(dsrc + (size_t)r0 * row_b, row_b)) ++r0;
+      while (r1 > r0 && row_is_zero(dsrc + (size_t)(r1 - 1) * row_b, row_b)) --r1;
+      if (r1 <= r0) continue;
+      const long long p0 = (long long)r0 * fp->width, np = (long long)(r1 - r0) * fp->width;
+      CK(c, cudaMemcpyAsync((char*)c->st_depth[s] + (size_t)((f * px + p0) * dbytes), dsrc + (size_t)(p0 * dbytes), (size_t)(np * dbytes), cudaMemcpyHostToDevice, c->s_in));
+      c->h2d_bytes += np * dbytes;
+      for (int k = 0; k < n_kpts; ++k) {
+        const long long plane = ((long long)f * n_kpts + k) * px + p0, src = ((long long)(f0 + f) * n_kpts + k) * px + p0;
+        CK(c, cudaMemcpyAsync(c->st_radius[s] + plane, radius + src, (size_t)(np * 4), cudaMemcpyHostToDevice, c->s_in2));
+        if (sem) CK(c, cudaMemcpyAsync(c->st_sem[s] + plane, sem + src, (size_t)(np * 4), cudaMemcpyHostToDevice, c->s_in2));
+        c->h2d_bytes += np * 4 * (sem ? 2 : 1);
+      }
+    }
     CK(c, cudaEventRecord(c->ev_in[s], c->s_in));
+    CK(c, cudaEventRecord(c->ev_in2[s], c->s_in2));
     CK(c, cudaStreamWaitEvent(c->s_run, c->ev_in[s], 0));
+    CK(c, cudaStreamWaitEvent(c->s_run, c->ev_in2[s], 0));
     const long long i0 = (long long)f0 * n_kpts;
     rc = rcv_vote_frames(c, nf, n_kpts, c->st_depth[s], c->st_radius[s], sem ? c->st_sem[s] : nullptr,
                          c->st_K + (fp->k_stride ? (long long)f0 * fp->k_stride : 0),
@@ -2146,6 +2245,7 @@ RCV_EXPORT int rcv_vote_frames_host(rcv_ctx* c, int n_frames, int n_kpts, const 
   if (n_points) CK(c, cudaMemcpyAsync(n_points, c->st_np, (size_t)total_items * 4, cudaMemcpyDeviceToHost, c->s_run));
   if (grid) CK(c, cudaMemcpyAsync(grid, c->st_grid, (size_t)total_items * 4, cudaMemcpyDeviceToHost, c->s_run));
   CK(c, cudaStreamSynchronize(c->s_in));
+  CK(c, cudaStreamSynchronize(c->s_in2));
   CK(c, cudaStreamSynchronize(c->s_run));
   return RCV_OK;
 }
@@ -2380,7 +2480,7 @@ RCV_EXPORT int rcv_ubench_smem_atomics(rcv_ctx* c, double* atomics_per_second) {
   CK(c, cudaSetDevice(c->device));
   unsigned* out = reinterpret_cast<unsigned*>(c->counters + 8);
   const int iters = 4096;
-  cudaEvent_t a = c->evr[63][0], b = c->evr[63][1];
+  cudaEvent_t a = c->ev_ubench[0], b = c->ev_ubench[1];   // its own pair: the ring evr[] belongs to the vote kernel's timings
   float best = 1e30f;
   for (int r = 0; r < 7; ++r) {
     CK(c, cudaEventRecord(a, 0));

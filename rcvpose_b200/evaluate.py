@@ -92,7 +92,8 @@ class FrameEvaluator:
                  icp=True, icp_max_iter=30):
         self.dev = torch.device("cuda", device)
         self.B, self.n_kpts, self.image = int(frames_per_batch), int(n_kpts), tuple(image)
-        self.ctx = api.VoteContext(device, max_items=self.B * n_kpts, max_points_total=self.B * n_kpts * image[0] * image[1], max_grid=max_grid)
+        self.ctx = api.VoteContext(device, max_items=self.B * n_kpts, max_points_total=self.B * n_kpts * image[0] * image[1], max_grid=max_grid,
+                                   image=self.image, max_model_points=len(cad_mm))
         self.cad_mm = torch.as_tensor(np.ascontiguousarray(cad_mm, dtype=np.float64), device=self.dev)
         self.kpts_mm = torch.as_tensor(np.ascontiguousarray(kpts_mm, dtype=np.float64), device=self.dev)
         self.symmetric, self.threshold_mm = bool(symmetric), float(threshold_mm)

@@ -59,8 +59,10 @@ class VotingPipeline:
     """One per process/GPU.  step() = K1 (mask + back-projection + compaction) -> prelude -> K2 vote
     (+ fused peak) -> finalize -> K4 Horn, all asynchronous on the current stream."""
 
-    def __init__(self, device=0, max_frames=4096, n_kpts=3, max_points_total=1 << 27, max_grid=256):
-        self.ctx = api.VoteContext(device, max_items=max_frames * n_kpts, max_points_total=max_points_total, max_grid=max_grid)
+    def __init__(self, device=0, max_frames=4096, n_kpts=3, max_points_total=1 << 27, max_grid=256, image=(480, 640), max_model_points=0):
+        # image / max_model_points: the context allocates its image- and model-sized scratch now, not on the first hot call
+        self.ctx = api.VoteContext(device, max_items=max_frames * n_kpts, max_points_total=max_points_total, max_grid=max_grid, image=image,
+                                   max_model_points=max_model_points)
         self.n_kpts = n_kpts
 
     def step(self, depth, radius, K, model_mm, sem=None, max_radii=None, mask_flags=api.RCV_MASK_RADIUS_NONZERO, **kw):

@@ -28,7 +28,7 @@ def ctx():
 def test_library_loaded_and_device_is_sm100():
     from rcvpose_b200 import _lib
     L = _lib.load()
-    assert L.rcv_abi_version() == 1
+    assert L.rcv_abi_version() == _lib.RCV_ABI_VERSION
     assert torch.cuda.get_device_capability(0)[0] == 10
 
 

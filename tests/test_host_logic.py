@@ -41,7 +41,7 @@ def test_no_gpu_means_loud_failure_not_fallback():
     from rcvpose_b200 import AccumulatorSpace as A
     with pytest.raises(Exception):
         A.Accumulator_3D(np.zeros((4, 3)), np.ones(4, np.float32))
-    assert _lib.load().rcv_abi_version() == 1
+    assert _lib.load().rcv_abi_version() == _lib.RCV_ABI_VERSION == 2
 
 
 def test_product_never_imports_the_oracle():
