@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--ref-frames", type=int, default=2, help="frames per step of --impl reference")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--shard", default="cost", choices=["cost", "count"],
+                    help="ycb workload: contiguous frame ranges balanced by the sum N*R^2 cost model (SURVEY 8e) or by frame count")
     ap.add_argument("--workload", default="linemod", choices=["linemod", "ycb"],
                     help="linemod = BASELINE configs[2] (the headline line); ycb = configs[3]-shaped frames (YCB camera, objects of 60-110 mm)")
     return ap.parse_args()
@@ -57,7 +59,8 @@ def config(frames, n_gpus, workload="linemod"):
             "(640x480 uint16 depth + 3 float32 radius maps, object radius 40-70 mm at 0.7-1.1 m, sigma 0.01 dm, 2%% outliers)" % frames)
     if workload == "ycb":
         what = ("BASELINE configs[3]-shaped: batched voting, %d synthetic YCB-Video-shaped frames x 3 keypoints per GPU (YCB camera, "
-                "640x480 uint16 depth + 3 float32 radius maps, object radius 60-110 mm at 0.7-1.1 m, sigma 0.01 dm, 2%% outliers)" % frames)
+                "640x480 uint16 depth + 3 float32 radius maps, object radius 60-110 mm at 0.7-1.1 m, sigma 0.01 dm, 2%% outliers; one global "
+                "sequence ordered by decreasing distance, cut into contiguous per-rank ranges)" % frames)
     return {"workload": what,
             "frames_per_gpu": frames, "global_frames": frames * n_gpus, "keypoints": KPTS, "image": [H, W],
             "parallelism": "frames sharded over %d GPU(s), no data-path collective, one all_gather of results" % n_gpus,
@@ -186,14 +189,28 @@ def run_ours(args):
     B = args.frames
     ycb = args.workload == "ycb"
     Knp = synth.ycb_K if ycb else synth.linemod_K
-    data = synth.torch_batch(B, KPTS, seed=1000 + rank, device=dev, K=Knp, obj_radius_mm=(60.0, 110.0) if ycb else (40.0, 70.0))
+    counts, shard_info = [B] * world, None
+    if ycb:
+        # One global sequence of world * B frames, ordered like a camera approaching the object (the cost of a frame grows along
+        # it), cut into contiguous per-rank ranges: by the sum N*R^2 cost model of SURVEY 8e (default) or by frame count.
+        gp = synth.frame_params(B * world, KPTS, seed=1000, obj_radius_mm=(60.0, 110.0), approach=True)
+        cost = synth.frame_cost(gp, Knp)
+        ranges = pipeline.shard_by_cost(cost, world) if args.shard == "cost" else [pipeline.shard_range(B * world, r, world) for r in range(world)]
+        sums = [float(cost[a:b].sum()) for a, b in ranges]
+        counts = [b - a for a, b in ranges]
+        shard_info = {"policy": args.shard, "frames_per_rank": counts, "cost_imbalance_max_over_mean": max(sums) / (sum(sums) / world),
+                      "cost_model": "sum over keypoints of N * R^2 (N = pixels of the projected object, R = keypoint distance in voxels)"}
+        lo, hi = ranges[rank]
+        B = hi - lo
+        data = synth.torch_batch(B, KPTS, seed=1000 + rank, device=dev, K=Knp, params={k: v[lo:hi] for k, v in gp.items()})
+    else:
+        data = synth.torch_batch(B, KPTS, seed=1000 + rank, device=dev, K=Knp, obj_radius_mm=(40.0, 70.0))
     depth, radius, model = data["depth"], data["radius"], data["model_mm"]
     K = torch.from_numpy(Knp).to(dev)
     pipe = pipeline.VotingPipeline(local, max_frames=B, n_kpts=KPTS, max_points_total=max(1 << 22, B * KPTS * (90000 if ycb else 12000)),
                                    max_grid=384 if ycb else 256)
     ctx = pipe.ctx
     atom_peak = ctx.measure_smem_atomic_peak()
-    counts = [B] * world
 
     def step():
         return pipe.step_gathered(depth, radius, K, model, counts=counts)
@@ -229,7 +246,7 @@ def run_ours(args):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms_total = float(ms.item())
     ms_step = ms_total / args.steps
-    frames_global = B * world
+    frames_global = sum(counts)
     value = frames_global / (ms_step * 1e-3)
     votes_global, points_global, bad_global = float(tot[0].item()), float(tot[1].item()), int(tot[2].item())
 
@@ -322,7 +339,7 @@ def run_ours(args):
         alg_bytes = B * H * W * (2 + 4 * KPTS) * 2 + points_global / world * 36 * 2   # K1 reads maps twice; pool written + read
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 geometry / int32 votes",
-                "data": "synthetic", "config": config(B, world, args.workload),
+                "data": "synthetic", "config": dict(config(args.frames, world, args.workload), global_frames=frames_global),
                 "gvotes_per_s": votes_global / (ms_step * 1e-3) / 1e9, "votes_per_frame": votes_global / frames_global,
                 "points_per_frame_kpt": points_global / frames_global / KPTS, "items_with_error_status": bad_global,
                 "roofline": {"kernel": "k_vote", "bound": "smem_atomic", "achieved": achieved, "peak": atom_peak / 1e9, "unit": "Gvotes/s",
@@ -333,6 +350,8 @@ def run_ours(args):
                                  "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                                  "algorithmic_bytes_per_step": alg_bytes},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "cpu_baseline": cpu, "parity_spot_check": parity}
+        if shard_info:
+            line["shard"] = shard_info
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -531,10 +531,15 @@ constexpr int kSortBins = 8192;   // bins of the (y voxel, R) counting sort that
 
 // Row stride of a tile: odd, so that consecutive rows start in different banks; dp_mod >= 0 (experiments) asks for a given
 // residue modulo 32.
-__device__ __forceinline__ int row_stride(int need, int dp_mod) {
-  if (dp_mod < 0) return need | 1;
+// gen 2: the 32 lanes of a warp mark ~10 neighbouring rows at nearly the same cell, so the stride decides the bank
+// conflicts of the atomics: residues near 0, 16 and +-1..3 modulo 32 fold neighbouring rows onto the same banks (2.0-2.8
+// wavefronts per atomic in a replay of the bench geometry), the residues kept here give 1.45-1.6.
+__device__ __forceinline__ int row_stride(int need, int dp_mod, int gen) {
+  if (dp_mod >= 0) { int dp = need; while ((dp & 31) != (dp_mod & 31)) ++dp; return dp; }
+  if (gen < 2) return need | 1;
+  const unsigned good = (1u << 5) | (1u << 7) | (1u << 9) | (1u << 11) | (1u << 13) | (1u << 19) | (1u << 21) | (1u << 23) | (1u << 25) | (1u << 27);
   int dp = need;
-  while ((dp & 31) != (dp_mod & 31)) ++dp;
+  while (!((good >> (dp & 31)) & 1u)) ++dp;
   return dp;
 }
 
@@ -645,9 +650,9 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
       // upper guard: the -1 that closes a run ending at the last cell lands there.
       // gen 2 also keeps TWO planes per slice (run starts, run ends: only `add 1` merges lanes that hit the same address).
       const int spare = a.gen >= 2 ? 1 : 0, planes = a.gen >= 2 ? 2 : 1;
-      int Dp = row_stride(D + glo + ghi + spare, a.dp_mod);
+      int Dp = row_stride(D + glo + ghi + spare, a.dp_mod, a.gen);
       long long slice = (long long)planes * (D + glo + ghi) * Dp;
-      if (slice > a.tile_words) { glo = 0; ghi = 0; Dp = row_stride(D + spare, a.dp_mod); slice = (long long)planes * D * Dp; }   // row-band tiles are not guarded
+      if (slice > a.tile_words) { glo = 0; ghi = 0; Dp = row_stride(D + spare, a.dp_mod, a.gen); slice = (long long)planes * D * Dp; }   // row-band tiles are not guarded
       m.Dp = Dp;
       m.guard = glo | (ghi << 16);
       m.clip = (slice > a.tile_words || ((need_lo > 0.0 || need_hi > 0.0) && glo == 0 && ghi == 0)) ? 1 : 0;
@@ -1490,7 +1495,11 @@ __device__ __forceinline__ void runs_columns(const RunPoint& c, const RunLane& L
   const Tile& t = rt.t;
   const int clo = -t.glo - c.ipc, chi = t.D + t.ghi - c.ipc;   // clip bounds of the boundary bits relative to `base` (CLIP)
   const float Dpf = (float)t.Dp;
+#ifdef RCV_RUNS_NO_PAIRS
+  constexpr bool PAIRS = false;
+#else
   constexpr bool PAIRS = !PARK && !CLIP && NC <= 2;
+#endif
 #pragma unroll 1
   for (int u0 = ua; u0 <= ub; u0 += 32) {
     unsigned flags = 0;
@@ -1609,7 +1618,11 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
     __syncthreads();
     // ---- scatter: a work item is (chunk of NC slices, group of 32 consecutive points of the vote order) ----
     const unsigned slice_bytes = (unsigned)(u.nj * Dp * 4), plane_bytes = (unsigned)plane_words * 4u;
+#ifdef RCV_RUNS_MAX_NC
+    const int NC = min(ring_chunk(u.ni), RCV_RUNS_MAX_NC);
+#else
     const int NC = ring_chunk(u.ni);
+#endif
     const int ngroups = (n + 31) >> 5, nchunks = (u.ni + NC - 1) / NC, nwork = ngroups * nchunks;
     const RunSlowCtx sc{a.pool.X + off, a.pool.Y + off, a.pool.Z + off, a.pool.perm + off};
     const RunTile rt{t, tile_s, slice_bytes, plane_bytes, a.pool.rec + 2 * off, sc, clip};
@@ -1633,9 +1646,12 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
       run_lane_setup(c, L);
       const int pidx = cur + lane;
       if (!clip) {
+#if !defined(RCV_RUNS_MAX_NC) || RCV_RUNS_MAX_NC >= 3
         if (NC == 4) runs_chunk<4, false>(c, L, rt, i0c, nsl, pidx, q, qn);
         else if (NC == 3) runs_chunk<3, false>(c, L, rt, i0c, nsl, pidx, q, qn);
-        else if (NC == 2) runs_chunk<2, false>(c, L, rt, i0c, nsl, pidx, q, qn);
+        else
+#endif
+        if (NC == 2) runs_chunk<2, false>(c, L, rt, i0c, nsl, pidx, q, qn);
         else runs_chunk<1, false>(c, L, rt, i0c, nsl, pidx, q, qn);
       } else {
         if (NC >= 3) { runs_chunk<2, true>(c, L, rt, i0c, min(nsl, 2), pidx, q, qn); if (nsl > 2) runs_chunk<2, true>(c, L, rt, i0c + 2, nsl - 2, pidx, q, qn); }

@@ -20,6 +20,27 @@ def shard_range(n_frames, rank, world):
     return lo, lo + q + (1 if rank < r else 0)
 
 
+def shard_by_cost(costs, world):
+    """Contiguous frame ranges with (nearly) equal summed cost -- SURVEY.md 8e: "for YCB-shaped work, balance by sum N*R^2
+    rather than by frame count, since per-item cost varies > 10x".  Rank r ends at the first frame where the running cost
+    reaches (r + 1) / world of the total.  Returns [(lo, hi)] * world; every frame belongs to exactly one range."""
+    import numpy as np
+    c = np.asarray(costs, dtype=np.float64)
+    n = len(c)
+    cum = np.cumsum(c)
+    total = float(cum[-1]) if n else 0.0
+    bounds = [0]
+    for r in range(1, int(world)):
+        t = total * r / world
+        k = int(np.searchsorted(cum, t, side="left")) + 1 if total > 0 else (n * r) // world
+        # the frame that crosses the target goes to whichever side leaves the smaller error
+        if total > 0 and 0 < k <= n and abs(cum[k - 2] - t if k >= 2 else t) < abs(cum[k - 1] - t):
+            k -= 1
+        bounds.append(min(max(k, bounds[-1]), n))
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(int(world))]
+
+
 def pack_results(centres_mm, RT, peak, status):
     """(B,Kp,3) f64, (B,4,4) f64, (B,Kp) i32, (B,Kp) i32 -> one (B, 3Kp+16+2Kp) f64 row per frame."""
     B = centres_mm.shape[0]

@@ -223,8 +223,35 @@ def frame_to_points(K, depth, radius):
     return xyz_mm / 1000, radius[dm.nonzero()]
 
 
+def frame_params(n_frames, n_kpts=3, seed=0, obj_radius_mm=(40.0, 70.0), z_mm=(700.0, 1100.0), approach=False):
+    """Scenes of a GLOBAL frame sequence (host, NumPy), to be sliced per rank and rendered with torch_batch(params=...): object
+    radius, centre and the keypoints in the object frame, drawn like torch_batch draws them.  approach=True orders the frames
+    by decreasing distance (a camera approaching the object), so that the cost of a frame grows along the sequence."""
+    rng = np.random.default_rng(seed)
+    obj_r = rng.uniform(obj_radius_mm[0], obj_radius_mm[1], n_frames)
+    z = rng.uniform(z_mm[0], z_mm[1], n_frames)
+    if approach:
+        z = np.sort(z)[::-1].copy()
+    centre = np.stack([rng.uniform(-150, 150, n_frames), rng.uniform(-150, 150, n_frames), z], axis=1)
+    base = np.array([[1.0, 0.2, 0.1], [-0.3, 1.0, 0.2], [0.2, -0.4, 1.0], [-1.0, -0.5, 0.3]])[:n_kpts]
+    dirs = base[None] + 0.15 * rng.normal(size=(n_frames, n_kpts, 3))
+    dirs /= np.linalg.norm(dirs, axis=2, keepdims=True)
+    model = dirs * (obj_r[:, None, None] * (1.5 + rng.random((n_frames, n_kpts, 1))))
+    return dict(obj_r=obj_r, centre=centre, model=model)
+
+
+def frame_cost(params, K=linemod_K, acc_unit_mm=5.0):
+    """The cost model of SURVEY.md 8e for a frame: sum over keypoints of N * R^2 -- N = surviving pixels (the projected disc of the
+    object), R = the keypoint's mean distance to the visible surface in voxels.  Votes of a point grow like 4 pi R^2 f, the
+    rasteriser's work like pi R^2 + 2 R columns."""
+    r, z = params["obj_r"], params["centre"][:, 2]
+    n_px = np.pi * (K[0, 0] * r / z) * (K[1, 1] * r / z)
+    R = np.linalg.norm(params["model"], axis=2) / acc_unit_mm
+    return (n_px[:, None] * R * R).sum(axis=1)
+
+
 def torch_batch(n_frames, n_kpts=3, seed=0, device="cuda", K=linemod_K, chunk=128, sigma_dm=0.01, outlier_frac=0.02, h=H, w=W,
-                obj_radius_mm=(40.0, 70.0)):
+                obj_radius_mm=(40.0, 70.0), params=None):
     """Config-3 shaped batch generated on the GPU: per frame an object sphere of radius
     U(obj_radius_mm) = U(40,70) mm at x,y U(-150,150), z U(700,1100) mm; `n_kpts` keypoints at 1.5-2.5 object radii in
     dispersed directions; radius maps (decimetres, float32) with N(0, sigma) noise and a fraction of
@@ -238,12 +265,18 @@ def torch_batch(n_frames, n_kpts=3, seed=0, device="cuda", K=linemod_K, chunk=12
     depth = torch.empty((n_frames, h, w), dtype=torch.int16, device=dev)
     radius = torch.empty((n_frames, n_kpts, h, w), dtype=torch.float32, device=dev)
     U = lambda *s: torch.rand(*s, generator=g, device=dev, dtype=torch.float64)  # noqa: E731
-    obj_r = obj_radius_mm[0] + (obj_radius_mm[1] - obj_radius_mm[0]) * U(n_frames)
-    centre = torch.stack([-150 + 300 * U(n_frames), -150 + 300 * U(n_frames), 700 + 400 * U(n_frames)], dim=1)
-    base = torch.tensor([[1.0, 0.2, 0.1], [-0.3, 1.0, 0.2], [0.2, -0.4, 1.0], [-1.0, -0.5, 0.3]], dtype=torch.float64, device=dev)[:n_kpts]
-    dirs = base[None] + 0.15 * torch.randn((n_frames, n_kpts, 3), generator=g, device=dev, dtype=torch.float64)
-    dirs = dirs / dirs.norm(dim=2, keepdim=True)
-    model = dirs * (obj_r[:, None, None] * (1.5 + U(n_frames, n_kpts, 1)))
+    if params is not None:     # the scene of every frame is given (frame_params: a rank's slice of a global sequence)
+        obj_r = torch.as_tensor(params["obj_r"], dtype=torch.float64, device=dev)
+        centre = torch.as_tensor(params["centre"], dtype=torch.float64, device=dev)
+        model = torch.as_tensor(params["model"], dtype=torch.float64, device=dev)
+        assert obj_r.shape[0] == n_frames and model.shape[1] == n_kpts
+    else:
+        obj_r = obj_radius_mm[0] + (obj_radius_mm[1] - obj_radius_mm[0]) * U(n_frames)
+        centre = torch.stack([-150 + 300 * U(n_frames), -150 + 300 * U(n_frames), 700 + 400 * U(n_frames)], dim=1)
+        base = torch.tensor([[1.0, 0.2, 0.1], [-0.3, 1.0, 0.2], [0.2, -0.4, 1.0], [-1.0, -0.5, 0.3]], dtype=torch.float64, device=dev)[:n_kpts]
+        dirs = base[None] + 0.15 * torch.randn((n_frames, n_kpts, 3), generator=g, device=dev, dtype=torch.float64)
+        dirs = dirs / dirs.norm(dim=2, keepdim=True)
+        model = dirs * (obj_r[:, None, None] * (1.5 + U(n_frames, n_kpts, 1)))
     kpts = centre[:, None, :] + model
     fx, fy, cx, cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
     vv, uu = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float64), torch.arange(w, device=dev, dtype=torch.float64), indexing="ij")

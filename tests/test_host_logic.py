@@ -186,3 +186,23 @@ oracle.lmshorn(P1, want, 3, RTo)
 assert np.allclose(RT, RTo, atol=1e-9), (RT, RTo)
 '''.format(root=ROOT)
     _run_dropin(body)
+
+
+def test_shard_by_cost_balances_contiguous_ranges():
+    """SURVEY 8e: YCB-shaped work is balanced by the sum N*R^2 cost model, not by frame count."""
+    from rcvpose_b200 import pipeline, synth
+    pr = synth.frame_params(2048, 3, seed=3, obj_radius_mm=(60.0, 110.0), approach=True)
+    cost = synth.frame_cost(pr, synth.ycb_K)
+    assert cost.max() / cost.min() > 10                       # "per-item cost varies > 10x"
+    for world in (1, 2, 4, 8):
+        rg = pipeline.shard_by_cost(cost, world)
+        assert rg[0][0] == 0 and rg[-1][1] == len(cost) and all(rg[r][1] == rg[r + 1][0] for r in range(world - 1))
+        sums = np.array([cost[a:b].sum() for a, b in rg])
+        eq = np.array([cost[slice(*pipeline.shard_range(len(cost), r, world))].sum() for r in range(world)])
+        assert sums.max() / sums.mean() < 1.01
+        if world > 1:
+            assert eq.max() / eq.mean() > 1.15                # the equal-count split of an approach sequence is not balanced
+    assert pipeline.shard_by_cost([], 3) == [(0, 0)] * 3
+    assert pipeline.shard_by_cost([0.0, 0.0, 0.0, 0.0], 2) == [(0, 2), (2, 4)]
+    rg = pipeline.shard_by_cost([5.0], 4)
+    assert sum(b - a for a, b in rg) == 1
