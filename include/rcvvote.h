@@ -173,6 +173,12 @@ int rcv_scene_clouds(rcv_ctx* ctx, int n_frames, int n_kpts, const void* depth, 
                      const double* K, const double* max_radii, const rcv_frame_params* fp, double scale, double* xyz_out,
                      long long xyz_capacity, long long* offsets_out, int* status_out, void* stream);
 
+/* The same scene clouds for the frames of the MOST RECENT rcv_vote_frames / rcv_head_vote_frames call on this context, from the
+ * survival bits that call left behind (their OR over the keypoints): no map is read again -- with the fused head the seg
+ * plane never existed in memory.  Consumes the bits; RCV_E_INVALID if the last frames call had another shape. */
+int rcv_scene_clouds_last(rcv_ctx* ctx, int n_frames, int n_kpts, const void* depth, const double* K, const rcv_frame_params* fp,
+                          double scale, double* xyz_out, long long xyz_capacity, long long* offsets_out, int* status_out, void* stream);
+
 /* ---- point-to-point ICP refinement of the Horn pose  -- AccumulatorSpace.py:704-718 (LM), :929-950 (LMO), :1152-1180 (YCB) ----
  * Replaces open3d 0.14.1 (rcvpose.yml:176; third-party, not in the reference tree)
  *   registration_icp(source = CAD model, target = scene, max_correspondence_distance, init,

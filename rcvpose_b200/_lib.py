@@ -16,7 +16,7 @@ RCV_ST_VOLUME_SKIPPED = 32
 
 EXPORTS = ["rcv_create", "rcv_destroy", "rcv_last_error", "rcv_abi_version", "rcv_backproject", "rcv_vote_points", "rcv_vote_frames",
            "rcv_vote_frames_host", "rcv_argmax_volume", "rcv_head_1x1", "rcv_horn_batch", "rcv_horn_batch_host", "rcv_launch_count", "rcv_last_h2d_bytes",
-           "rcv_last_vote_kernel_ms", "rcv_vote_kernel_times", "rcv_ubench_smem_atomics", "rcv_add_metric_batch", "rcv_scene_clouds", "rcv_icp_batch", "rcv_head_vote_frames"]
+           "rcv_last_vote_kernel_ms", "rcv_vote_kernel_times", "rcv_ubench_smem_atomics", "rcv_add_metric_batch", "rcv_scene_clouds", "rcv_scene_clouds_last", "rcv_icp_batch", "rcv_head_vote_frames"]
 
 
 class rcv_config(C.Structure):
@@ -75,6 +75,8 @@ def load():
     L.rcv_horn_batch.argtypes = [vp, vp, C.c_longlong, vp, C.c_int, C.c_int, vp, vp]
     L.rcv_add_metric_batch.restype = C.c_int
     L.rcv_add_metric_batch.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]
+    L.rcv_scene_clouds_last.restype = C.c_int
+    L.rcv_scene_clouds_last.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.POINTER(rcv_frame_params), C.c_double, vp, C.c_longlong, vp, vp, vp]
     L.rcv_scene_clouds.restype = C.c_int
     L.rcv_scene_clouds.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.POINTER(rcv_frame_params), C.c_double, vp, C.c_longlong, llp,
                                    ip, vp]

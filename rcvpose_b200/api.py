@@ -264,6 +264,22 @@ class VoteContext:
                                                float(scale), _ptr(xyz), cap, _ptr(offsets), _ptr(status), _stream()))
         return xyz, offsets, status
 
+    def scene_clouds_last(self, depth, K, n_kpts, depth_div=1.0, scale=1.0, capacity=None):
+        """scene_clouds for the frames of the most recent vote_frames / head_vote_frames call on this context, from the survival
+        bits that call left behind (no map is read again).  depth (B,H,W), K (3,3) or (B,3,3) as in that call."""
+        _check_cuda(depth, None, "depth")
+        _check_cuda(K, torch.float64, "K")
+        B, H, W = depth.shape
+        cap = int(capacity if capacity is not None else min(self.max_points_total, B * H * W))
+        fp = _lib.rcv_frame_params(H, W, _DEPTH_DTYPES[depth.dtype], float(depth_div), 1000.0, 0, 0.0, 9 if (K.dim() == 3 and K.shape[0] == B) else 0, 0)
+        xyz = torch.empty((cap, 3), dtype=torch.float64, device=depth.device)
+        offsets = torch.empty(B + 1, dtype=torch.int64, device=depth.device)
+        status = torch.empty(B, dtype=torch.int32, device=depth.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_scene_clouds_last(self.h, B, int(n_kpts), _ptr(depth), _ptr(K), C.byref(fp), float(scale), _ptr(xyz), cap,
+                                                    _ptr(offsets), _ptr(status), _stream()))
+        return xyz, offsets, status
+
     # ---- open3d registration_icp, point to point (AccumulatorSpace.py:704-718) ----
     def icp(self, model, scene, scene_offsets, RT_init, max_dist, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6):
         """model (M,3), scene (N,3), scene_offsets (B+1,) int64, RT_init (B,4,4), max_dist (B,) -- all CUDA, float64 unless noted ->

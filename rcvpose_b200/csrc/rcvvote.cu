@@ -265,11 +265,11 @@ __global__ void __launch_bounds__(kCompactThreads) k_frame_mask(FrameArgs a, int
 
 // Survivors' pixel indices in row-major order: pix[off .. off + n) for every item (pix aliases the pool's perm array).
 __global__ void __launch_bounds__(kCompactThreads) k_frame_emit(const unsigned* __restrict__ bits, int words_per_item, const ItemMeta* __restrict__ meta,
-                                                               int* __restrict__ pix) {
+                                                               int* __restrict__ pix, long long item_stride_words) {
   const int item = blockIdx.x;
   const ItemMeta m = meta[item];
   if (m.n == 0) return;   // empty or overflowed item
-  const unsigned* in = bits + (long long)item * words_per_item;
+  const unsigned* in = bits + (long long)item * item_stride_words;
   int* out = pix + m.off;
   __shared__ int s_warp[kCompactThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1917,6 +1917,7 @@ struct rcv_ctx {
   int* counters;  // [0] units queued, [1] queue cursor
   int* cnt;
   unsigned* mask_bits; long long mask_words;
+  int last_mask_frames, last_mask_kpts, last_mask_words_per_item;   // survival bits left by the most recent frames call (rcv_scene_clouds_last)
   float* head_radius; long long head_radius_cap;   // fused head: radius planes of the items of a call
   double* icp_scratch; long long icp_cap;         // ICP scratch: per-frame state + per-(frame, tile) partial sums
   double* add_part; long long add_part_cap;     // ADD metric scratch: per-(frame, tile) partial sums and minima   // K1 scratch: one survival bit per pixel of every item of a call (grown on demand)
@@ -2133,8 +2134,9 @@ RCV_EXPORT int rcv_vote_frames(rcv_ctx* c, int n_frames, int n_kpts, const void*
     c->mask_words = need;
   }
   k_frame_mask<<<n_items, kCompactThreads, 0, st>>>(fa, c->cnt, c->mask_bits, words);
+  c->last_mask_frames = n_frames; c->last_mask_kpts = n_kpts; c->last_mask_words_per_item = words;
   k_scan_items<<<1, 1024, 0, st>>>(c->cnt, n_items, c->pool.cap, c->meta);
-  k_frame_emit<<<n_items, kCompactThreads, 0, st>>>(c->mask_bits, words, c->meta, c->pool.perm);
+  k_frame_emit<<<n_items, kCompactThreads, 0, st>>>(c->mask_bits, words, c->meta, c->pool.perm, words);
   k_points_from_pixels<<<dim3(n_items, 4), 256, 0, st>>>(fa, c->meta, c->pool);
   c->launches += 4;
   return run_items(c, n_items, vp, centre_mm, peak, votes, n_points, grid, nullptr, status, nullptr, 0, st);
@@ -2352,10 +2354,55 @@ RCV_EXPORT int rcv_scene_clouds(rcv_ctx* c, int n_frames, int n_kpts, const void
     c->mask_words = need;
   }
   const long long cap = xyz_capacity < c->pool.cap ? xyz_capacity : c->pool.cap;   // the pixel list lives in the pool's index array
+  c->last_mask_frames = 0;   // the item bits of an earlier frames call are overwritten
   k_scene_mask<<<n_frames, kCompactThreads, 0, st>>>(fa, c->cnt, c->mask_bits, words);
   k_scene_scan<<<1, 1024, 0, st>>>(c->cnt, n_frames, cap, c->meta, offsets_out, status_out);
-  k_frame_emit<<<n_frames, kCompactThreads, 0, st>>>(c->mask_bits, words, c->meta, c->pool.perm);
+  k_frame_emit<<<n_frames, kCompactThreads, 0, st>>>(c->mask_bits, words, c->meta, c->pool.perm, words);
   k_scene_points<<<dim3(n_frames, 4), 256, 0, st>>>(fa, c->meta, c->pool.perm, scale, xyz_out);
+  c->launches += 4;
+  CK(c, cudaGetLastError());
+  return RCV_OK;
+}
+
+// OR of the keypoints' survival bits of each frame, left in the frame's first plane; count of survivors per frame
+__global__ void __launch_bounds__(256) k_scene_or_bits(unsigned* __restrict__ bits, int words_per_item, int n_kpts, int* __restrict__ cnt) {
+  const int frame = blockIdx.x;
+  unsigned* base = bits + (long long)frame * n_kpts * words_per_item;
+  int n = 0;
+  for (int w = threadIdx.x; w < words_per_item; w += blockDim.x) {
+    unsigned m = base[w];
+    for (int k = 1; k < n_kpts; ++k) m |= base[(long long)k * words_per_item + w];
+    base[w] = m;
+    n += __popc(m);
+  }
+  __shared__ int s_n[8];
+  n = __reduce_add_sync(0xffffffffu, n);
+  if ((threadIdx.x & 31) == 0) s_n[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_n[w]; cnt[frame] = t; }
+}
+
+// rcv_scene_clouds for the frames of the MOST RECENT rcv_vote_frames / rcv_head_vote_frames call on this context: the union of
+// the keypoints' masks is the OR of the survival bits that call left behind, so no map is read again (the fused head never
+// wrote the seg plane to memory).  Consumes those bits.
+RCV_EXPORT int rcv_scene_clouds_last(rcv_ctx* c, int n_frames, int n_kpts, const void* depth, const double* K, const rcv_frame_params* fp,
+                                     double scale, double* xyz_out, long long xyz_capacity, long long* offsets_out, int* status_out, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!depth || !K || !fp || !xyz_out || !offsets_out || xyz_capacity <= 0) FAIL(c, RCV_E_INVALID, "rcv_scene_clouds_last: bad argument");
+  const long long npx = (long long)fp->height * fp->width;
+  const int words = (int)((npx + 255) / 256) * 8;
+  if (n_frames != c->last_mask_frames || n_kpts != c->last_mask_kpts || words != c->last_mask_words_per_item)
+    FAIL(c, RCV_E_INVALID, "rcv_scene_clouds_last: no survival bits of %d frames x %d keypoints of %d x %d pixels on this context", n_frames, n_kpts,
+         fp->height, fp->width);
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(c, cudaSetDevice(c->device));
+  FrameArgs fa{depth, nullptr, nullptr, K, nullptr, *fp, 1.0, 1.0, n_kpts, 0};
+  const long long cap = xyz_capacity < c->pool.cap ? xyz_capacity : c->pool.cap;
+  k_scene_or_bits<<<n_frames, 256, 0, st>>>(c->mask_bits, words, n_kpts, c->cnt);
+  k_scene_scan<<<1, 1024, 0, st>>>(c->cnt, n_frames, cap, c->meta, offsets_out, status_out);
+  k_frame_emit<<<n_frames, kCompactThreads, 0, st>>>(c->mask_bits, words, c->meta, c->pool.perm, (long long)n_kpts * words);
+  k_scene_points<<<dim3(n_frames, 4), 256, 0, st>>>(fa, c->meta, c->pool.perm, scale, xyz_out);
+  c->last_mask_frames = 0;
   c->launches += 4;
   CK(c, cudaGetLastError());
   return RCV_OK;
@@ -2465,9 +2512,10 @@ RCV_EXPORT int rcv_head_vote_frames(rcv_ctx* c, int n_frames, int n_kpts, const 
   CK(c, cudaMemsetAsync(c->cnt, 0, 4 * (size_t)n_items, st));
   CK(c, (cudaError_t)rcv_head1x1_fused_launch(up_bf16, weight, bias, rad, n_items, npx, c->sms, depth, fp->depth_dtype, n_kpts, max_radii,
                                               fp->max_radii_stride, fp->mask_flags, fp->sem_threshold, c->mask_bits, words, c->cnt, stream));
+  c->last_mask_frames = n_frames; c->last_mask_kpts = n_kpts; c->last_mask_words_per_item = words;
   FrameArgs fa{depth, rad, nullptr, K, max_radii, *fp, vp->acc_unit, vp->radius_scale, n_kpts, 0};
   k_scan_items<<<1, 1024, 0, st>>>(c->cnt, n_items, c->pool.cap, c->meta);
-  k_frame_emit<<<n_items, kCompactThreads, 0, st>>>(c->mask_bits, words, c->meta, c->pool.perm);
+  k_frame_emit<<<n_items, kCompactThreads, 0, st>>>(c->mask_bits, words, c->meta, c->pool.perm, words);
   k_points_from_pixels<<<dim3(n_items, 4), 256, 0, st>>>(fa, c->meta, c->pool);
   c->launches += 4;
   return run_items(c, n_items, vp, centre_mm, peak, votes, n_points, grid, nullptr, status, nullptr, 0, st);
