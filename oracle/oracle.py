@@ -26,7 +26,16 @@ def build(force=False):
     so = os.path.join(_HERE, "librcv_oracle.so")
     src = os.path.join(_HERE, "rcv_oracle.c")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+        import fcntl
+        with open(so + ".lock", "w") as lock:      # ranks / xdist workers may all get here at once
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+                    tmp = "librcv_oracle.tmp.%d.so" % os.getpid()
+                    subprocess.run(["make", "-C", _HERE, "-B", tmp], check=True, capture_output=True)
+                    os.replace(os.path.join(_HERE, tmp), so)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return so
 
 

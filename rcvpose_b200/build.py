@@ -28,18 +28,32 @@ def needs_build():
 
 
 def build_library(force=False, verbose=False):
-    """nvcc cross-compiles without a GPU. Returns the path of the shared library."""
+    """nvcc cross-compiles without a GPU.  Returns the path of the shared library.  Safe when several processes (the ranks of a
+    torchrun job on a fresh checkout) call it at once: one builds under a file lock, into a temporary file that replaces the
+    library atomically; the others wait and find it up to date."""
+    import fcntl
     if not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: librcvvote.so cannot be built (and there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():          # another process built it while this one waited
+                return LIB
+            tmp = "%s.tmp.%d" % (LIB, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -69,6 +69,23 @@ def reduce_counts(values):
     return [int(v) for v in t.tolist()]
 
 
+def sync_failure(exc):
+    """In a sharded evaluation a rank that fails inside its batch loop must not leave the others waiting in the final
+    all_reduce: every rank reports a failure flag first, and all raise together (the failing rank its own exception)."""
+    import torch.distributed as dist
+    rank, world = _world()
+    if world > 1:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor([1 if exc is not None else 0, rank if exc is not None else world], dtype=torch.int64, device=dev)
+        flag = t[:1].clone(); who = t[1:].clone()
+        dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+        dist.all_reduce(who, op=dist.ReduceOp.MIN)
+        if exc is None and int(flag.item()) > 0:
+            raise RuntimeError("evaluation failed on rank %d (%d rank(s) in all); see that rank's exception" % (int(who.item()), int(flag.item())))
+    if exc is not None:
+        raise exc
+
+
 def _default_device(opts):
     """opts.device if given, else the process's GPU under torchrun (LOCAL_RANK), else 0."""
     d = getattr(opts, "device", None)
@@ -89,15 +106,50 @@ class FrameEvaluator:
     """Device-side stage chain for batches of frames of ONE object class (one CAD model, one keypoint set)."""
 
     def __init__(self, cad_mm, kpts_mm, symmetric, threshold_mm, device=0, frames_per_batch=64, image=(480, 640), n_kpts=3, max_grid=256,
-                 icp=True, icp_max_iter=30):
-        self.dev = torch.device("cuda", device)
+                 icp=True, icp_max_iter=30, ctx=None):
         self.B, self.n_kpts, self.image = int(frames_per_batch), int(n_kpts), tuple(image)
-        self.ctx = api.VoteContext(device, max_items=self.B * n_kpts, max_points_total=self.B * n_kpts * image[0] * image[1], max_grid=max_grid,
-                                   image=self.image, max_model_points=len(cad_mm))
+        if ctx is None:
+            ctx = api.VoteContext(device, max_items=self.B * n_kpts, max_points_total=self.B * n_kpts * image[0] * image[1], max_grid=max_grid,
+                                  image=self.image, max_model_points=len(cad_mm))
+        self.ctx = ctx                     # (a ProducerStage's own context when the maps come from the fused head)
+        self.dev = ctx.device
         self.cad_mm = torch.as_tensor(np.ascontiguousarray(cad_mm, dtype=np.float64), device=self.dev)
         self.kpts_mm = torch.as_tensor(np.ascontiguousarray(kpts_mm, dtype=np.float64), device=self.dev)
         self.symmetric, self.threshold_mm = bool(symmetric), float(threshold_mm)
         self.icp, self.icp_max_iter = bool(icp), int(icp_max_iter)
+
+    def _gt(self, RT_gt_mm, B):
+        gt = torch.zeros((B, 4, 4), dtype=torch.float64, device=self.dev)
+        g = _to_device(RT_gt_mm, self.dev, torch.float64)
+        gt[:, :g.shape[1], :] = g
+        gt[:, 3, 3] = 1.0
+        return gt
+
+    def _after_vote(self, out, gt, scene_fn, centres_override=None, icp_rel_fitness=1e-6, icp_rel_rmse=1e-6, zero_empty_centres=False,
+                    icp_threshold_mean=False):
+        """Horn -> ADD(-S) -> [scene cloud -> ICP -> ADD(-S)] on the keypoint centres of a frames call."""
+        ctx, dev = self.ctx, self.dev
+        centres = out["centre_mm"]
+        if zero_empty_centres:   # the LMO evaluator leaves the row of a keypoint without pixels at zero (AccumulatorSpace.py:795, :858)
+            centres[(out["status"] & api.RCV_ST_EMPTY_MASK) != 0] = 0.0
+        if centres_override is not None:   # frames voted outside the fused path (float64 radius maps), see LinemodEvaluator
+            idx, val = centres_override
+            centres[idx[0].to(dev), idx[1].to(dev)] = _to_device(val, dev, torch.float64)
+        RT = ctx.horn_batch(self.kpts_mm, centres)
+        mean, mn = ctx.add_metric(self.cad_mm, RT, gt)
+        before = mn if self.symmetric else mean
+        res = dict(centre_mm=centres, RT=RT, dist_before=before, passed_before=before <= self.threshold_mm, status=out["status"],
+                   n_points=out["n_points"], peak=out["peak"], grid=out["grid"], mean_before=mean)
+        if self.icp:
+            scene, offs, _ = scene_fn()
+            # correspondence threshold: the ADD(-S) figure of the class (LM / LMO, :706-707, :929) or always the mean distance (YCB, :1151)
+            thr = (mean if icp_threshold_mean else before).contiguous()
+            reg = ctx.icp(self.cad_mm, scene, offs, RT, thr, max_iter=self.icp_max_iter, rel_fitness=icp_rel_fitness, rel_rmse=icp_rel_rmse)
+            mean2, mn2 = ctx.add_metric(self.cad_mm, reg["RT"], gt)
+            after = mn2 if self.symmetric else mean2
+            res.update(RT_icp=reg["RT"], dist_after=after, passed_after=after <= self.threshold_mm, icp_fitness=reg["fitness"],
+                       icp_rmse=reg["rmse"], icp_iters=reg["iters"], scene_points=offs[1:] - offs[:-1])
+        return {k: v.cpu().numpy() for k, v in res.items()}
 
     def run(self, depth, radius, K, RT_gt_mm, max_radii=None, sem=None, mask_flags=api.MASK_LM_NPY, sem_threshold=0.8, depth_div=1.0,
             scene_scale=1.0, centres_override=None, icp_rel_fitness=1e-6, icp_rel_rmse=1e-6, zero_empty_centres=False,
@@ -110,35 +162,41 @@ class FrameEvaluator:
         to = lambda a, dt=None: _to_device(a, dev, dt)  # noqa: E731
         depth, radius, sem = to(depth), to(radius, torch.float32), to(sem, torch.float32)
         K, max_radii = to(K, torch.float64), to(max_radii, torch.float64)
-        B = radius.shape[0]
-        gt = torch.zeros((B, 4, 4), dtype=torch.float64, device=dev)
-        g = to(RT_gt_mm, torch.float64)
-        gt[:, :g.shape[1], :] = g
-        gt[:, 3, 3] = 1.0
+        gt = self._gt(RT_gt_mm, radius.shape[0])
         out = ctx.vote_frames(depth, radius, K, sem=sem, max_radii=max_radii, mask_flags=mask_flags, sem_threshold=sem_threshold,
                               depth_div=depth_div, **vote_kw)
-        centres = out["centre_mm"]
-        if zero_empty_centres:   # the LMO evaluator leaves the row of a keypoint without pixels at zero (AccumulatorSpace.py:795, :858)
-            centres[(out["status"] & api.RCV_ST_EMPTY_MASK) != 0] = 0.0
-        if centres_override is not None:   # frames voted outside the fused path (float64 radius maps), see LinemodEvaluator
-            idx, val = centres_override
-            centres[idx[0].to(dev), idx[1].to(dev)] = to(val, torch.float64)
-        RT = ctx.horn_batch(self.kpts_mm, centres)
-        mean, mn = ctx.add_metric(self.cad_mm, RT, gt)
-        before = mn if self.symmetric else mean
-        res = dict(centre_mm=centres, RT=RT, dist_before=before, passed_before=before <= self.threshold_mm, status=out["status"],
-                   n_points=out["n_points"], peak=out["peak"], grid=out["grid"], mean_before=mean)
-        if self.icp:
-            scene, offs, _ = ctx.scene_clouds(depth, radius, K, sem=sem, max_radii=max_radii, mask_flags=mask_flags, sem_threshold=sem_threshold,
-                                              depth_div=depth_div, scale=scene_scale)
-            # correspondence threshold: the ADD(-S) figure of the class (LM / LMO, :706-707, :929) or always the mean distance (YCB, :1151)
-            thr = (mean if icp_threshold_mean else before).contiguous()
-            reg = ctx.icp(self.cad_mm, scene, offs, RT, thr, max_iter=self.icp_max_iter, rel_fitness=icp_rel_fitness, rel_rmse=icp_rel_rmse)
-            mean2, mn2 = ctx.add_metric(self.cad_mm, reg["RT"], gt)
-            after = mn2 if self.symmetric else mean2
-            res.update(RT_icp=reg["RT"], dist_after=after, passed_after=after <= self.threshold_mm, icp_fitness=reg["fitness"],
-                       icp_rmse=reg["rmse"], icp_iters=reg["iters"], scene_points=offs[1:] - offs[:-1])
-        return {k: v.cpu().numpy() for k, v in res.items()}
+        scene_fn = lambda: ctx.scene_clouds(depth, radius, K, sem=sem, max_radii=max_radii, mask_flags=mask_flags, sem_threshold=sem_threshold,  # noqa: E731
+                                            depth_div=depth_div, scale=scene_scale)
+        return self._after_vote(out, gt, scene_fn, centres_override, icp_rel_fitness, icp_rel_rmse, zero_empty_centres, icp_threshold_mean)
+
+    def run_stage(self, stage, images, depth, K, RT_gt_mm, max_radii, mask_flags=api.MASK_LM_CKPT, sem_threshold=0.8, depth_div=1.0,
+                  scene_scale=1.0, icp_rel_fitness=1e-6, icp_rel_rmse=1e-6, zero_empty_centres=False, icp_threshold_mean=False, **vote_kw):
+        """The checkpoint branch through the fused producer: images (B,3,H,W) normalised RGB -> the stage's three
+        trunks -> rcv_head_vote_frames (conv8 + mask rule + vote; the seg plane never reaches memory) -> the same chain as run().
+        The ICP scene cloud comes from the survival bits that call left behind (rcv_scene_clouds_last).  `stage` must have been
+        built on this evaluator's context."""
+        assert stage.ctx is self.ctx, "build the FrameEvaluator with ctx=stage.ctx"
+        dev = self.dev
+        depth, K, max_radii = _to_device(depth, dev), _to_device(K, dev, torch.float64), _to_device(max_radii, dev, torch.float64)
+        gt = self._gt(RT_gt_mm, depth.shape[0])
+        out = stage.vote(images, depth, K, max_radii, mask_flags=mask_flags, sem_threshold=sem_threshold, depth_div=depth_div, **vote_kw)
+        scene_fn = lambda: self.ctx.scene_clouds_last(depth, K, self.n_kpts, depth_div=depth_div, scale=scene_scale)  # noqa: E731
+        return self._after_vote(out, gt, scene_fn, None, icp_rel_fitness, icp_rel_rmse, zero_empty_centres, icp_threshold_mean)
+
+
+def _revote_oversized(res, status_mask, radius, sem, depth, K, rule, shim, override_idx, override_val):
+    """Items whose accumulator is larger than the evaluator context allows (RCV_ST_D_EXCEEDS_CAP: one false-positive mask pixel on
+    background depth is enough) are voted again through the exact drop-in surface, whose context takes grids up to 640 -- the
+    reference handles any size, slowly.  rule(radius_map, sem_map) -> boolean mask of surviving pixels (before depth != 0).
+    Appends to the override lists; returns True if anything was re-voted."""
+    todo = np.argwhere(status_mask)
+    for i, k in todo:
+        m = rule(radius[i, k], None if sem is None else sem[i, k], k)
+        dm = depth[i] * np.where(m, 1, 0)
+        xyz = shim.rgbd_to_point_cloud(K, dm)
+        override_idx.append((int(i), int(k)))
+        override_val.append(shim.Accumulator_3D(xyz / 1000, radius[i, k][dm.nonzero()])[0])
+    return len(todo) > 0
 
 
 class LinemodClass:
@@ -174,7 +232,8 @@ class LinemodClass:
         return np.load(os.path.join(self.est, "Out_pt" + str(k) + "_dm", stem + ".npy"))
 
 
-def evaluate_lm_class(root_dataset, class_name, using_ckpts=False, producer=None, device=0, frames_per_batch=64, icp=True, verbose=True):
+def evaluate_lm_class(root_dataset, class_name, using_ckpts=False, producer=None, device=0, frames_per_batch=64, icp=True, verbose=True,
+                      max_grid=256):
     """One class of estimate_6d_pose_lm.  `producer(class_name, k, image_path) -> (sem, radial)` supplies the (H,W) float32 maps of
     keypoint k = 1..3 when using_ckpts (the reference's FCResBackbone + DenseFCNResNet152 stay PyTorch code outside this package).
     Returns dict(n, add_before, add_after, frames=[...], per-frame arrays)."""
@@ -182,63 +241,98 @@ def evaluate_lm_class(root_dataset, class_name, using_ckpts=False, producer=None
     cls = LinemodClass(root_dataset, class_name)
     sym = class_name in lm_syms
     if using_ckpts and producer is None:
-        raise ValueError("using_ckpts needs a producer(class_name, k, image_path) -> (sem, radial): the radius-map network is not part of rcvpose_b200")
+        raise ValueError("using_ckpts needs a producer(class_name, k, image_path) -> (sem, radial), or a rcvpose_b200.producer.ProducerStage "
+                         "holding the class's three networks")
+    staged = using_ckpts and hasattr(producer, "vote") and hasattr(producer, "activations")     # a ProducerStage: fused head + vote (N2)
     ev = None
     acc = {}
     my_stems = shard_frames(cls.stems)        # under torchrun every rank takes a contiguous range of the frames
     verbose = verbose and _world()[0] == 0
-    for b0 in range(0, len(my_stems), frames_per_batch):
-        stems = my_stems[b0:b0 + frames_per_batch]
-        depth = np.stack([cls.depth(s) for s in stems])
-        H, W = depth.shape[1:]
-        radius = np.empty((len(stems), 3, H, W), np.float32)
-        sem = np.empty_like(radius) if using_ckpts else None
-        override_idx, override_val = [], []
-        for i, s in enumerate(stems):
-            for k in range(1, 4):
-                if using_ckpts:
-                    sm, rd = producer(class_name, k, cls.image_path(s))
-                    sem[i, k - 1], radius[i, k - 1] = sm, rd
-                    continue
-                rd = cls.radial_est(s, k)
-                if rd.dtype == np.float32:
-                    radius[i, k - 1] = rd
-                    continue
-                # A map that is not float32 keeps its dtype through the reference's radius arithmetic (r*100/5), which
-                # the fused float32 path would not reproduce: vote this (frame, keypoint) through the exact drop-in surface
-                # (Accumulator_3D with the radii as they are, :612-628) and hand the fused path a float32 map with the same mask.
-                rd = np.where(rd <= cls.max_radii_dm[k - 1], rd, 0)
-                dm = depth[i] * np.where(rd != 0, 1, 0)
-                xyz_mm = shim.rgbd_to_point_cloud(linemod_K, dm)
-                override_idx.append((i, k - 1))
-                override_val.append(shim.Accumulator_3D(xyz_mm / 1000, rd[dm.nonzero()])[0])
-                radius[i, k - 1] = np.where(rd != 0, np.float32(1e-3), np.float32(0))
-        if ev is None:
-            ev = FrameEvaluator(cls.cad_m * 1000, cls.keypoints_m[1:4, :] * 1000, sym, add_threshold[class_name] * 1000, device=device,
-                                frames_per_batch=frames_per_batch, image=(H, W), icp=icp)
-        gt = np.stack([cls.pose_mm(s) for s in stems])
-        ov = None
-        if override_idx:
-            ii = np.array(override_idx)
-            ov = ((torch.as_tensor(ii[:, 0]), torch.as_tensor(ii[:, 1])), np.array(override_val))
-        res = ev.run(depth, radius, linemod_K, gt, max_radii=cls.max_radii_dm, sem=sem,
-                     mask_flags=api.MASK_LM_CKPT if using_ckpts else api.MASK_LM_NPY, centres_override=ov)
-        st = res["status"].copy()
-        if override_idx:
-            st[ii[:, 0], ii[:, 1]] = 0
-        bad = (st & api.RCV_ST_EMPTY_MASK) != 0
-        if bad.any():   # the reference dies in Accumulator_3D on an empty cloud (ValueError from .min())
-            i, k = np.argwhere(bad)[0]
-            raise ValueError("zero-size array to reduction operation minimum which has no identity (frame %s, keypoint %d: empty mask)" % (stems[i], k + 1))
-        if st.any():
-            raise api.RcvError("voting failed with status %s" % np.unique(st))
-        for k, v in res.items():
-            acc.setdefault(k, []).append(v)
-        if verbose:
-            n = sum(len(a) for a in acc["passed_before"])
-            print("Current ADD\\(s\\) of " + class_name + " before ICP: ", np.concatenate(acc["passed_before"]).sum() / n)
-            if icp:
-                print("Currnet ADD\\(s\\) of " + class_name + " after ICP: ", np.concatenate(acc["passed_after"]).sum() / n)
+    failure = None
+    try:
+        for b0 in range(0, len(my_stems), frames_per_batch):
+            stems = my_stems[b0:b0 + frames_per_batch]
+            depth = np.stack([cls.depth(s) for s in stems])
+            H, W = depth.shape[1:]
+            if staged:
+                # RGB -> three trunks -> fused conv8 + mask rule (sem > 0.8, radial <= max_radii, :603-605) + vote, all on the device
+                from .producer import normalise_rgb
+                if ev is None:
+                    ev = FrameEvaluator(cls.cad_m * 1000, cls.keypoints_m[1:4, :] * 1000, sym, add_threshold[class_name] * 1000,
+                                        frames_per_batch=frames_per_batch, image=(H, W), icp=icp, ctx=producer.ctx)
+                images = normalise_rgb(np.stack([formats.read_rgb(cls.image_path(s)) for s in stems]))
+                gt = np.stack([cls.pose_mm(s) for s in stems])
+                res = ev.run_stage(producer, images, depth.view(np.int16) if depth.dtype == np.uint16 else depth, linemod_K, gt, cls.max_radii_dm)
+                st = res["status"]
+                bad = (st & api.RCV_ST_EMPTY_MASK) != 0
+                if bad.any():
+                    i, k = np.argwhere(bad)[0]
+                    raise ValueError("zero-size array to reduction operation minimum which has no identity (frame %s, keypoint %d: empty mask)" % (stems[i], k + 1))
+                if st.any():
+                    raise api.RcvError("voting failed with status %s" % np.unique(st))
+                for k, v in res.items():
+                    acc.setdefault(k, []).append(v)
+                continue
+            radius = np.empty((len(stems), 3, H, W), np.float32)
+            sem = np.empty_like(radius) if using_ckpts else None
+            override_idx, override_val = [], []
+            for i, s in enumerate(stems):
+                for k in range(1, 4):
+                    if using_ckpts:
+                        sm, rd = producer(class_name, k, cls.image_path(s))
+                        sem[i, k - 1], radius[i, k - 1] = sm, rd
+                        continue
+                    rd = cls.radial_est(s, k)
+                    if rd.dtype == np.float32:
+                        radius[i, k - 1] = rd
+                        continue
+                    # A map that is not float32 keeps its dtype through the reference's radius arithmetic (r*100/5), which
+                    # the fused float32 path would not reproduce: vote this (frame, keypoint) through the exact drop-in surface
+                    # (Accumulator_3D with the radii as they are, :612-628) and hand the fused path a float32 map with the same mask.
+                    rd = np.where(rd <= cls.max_radii_dm[k - 1], rd, 0)
+                    dm = depth[i] * np.where(rd != 0, 1, 0)
+                    xyz_mm = shim.rgbd_to_point_cloud(linemod_K, dm)
+                    override_idx.append((i, k - 1))
+                    override_val.append(shim.Accumulator_3D(xyz_mm / 1000, rd[dm.nonzero()])[0])
+                    radius[i, k - 1] = np.where(rd != 0, np.float32(1e-3), np.float32(0))
+            if ev is None:
+                ev = FrameEvaluator(cls.cad_m * 1000, cls.keypoints_m[1:4, :] * 1000, sym, add_threshold[class_name] * 1000, device=device,
+                                    frames_per_batch=frames_per_batch, image=(H, W), icp=icp, max_grid=max_grid)
+            gt = np.stack([cls.pose_mm(s) for s in stems])
+            ov = None
+            if override_idx:
+                ii = np.array(override_idx)
+                ov = ((torch.as_tensor(ii[:, 0]), torch.as_tensor(ii[:, 1])), np.array(override_val))
+            res = ev.run(depth, radius, linemod_K, gt, max_radii=cls.max_radii_dm, sem=sem,
+                         mask_flags=api.MASK_LM_CKPT if using_ckpts else api.MASK_LM_NPY, centres_override=ov)
+            st = res["status"].copy()
+            if override_idx:
+                st[ii[:, 0], ii[:, 1]] = 0
+            if ((st & api.RCV_ST_D_EXCEEDS_CAP) != 0).any():     # grids beyond max_grid: exact surface for those items, then the chain again
+                rule = (lambda r, sm, k: (sm > 0.8) & (r <= cls.max_radii_dm[k])) if using_ckpts else (lambda r, sm, k: (r <= cls.max_radii_dm[k]) & (r != 0))
+                _revote_oversized(res, (st & api.RCV_ST_D_EXCEEDS_CAP) != 0, radius, sem, depth, linemod_K, rule, shim, override_idx, override_val)
+                ii = np.array(override_idx)
+                ov = ((torch.as_tensor(ii[:, 0]), torch.as_tensor(ii[:, 1])), np.array(override_val))
+                res = ev.run(depth, radius, linemod_K, gt, max_radii=cls.max_radii_dm, sem=sem,
+                             mask_flags=api.MASK_LM_CKPT if using_ckpts else api.MASK_LM_NPY, centres_override=ov)
+                st = res["status"].copy()
+                st[ii[:, 0], ii[:, 1]] = 0
+            bad = (st & api.RCV_ST_EMPTY_MASK) != 0
+            if bad.any():   # the reference dies in Accumulator_3D on an empty cloud (ValueError from .min())
+                i, k = np.argwhere(bad)[0]
+                raise ValueError("zero-size array to reduction operation minimum which has no identity (frame %s, keypoint %d: empty mask)" % (stems[i], k + 1))
+            if st.any():
+                raise api.RcvError("voting failed with status %s" % np.unique(st))
+            for k, v in res.items():
+                acc.setdefault(k, []).append(v)
+            if verbose:
+                n = sum(len(a) for a in acc["passed_before"])
+                print("Current ADD\\(s\\) of " + class_name + " before ICP: ", np.concatenate(acc["passed_before"]).sum() / n)
+                if icp:
+                    print("Currnet ADD\\(s\\) of " + class_name + " after ICP: ", np.concatenate(acc["passed_after"]).sum() / n)
+    except Exception as e:   # noqa: BLE001 -- re-raised by sync_failure on every rank
+        failure = e
+    sync_failure(failure)
     out = {k: np.concatenate(v) for k, v in acc.items()}
     nb, na = reduce_counts([out["passed_before"].sum() if acc else 0, out["passed_after"].sum() if (acc and icp) else 0])
     n = len(cls.stems)
@@ -260,7 +354,7 @@ def estimate_6d_pose_lm(opts):
         print("Evaluation on ", class_name)
         results[class_name] = evaluate_lm_class(opts.root_dataset, class_name, using_ckpts=bool(getattr(opts, "using_ckpts", False)),
                                                 producer=getattr(opts, "producer", None), device=_default_device(opts),
-                                                frames_per_batch=getattr(opts, "frames_per_batch", 64))
+                                                frames_per_batch=getattr(opts, "frames_per_batch", 64), max_grid=getattr(opts, "max_grid", 256))
     return results
 
 
@@ -317,7 +411,8 @@ class LmoClass:
         return rt
 
 
-def evaluate_lmo_class(root_dataset, class_name, using_ckpts=False, producer=None, device=0, frames_per_batch=64, icp=True, verbose=True):
+def evaluate_lmo_class(root_dataset, class_name, using_ckpts=False, producer=None, device=0, frames_per_batch=64, icp=True, verbose=True,
+                       max_grid=256):
     """One class of estimate_6d_pose_lmo (AccumulatorSpace.py:741-983).  Differences from the LINEMOD evaluator, all the
     reference's: float64 depth images in mm (:833), mask rule `radial > 0` (npy, :849-851) or `sem >= 0.5` (ckpt, :837-840), a
     keypoint whose thresholded radius map is all zero is skipped and its row stays 0 (:858, :795), ICP runs with
@@ -332,57 +427,72 @@ def evaluate_lmo_class(root_dataset, class_name, using_ckpts=False, producer=Non
     ev, acc = None, {}
     my_stems = shard_frames(cls.stems)
     verbose = verbose and _world()[0] == 0
-    for b0 in range(0, len(my_stems), frames_per_batch):
-        stems = my_stems[b0:b0 + frames_per_batch]
-        depth = np.stack([cls.depth(s) for s in stems])
-        H, W = depth.shape[1:]
-        radius = np.empty((len(stems), 3, H, W), np.float32)
-        sem = np.empty_like(radius) if using_ckpts else None
-        zero_map = np.zeros((len(stems), 3), bool)
-        override_idx, override_val = [], []
-        for i, s in enumerate(stems):
-            for k in range(1, 4):
-                if using_ckpts:
-                    sm, rd = producer(class_name, k, cls.image_path(s))
-                    sem[i, k - 1], radius[i, k - 1] = sm, rd
-                    m = (np.asarray(sm) >= 0.5) & (np.asarray(rd) <= cls.max_radii_dm[k - 1])
-                    zero_map[i, k - 1] = (np.asarray(rd) * m).max() == 0
-                    continue
-                rd = np.load(cls.radial_path(s, k))
-                rd = np.where(rd <= cls.max_radii_dm[k - 1], rd, 0)
-                zero_map[i, k - 1] = rd.max() == 0
-                if rd.dtype == np.float32:
-                    radius[i, k - 1] = rd
-                    continue
-                # not float32: exact drop-in surface for this (frame, keypoint), as in evaluate_lm_class
-                radius[i, k - 1] = np.where(rd > 0, np.float32(1e-3), np.float32(0))
-                if not zero_map[i, k - 1]:
-                    dm = depth[i] * np.where(rd > 0, 1, 0)
-                    xyz_mm = shim.rgbd_to_point_cloud(linemod_K, dm)
-                    override_idx.append((i, k - 1))
-                    override_val.append(shim.Accumulator_3D(xyz_mm / 1000, rd[dm.nonzero()])[0])
-        if ev is None:
-            ev = FrameEvaluator(cls.cad_m * 1000, cls.keypoints_m[1:4, :] * 1000, sym, thr, device=device, frames_per_batch=frames_per_batch,
-                                image=(H, W), icp=icp)
-        gt = np.stack([cls.pose_mm(s) for s in stems])
-        ov = None
-        if override_idx:
-            ii = np.array(override_idx)
-            ov = ((torch.as_tensor(ii[:, 0]), torch.as_tensor(ii[:, 1])), np.array(override_val))
-        res = ev.run(depth, radius, linemod_K, gt, max_radii=cls.max_radii_dm, sem=sem, sem_threshold=0.5,
-                     mask_flags=api.MASK_LMO_CKPT if using_ckpts else api.MASK_LMO_NPY, centres_override=ov, icp_rel_fitness=thr,
-                     icp_rel_rmse=thr, zero_empty_centres=True)
-        st = res["status"].copy()
-        if override_idx:
-            st[ii[:, 0], ii[:, 1]] = 0
-        empty = (st & api.RCV_ST_EMPTY_MASK) != 0
-        if (empty & ~zero_map).any():   # radii survive but no depth under them: the reference calls Accumulator_3D on an empty cloud
-            i, k = np.argwhere(empty & ~zero_map)[0]
-            raise ValueError("zero-size array to reduction operation minimum which has no identity (frame %s, keypoint %d: empty cloud)" % (stems[i], k + 1))
-        if (st & ~api.RCV_ST_EMPTY_MASK).any():
-            raise api.RcvError("voting failed with status %s" % np.unique(st))
-        for k, v in res.items():
-            acc.setdefault(k, []).append(v)
+    failure = None
+    try:
+        for b0 in range(0, len(my_stems), frames_per_batch):
+            stems = my_stems[b0:b0 + frames_per_batch]
+            depth = np.stack([cls.depth(s) for s in stems])
+            H, W = depth.shape[1:]
+            radius = np.empty((len(stems), 3, H, W), np.float32)
+            sem = np.empty_like(radius) if using_ckpts else None
+            zero_map = np.zeros((len(stems), 3), bool)
+            override_idx, override_val = [], []
+            for i, s in enumerate(stems):
+                for k in range(1, 4):
+                    if using_ckpts:
+                        sm, rd = producer(class_name, k, cls.image_path(s))
+                        sem[i, k - 1], radius[i, k - 1] = sm, rd
+                        m = (np.asarray(sm) >= 0.5) & (np.asarray(rd) <= cls.max_radii_dm[k - 1])
+                        zero_map[i, k - 1] = (np.asarray(rd) * m).max() == 0
+                        continue
+                    rd = np.load(cls.radial_path(s, k))
+                    rd = np.where(rd <= cls.max_radii_dm[k - 1], rd, 0)
+                    zero_map[i, k - 1] = rd.max() == 0
+                    if rd.dtype == np.float32:
+                        radius[i, k - 1] = rd
+                        continue
+                    # not float32: exact drop-in surface for this (frame, keypoint), as in evaluate_lm_class
+                    radius[i, k - 1] = np.where(rd > 0, np.float32(1e-3), np.float32(0))
+                    if not zero_map[i, k - 1]:
+                        dm = depth[i] * np.where(rd > 0, 1, 0)
+                        xyz_mm = shim.rgbd_to_point_cloud(linemod_K, dm)
+                        override_idx.append((i, k - 1))
+                        override_val.append(shim.Accumulator_3D(xyz_mm / 1000, rd[dm.nonzero()])[0])
+            if ev is None:
+                ev = FrameEvaluator(cls.cad_m * 1000, cls.keypoints_m[1:4, :] * 1000, sym, thr, device=device, frames_per_batch=frames_per_batch,
+                                    image=(H, W), icp=icp, max_grid=max_grid)
+            gt = np.stack([cls.pose_mm(s) for s in stems])
+            ov = None
+            if override_idx:
+                ii = np.array(override_idx)
+                ov = ((torch.as_tensor(ii[:, 0]), torch.as_tensor(ii[:, 1])), np.array(override_val))
+            res = ev.run(depth, radius, linemod_K, gt, max_radii=cls.max_radii_dm, sem=sem, sem_threshold=0.5,
+                         mask_flags=api.MASK_LMO_CKPT if using_ckpts else api.MASK_LMO_NPY, centres_override=ov, icp_rel_fitness=thr,
+                         icp_rel_rmse=thr, zero_empty_centres=True)
+            st = res["status"].copy()
+            if override_idx:
+                st[ii[:, 0], ii[:, 1]] = 0
+            if ((st & api.RCV_ST_D_EXCEEDS_CAP) != 0).any():
+                rule = (lambda r, sm, k: (sm >= 0.5) & (r <= cls.max_radii_dm[k])) if using_ckpts else (lambda r, sm, k: (r <= cls.max_radii_dm[k]) & (r > 0))
+                _revote_oversized(res, (st & api.RCV_ST_D_EXCEEDS_CAP) != 0, radius, sem, depth, linemod_K, rule, shim, override_idx, override_val)
+                ii = np.array(override_idx)
+                ov = ((torch.as_tensor(ii[:, 0]), torch.as_tensor(ii[:, 1])), np.array(override_val))
+                res = ev.run(depth, radius, linemod_K, gt, max_radii=cls.max_radii_dm, sem=sem, sem_threshold=0.5,
+                             mask_flags=api.MASK_LMO_CKPT if using_ckpts else api.MASK_LMO_NPY, centres_override=ov, icp_rel_fitness=thr,
+                             icp_rel_rmse=thr, zero_empty_centres=True)
+                st = res["status"].copy()
+                st[ii[:, 0], ii[:, 1]] = 0
+            empty = (st & api.RCV_ST_EMPTY_MASK) != 0
+            if (empty & ~zero_map).any():   # radii survive but no depth under them: the reference calls Accumulator_3D on an empty cloud
+                i, k = np.argwhere(empty & ~zero_map)[0]
+                raise ValueError("zero-size array to reduction operation minimum which has no identity (frame %s, keypoint %d: empty cloud)" % (stems[i], k + 1))
+            if (st & ~api.RCV_ST_EMPTY_MASK).any():
+                raise api.RcvError("voting failed with status %s" % np.unique(st))
+            for k, v in res.items():
+                acc.setdefault(k, []).append(v)
+    except Exception as e:   # noqa: BLE001 -- re-raised by sync_failure on every rank
+        failure = e
+    sync_failure(failure)
     n = len(cls.entries)
     out = {k: np.concatenate(v) for k, v in acc.items()}
     nb, na = reduce_counts([out["passed_before"].sum() if acc else 0, out["passed_after"].sum() if (acc and icp) else 0])
@@ -402,7 +512,7 @@ def estimate_6d_pose_lmo(opts):
         print(class_name)
         results[class_name] = evaluate_lmo_class(opts.root_dataset, class_name, using_ckpts=bool(getattr(opts, "using_ckpts", False)),
                                                  producer=getattr(opts, "producer", None), device=_default_device(opts),
-                                                 frames_per_batch=getattr(opts, "frames_per_batch", 64))
+                                                 frames_per_batch=getattr(opts, "frames_per_batch", 64), max_grid=getattr(opts, "max_grid", 256))
     return results
 
 
@@ -509,40 +619,45 @@ def evaluate_ycb_class(root_dataset, class_id, producer, device=0, frames_per_ba
     ev, acc = None, {}
     my_stems = shard_frames(cls.stems)
     verbose = verbose and _world()[0] == 0
-    for b0 in range(0, len(my_stems), frames_per_batch):
-        stems = my_stems[b0:b0 + frames_per_batch]
-        metas = [cls.meta(s) for s in stems]
-        factor = metas[0]["factor_depth"]
-        if any(m["factor_depth"] != factor for m in metas):
-            raise ValueError("frames of one batch must share factor_depth (got %s)" % sorted({m["factor_depth"] for m in metas}))
-        depth = np.stack([cls.depth_raw(s) for s in stems])
-        H, W = depth.shape[1:]
-        radius = np.empty((len(stems), 3, H, W), np.float32)
-        sem = np.empty_like(radius)
-        gt = np.zeros((len(stems), 3, 4))
-        for i, s in enumerate(stems):
-            rt = formats.pose_of(metas[i], cls.id)
-            if rt is None:
-                raise ValueError("frame %s does not contain object %d (%s)" % (s, cls.id, cls.name))
-            gt[i] = rt
-            gt[i, :, 3] *= 1000
-            for k in range(1, 4):
-                sem[i, k - 1], radius[i, k - 1] = producer(cls.name, k, cls.image_path(s))
-        if ev is None:
-            ev = FrameEvaluator(cls.cad_m * 1000, cls.keypoints_m[k0:k1, :] * 1000, sym, thr_mm, device=device, frames_per_batch=frames_per_batch,
-                                image=(H, W), icp=icp, icp_max_iter=2000000, max_grid=max_grid)
-        Ks = np.stack([m["intrinsic_matrix"] for m in metas])
-        d = depth.view(np.int16) if depth.dtype == np.uint16 else depth.astype(np.float64)
-        res = ev.run(d, radius, Ks, gt, sem=sem, mask_flags=api.MASK_YCB, sem_threshold=0.8, depth_div=factor, xyz_div=1.0, scene_scale=1000.0,
-                     icp_threshold_mean=True)
-        st = res["status"]
-        if ((st & api.RCV_ST_EMPTY_MASK) != 0).any():
-            i, k = np.argwhere((st & api.RCV_ST_EMPTY_MASK) != 0)[0]
-            raise ValueError("zero-size array to reduction operation minimum which has no identity (frame %s, keypoint %d: empty mask)" % (stems[i], k + 1))
-        if st.any():
-            raise api.RcvError("voting failed with status %s" % np.unique(st))
-        for k, v in res.items():
-            acc.setdefault(k, []).append(v)
+    failure = None
+    try:
+        for b0 in range(0, len(my_stems), frames_per_batch):
+            stems = my_stems[b0:b0 + frames_per_batch]
+            metas = [cls.meta(s) for s in stems]
+            factor = metas[0]["factor_depth"]
+            if any(m["factor_depth"] != factor for m in metas):
+                raise ValueError("frames of one batch must share factor_depth (got %s)" % sorted({m["factor_depth"] for m in metas}))
+            depth = np.stack([cls.depth_raw(s) for s in stems])
+            H, W = depth.shape[1:]
+            radius = np.empty((len(stems), 3, H, W), np.float32)
+            sem = np.empty_like(radius)
+            gt = np.zeros((len(stems), 3, 4))
+            for i, s in enumerate(stems):
+                rt = formats.pose_of(metas[i], cls.id)
+                if rt is None:
+                    raise ValueError("frame %s does not contain object %d (%s)" % (s, cls.id, cls.name))
+                gt[i] = rt
+                gt[i, :, 3] *= 1000
+                for k in range(1, 4):
+                    sem[i, k - 1], radius[i, k - 1] = producer(cls.name, k, cls.image_path(s))
+            if ev is None:
+                ev = FrameEvaluator(cls.cad_m * 1000, cls.keypoints_m[k0:k1, :] * 1000, sym, thr_mm, device=device, frames_per_batch=frames_per_batch,
+                                    image=(H, W), icp=icp, icp_max_iter=2000000, max_grid=max_grid)
+            Ks = np.stack([m["intrinsic_matrix"] for m in metas])
+            d = depth.view(np.int16) if depth.dtype == np.uint16 else depth.astype(np.float64)
+            res = ev.run(d, radius, Ks, gt, sem=sem, mask_flags=api.MASK_YCB, sem_threshold=0.8, depth_div=factor, xyz_div=1.0, scene_scale=1000.0,
+                         icp_threshold_mean=True)
+            st = res["status"]
+            if ((st & api.RCV_ST_EMPTY_MASK) != 0).any():
+                i, k = np.argwhere((st & api.RCV_ST_EMPTY_MASK) != 0)[0]
+                raise ValueError("zero-size array to reduction operation minimum which has no identity (frame %s, keypoint %d: empty mask)" % (stems[i], k + 1))
+            if st.any():
+                raise api.RcvError("voting failed with status %s" % np.unique(st))
+            for k, v in res.items():
+                acc.setdefault(k, []).append(v)
+    except Exception as e:   # noqa: BLE001 -- re-raised by sync_failure on every rank
+        failure = e
+    sync_failure(failure)
     out = {k: np.concatenate(v) for k, v in acc.items()}
     n = len(cls.stems)
     thr = np.array(ycb_auc_thresholds_m) * 1000

@@ -111,6 +111,12 @@ def write_ply_points(path, xyz, binary=True):
                 f.write(("%.9g %.9g %.9g\n" % tuple(row)).encode("ascii"))
 
 
+def read_rgb(path):
+    """(H,W,3) uint8 RGB of an image file, as FCResBackbone opens it (AccumulatorSpace.py:140-142: Image.open(...).convert('RGB'))."""
+    from PIL import Image
+    return np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
+
+
 def read_split(path):
     """One frame stem per line (AccumulatorSpace.py:502-503)."""
     with open(path, "r") as f:

@@ -95,24 +95,76 @@ def normalise_rgb(img_u8):
 class ProducerStage:
     """Three keypoint networks (AccumulatorSpace.py:516-527) in bf16 on one GPU, feeding the fused head + vote entry point:
     images -> conv7 activations (B,3,32,H,W) bf16 -> VoteContext.head_vote_frames.  The trunks are ordinary PyTorch modules in
-    eval mode; the head and everything after it are this package's CUDA kernels."""
+    eval mode; the head and everything after it are this package's CUDA kernels.
 
-    def __init__(self, trunks, ctx, dtype=torch.bfloat16):
+    `capture(batch, H, W)` records the three trunk forwards of a fixed batch shape in ONE CUDA graph (the trunks on three
+    forked streams, joined before the head): a 480x640 forward of one trunk is ~500 small cuDNN launches, launch-bound at the
+    batch sizes an evaluator uses, and the reference runs them one image and one network at a time (:594-599)."""
+
+    def __init__(self, trunks, ctx, dtype=torch.bfloat16, channels_last=False):
         assert len(trunks) >= 1
         self.ctx, self.dtype = ctx, dtype
         self.trunks = [t.to(device=ctx.device, dtype=dtype).eval() for t in trunks]
+        self.channels_last = bool(channels_last)
+        if self.channels_last:
+            self.trunks = [t.to(memory_format=torch.channels_last) for t in self.trunks]
         w, b = zip(*[t.head() for t in self.trunks])
         self.weight = torch.stack([x.float() for x in w]).contiguous()     # (Kp,2,32)
         self.bias = torch.stack([x.float() for x in b]).contiguous()       # (Kp,2)
+        self._graph = None
+
+    @torch.no_grad()
+    def _run(self, x, up, concurrent):
+        """x (B,3,H,W) -> up (B,Kp,32,H,W) (NCHW planes per (frame, keypoint): what the head's TMA boxes read)."""
+        if self.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+        if not concurrent or len(self.trunks) == 1:
+            for k, t in enumerate(self.trunks):
+                up[:, k] = t(x)
+            return
+        main = torch.cuda.current_stream()
+        side = self._side_streams
+        for k, t in enumerate(self.trunks):
+            st = main if k == 0 else side[k - 1]
+            if k:
+                st.wait_stream(main)
+            with torch.cuda.stream(st):
+                up[:, k] = t(x)
+        for st in side[:len(self.trunks) - 1]:
+            main.wait_stream(st)
+
+    @torch.no_grad()
+    def capture(self, batch, H, W, concurrent=True):
+        """CUDA-graphs the trunk forwards for images of shape (batch,3,H,W); afterwards `activations` replays the graph for
+        inputs of that shape (and runs eagerly for any other)."""
+        dev = self.ctx.device
+        self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(max(0, len(self.trunks) - 1))]
+        self._static_in = torch.zeros((batch, 3, H, W), dtype=self.dtype, device=dev)
+        self._static_up = torch.empty((batch, len(self.trunks), 32, H, W), dtype=self.dtype, device=dev)
+        warm = torch.cuda.Stream(device=dev)
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm):
+            for _ in range(3):                                   # cuDNN autotuning and workspace allocation happen outside the capture
+                self._run(self._static_in, self._static_up, concurrent)
+        torch.cuda.current_stream().wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._run(self._static_in, self._static_up, concurrent)
+        self._graph = g
+        return self
 
     @torch.no_grad()
     def activations(self, images):
         """images (B,3,H,W) float -> (B,Kp,32,H,W) in the stage's dtype, NCHW-contiguous per (frame, keypoint)."""
         x = images.to(device=self.ctx.device, dtype=self.dtype)
+        if self._graph is not None and tuple(x.shape) == tuple(self._static_in.shape):
+            self._static_in.copy_(x)
+            self._graph.replay()
+            return self._static_up
         B, _, H, W = x.shape
         up = torch.empty((B, len(self.trunks), 32, H, W), dtype=self.dtype, device=x.device)
-        for k, t in enumerate(self.trunks):
-            up[:, k] = t(x)
+        self._run(x, up, False)
         return up
 
     def vote(self, images, depth, K, max_radii, **kw):

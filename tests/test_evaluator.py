@@ -759,3 +759,21 @@ def test_ycb_format_readers(tmp_path):
     scipy.io.savemat(q, dict(intrinsic_matrix=K))
     with pytest.raises(ValueError):
         formats.load_ycb_meta(q)
+
+
+@_pending_gpu
+def test_lm_evaluator_revotes_items_beyond_max_grid(tmp_path):
+    """a grid beyond the evaluator context's max_grid (D_EXCEEDS_CAP) no longer aborts the class -- the offending items
+    are voted through the exact drop-in surface (grids up to 640) and the chain runs again with those centres.  With max_grid = 64
+    every item of this dataset takes that route and must give the default run's results."""
+    from rcvpose_b200 import evaluate
+    root = str(tmp_path) + "/"
+    synth.write_lm_dataset(root, "ape", 2, seed=9)
+    a = evaluate.evaluate_lm_class(root, "ape", frames_per_batch=2, verbose=False)
+    b = evaluate.evaluate_lm_class(root, "ape", frames_per_batch=2, verbose=False, max_grid=64)
+    assert (a["grid"] > 64).all()
+    for key in ("centre_mm", "scene_points"):
+        assert np.array_equal(a[key], b[key]), key
+    for key in ("RT", "dist_before", "RT_icp", "dist_after"):
+        np.testing.assert_allclose(a[key], b[key], rtol=1e-12, atol=1e-9, err_msg=key)
+    assert a["add_before"] == b["add_before"] and a["add_after"] == b["add_after"]

@@ -107,3 +107,58 @@ def test_producer_stage_feeds_the_fused_head_vote():
         up32 = trunks[0].float()(rgb.cuda()[:1])
     err = (up[:1, 0].float() - up32).abs().max().item()
     assert err <= 0.1 * max(1.0, up32.abs().max().item()), err
+
+
+@_pending_gpu
+def test_cuda_graphed_stage_equals_eager():
+    """The CUDA-graphed producer (three trunks on forked streams inside one graph) gives the eager activations, replay after replay."""
+    from rcvpose_b200 import api
+    ctx = api.VoteContext(0, max_items=8, max_points_total=1 << 20, max_grid=256)
+    torch.manual_seed(7)
+    stage = producer.ProducerStage([producer.RadiusTrunk() for _ in range(3)], ctx)
+    rgb = [torch.rand((1, 3, 96, 128)) for _ in range(3)]
+    want = [stage.activations(x).clone() for x in rgb]
+    stage.capture(1, 96, 128, concurrent=True)
+    for x, w in zip(rgb + rgb[:1], want + want[:1]):
+        got = stage.activations(x)
+        torch.cuda.synchronize()
+        assert got.shape == w.shape and torch.allclose(got.float(), w.float(), rtol=2e-2, atol=2e-2)     # cuDNN may pick another algorithm under capture
+    assert stage.activations(torch.rand((2, 3, 96, 128))).shape[0] == 2                                      # another shape runs eagerly
+
+
+@_pending_gpu
+def test_lm_evaluator_checkpoint_branch_through_the_fused_stage(tmp_path):
+    """N1 uses N2: evaluate_lm_class(using_ckpts=True, producer=<ProducerStage>) -- RGB -> trunks -> fused conv8 + mask rule + vote,
+    ICP scene from the survival bits -- against the same evaluator fed sem / radius MAPS that rcv_head_1x1 produced from the same
+    activations (the two-call route): keypoints, poses, ADD, scene sizes and ICP poses identical."""
+    from PIL import Image
+    from rcvpose_b200 import api, evaluate, formats, synth
+    root = str(tmp_path) + "/"
+    cls = "cat"
+    stems = synth.write_lm_dataset(root, cls, 3, seed=5)
+    rng = np.random.default_rng(0)
+    for s in os.listdir(root + "LINEMOD/" + cls + "/JPEGImages/"):
+        Image.fromarray(rng.integers(0, 256, size=(480, 640, 3)).astype(np.uint8)).save(root + "LINEMOD/" + cls + "/JPEGImages/" + s, quality=95)
+    ctx = api.VoteContext(0, max_items=16, max_points_total=1 << 22, max_grid=400, image=(480, 640), max_model_points=1500)
+    torch.manual_seed(11)
+    trunks = [producer.RadiusTrunk() for _ in range(3)]
+    for k, t in enumerate(trunks):          # untrained networks: make the head say "object everywhere, radius 1.1 .. 1.3 dm" so that the mask rule has work
+        with torch.no_grad():
+            t.conv8.weight.zero_()
+            t.conv8.bias.copy_(torch.tensor([3.0, 1.1 + 0.1 * k]))
+    stage = producer.ProducerStage(trunks, ctx)
+
+    def maps(class_name, k, image_path):      # the two-call route: the same activations through rcv_head_1x1, maps on the host
+        img = producer.normalise_rgb(formats.read_rgb(image_path))
+        up = stage.activations(img)
+        m = ctx.head_1x1(up[:, k - 1].contiguous(), stage.weight[k - 1], stage.bias[k - 1])
+        return m[0, 0].cpu().numpy(), m[0, 1].cpu().numpy()
+
+    a = evaluate.evaluate_lm_class(root, cls, using_ckpts=True, producer=stage, frames_per_batch=2, verbose=False)
+    b = evaluate.evaluate_lm_class(root, cls, using_ckpts=True, producer=maps, frames_per_batch=2, verbose=False)
+    assert a["frames"] == b["frames"] == sorted(stems)
+    for key in ("centre_mm", "n_points", "peak", "scene_points", "icp_iters"):
+        assert np.array_equal(a[key], b[key]), key
+    for key in ("RT", "dist_before", "RT_icp", "dist_after"):
+        np.testing.assert_allclose(a[key], b[key], rtol=1e-12, atol=1e-9, err_msg=key)
+    assert (a["n_points"] > 1000).all()

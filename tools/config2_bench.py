@@ -1,7 +1,6 @@
 """BASELINE configs[1] (LINEMOD 'ape' full test path on synthetic RGB-D): RGB -> three FCN-ResNet trunks (PyTorch bf16, random
 weights: there are no checkpoints offline) -> fused tcgen05 head + mask rule + vote -> Horn pose, on one B200.  Prints one JSON line
-with the time per stage (CUDA events on torch's current stream).  NOT YET RUN ON A GPU (written after round 1's GPU budget was
-spent); tools/gpu_round.sh runs it.  Because untrained networks give meaningless radii, the keypoints are not checked here --
+with the time per stage (CUDA events on torch's current stream).  Three producer variants: eager, CUDA-graphed, CUDA-graphed with channels_last trunks.  Because untrained networks give meaningless radii, the keypoints are not checked here --
 stage-wise parity is in tests/test_producer.py (trunk vs the reference model) and tests/test_evaluator.py (fused head + vote)."""
 import json
 import os
@@ -25,30 +24,45 @@ model_mm = torch.from_numpy(np.stack([f["kpts_mm"] - f["centre_mm"] for f in fra
 flags = api.RCV_MASK_MAX_RADIUS | api.RCV_MASK_RADIUS_POSITIVE    # random-init seg scores never reach 0.8: keep the radius rules only
 
 
-def step(ev=None):
-    mark = (lambda i: ev[i].record()) if ev is not None else (lambda i: None)
-    mark(0)
-    up = stage.activations(rgb)
-    mark(1)
-    out = ctx.head_vote_frames(up, stage.weight, stage.bias, depth, K, max_radii=max_radii, mask_flags=flags)
-    mark(2)
-    RT = ctx.horn_batch(model_mm, out["centre_mm"])
-    mark(3)
-    return out, RT
+def measure(stage, label):
+    def step(ev=None):
+        mark = (lambda i: ev[i].record()) if ev is not None else (lambda i: None)
+        mark(0)
+        up = stage.activations(rgb)
+        mark(1)
+        out = ctx.head_vote_frames(up, stage.weight, stage.bias, depth, K, max_radii=max_radii, mask_flags=flags)
+        mark(2)
+        RT = ctx.horn_batch(model_mm, out["centre_mm"])
+        mark(3)
+        return out, RT
 
-
-step()
-torch.cuda.synchronize()
-tot = np.zeros(3)
-for _ in range(REPS):
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    out, RT = step(ev)
+    step()
     torch.cuda.synchronize()
-    tot += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
-ms = tot / REPS
+    tot = np.zeros(3)
+    for _ in range(REPS):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        out, RT = step(ev)
+        torch.cuda.synchronize()
+        tot += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+    ms = tot / REPS
+    return out, {"producer": label, "stage_ms": {"trunks_pytorch_bf16": round(float(ms[0]), 3), "head_mask_vote": round(float(ms[1]), 3),
+                                                 "horn": round(float(ms[2]), 3)},
+                 "frames_per_s": round(B / ms.sum() * 1e3, 2), "frames_per_s_after_trunks": round(B / ms[1:].sum() * 1e3, 1),
+                 "trunk_tflops": round(3 * 265.6e9 * B / (ms[0] * 1e-3) / 1e12, 1)}
+
+
+rows = []
+out, r = measure(stage, "eager, one trunk after the other")
+rows.append(r)
+ref_centres = out["centre_mm"].clone()
+out, r = measure(stage.capture(B, 480, 640, concurrent=True), "one CUDA graph, the three trunks on forked streams")
+rows.append(r)
+same = bool(torch.equal(out["centre_mm"], ref_centres))
+del stage
+torch.manual_seed(0)
+stage_cl = producer.ProducerStage([producer.RadiusTrunk() for _ in range(3)], ctx, channels_last=True).capture(B, 480, 640, concurrent=True)
+out, r = measure(stage_cl, "CUDA graph + channels_last trunks")
+rows.append(r)
 print(json.dumps({"tool": "config2_bench", "workload": "BASELINE configs[1]: RGB -> 3 x FCN-ResNet-152 trunk (bf16, random weights) -> fused head + vote -> Horn",
-                  "frames": B, "reps": REPS, "stage_ms": {"trunks_pytorch_bf16": round(float(ms[0]), 3), "head_mask_vote": round(float(ms[1]), 3),
-                                                           "horn": round(float(ms[2]), 3)},
-                  "frames_per_s": round(B / ms.sum() * 1e3, 2), "frames_per_s_after_trunks": round(B / ms[1:].sum() * 1e3, 1),
-                  "points_per_item_mean": round(float(out["n_points"].float().mean()), 1), "status_nonzero": int((out["status"] != 0).sum()),
-                  "trunk_tflops": round(3 * 265.6e9 * B / (ms[0] * 1e-3) / 1e12, 1)}))
+                  "frames": B, "reps": REPS, "variants": rows, "graph_output_equals_eager": same,
+                  "points_per_item_mean": round(float(out["n_points"].float().mean()), 1), "status_nonzero": int((out["status"] != 0).sum())}))
