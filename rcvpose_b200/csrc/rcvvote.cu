@@ -520,6 +520,13 @@ __device__ double pw_leaf_sum(const double* __restrict__ a, int n) {
   return res;
 }
 
+// vote order of an item's points: bins of (y voxel, R), y major -- or R major (RCV_SORT_R_FIRST, experiments)
+#ifdef RCV_SORT_R_FIRST
+#define RCV_SORT_BIN(A, R) ((R) * nAq + (A))
+#else
+#define RCV_SORT_BIN(A, R) ((A) * nRq + (R))
+#endif
+
 struct PreludeArgs {
   Pool pool; ItemMeta* meta; Unit* units; int* counters; int max_units; int max_grid; int policy; int tile_words; int gen; int dp_mod;
   PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
@@ -713,7 +720,7 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
     __syncthreads();
     for (int q = threadIdx.x; q < n; q += blockDim.x) {
       const int ya = __double2int_rn(Y[q]), r = max(Ri[q], 0);
-      atomicAdd(&s_hist[((ya - amin) >> ash) * nRq + ((r - rmin) >> sh)], 1);
+      atomicAdd(&s_hist[RCV_SORT_BIN((ya - amin) >> ash, (r - rmin) >> sh)], 1);
     }
     __syncthreads();
     // exclusive scan of the bins: each thread owns a run of consecutive bins
@@ -734,7 +741,7 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
     int* perm = a.pool.perm + m.off;
     for (int q = threadIdx.x; q < n; q += blockDim.x) {
       const int ya = __double2int_rn(Y[q]), r = max(Ri[q], 0);
-      const int pos = atomicAdd(&s_hist[((ya - amin) >> ash) * nRq + ((r - rmin) >> sh)], 1);
+      const int pos = atomicAdd(&s_hist[RCV_SORT_BIN((ya - amin) >> ash, (r - rmin) >> sh)], 1);
       perm[pos] = q;
       if (a.gen >= 2) {   // internal axes (A,B,C) = reference (y,x,z)
         RunPoint rp;
@@ -1364,6 +1371,11 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
 constexpr int kRunsThreads = RCV_RUNS_THREADS;
 constexpr int kRunsWarps = kRunsThreads / 32;
 constexpr int kRunsTileWords = kSmemBytes / 4 - 192 - 2 * 64 * (RCV_RUNS_THREADS / 32);    // static shared variables: 192 words + the per-warp queues of deferred exact decisions
+// The two planes of a tile sit at a fixed distance (half the tile memory), so the address of an end mark is the start
+// plane's address plus an immediate.
+constexpr int kRunsPlaneWords = (kRunsTileWords / 2) & ~3;
+constexpr unsigned kRunsPlaneBytes = (unsigned)kRunsPlaneWords * 4u;
+__device__ __forceinline__ void smem_inc_e(unsigned addr) { asm volatile("red.shared.add.u32 [%0+%1], 1;" ::"r"(addr), "n"(kRunsPlaneBytes) : "memory"); }
 
 // Only `add 1` (ATOMS.POPC.INC) merges the lanes of a warp that hit the same address; every other shared-memory atomic
 // (add of a register or of -1, inc, dec) replays once per duplicate lane (tools/ubench_atoms2.cu,
@@ -1380,7 +1392,7 @@ struct RunSlowCtx {
 };
 template <bool CLIP>
 __device__ __noinline__ void runs_slow_column(RunPoint c, int pidx, RunSlowCtx sc, int u, int uc, int i0c, int nsl, int Dp, unsigned K0, unsigned slice_bytes,
-                                              unsigned plane_bytes, int clo, int chi) {
+                                              int clo, int chi) {
   RunLane L;
   run_lane_setup(c, L);
   RunCol C;
@@ -1397,8 +1409,8 @@ __device__ __noinline__ void runs_slow_column(RunPoint c, int pidx, RunSlowCtx s
     auto fix = [&](unsigned nbits, int delta) {   // voxel m joins (delta = +1) or leaves (-1) the set: a run [m, m+1) added to / taken from the planes
       int b0 = (int)nbits, b1 = (int)nbits + 1;
       if (CLIP) { b0 = min(max(b0, (int)base + clo), (int)base + chi); b1 = min(max(b1, (int)base + clo), (int)base + chi); }
-      smem_inc((unsigned)b0 * 4u + K + (delta > 0 ? 0u : plane_bytes));
-      smem_inc((unsigned)b1 * 4u + K + (delta > 0 ? plane_bytes : 0u));
+      smem_inc((unsigned)b0 * 4u + K + (delta > 0 ? 0u : kRunsPlaneBytes));
+      smem_inc((unsigned)b1 * 4u + K + (delta > 0 ? kRunsPlaneBytes : 0u));
     };
     run_slow_slice(L, C, aa, base, exact, fix);
   }
@@ -1411,7 +1423,7 @@ __device__ __noinline__ void runs_slow_column(RunPoint c, int pidx, RunSlowCtx s
 constexpr int kRunsQueue = 64;
 struct RunTile {               // per-tile constants of the rare path
   Tile t;
-  unsigned tile_s, slice_bytes, plane_bytes;
+  unsigned tile_s, slice_bytes;
   const int4* rec;             // point records of the item (item base already added)
   RunSlowCtx sc;
   bool clip;
@@ -1432,13 +1444,14 @@ __device__ __noinline__ void runs_slow_item(const RunTile& rt, unsigned long lon
   const int u = (int)(hi & 0xfffu) - 2048, nsl = (int)((hi >> 12) & 0xfu), i0c = (int)(hi >> 16);
   const RunPoint c = run_load_point(rt.rec, pidx);
   const int clo = -rt.t.glo - c.ipc, chi = rt.t.D + rt.t.ghi - c.ipc;
-  if (rt.clip) runs_slow_column<true>(c, pidx, rt.sc, u, u, i0c, nsl, rt.t.Dp, run_K0(rt, c, i0c), rt.slice_bytes, rt.plane_bytes, clo, chi);
-  else runs_slow_column<false>(c, pidx, rt.sc, u, u, i0c, nsl, rt.t.Dp, run_K0(rt, c, i0c), rt.slice_bytes, rt.plane_bytes, clo, chi);
+  if (rt.clip) runs_slow_column<true>(c, pidx, rt.sc, u, u, i0c, nsl, rt.t.Dp, run_K0(rt, c, i0c), rt.slice_bytes, clo, chi);
+  else runs_slow_column<false>(c, pidx, rt.sc, u, u, i0c, nsl, rt.t.Dp, run_K0(rt, c, i0c), rt.slice_bytes, clo, chi);
 }
 // Drains the warp's queue: whole batches of 32 items, or everything when `all`.  Called by all 32 lanes.
 __device__ __forceinline__ void runs_drain(const RunTile& rt, unsigned long long* q, int* qn, bool all) {
   __syncwarp();
   int n = min(*qn, kRunsQueue);
+  __syncwarp();                       // every lane has read the count before lane 0 may write it back
   const int lane = threadIdx.x & 31;
   while (n >= 32 || (all && n > 0)) {
     const int take = min(n, 32);
@@ -1464,8 +1477,7 @@ __device__ __forceinline__ void runs_push(const RunTile& rt, unsigned long long*
 
 // One column of the chunk for this lane: the four marks per slice; returns 1 if a boundary of the column is flagged.
 template <int NC, bool CLIP>
-__device__ __forceinline__ unsigned runs_one_column(const RunLane& L, const RunCol& C, const f2 (&aa)[NC], const unsigned (&K)[NC], const unsigned (&KE)[NC],
-                                                    int lo, int hi) {
+__device__ __forceinline__ unsigned runs_one_column(const RunLane& L, const RunCol& C, const f2 (&aa)[NC], const unsigned (&K)[NC], int lo, int hi) {
   unsigned amb = 0u;
 #pragma unroll
   for (int s = 0; s < NC; ++s) {
@@ -1474,9 +1486,9 @@ __device__ __forceinline__ unsigned runs_one_column(const RunLane& L, const RunC
     int b1 = (int)o.b1, b2 = (int)o.b2, b3 = (int)o.b3, b4 = (int)o.b4;
     if (CLIP) { b1 = min(max(b1, lo), hi); b2 = min(max(b2, lo), hi); b3 = min(max(b3, lo), hi); b4 = min(max(b4, lo), hi); }
     smem_inc((unsigned)b1 * 4u + K[s]);
-    smem_inc((unsigned)b2 * 4u + KE[s]);
+    smem_inc_e((unsigned)b2 * 4u + K[s]);
     smem_inc((unsigned)b3 * 4u + K[s]);
-    smem_inc((unsigned)b4 * 4u + KE[s]);
+    smem_inc_e((unsigned)b4 * 4u + K[s]);
     run_flag_acc(amb, o);
   }
   return amb;
@@ -1490,7 +1502,7 @@ __device__ __forceinline__ unsigned runs_one_column(const RunLane& L, const RunC
 //        (= MAGIC_BITS + uc * Dp + lattice offset) is  b * 4 + K0 + s * slice_bytes.
 template <int NC, bool CLIP, bool PARK>
 __device__ __forceinline__ void runs_columns(const RunPoint& c, const RunLane& L, const RunTile& rt, const f2 (&aa)[NC], const unsigned (&K)[NC],
-                                             const unsigned (&KE)[NC], int ua, int ub, int ulo, int uhi, int pidx, int i0c, int nsl,
+                                             int ua, int ub, int ulo, int uhi, int pidx, int i0c, int nsl,
                                              unsigned long long* q, int* qn) {
   const Tile& t = rt.t;
   const int clo = -t.glo - c.ipc, chi = t.D + t.ghi - c.ipc;   // clip bounds of the boundary bits relative to `base` (CLIP)
@@ -1514,8 +1526,8 @@ __device__ __forceinline__ void runs_columns(const RunPoint& c, const RunLane& L
         const float du0 = f_sub(uf, c.fb), uf1 = f_add(uf, 1.0f), du1 = f_sub(uf1, c.fb);
         C0.mu = f2_dup(f_fma(uf, Dpf, RCV_MAGIC)); C0.du = f2_dup(du0); C0.ndu = f2_dup(-du0);
         C1.mu = f2_dup(f_fma(uf1, Dpf, RCV_MAGIC)); C1.du = f2_dup(du1); C1.ndu = f2_dup(-du1);
-        const unsigned a0 = runs_one_column<NC, false>(L, C0, aa, K, KE, 0, 0);
-        const unsigned a1 = runs_one_column<NC, false>(L, C1, aa, K, KE, 0, 0);
+        const unsigned a0 = runs_one_column<NC, false>(L, C0, aa, K, 0, 0);
+        const unsigned a1 = runs_one_column<NC, false>(L, C1, aa, K, 0, 0);
         if (a0) flags |= bit;
         if (a1) flags |= bit << 1;
       }
@@ -1534,7 +1546,7 @@ __device__ __forceinline__ void runs_columns(const RunPoint& c, const RunLane& L
       }
       C.du = f2_dup(du); C.ndu = f2_dup(-du);
       const int base = RCV_MAGIC_BITS + uc * t.Dp;
-      if (runs_one_column<NC, CLIP>(L, C, aa, K, KE, base + clo, base + chi)) flags |= bit;
+      if (runs_one_column<NC, CLIP>(L, C, aa, K, base + clo, base + chi)) flags |= bit;
     }
     if (__any_sync(0xffffffffu, flags != 0u)) {
       runs_push(rt, q, qn, flags, pidx, u0, i0c, nsl);            // (a flagged column is never a parked one)
@@ -1570,15 +1582,15 @@ __device__ __forceinline__ void runs_chunk(const RunPoint& c, const RunLane& L, 
   // starts go to plane 0, ends to plane 1; a slice of the chunk beyond the tile (its columns are all empty) re-uses the
   // last real slice's cells, where its four marks cancel
   const unsigned K0 = run_K0(rt, c, i0c);
-  unsigned K[NC], KE[NC];
+  unsigned K[NC];
 #pragma unroll
-  for (int s = 0; s < NC; ++s) { K[s] = K0 + (unsigned)min(s, nsl - 1) * rt.slice_bytes; KE[s] = K[s] + rt.plane_bytes; }
+  for (int s = 0; s < NC; ++s) K[s] = K0 + (unsigned)min(s, nsl - 1) * rt.slice_bytes;
   if (CLIP || mlo > mhi) {
-    runs_columns<NC, CLIP, true>(c, L, rt, aa, K, KE, wlo, whi, ulo, uhi, pidx, i0c, nsl, q, qn);
+    runs_columns<NC, CLIP, true>(c, L, rt, aa, K, wlo, whi, ulo, uhi, pidx, i0c, nsl, q, qn);
   } else {
-    if (wlo < mlo) runs_columns<NC, CLIP, true>(c, L, rt, aa, K, KE, wlo, mlo - 1, ulo, uhi, pidx, i0c, nsl, q, qn);
-    runs_columns<NC, CLIP, false>(c, L, rt, aa, K, KE, mlo, mhi, ulo, uhi, pidx, i0c, nsl, q, qn);
-    if (mhi < whi) runs_columns<NC, CLIP, true>(c, L, rt, aa, K, KE, mhi + 1, whi, ulo, uhi, pidx, i0c, nsl, q, qn);
+    if (wlo < mlo) runs_columns<NC, CLIP, true>(c, L, rt, aa, K, wlo, mlo - 1, ulo, uhi, pidx, i0c, nsl, q, qn);
+    runs_columns<NC, CLIP, false>(c, L, rt, aa, K, mlo, mhi, ulo, uhi, pidx, i0c, nsl, q, qn);
+    if (mhi < whi) runs_columns<NC, CLIP, true>(c, L, rt, aa, K, mhi + 1, whi, ulo, uhi, pidx, i0c, nsl, q, qn);
   }
 }
 
@@ -1609,15 +1621,16 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
     // whole-slice tiles whose guard band holds every sphere of the item need no clipping (the prelude sized the guards);
     // row bands and unguarded grids (guard = 0 although spheres overhang) take the clipped variant
     const bool clip = m.clip != 0;
-    const int plane_words = (u.ni * u.nj * Dp + 3) & ~3;   // plane 0: run starts, plane 1: run ends
+    const int plane_words = (u.ni * u.nj * Dp + 3) & ~3;   // plane 0: run starts at word 0, plane 1: run ends at word kRunsPlaneWords
     {
       int4* t4 = reinterpret_cast<int4*>(tile);
-      const int n4 = plane_words >> 1;
-      for (int w = threadIdx.x; w < n4; w += kRunsThreads) t4[w] = make_int4(0, 0, 0, 0);
+      int4* e4 = reinterpret_cast<int4*>(tile + kRunsPlaneWords);
+      const int n4 = plane_words >> 2;
+      for (int w = threadIdx.x; w < n4; w += kRunsThreads) { t4[w] = make_int4(0, 0, 0, 0); e4[w] = make_int4(0, 0, 0, 0); }
     }
     __syncthreads();
     // ---- scatter: a work item is (chunk of NC slices, group of 32 consecutive points of the vote order) ----
-    const unsigned slice_bytes = (unsigned)(u.nj * Dp * 4), plane_bytes = (unsigned)plane_words * 4u;
+    const unsigned slice_bytes = (unsigned)(u.nj * Dp * 4);
 #ifdef RCV_RUNS_MAX_NC
     const int NC = min(ring_chunk(u.ni), RCV_RUNS_MAX_NC);
 #else
@@ -1625,7 +1638,7 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
 #endif
     const int ngroups = (n + 31) >> 5, nchunks = (u.ni + NC - 1) / NC, nwork = ngroups * nchunks;
     const RunSlowCtx sc{a.pool.X + off, a.pool.Y + off, a.pool.Z + off, a.pool.perm + off};
-    const RunTile rt{t, tile_s, slice_bytes, plane_bytes, a.pool.rec + 2 * off, sc, clip};
+    const RunTile rt{t, tile_s, slice_bytes, a.pool.rec + 2 * off, sc, clip};
     unsigned long long* q = s_q[warp];
     int* qn = &s_qn[warp];
     for (;;) {
@@ -1671,7 +1684,7 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
       const int sa = r / njr, gb = jr0 + r - sa * njr, ga = u.i0 + sa;
       const unsigned lin0 = ((unsigned)gb * (unsigned)D + (unsigned)ga) * (unsigned)D;
       int* row = tile + (sa * u.nj + (gb - u.j0)) * Dp;
-      const int* rowe = row + plane_words;
+      const int* rowe = row + kRunsPlaneWords;
       int run = 0;
       for (int k = 0; k < glo; ++k) run += row[k] - rowe[k];
       int best = -1, bestk = 0;
@@ -2057,7 +2070,7 @@ static int run_items(rcv_ctx* c, int n_items, const rcv_vote_params* vp, double*
   CK(c, cudaMemsetAsync(c->best, 0, 8 * (size_t)n_items, st));
   CK(c, cudaMemsetAsync(c->votes, 0, 8 * (size_t)n_items, st));
   PreludeArgs pa{c->pool, c->meta, c->units, c->counters, c->cfg.max_units, c->cfg.max_grid, vp->grid_policy,
-                 c->gen >= 2 ? kRunsTileWords : kTileWords, c->gen, c->dp_mod, c->leaves, c->leaf_sums, c->leaf_cap};
+                 c->gen >= 2 ? 2 * kRunsPlaneWords : kTileWords, c->gen, c->dp_mod, c->leaves, c->leaf_sums, c->leaf_cap};
   k_prelude<<<n_items, kPreludeThreads, 0, st>>>(pa);
   VoteArgs va{c->pool, c->meta, c->units, c->counters, c->best, c->votes, volume, volume_cap};
   const int slot = (int)(c->ev_count % 64);
