@@ -68,6 +68,7 @@ struct Pool {
   int* Ri;                 // np.around(radius) -- AccumulatorSpace.py:332
   int* perm;               // per item: its points ordered by (y voxel, R) so that the 32 points of a warp of k_vote draw alike
   int4* rec;               // per point IN VOTE ORDER: the float32 record of the run rasteriser (RunPoint, 2 x int4)
+  int* grp;                // per group of 32 points in vote order: the y-slices its spheres reach, lo | hi << 16 (item b starts at off / 32 + b)
   long long cap;
 };
 
@@ -520,11 +521,12 @@ __device__ double pw_leaf_sum(const double* __restrict__ a, int n) {
   return res;
 }
 
-// vote order of an item's points: bins of (y voxel, R), y major -- or R major (RCV_SORT_R_FIRST, experiments)
-#ifdef RCV_SORT_R_FIRST
-#define RCV_SORT_BIN(A, R) ((R) * nAq + (A))
-#else
+// vote order of an item's points: bins of (R, y voxel), R major.  (y major, generation 1's order, leaves 79 % of the run
+// kernel's lane-slots live against 84 %: lanes of equal radius keep the same column range in every slice of a chunk.)
+#ifdef RCV_SORT_Y_FIRST
 #define RCV_SORT_BIN(A, R) ((A) * nRq + (R))
+#else
+#define RCV_SORT_BIN(A, R) ((R) * nAq + (A))
 #endif
 
 struct PreludeArgs {
@@ -750,6 +752,22 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
         rec[0] = make_int4(rp.ipa, rp.ipb, rp.ipc, rp.R);
         rec[1] = make_int4(__float_as_int(rp.fa), __float_as_int(rp.fb), __float_as_int(rp.fc), __float_as_int(rp.W));
       }
+    }
+  }
+  // gen 2: slice range reached by each group of 32 points in vote order (the vote kernel builds a tile's work list from these)
+  if (a.gen >= 2) {
+    __syncthreads();
+    int* grp = a.pool.grp + (m.off >> 5) + item;
+    const int4* rec = a.pool.rec + 2 * m.off;
+    for (int g = warp; g * 32 < n; g += kPreludeThreads / 32) {
+      const int q = g * 32 + lane;
+      int lo = 0x7fff, hi = -0x8000;
+      if (q < n) {
+        const int4 r0 = rec[2 * q];
+        if (r0.w > 0) { lo = max(r0.x - r0.w - 1, -0x8000); hi = min(r0.x + r0.w + 1, 0x7fff); }
+      }
+      lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+      if (lane == 0) grp[g] = (lo & 0xffff) | (hi << 16);
     }
   }
   // tile work list
@@ -1366,11 +1384,12 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
 // vote tally.
 // ------------------------------------------------------------------------------------------------
 #ifndef RCV_RUNS_THREADS
-#define RCV_RUNS_THREADS 512
+#define RCV_RUNS_THREADS 640
 #endif
 constexpr int kRunsThreads = RCV_RUNS_THREADS;
 constexpr int kRunsWarps = kRunsThreads / 32;
-constexpr int kRunsTileWords = kSmemBytes / 4 - 192 - 2 * 64 * (RCV_RUNS_THREADS / 32);    // static shared variables: 192 words + the per-warp queues of deferred exact decisions
+constexpr int kRunsWorkList = 1024;
+constexpr int kRunsTileWords = kSmemBytes / 4 - 192 - kRunsWorkList / 2 - 2 * 64 * (RCV_RUNS_THREADS / 32);    // static shared variables: 192 words + the per-warp queues of deferred exact decisions
 // The two planes of a tile sit at a fixed distance (half the tile memory), so the address of an end mark is the start
 // plane's address plus an immediate.
 constexpr int kRunsPlaneWords = (kRunsTileWords / 2) & ~3;
@@ -1601,6 +1620,8 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
   __shared__ unsigned long long s_key[kRunsWarps], s_sum[kRunsWarps];
   __shared__ unsigned long long s_q[kRunsWarps][kRunsQueue];
   __shared__ int s_qn[kRunsWarps];
+  __shared__ unsigned short s_work[kRunsWorkList];   // the tile's work items (chunk * ngroups + group) whose spheres reach the chunk
+  __shared__ int s_nwork;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
   asm volatile("mov.u32 %0, %0;" : "+r"(tile_s));
@@ -1608,7 +1629,7 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
   if (lane == 0) s_qn[warp] = 0;
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) { s_unit = atomicAdd(&a.counters[1], 1); s_next = 0; }
+    if (threadIdx.x == 0) { s_unit = atomicAdd(&a.counters[1], 1); s_next = 0; s_nwork = 0; }
     __syncthreads();
     const int ui = s_unit;
     if (ui >= n_units) break;
@@ -1628,7 +1649,6 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
       const int n4 = plane_words >> 2;
       for (int w = threadIdx.x; w < n4; w += kRunsThreads) { t4[w] = make_int4(0, 0, 0, 0); e4[w] = make_int4(0, 0, 0, 0); }
     }
-    __syncthreads();
     // ---- scatter: a work item is (chunk of NC slices, group of 32 consecutive points of the vote order) ----
     const unsigned slice_bytes = (unsigned)(u.nj * Dp * 4);
 #ifdef RCV_RUNS_MAX_NC
@@ -1636,21 +1656,55 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
 #else
     const int NC = ring_chunk(u.ni);
 #endif
-    const int ngroups = (n + 31) >> 5, nchunks = (u.ni + NC - 1) / NC, nwork = ngroups * nchunks;
+    const int ngroups = (n + 31) >> 5, nchunks = (u.ni + NC - 1) / NC, nall = ngroups * nchunks;
+    // Work list: only the (chunk, group) pairs whose spheres reach the chunk's slices (group summaries from the prelude), so
+    // that no warp fetches the records of a group just to find that it has nothing to draw.  Too many pairs for the list
+    // (huge items): every pair is a work item and the test is made on the records, as before.
+    const bool listed = nall <= 65535;
+    if (listed) {
+      const int* grp = a.pool.grp + (off >> 5) + u.item;
+      for (int w = threadIdx.x; w < nall; w += kRunsThreads) {
+        const int ch = w / ngroups, g = w - ch * ngroups;
+        const int i0c = u.i0 + ch * NC, i1c = min(i0c + NC, u.i0 + u.ni) - 1;
+        const int r = __ldg(grp + g);
+        const int lo = (short)(r & 0xffff), hi = r >> 16;
+        if (hi >= i0c && lo <= i1c) {
+          const int slot = atomicAdd(&s_nwork, 1);
+          if (slot < kRunsWorkList) s_work[slot] = (unsigned short)w;
+        }
+      }
+    }
+    __syncthreads();
+    const bool use_list = listed && s_nwork <= kRunsWorkList;
+    const int nwork = use_list ? s_nwork : nall;
     const RunSlowCtx sc{a.pool.X + off, a.pool.Y + off, a.pool.Z + off, a.pool.perm + off};
     const RunTile rt{t, tile_s, slice_bytes, a.pool.rec + 2 * off, sc, clip};
     unsigned long long* q = s_q[warp];
     int* qn = &s_qn[warp];
+    // The next work item is pulled, and its point records requested, before the current one is drawn: the L2 latency of the
+    // records hides behind the column loops.
+    auto pull = [&](int& w, int4& r0, int4& r1) {
+      int k = 0;
+      if (lane == 0) k = atomicAdd(&s_next, 1);
+      k = __shfl_sync(0xffffffffu, k, 0);
+      w = k < nwork ? (use_list ? (int)s_work[k] : k) : -1;
+      r0 = make_int4(0, 0, 0, 0); r1 = make_int4(0, 0, 0, 0);
+      if (w >= 0) {
+        const int pi = ((w % ngroups) << 5) + lane;
+        if (pi < n) { r0 = __ldg(rt.rec + 2 * pi); r1 = __ldg(rt.rec + 2 * pi + 1); }
+      }
+    };
+    int w_nxt; int4 n0, n1;
+    pull(w_nxt, n0, n1);
     for (;;) {
-      int w = 0;
-      if (lane == 0) w = atomicAdd(&s_next, 1);
-      w = __shfl_sync(0xffffffffu, w, 0);
-      if (w >= nwork) break;
+      const int w = w_nxt;
+      if (w < 0) break;
+      RunPoint c;
+      c.ipa = n0.x; c.ipb = n0.y; c.ipc = n0.z; c.R = n0.w;
+      c.fa = __int_as_float(n1.x); c.fb = __int_as_float(n1.y); c.fc = __int_as_float(n1.z); c.W = __int_as_float(n1.w);
+      pull(w_nxt, n0, n1);
       const int ch = w / ngroups, cur = (w - ch * ngroups) << 5;
       const int i0c = u.i0 + ch * NC, nsl = min(NC, u.i0 + u.ni - i0c);
-      RunPoint c;
-      c.ipa = 0; c.ipb = 0; c.ipc = 0; c.R = 0; c.fa = 0.f; c.fb = 0.f; c.fc = 0.f; c.W = 0.f;
-      if (cur + lane < n) c = run_load_point(rt.rec, cur + lane);
       // does any sphere of the group reach the chunk's slices?
       const bool here = c.R > 0 && (c.ipa + c.R + 1 >= i0c) && (c.ipa - c.R - 1 <= i0c + nsl - 1);
       if (!__any_sync(0xffffffffu, here)) continue;
@@ -1978,7 +2032,7 @@ RCV_EXPORT long long rcv_last_h2d_bytes(const rcv_ctx* ctx) { return ctx ? ctx->
 RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri); cudaFree(c->pool.perm); cudaFree(c->pool.rec);
+  cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri); cudaFree(c->pool.perm); cudaFree(c->pool.rec); cudaFree(c->pool.grp);
   cudaFree(c->meta); cudaFree(c->units); cudaFree(c->counters); cudaFree(c->cnt); cudaFree(c->best); cudaFree(c->votes);
   cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits); cudaFree(c->add_part); cudaFree(c->icp_scratch); cudaFree(c->head_radius);
   for (int s = 0; s < 2; ++s) { cudaFree(c->st_depth[s]); cudaFree(c->st_radius[s]); cudaFree(c->st_sem[s]); }
@@ -2032,6 +2086,7 @@ RCV_EXPORT int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out) {
   CKC(cudaMalloc(&c->pool.X, cap * 8)); CKC(cudaMalloc(&c->pool.Y, cap * 8)); CKC(cudaMalloc(&c->pool.Z, cap * 8));
   CKC(cudaMalloc(&c->pool.Rd, cap * 8)); CKC(cudaMalloc(&c->pool.Ri, cap * 4)); CKC(cudaMalloc(&c->pool.perm, cap * 4));
   CKC(cudaMalloc(&c->pool.rec, cap * 32));
+  CKC(cudaMalloc(&c->pool.grp, (size_t)(cap / 32 + cfg->max_items + 8) * 4));
   CKC(cudaMalloc(&c->meta, sizeof(ItemMeta) * (size_t)cfg->max_items));
   CKC(cudaMalloc(&c->units, sizeof(Unit) * (size_t)c->cfg.max_units));
   CKC(cudaMalloc(&c->counters, 64 + 4096));
