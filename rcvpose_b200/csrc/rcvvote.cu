@@ -1386,10 +1386,14 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
 #ifndef RCV_RUNS_THREADS
 #define RCV_RUNS_THREADS 640
 #endif
+#ifndef RCV_RUNS_CTAS
+#define RCV_RUNS_CTAS 1            // resident CTAs per SM (each gets 1/RCV_RUNS_CTAS of the shared memory)
+#endif
 constexpr int kRunsThreads = RCV_RUNS_THREADS;
 constexpr int kRunsWarps = kRunsThreads / 32;
 constexpr int kRunsWorkList = 1024;
-constexpr int kRunsTileWords = kSmemBytes / 4 - 192 - kRunsWorkList / 2 - 2 * 64 * (RCV_RUNS_THREADS / 32);    // static shared variables: 192 words + the per-warp queues of deferred exact decisions
+constexpr int kRunsSmemBytes = RCV_RUNS_CTAS == 1 ? kSmemBytes : (228 * 1024 / RCV_RUNS_CTAS - 1024) & ~15;   // 228 KB per SM, 1 KB reserved per CTA
+constexpr int kRunsTileWords = kRunsSmemBytes / 4 - 192 - kRunsWorkList / 2 - 2 * 64 * (RCV_RUNS_THREADS / 32);    // static shared variables: 192 words + the per-warp queues of deferred exact decisions
 // The two planes of a tile sit at a fixed distance (half the tile memory), so the address of an end mark is the start
 // plane's address plus an immediate.
 constexpr int kRunsPlaneWords = (kRunsTileWords / 2) & ~3;
@@ -1591,10 +1595,11 @@ __device__ __forceinline__ void runs_chunk(const RunPoint& c, const RunLane& L, 
   if (CLIP) { ulo = max(ulo, t.j0 - c.ipb); uhi = min(uhi, t.j0 + t.nj - 1 - c.ipb); }
   if (Hl < 0) { ulo = 1; uhi = 0; }
   const bool some = ulo <= uhi;
-  const int wlo = __reduce_min_sync(0xffffffffu, some ? ulo : 0x7fffffff), whi = __reduce_max_sync(0xffffffffu, some ? uhi : -0x7fffffff);
+  int wlo = __reduce_min_sync(0xffffffffu, some ? ulo : 0x7fffffff), whi = __reduce_max_sync(0xffffffffu, some ? uhi : -0x7fffffff);
   if (wlo > whi) return;
   // the stretch every lane covers with its own range: there the column body needs no parking logic
   int mlo = __reduce_max_sync(0xffffffffu, some ? ulo : 0x7fffffff), mhi = __reduce_min_sync(0xffffffffu, some ? uhi : -0x7fffffff);
+  mlo = max(mlo, wlo); mhi = min(mhi, whi);
   // a lane without columns parks on a row that is certainly inside the tile
   const int upark = CLIP ? min(max(0, t.j0 - c.ipb), t.j0 + t.nj - 1 - c.ipb) : 0;
   if (!some) { ulo = upark; uhi = upark; }
@@ -1613,7 +1618,7 @@ __device__ __forceinline__ void runs_chunk(const RunPoint& c, const RunLane& L, 
   }
 }
 
-__global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
+__global__ void __launch_bounds__(kRunsThreads, RCV_RUNS_CTAS) k_vote_runs(VoteArgs a) {
   extern __shared__ __align__(16) int smem[];
   int* tile = smem;
   __shared__ int s_unit, s_next;
@@ -1628,7 +1633,7 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
   const int n_units = a.counters[0];
   if (lane == 0) s_qn[warp] = 0;
   for (;;) {
-    __syncthreads();
+    __syncthreads();                     // the previous tile is finished
     if (threadIdx.x == 0) { s_unit = atomicAdd(&a.counters[1], 1); s_next = 0; s_nwork = 0; }
     __syncthreads();
     const int ui = s_unit;
@@ -1676,13 +1681,13 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
     }
     __syncthreads();
     const bool use_list = listed && s_nwork <= kRunsWorkList;
+    // (Measured and dropped, r02q/r02r: splitting the tile's last work items into column halves, fetching the next tile's
+    // unit index during the scatter, and requesting the next item's records one item ahead -- each 0.5-4% slower.)
     const int nwork = use_list ? s_nwork : nall;
     const RunSlowCtx sc{a.pool.X + off, a.pool.Y + off, a.pool.Z + off, a.pool.perm + off};
     const RunTile rt{t, tile_s, slice_bytes, a.pool.rec + 2 * off, sc, clip};
     unsigned long long* q = s_q[warp];
     int* qn = &s_qn[warp];
-    // The next work item is pulled, and its point records requested, before the current one is drawn: the L2 latency of the
-    // records hides behind the column loops.
     auto pull = [&](int& w, int4& r0, int4& r1) {
       int k = 0;
       if (lane == 0) k = atomicAdd(&s_next, 1);
@@ -1694,15 +1699,13 @@ __global__ void __launch_bounds__(kRunsThreads, 1) k_vote_runs(VoteArgs a) {
         if (pi < n) { r0 = __ldg(rt.rec + 2 * pi); r1 = __ldg(rt.rec + 2 * pi + 1); }
       }
     };
-    int w_nxt; int4 n0, n1;
-    pull(w_nxt, n0, n1);
     for (;;) {
-      const int w = w_nxt;
+      int w; int4 n0, n1;
+      pull(w, n0, n1);
       if (w < 0) break;
       RunPoint c;
       c.ipa = n0.x; c.ipb = n0.y; c.ipc = n0.z; c.R = n0.w;
       c.fa = __int_as_float(n1.x); c.fb = __int_as_float(n1.y); c.fc = __int_as_float(n1.z); c.W = __int_as_float(n1.w);
-      pull(w_nxt, n0, n1);
       const int ch = w / ngroups, cur = (w - ch * ngroups) << 5;
       const int i0c = u.i0 + ch * NC, nsl = min(NC, u.i0 + u.ni - i0c);
       // does any sphere of the group reach the chunk's slices?
@@ -2130,7 +2133,7 @@ static int run_items(rcv_ctx* c, int n_items, const rcv_vote_params* vp, double*
   VoteArgs va{c->pool, c->meta, c->units, c->counters, c->best, c->votes, volume, volume_cap};
   const int slot = (int)(c->ev_count % 64);
   CK(c, cudaEventRecord(c->evr[slot][0], st));
-  if (c->gen >= 2) k_vote_runs<<<c->sms, kRunsThreads, kRunsTileWords * 4, st>>>(va);
+  if (c->gen >= 2) k_vote_runs<<<c->sms * RCV_RUNS_CTAS, kRunsThreads, kRunsTileWords * 4, st>>>(va);
   else k_vote<<<c->sms, kVoteThreads, (kTileWords + kDummyWords) * 4, st>>>(va);
   CK(c, cudaEventRecord(c->evr[slot][1], st));
   c->ev_count += 1;
