@@ -1386,6 +1386,9 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
 #ifndef RCV_RUNS_THREADS
 #define RCV_RUNS_THREADS 640
 #endif
+#ifndef RCV_RUNS_SMALL_FRAC
+#define RCV_RUNS_SMALL_FRAC 0.36f   // a work item is "short" if its chord is below 0.6 of the item's widest
+#endif
 #ifndef RCV_RUNS_CTAS
 #define RCV_RUNS_CTAS 1            // resident CTAs per SM (each gets 1/RCV_RUNS_CTAS of the shared memory)
 #endif
@@ -1626,7 +1629,7 @@ __global__ void __launch_bounds__(kRunsThreads, RCV_RUNS_CTAS) k_vote_runs(VoteA
   __shared__ unsigned long long s_q[kRunsWarps][kRunsQueue];
   __shared__ int s_qn[kRunsWarps];
   __shared__ unsigned short s_work[kRunsWorkList];   // the tile's work items (chunk * ngroups + group) whose spheres reach the chunk
-  __shared__ int s_nwork;
+  __shared__ int s_nwork, s_nsmall;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
   asm volatile("mov.u32 %0, %0;" : "+r"(tile_s));
@@ -1634,7 +1637,7 @@ __global__ void __launch_bounds__(kRunsThreads, RCV_RUNS_CTAS) k_vote_runs(VoteA
   if (lane == 0) s_qn[warp] = 0;
   for (;;) {
     __syncthreads();                     // the previous tile is finished
-    if (threadIdx.x == 0) { s_unit = atomicAdd(&a.counters[1], 1); s_next = 0; s_nwork = 0; }
+    if (threadIdx.x == 0) { s_unit = atomicAdd(&a.counters[1], 1); s_next = 0; s_nwork = 0; s_nsmall = 0; }
     __syncthreads();
     const int ui = s_unit;
     if (ui >= n_units) break;
@@ -1663,50 +1666,60 @@ __global__ void __launch_bounds__(kRunsThreads, RCV_RUNS_CTAS) k_vote_runs(VoteA
 #endif
     const int ngroups = (n + 31) >> 5, nchunks = (u.ni + NC - 1) / NC, nall = ngroups * nchunks;
     // Work list: only the (chunk, group) pairs whose spheres reach the chunk's slices (group summaries from the prelude), so
-    // that no warp fetches the records of a group just to find that it has nothing to draw.  Too many pairs for the list
-    // (huge items): every pair is a work item and the test is made on the records, as before.
-    const bool listed = nall <= 65535;
+    // that no warp fetches the records of a group just to find that it has nothing to draw.  An entry is chunk << 11 | group.
+    // Long items (chunks near the groups' centre slices: many columns) fill the list from the front, short ones (near the
+    // poles of the spheres along A) from the back, and the warps pull front first: the items still running when the first
+    // warp reaches the end-of-tile barrier are short ones.  Too many pairs for the list (huge items): every pair is a work
+    // item and the reach test is made on the records.
+    const bool listed = ngroups <= 2048 && nchunks <= 32;
     if (listed) {
       const int* grp = a.pool.grp + (off >> 5) + u.item;
-      for (int w = threadIdx.x; w < nall; w += kRunsThreads) {
-        const int ch = w / ngroups, g = w - ch * ngroups;
+      const float hm = 2.0f * (float)m.rmax + 2.0f, small_below = RCV_RUNS_SMALL_FRAC * hm * hm;
+      for (int ch = 0; ch < nchunks; ++ch) {
         const int i0c = u.i0 + ch * NC, i1c = min(i0c + NC, u.i0 + u.ni) - 1;
-        const int r = __ldg(grp + g);
-        const int lo = (short)(r & 0xffff), hi = r >> 16;
-        if (hi >= i0c && lo <= i1c) {
-          const int slot = atomicAdd(&s_nwork, 1);
-          if (slot < kRunsWorkList) s_work[slot] = (unsigned short)w;
+        for (int g = threadIdx.x; g < ngroups; g += kRunsThreads) {
+          const int r = __ldg(grp + g);
+          const int lo = (short)(r & 0xffff), hi = r >> 16;
+          if (hi >= i0c && lo <= i1c) {
+            // (twice the) chord of the group's largest sphere at the chunk's middle slice, squared
+            const int e = i0c + i1c - (hi + lo), c4 = (hi - lo) * (hi - lo) - e * e;
+            const bool small = (float)c4 < small_below;
+            const int slot = atomicAdd(small ? &s_nsmall : &s_nwork, 1);
+            if (slot < kRunsWorkList) s_work[small ? kRunsWorkList - 1 - slot : slot] = (unsigned short)(ch << 11 | g);
+          }
         }
       }
     }
     __syncthreads();
-    const bool use_list = listed && s_nwork <= kRunsWorkList;
+    const int nbig = s_nwork;
+    const bool use_list = listed && nbig + s_nsmall <= kRunsWorkList;
     // (Measured and dropped, r02q/r02r: splitting the tile's last work items into column halves, fetching the next tile's
     // unit index during the scatter, and requesting the next item's records one item ahead -- each 0.5-4% slower.)
-    const int nwork = use_list ? s_nwork : nall;
+    const int nwork = use_list ? nbig + s_nsmall : nall;
     const RunSlowCtx sc{a.pool.X + off, a.pool.Y + off, a.pool.Z + off, a.pool.perm + off};
     const RunTile rt{t, tile_s, slice_bytes, a.pool.rec + 2 * off, sc, clip};
     unsigned long long* q = s_q[warp];
     int* qn = &s_qn[warp];
-    auto pull = [&](int& w, int4& r0, int4& r1) {
+    auto pull = [&](int& ch, int& g, int4& r0, int4& r1) {
       int k = 0;
       if (lane == 0) k = atomicAdd(&s_next, 1);
       k = __shfl_sync(0xffffffffu, k, 0);
-      w = k < nwork ? (use_list ? (int)s_work[k] : k) : -1;
+      ch = -1; g = 0;
       r0 = make_int4(0, 0, 0, 0); r1 = make_int4(0, 0, 0, 0);
-      if (w >= 0) {
-        const int pi = ((w % ngroups) << 5) + lane;
-        if (pi < n) { r0 = __ldg(rt.rec + 2 * pi); r1 = __ldg(rt.rec + 2 * pi + 1); }
-      }
+      if (k >= nwork) return;
+      if (use_list) { const int e = (int)s_work[k < nbig ? k : kRunsWorkList - 1 - (k - nbig)]; ch = e >> 11; g = e & 2047; }
+      else { ch = k / ngroups; g = k - ch * ngroups; }
+      const int pi = (g << 5) + lane;
+      if (pi < n) { r0 = __ldg(rt.rec + 2 * pi); r1 = __ldg(rt.rec + 2 * pi + 1); }
     };
     for (;;) {
-      int w; int4 n0, n1;
-      pull(w, n0, n1);
-      if (w < 0) break;
+      int ch, g; int4 n0, n1;
+      pull(ch, g, n0, n1);
+      if (ch < 0) break;
       RunPoint c;
       c.ipa = n0.x; c.ipb = n0.y; c.ipc = n0.z; c.R = n0.w;
       c.fa = __int_as_float(n1.x); c.fb = __int_as_float(n1.y); c.fc = __int_as_float(n1.z); c.W = __int_as_float(n1.w);
-      const int ch = w / ngroups, cur = (w - ch * ngroups) << 5;
+      const int cur = g << 5;
       const int i0c = u.i0 + ch * NC, nsl = min(NC, u.i0 + u.ni - i0c);
       // does any sphere of the group reach the chunk's slices?
       const bool here = c.R > 0 && (c.ipa + c.R + 1 >= i0c) && (c.ipa - c.R - 1 <= i0c + nsl - 1);
