@@ -217,6 +217,26 @@ int rcv_head_vote_frames(rcv_ctx* ctx, int n_frames, int n_kpts, const void* up_
                          const rcv_vote_params* vp, double* centre_mm, int* peak, long long* votes, int* n_points, int* grid, int* status,
                          float* radius_out, void* stream);
 
+/* ---- the producer's tail in one kernel  -- models/fcnresnet.py:114-118 (definition), :183-189 (use) -----------
+ * conv7 = Conv2d(64 -> 32, 3x3, padding 1) + BatchNorm2d(32) (eval) + ReLU, then conv8 = Conv2d(32 -> 2, 1x1): an implicit-GEMM
+ * tcgen05 kernel (bf16 operands, fp32 accumulation in tensor memory; BatchNorm folded into scale / shift, ReLU, bf16 rounding of
+ * the activation and conv8 in the epilogue), so that the 32-channel activation never reaches HBM.
+ *   x        [n_images][H][W][64] bfloat16: the output of up1 in channels_last (NHWC) memory, 16-byte aligned; W % 128 == 0
+ *   w7       [32][64][3][3] float32 (rounded to bf16 by the kernel)
+ *   bn_scale [32] = gamma / sqrt(running_var + eps);  bn_shift [32] = (conv7.bias - running_mean) * bn_scale + beta
+ *   w8 [2][32], b8 [2] float32: conv8 (w8 rounded to bf16 like rcv_head_1x1 does)
+ *   out      [n_images][2][H*W] float32: plane 0 = seg_pred, plane 1 = radial_pred */
+int rcv_conv7_head(rcv_ctx* ctx, const void* x_nhwc_bf16, const float* w7, const float* bn_scale, const float* bn_shift, const float* w8,
+                   const float* b8, float* out, int n_images, int height, int width, void* stream);
+
+/* rcv_head_vote_frames with the tail above instead of conv8 alone: x is a HOST array of n_kpts device pointers (the up1 output of
+ * each keypoint network, [n_frames][H][W][64] bfloat16 NHWC); w7 [n_kpts][32][64][3][3], bn_scale / bn_shift [n_kpts][32],
+ * w8 [n_kpts][2][32], b8 [n_kpts][2].  Everything else as in rcv_head_vote_frames. */
+int rcv_conv7_head_vote_frames(rcv_ctx* ctx, int n_frames, int n_kpts, const void* const* x_nhwc_bf16, const float* w7, const float* bn_scale,
+                               const float* bn_shift, const float* w8, const float* b8, const void* depth, const double* K,
+                               const double* max_radii, const rcv_frame_params* fp, const rcv_vote_params* vp, double* centre_mm, int* peak,
+                               long long* votes, int* n_points, int* grid, int* status, float* radius_out, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (the bench's gpu_launches claim). */
 long long rcv_launch_count(const rcv_ctx* ctx);

@@ -16,7 +16,8 @@ RCV_ST_VOLUME_SKIPPED = 32
 
 EXPORTS = ["rcv_create", "rcv_destroy", "rcv_last_error", "rcv_abi_version", "rcv_backproject", "rcv_vote_points", "rcv_vote_frames",
            "rcv_vote_frames_host", "rcv_argmax_volume", "rcv_head_1x1", "rcv_horn_batch", "rcv_horn_batch_host", "rcv_launch_count", "rcv_last_h2d_bytes",
-           "rcv_last_vote_kernel_ms", "rcv_vote_kernel_times", "rcv_ubench_smem_atomics", "rcv_add_metric_batch", "rcv_scene_clouds", "rcv_scene_clouds_last", "rcv_icp_batch", "rcv_head_vote_frames"]
+           "rcv_last_vote_kernel_ms", "rcv_vote_kernel_times", "rcv_ubench_smem_atomics", "rcv_add_metric_batch", "rcv_scene_clouds", "rcv_scene_clouds_last", "rcv_icp_batch", "rcv_head_vote_frames",
+           "rcv_conv7_head", "rcv_conv7_head_vote_frames"]
 
 
 class rcv_config(C.Structure):
@@ -89,6 +90,11 @@ def load():
     L.rcv_head_vote_frames.restype = C.c_int
     L.rcv_head_vote_frames.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.POINTER(rcv_frame_params), C.POINTER(rcv_vote_params),
                                        vp, ip, llp, ip, ip, ip, vp, vp]
+    L.rcv_conv7_head.restype = C.c_int
+    L.rcv_conv7_head.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    L.rcv_conv7_head_vote_frames.restype = C.c_int
+    L.rcv_conv7_head_vote_frames.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(rcv_frame_params),
+                                             C.POINTER(rcv_vote_params), vp, ip, llp, ip, ip, ip, vp, vp]
     L.rcv_launch_count.restype = C.c_longlong
     L.rcv_launch_count.argtypes = [vp]
     L.rcv_last_h2d_bytes.restype = C.c_longlong

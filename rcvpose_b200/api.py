@@ -350,6 +350,61 @@ class VoteContext:
             out["radius"] = rad
         return out
 
+    # ---- conv7 + BN + ReLU + conv8 in one kernel (models/fcnresnet.py:114-118, :183-189) ----
+    @staticmethod
+    def _nhwc(x, name):
+        """(B,64,H,W) bfloat16 CUDA tensor -> the same tensor in channels_last memory (no copy if it already is)."""
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] == 64):
+            raise RcvError("%s: (B,64,H,W) bfloat16 CUDA tensor" % name)
+        return x.contiguous(memory_format=torch.channels_last)
+
+    def conv7_head(self, x, w7, bn_scale, bn_shift, w8, b8):
+        """x (B,64,H,W) bfloat16 (the output of up1; channels_last memory is used as is), w7 (32,64,3,3), bn_scale / bn_shift (32,)
+        (BatchNorm folded: producer.fold_conv7_bn), w8 (2,32[,1,1]), b8 (2,) -> out (B,2,H,W) float32: seg, radial."""
+        x = self._nhwc(x, "x")
+        B, _, H, W = x.shape
+        dev = x.device
+        f = lambda t, shape: t.detach().reshape(shape).to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        w7, bn_scale, bn_shift, w8, b8 = f(w7, (32, 64, 3, 3)), f(bn_scale, (32,)), f(bn_shift, (32,)), f(w8, (2, 32)), f(b8, (2,))
+        out = torch.empty((B, 2, H, W), dtype=torch.float32, device=dev)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_conv7_head(self.h, _ptr(x), _ptr(w7), _ptr(bn_scale), _ptr(bn_shift), _ptr(w8), _ptr(b8), _ptr(out), B, H, W, _stream()))
+        return out
+
+    def conv7_head_vote_frames(self, xs, w7, bn_scale, bn_shift, w8, b8, depth, K, max_radii=None, mask_flags=MASK_LM_CKPT, sem_threshold=0.8,
+                               depth_div=1.0, xyz_div=1000.0, acc_unit=5.0, radius_scale=100.0, policy=RCV_POLICY_LM, want_radius=False):
+        """xs: Kp tensors (B,64,H,W) bfloat16 (up1 output of each keypoint network), w7 (Kp,32,64,3,3), bn_scale / bn_shift (Kp,32),
+        w8 (Kp,2,32[,1,1]), b8 (Kp,2), depth (B,H,W), K (3,3)/(B,3,3) float64 -- CUDA.  Outputs as head_vote_frames."""
+        xs = [self._nhwc(x, "xs[%d]" % i) for i, x in enumerate(xs)]
+        Kp = len(xs)
+        B, _, H, W = xs[0].shape
+        _check_cuda(depth, None, "depth")
+        _check_cuda(K, torch.float64, "K")
+        if any(tuple(x.shape) != (B, 64, H, W) for x in xs) or tuple(depth.shape) != (B, H, W):
+            raise RcvError("conv7_head_vote_frames: xs Kp x (B,64,H,W), depth (B,H,W)")
+        dev = xs[0].device
+        f = lambda t, shape: t.detach().reshape(shape).to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        w7, bn_scale, bn_shift, w8, b8 = f(w7, (Kp, 32, 64, 3, 3)), f(bn_scale, (Kp, 32)), f(bn_shift, (Kp, 32)), f(w8, (Kp, 2, 32)), f(b8, (Kp, 2))
+        if max_radii is not None:
+            _check_cuda(max_radii, torch.float64, "max_radii")
+        fp = _lib.rcv_frame_params(H, W, _DEPTH_DTYPES[depth.dtype], float(depth_div), float(xyz_div), int(mask_flags), float(sem_threshold),
+                                   9 if (K.dim() == 3 and K.shape[0] == B) else 0,
+                                   Kp if (max_radii is not None and max_radii.dim() == 2 and max_radii.shape[0] == B) else 0)
+        vp = _lib.rcv_vote_params(float(acc_unit), float(radius_scale), int(policy), RCV_F32)
+        out = dict(centre_mm=torch.empty((B, Kp, 3), dtype=torch.float64, device=dev), peak=torch.empty((B, Kp), dtype=torch.int32, device=dev),
+                   votes=torch.empty((B, Kp), dtype=torch.int64, device=dev), n_points=torch.empty((B, Kp), dtype=torch.int32, device=dev),
+                   grid=torch.empty((B, Kp), dtype=torch.int32, device=dev), status=torch.empty((B, Kp), dtype=torch.int32, device=dev))
+        rad = torch.empty((B, Kp, H, W), dtype=torch.float32, device=dev) if want_radius else None
+        xp = (C.c_void_p * Kp)(*[x.data_ptr() for x in xs])
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.rcv_conv7_head_vote_frames(self.h, B, Kp, xp, _ptr(w7), _ptr(bn_scale), _ptr(bn_shift), _ptr(w8), _ptr(b8), _ptr(depth),
+                                                         _ptr(K), _ptr(max_radii), C.byref(fp), C.byref(vp), _ptr(out["centre_mm"]), _ptr(out["peak"]),
+                                                         _ptr(out["votes"]), _ptr(out["n_points"]), _ptr(out["grid"]), _ptr(out["status"]), _ptr(rad),
+                                                         _stream()))
+        if rad is not None:
+            out["radius"] = rad
+        return out
+
     def horn_batch_host(self, model, est):
         model = np.ascontiguousarray(model, dtype=np.float64)
         est = np.ascontiguousarray(est, dtype=np.float64)

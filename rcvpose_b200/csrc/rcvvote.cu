@@ -20,6 +20,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include "../../include/rcvvote.h"
 #include "raster_core.h"
 #include "runs_core.h"
@@ -2243,6 +2247,20 @@ static bool row_is_zero(const char* p, long long n) {
   return true;
 }
 
+// helper threads of the host entry points (row-range scan); RCV_HOST_THREADS overrides, 0 = scan on the calling thread
+static int host_helper_threads() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RCV_HOST_THREADS");
+    v = e ? atoi(e) : 3;
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && v > hw - 1) v = hw - 1;
+    if (v < 0) v = 0;
+    if (v > 16) v = 16;
+  }
+  return v;
+}
+
 static int ensure_staging(rcv_ctx* c, int frames, int kpts, long long px, long long depth_bytes, int has_sem, long long total_items) {
   if (c->st_frames >= frames && c->st_kpts == kpts && c->st_px == px && c->st_depth_bytes == depth_bytes && c->st_has_sem >= has_sem &&
       c->st_total_items >= total_items)
@@ -2301,32 +2319,62 @@ RCV_EXPORT int rcv_vote_frames_host(rcv_ctx* c, int n_frames, int n_kpts, const 
   c->h2d_bytes = (nK * 9 + (max_radii ? nM * n_kpts : 0)) * 8;
   CK(c, cudaMemcpyAsync(c->st_K, K, (size_t)(nK * 9 * 8), cudaMemcpyHostToDevice, c->s_in));
   if (max_radii) CK(c, cudaMemcpyAsync(c->st_maxr, max_radii, (size_t)(nM * n_kpts * 8), cudaMemcpyHostToDevice, c->s_in));
+  // Row-range cropping.  Every mask rule keeps a pixel only where depth != 0, so the rows above the first and
+  // below the last non-zero depth row of a frame cannot contribute: only rows [r0, r1) of the depth image and of each radius /
+  // seg plane cross the bus; the depth slot is cleared first, and whatever the other planes still hold outside the range sits
+  // under zero depth.  Results are bit-identical to copying whole images; a dense depth image costs one row of scanning.
+  // The scan reads most of every depth image from host DRAM, so helper threads run ahead of the thread that issues the copies
+  // (frame f belongs to helper f % T; RCV_HOST_THREADS, default 3; small calls scan inline).
+  const long long row_b = (long long)fp->width * dbytes;
+  const int height = fp->height;
+  auto scan_frame = [depth, px, dbytes, row_b, height](int f, int& r0, int& r1) {
+    const char* dsrc = (const char*)depth + (size_t)f * (size_t)(px * dbytes);
+    r0 = 0; r1 = height;
+    while (r0 < r1 && row_is_zero(dsrc + (size_t)r0 * row_b, row_b)) ++r0;
+    while (r1 > r0 && row_is_zero(dsrc + (size_t)(r1 - 1) * row_b, row_b)) --r1;
+  };
+  struct RowRange { int r0, r1; std::atomic<int> ready; };
+  int n_helpers = host_helper_threads();
+  if (n_frames < 64) n_helpers = 0;
+  std::vector<RowRange> ranges(n_helpers ? (size_t)n_frames : 0);
+  std::vector<std::thread> helpers;
+  struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (auto& h : t) if (h.joinable()) h.join(); } } joiner{helpers};   // also on the error returns below
+  if (n_helpers) {
+    for (auto& r : ranges) r.ready.store(0, std::memory_order_relaxed);
+    RowRange* rr = ranges.data();
+    for (int t = 0; t < n_helpers; ++t)
+      helpers.emplace_back([=]() {
+        for (int f = t; f < n_frames; f += n_helpers) { scan_frame(f, rr[f].r0, rr[f].r1); rr[f].ready.store(1, std::memory_order_release); }
+      });
+  }
+  // The first copy is not hidden behind any voting: the first two chunks are a quarter and a half of the regular size.
   int chunk = 0;
-  for (int f0 = 0; f0 < n_frames; f0 += frames_per_chunk, ++chunk) {
-    const int nf = n_frames - f0 < frames_per_chunk ? n_frames - f0 : frames_per_chunk;
+  for (int f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++chunk) {
+    int want = frames_per_chunk;
+    if (n_frames >= 4 * frames_per_chunk && frames_per_chunk >= 128) want = chunk == 0 ? frames_per_chunk / 4 : chunk == 1 ? frames_per_chunk / 2 : frames_per_chunk;
+    nf = n_frames - f0 < want ? n_frames - f0 : want;
     const int s = chunk & 1;
     if (chunk >= 2) { CK(c, cudaStreamWaitEvent(c->s_in, c->ev_done[s], 0)); CK(c, cudaStreamWaitEvent(c->s_in2, c->ev_done[s], 0)); }  // slot reuse: previous occupant finished voting
-    // Row-range cropping.  Every mask rule keeps a pixel only where depth != 0, so the rows above the first and
-    // below the last non-zero depth row of a frame cannot contribute: only rows [r0, r1) of the depth image and of each radius /
-    // seg plane cross the bus; the depth slot is cleared first, and whatever the other planes still hold outside the range sits
-    // under zero depth.  Results are bit-identical to copying whole images; a dense depth image costs one row of scanning.
     CK(c, cudaMemsetAsync(c->st_depth[s], 0, (size_t)(nf * px * dbytes), c->s_in));
-    const long long row_b = (long long)fp->width * dbytes;
     for (int f = 0; f < nf; ++f) {
       const char* dsrc = (const char*)depth + (size_t)((f0 + f) * px * dbytes);
-      int r0 = 0, r1 = fp->height;
-      while (r0 < r1 && row_is_zero(dsrc + (size_t)r0 * row_b, row_b)) ++r0;
-      while (r1 > r0 && row_is_zero(dsrc + (size_t)(r1 - 1) * row_b, row_b)) --r1;
+      int r0, r1;
+      if (n_helpers) {
+        RowRange& r = ranges[(size_t)(f0 + f)];
+        while (!r.ready.load(std::memory_order_acquire)) std::this_thread::yield();
+        r0 = r.r0; r1 = r.r1;
+      } else {
+        scan_frame(f0 + f, r0, r1);
+      }
       if (r1 <= r0) continue;
       const long long p0 = (long long)r0 * fp->width, np = (long long)(r1 - r0) * fp->width;
       CK(c, cudaMemcpyAsync((char*)c->st_depth[s] + (size_t)((f * px + p0) * dbytes), dsrc + (size_t)(p0 * dbytes), (size_t)(np * dbytes), cudaMemcpyHostToDevice, c->s_in));
       c->h2d_bytes += np * dbytes;
-      for (int k = 0; k < n_kpts; ++k) {
-        const long long plane = ((long long)f * n_kpts + k) * px + p0, src = ((long long)(f0 + f) * n_kpts + k) * px + p0;
-        CK(c, cudaMemcpyAsync(c->st_radius[s] + plane, radius + src, (size_t)(np * 4), cudaMemcpyHostToDevice, c->s_in2));
-        if (sem) CK(c, cudaMemcpyAsync(c->st_sem[s] + plane, sem + src, (size_t)(np * 4), cudaMemcpyHostToDevice, c->s_in2));
-        c->h2d_bytes += np * 4 * (sem ? 2 : 1);
-      }
+      // the same rows of the frame's n_kpts radius (and seg) planes: one strided copy (n_kpts "rows" of np floats, a plane apart)
+      const long long plane = (long long)f * n_kpts * px + p0, src = (long long)(f0 + f) * n_kpts * px + p0;
+      CK(c, cudaMemcpy2DAsync(c->st_radius[s] + plane, (size_t)px * 4, radius + src, (size_t)px * 4, (size_t)np * 4, (size_t)n_kpts, cudaMemcpyHostToDevice, c->s_in2));
+      if (sem) CK(c, cudaMemcpy2DAsync(c->st_sem[s] + plane, (size_t)px * 4, sem + src, (size_t)px * 4, (size_t)np * 4, (size_t)n_kpts, cudaMemcpyHostToDevice, c->s_in2));
+      c->h2d_bytes += np * 4 * n_kpts * (sem ? 2 : 1);
     }
     CK(c, cudaEventRecord(c->ev_in[s], c->s_in));
     CK(c, cudaEventRecord(c->ev_in2[s], c->s_in2));
@@ -2602,6 +2650,78 @@ RCV_EXPORT int rcv_head_vote_frames(rcv_ctx* c, int n_frames, int n_kpts, const 
   k_frame_emit<<<n_items, kCompactThreads, 0, st>>>(c->mask_bits, words, c->meta, c->pool.perm, words);
   k_points_from_pixels<<<dim3(n_items, 4), 256, 0, st>>>(fa, c->meta, c->pool);
   c->launches += 4;
+  return run_items(c, n_items, vp, centre_mm, peak, votes, n_points, grid, nullptr, status, nullptr, 0, st);
+}
+
+// ---- K6: conv7 + BN + ReLU + conv8 (+ mask rule) in one kernel (conv7head.cu) ----
+extern "C" int rcv_conv7_head_launch(const void* x_nhwc_bf16, const float* w7, const float* bn_scale, const float* bn_shift, const float* w8,
+                                     const float* b8, float* out, int n_images, int H, int W, int sms, void* stream);
+extern "C" int rcv_conv7_head_fused_launch(const void* x_nhwc_bf16, const float* w7, const float* bn_scale, const float* bn_shift, const float* w8,
+                                           const float* b8, float* radius_out, int n_frames, int H, int W, int sms, const void* depth,
+                                           int depth_dtype, int n_kpts, int kp, const double* max_radii, int max_radii_stride, int flags,
+                                           float sem_threshold, unsigned* bits, int words_per_item, int* cnt, void* stream);
+
+RCV_EXPORT int rcv_conv7_head(rcv_ctx* c, const void* x_nhwc_bf16, const float* w7, const float* bn_scale, const float* bn_shift, const float* w8,
+                              const float* b8, float* out, int n_images, int height, int width, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!x_nhwc_bf16 || !w7 || !bn_scale || !bn_shift || !w8 || !b8 || !out || n_images <= 0 || height <= 0 || width <= 0)
+    FAIL(c, RCV_E_INVALID, "rcv_conv7_head: bad argument");
+  if (width % 128 != 0 || ((uintptr_t)x_nhwc_bf16 & 15) != 0) FAIL(c, RCV_E_INVALID, "rcv_conv7_head: width must be a multiple of 128 and x 16-byte aligned");
+  CK(c, cudaSetDevice(c->device));
+  const int rc = rcv_conv7_head_launch(x_nhwc_bf16, w7, bn_scale, bn_shift, w8, b8, out, n_images, height, width, c->sms, stream);
+  if (rc != 0) FAIL(c, RCV_E_CUDA, "rcv_conv7_head: launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  c->launches += 1;
+  return RCV_OK;
+}
+
+RCV_EXPORT int rcv_conv7_head_vote_frames(rcv_ctx* c, int n_frames, int n_kpts, const void* const* x_nhwc_bf16, const float* w7, const float* bn_scale,
+                                          const float* bn_shift, const float* w8, const float* b8, const void* depth, const double* K,
+                                          const double* max_radii, const rcv_frame_params* fp, const rcv_vote_params* vp, double* centre_mm,
+                                          int* peak, long long* votes, int* n_points, int* grid, int* status, float* radius_out, void* stream) {
+  if (!c) return RCV_E_INVALID;
+  if (!x_nhwc_bf16 || !w7 || !bn_scale || !bn_shift || !w8 || !b8 || !depth || !K || !centre_mm || !status)
+    FAIL(c, RCV_E_INVALID, "rcv_conv7_head_vote_frames: null pointer");
+  int rc = check_vote_params(c, vp);
+  if (rc) return rc;
+  rc = check_frame_params(c, n_frames, n_kpts, fp, true /* the seg values come from the head */, max_radii);
+  if (rc) return rc;
+  const long long npx = (long long)fp->height * fp->width;
+  if (n_kpts > 8 || fp->width % 128 != 0) FAIL(c, RCV_E_INVALID, "rcv_conv7_head_vote_frames: n_kpts <= 8, width %% 128 == 0");
+  for (int k = 0; k < n_kpts; ++k)
+    if (!x_nhwc_bf16[k] || ((uintptr_t)x_nhwc_bf16[k] & 15)) FAIL(c, RCV_E_INVALID, "rcv_conv7_head_vote_frames: x[%d] null or not 16-byte aligned", k);
+  if (vp->radius_dtype != RCV_F32) FAIL(c, RCV_E_INVALID, "rcv_conv7_head_vote_frames: the head's radius maps are float32");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(c, cudaSetDevice(c->device));
+  const int n_items = n_frames * n_kpts;
+  const int words = (int)((npx + 255) / 256) * 8;
+  const long long need = (long long)n_items * words;
+  if (need > c->mask_words) {
+    CK(c, cudaStreamSynchronize(st));
+    cudaFree(c->mask_bits); c->mask_bits = nullptr; c->mask_words = 0;
+    CK(c, cudaMalloc(&c->mask_bits, (size_t)need * 4));
+    c->mask_words = need;
+  }
+  float* rad = radius_out;
+  if (!rad) {   // context-owned radius planes (the vote only gathers them at the surviving pixels)
+    if ((long long)n_items * npx > c->head_radius_cap) {
+      CK(c, cudaStreamSynchronize(st));
+      cudaFree(c->head_radius); c->head_radius = nullptr; c->head_radius_cap = 0;
+      CK(c, cudaMalloc(&c->head_radius, (size_t)n_items * npx * 4));
+      c->head_radius_cap = (long long)n_items * npx;
+    }
+    rad = c->head_radius;
+  }
+  CK(c, cudaMemsetAsync(c->cnt, 0, 4 * (size_t)n_items, st));
+  for (int k = 0; k < n_kpts; ++k)
+    CK(c, (cudaError_t)rcv_conv7_head_fused_launch(x_nhwc_bf16[k], w7 + (size_t)k * 32 * 64 * 9, bn_scale + k * 32, bn_shift + k * 32, w8 + k * 64, b8 + k * 2,
+                                                   rad, n_frames, fp->height, fp->width, c->sms, depth, fp->depth_dtype, n_kpts, k, max_radii,
+                                                   fp->max_radii_stride, fp->mask_flags, fp->sem_threshold, c->mask_bits, words, c->cnt, stream));
+  c->last_mask_frames = n_frames; c->last_mask_kpts = n_kpts; c->last_mask_words_per_item = words;
+  FrameArgs fa{depth, rad, nullptr, K, max_radii, *fp, vp->acc_unit, vp->radius_scale, n_kpts, 0};
+  k_scan_items<<<1, 1024, 0, st>>>(c->cnt, n_items, c->pool.cap, c->meta);
+  k_frame_emit<<<n_items, kCompactThreads, 0, st>>>(c->mask_bits, words, c->meta, c->pool.perm, words);
+  k_points_from_pixels<<<dim3(n_items, 4), 256, 0, st>>>(fa, c->meta, c->pool);
+  c->launches += 3 + n_kpts;
   return run_items(c, n_items, vp, centre_mm, peak, votes, n_points, grid, nullptr, status, nullptr, 0, st);
 }
 

@@ -6,6 +6,10 @@
     load_keypoints / load_pose  `Outside9.npy` (:535) and `pose/pose<N>.npy` (:566)
     read_xyz_points(path)     YCB-Video `models/<cls>/points.xyz` (AccumulatorSpace.py:988; 3DRadius_ycb.py)
     load_ycb_meta(path)       YCB-Video `<seq>/<frame>-meta.mat`: intrinsics, factor_depth, poses, class indices (:1015-1016, :1050-1057)
+    read_ycb_radius_h5(...)   the per-class `<cls>.hdf5` the reference's YCB ground-truth generator writes (3DRadius_ycb.py:200-251):
+                              `/3Dradius_pt<k>_dm/<seq>_<frame>` float64 (H, W) radius maps in decimetres, `/JPEGImages/<seq>_<frame>`
+                              uint8 RGB.  Needs `h5py` (as the reference does, rmap_dataset.py:7); it is not in this image, so the
+                              reader is gated: without h5py it raises ImportError naming the missing module.
 
 The writers exist so that tests and tools can lay out a synthetic dataset in the reference's directory structure.
 """
@@ -168,3 +172,29 @@ def pose_of(meta, class_id):
     """(3,4) ground-truth pose of object `class_id` in a frame's meta, or None if the object is not in the frame."""
     hit = np.nonzero(meta["cls_indexes"] == class_id)[0]
     return meta["poses"][hit[0]] if len(hit) else None
+
+
+def read_ycb_radius_h5(path, frame_key, keypoints=(1, 2, 3), with_image=False):
+    """Radius maps of one frame from the per-class HDF5 file of the reference's YCB generator (3DRadius_ycb.py:200-251).
+
+    path       `<root_save>/<class>.hdf5`
+    frame_key  `<sequence>_<6-digit frame>` (the dataset name the generator uses, :213, :250)
+    keypoints  indices k of `/3Dradius_pt<k>_dm` (the evaluators vote for keypoints 1..3 of Outside9.npy)
+    Returns (Kp, H, W) float32 radius maps in DECIMETRES (the generator stores Radius3DMap * 10; the voting entry points take
+    decimetres with radius_scale = 100 mm, the convention of the networks' output), and the (H, W, 3) uint8 image if asked.
+    h5py is imported here, not at module import: the voting path does not depend on it."""
+    try:
+        import h5py
+    except ImportError as e:   # not in this image; the reference needs it too (rmap_dataset.py:7)
+        raise ImportError("read_ycb_radius_h5 needs the h5py module (HDF5 radius maps of 3DRadius_ycb.py): %s" % e)
+    with h5py.File(path, "r") as f:
+        maps = []
+        for k in keypoints:
+            node = "/3Dradius_pt%d_dm/%s" % (k, frame_key)
+            if node not in f:
+                raise KeyError("%s: no dataset %s" % (path, node))
+            maps.append(np.asarray(f[node], dtype=np.float32))
+        out = np.stack(maps, axis=0)
+        if with_image:
+            return out, np.asarray(f["/JPEGImages/%s" % frame_key], dtype=np.uint8)
+    return out

@@ -63,6 +63,10 @@ class RadiusTrunk(nn.Module):
         self.conv8 = nn.Conv2d(32, 2, kernel_size=1)
 
     def forward(self, x):
+        return self.conv7(self.forward_up1(x))
+
+    def forward_up1(self, x):
+        """(B,3,H,W) -> (B,64,H,W): everything before conv7 (the input of the fused tail kernel, rcv_conv7_head)."""
         stem = F.relu(self.bn1(self.conv1(x)))               # the reference's ReLU is in place, so its last skip is the ReLU'd stem (:121-123,180)
         skips = [stem]
         y = F.max_pool2d(stem, kernel_size=3, stride=2, padding=1)
@@ -73,10 +77,20 @@ class RadiusTrunk(nn.Module):
         for level, _, _ in _DECODER:
             up = getattr(self, "conv_up%d" % level)(torch.cat((up, skips[level - 1]), 1))
             up = F.interpolate(up, scale_factor=2, mode="bilinear", align_corners=False)
-        return self.conv7(up)
+        return up
 
     def head(self):
         return self.conv8.weight.detach().reshape(2, 32), self.conv8.bias.detach().reshape(2)
+
+    def tail(self):
+        """Parameters of the fused tail kernel (rcv_conv7_head): conv7's weight (32,64,3,3), its BatchNorm (eval mode) folded with
+        the convolution's bias into scale / shift (32,), conv8's weight (2,32) and bias (2,) -- float32."""
+        conv, bn = self.conv7[0], self.conv7[1]
+        scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        cb = conv.bias.detach().double() if conv.bias is not None else torch.zeros_like(scale)
+        shift = (cb - bn.running_mean.detach().double()) * scale + bn.bias.detach().double()
+        w8, b8 = self.head()
+        return conv.weight.detach().float(), scale.float(), shift.float(), w8.float(), b8.float()
 
     def forward_reference(self, x):
         out = self.conv8(self.forward(x))
@@ -101,9 +115,13 @@ class ProducerStage:
     forked streams, joined before the head): a 480x640 forward of one trunk is ~500 small cuDNN launches, launch-bound at the
     batch sizes an evaluator uses, and the reference runs them one image and one network at a time (:594-599)."""
 
-    def __init__(self, trunks, ctx, dtype=torch.bfloat16, channels_last=False):
+    def __init__(self, trunks, ctx, dtype=torch.bfloat16, channels_last=False, fuse_tail=False):
+        """fuse_tail: the trunks stop before conv7 and conv7 + BN + ReLU + conv8 + the mask rule run as ONE kernel of this package
+        (rcv_conv7_head_vote_frames): the 32-channel activation never reaches HBM.  Needs W % 128 == 0 and uses channels_last."""
         assert len(trunks) >= 1
         self.ctx, self.dtype = ctx, dtype
+        self.fuse_tail = bool(fuse_tail)
+        channels_last = channels_last or self.fuse_tail
         self.trunks = [t.to(device=ctx.device, dtype=dtype).eval() for t in trunks]
         self.channels_last = bool(channels_last)
         if self.channels_last:
@@ -111,16 +129,25 @@ class ProducerStage:
         w, b = zip(*[t.head() for t in self.trunks])
         self.weight = torch.stack([x.float() for x in w]).contiguous()     # (Kp,2,32)
         self.bias = torch.stack([x.float() for x in b]).contiguous()       # (Kp,2)
+        if self.fuse_tail:
+            tails = [t.tail() for t in self.trunks]                         # from the trunk's parameters as the unfused modules see them (rounded to `dtype`), folded in float64
+            self.tail_params = [torch.stack([tl[i].float() for tl in tails]).contiguous().to(ctx.device) for i in range(5)]
         self._graph = None
 
     @torch.no_grad()
     def _run(self, x, up, concurrent):
-        """x (B,3,H,W) -> up (B,Kp,32,H,W) (NCHW planes per (frame, keypoint): what the head's TMA boxes read)."""
+        """x (B,3,H,W) -> up (B,Kp,32,H,W) (NCHW planes per (frame, keypoint): what the head's TMA boxes read); with fuse_tail
+        up is a list of Kp (B,64,H,W) channels_last tensors (the up1 outputs)."""
         if self.channels_last:
             x = x.contiguous(memory_format=torch.channels_last)
+        if self.fuse_tail:
+            fwd = lambda k, t: up[k].copy_(t.forward_up1(x))  # noqa: E731
+        else:
+            def fwd(k, t):
+                up[:, k] = t(x)
         if not concurrent or len(self.trunks) == 1:
             for k, t in enumerate(self.trunks):
-                up[:, k] = t(x)
+                fwd(k, t)
             return
         main = torch.cuda.current_stream()
         side = self._side_streams
@@ -129,7 +156,7 @@ class ProducerStage:
             if k:
                 st.wait_stream(main)
             with torch.cuda.stream(st):
-                up[:, k] = t(x)
+                fwd(k, t)
         for st in side[:len(self.trunks) - 1]:
             main.wait_stream(st)
 
@@ -140,7 +167,7 @@ class ProducerStage:
         dev = self.ctx.device
         self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(max(0, len(self.trunks) - 1))]
         self._static_in = torch.zeros((batch, 3, H, W), dtype=self.dtype, device=dev)
-        self._static_up = torch.empty((batch, len(self.trunks), 32, H, W), dtype=self.dtype, device=dev)
+        self._static_up = self._alloc_up(batch, H, W)
         warm = torch.cuda.Stream(device=dev)
         warm.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(warm):
@@ -154,6 +181,12 @@ class ProducerStage:
         self._graph = g
         return self
 
+    def _alloc_up(self, B, H, W):
+        dev = self.ctx.device
+        if self.fuse_tail:
+            return [torch.empty((B, 64, H, W), dtype=self.dtype, device=dev).contiguous(memory_format=torch.channels_last) for _ in self.trunks]
+        return torch.empty((B, len(self.trunks), 32, H, W), dtype=self.dtype, device=dev)
+
     @torch.no_grad()
     def activations(self, images):
         """images (B,3,H,W) float -> (B,Kp,32,H,W) in the stage's dtype, NCHW-contiguous per (frame, keypoint)."""
@@ -163,10 +196,14 @@ class ProducerStage:
             self._graph.replay()
             return self._static_up
         B, _, H, W = x.shape
-        up = torch.empty((B, len(self.trunks), 32, H, W), dtype=self.dtype, device=x.device)
+        up = self._alloc_up(B, H, W)
         self._run(x, up, False)
         return up
 
     def vote(self, images, depth, K, max_radii, **kw):
-        """RGB + depth -> keypoint centres: conv7 activations, then rcv_head_vote_frames (mask rule sem > 0.8, radial <= max_radii)."""
+        """RGB + depth -> keypoint centres: conv7 activations, then rcv_head_vote_frames (mask rule sem > 0.8, radial <= max_radii);
+        with fuse_tail: up1 activations, then rcv_conv7_head_vote_frames."""
+        if self.fuse_tail:
+            w7, sc, sh, w8, b8 = self.tail_params
+            return self.ctx.conv7_head_vote_frames(self.activations(images), w7, sc, sh, w8, b8, depth, K, max_radii=max_radii, **kw)
         return self.ctx.head_vote_frames(self.activations(images), self.weight, self.bias, depth, K, max_radii=max_radii, **kw)

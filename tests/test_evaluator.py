@@ -73,6 +73,30 @@ def test_read_ply_rejects_garbage(tmp_path):
         formats.read_ply_points(p)
 
 
+def test_ycb_radius_h5_reader(tmp_path):
+    """The reference's YCB generator stores radius maps in HDF5 (3DRadius_ycb.py:200-251); the reader needs h5py like the
+    reference does.  With h5py: round trip of the generator's layout.  Without (this image): a clear ImportError."""
+    p = str(tmp_path / "002_master_chef_can.hdf5")
+    try:
+        import h5py
+    except ImportError:
+        with pytest.raises(ImportError, match="h5py"):
+            formats.read_ycb_radius_h5(p, "0048_000001")
+        return
+    rng = np.random.default_rng(3)
+    maps = rng.random((9, 12, 16)) * 10.0
+    img = rng.integers(0, 255, (12, 16, 3), dtype=np.uint8)
+    with h5py.File(p, "a") as f:
+        f.create_group("/JPEGImages/").create_dataset("0048_000001", data=img, compression="gzip", compression_opts=9)
+        for k in range(9):
+            f.create_group("/3Dradius_pt%d_dm/" % k).create_dataset("0048_000001", data=maps[k], compression="gzip", compression_opts=9)
+    got, im = formats.read_ycb_radius_h5(p, "0048_000001", with_image=True)
+    assert got.dtype == np.float32 and got.shape == (3, 12, 16)
+    assert np.array_equal(got, maps[1:4].astype(np.float32)) and np.array_equal(im, img)
+    with pytest.raises(KeyError):
+        formats.read_ycb_radius_h5(p, "0048_000002")
+
+
 def test_linemod_layout_and_max_radii(tmp_path):
     from rcvpose_b200 import evaluate
     root = str(tmp_path) + "/"

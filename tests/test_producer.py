@@ -6,6 +6,7 @@ import sys
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from rcvpose_b200 import producer
 
@@ -66,6 +67,23 @@ def test_normalise_rgb_is_the_reference_preprocessing():
     assert t.shape == (1, 3, 5, 7) and t.dtype == torch.float32
     assert np.array_equal(t[0].numpy(), want.transpose(2, 0, 1).astype(np.float32))
     assert producer.normalise_rgb(np.stack([img, img])).shape == (2, 3, 5, 7)
+
+
+def test_tail_fold_is_conv7_bn_relu():
+    """RadiusTrunk.tail(): conv7's bias and its eval-mode BatchNorm folded into scale / shift (what rcv_conv7_head applies after
+    the implicit GEMM) reproduce the module (models/fcnresnet.py:114-116)."""
+    torch.manual_seed(2)
+    t = producer.RadiusTrunk().eval()
+    bn = t.conv7[1]
+    with torch.no_grad():
+        bn.running_mean.normal_(0.0, 0.2); bn.running_var.uniform_(0.3, 2.0); bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0.0, 0.2)
+        x = torch.randn((2, 64, 9, 11))
+        want = t.conv7(x)
+        w7, sc, sh, w8, b8 = t.tail()
+        got = torch.relu(F.conv2d(x, w7, padding=1) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+        assert w8.shape == (2, 32) and b8.shape == (2,)
+        assert torch.allclose(t(torch.zeros((1, 3, 32, 32))), t.conv7(t.forward_up1(torch.zeros((1, 3, 32, 32)))))
 
 
 _pending = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
@@ -162,3 +180,106 @@ def test_lm_evaluator_checkpoint_branch_through_the_fused_stage(tmp_path):
     for key in ("RT", "dist_before", "RT_icp", "dist_after"):
         np.testing.assert_allclose(a[key], b[key], rtol=1e-12, atol=1e-9, err_msg=key)
     assert (a["n_points"] > 1000).all()
+
+
+def _tail_reference(x_bf16, w7, scale, shift, w8, b8):
+    """conv7 + folded BN + ReLU + conv8 in float64 PyTorch on the operands the kernel sees (x, w7, w8 rounded to bf16; the
+    activation rounded to bf16 before conv8): models/fcnresnet.py:114-118, :183-189."""
+    x = x_bf16.double()
+    a = F.conv2d(x, w7.bfloat16().double(), padding=1) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+    a = torch.relu(a).float().bfloat16().double()
+    return F.conv2d(a, w8.bfloat16().double().view(2, 32, 1, 1)) + b8.double().view(1, 2, 1, 1)
+
+
+@_pending_gpu
+@pytest.mark.parametrize("shape", [(1, 8, 128), (2, 19, 256), (1, 480, 640)])
+def test_conv7_head_kernel_vs_torch(shape):
+    """K6 (conv7head.cu): the implicit-GEMM tail against PyTorch float64 on the same bf16 operands, image borders (zero padding)
+    included.  fp32 accumulation order can flip the bf16 rounding of an activation (2^-8 relative on one of 32 terms)."""
+    from rcvpose_b200 import api
+    B, H, W = shape
+    ctx = api.VoteContext(0, max_items=8, max_points_total=1 << 20, max_grid=256)
+    g = torch.Generator(device="cpu").manual_seed(11 + H)
+    x = (torch.randn((B, 64, H, W), generator=g) * 0.7).bfloat16().cuda()
+    w7 = (torch.randn((32, 64, 3, 3), generator=g) * 0.06).cuda()
+    scale = (0.5 + torch.rand((32,), generator=g)).cuda()
+    shift = (torch.randn((32,), generator=g) * 0.3).cuda()
+    w8 = (torch.randn((2, 32), generator=g) * 0.3).cuda()
+    b8 = torch.randn((2,), generator=g).cuda()
+    got = ctx.conv7_head(x, w7, scale, shift, w8, b8)
+    want = _tail_reference(x, w7, scale, shift, w8, b8)
+    torch.cuda.synchronize()
+    assert got.shape == (B, 2, H, W) and got.dtype == torch.float32
+    err = (got.double() - want).abs()
+    tol = 2.0 ** -8 * 4.0 * float(want.abs().max())
+    assert float(err.max()) <= tol, (float(err.max()), tol)
+    assert float(err.mean()) <= 1e-4 * float(want.abs().mean() + 1.0), float(err.mean())
+    # channels_last input is used in place, an NCHW tensor is converted: same result
+    got2 = ctx.conv7_head(x.contiguous(memory_format=torch.channels_last), w7, scale, shift, w8, b8)
+    assert torch.equal(got, got2)
+
+
+@_pending_gpu
+def test_conv7_head_vote_frames_equals_the_two_call_route():
+    """rcv_conv7_head_vote_frames (tail + mask rule in the epilogue) against rcv_conv7_head + rcv_vote_frames on the maps it wrote:
+    same kernel arithmetic for seg / radial, so radius planes, survivors, centres and peaks must be identical."""
+    from rcvpose_b200 import api, synth
+    ctx = api.VoteContext(0, max_items=16, max_points_total=1 << 22, max_grid=400)
+    frames = [synth.config3_frame(f) for f in (51, 52)]
+    depth = torch.from_numpy(np.stack([f["depth"] for f in frames]).view(np.int16)).cuda()
+    K = torch.from_numpy(frames[0]["K"]).cuda()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    Kp = 3
+    xs = [(torch.randn((2, 64, 480, 640), generator=g) * 0.5).bfloat16().cuda().contiguous(memory_format=torch.channels_last) for _ in range(Kp)]
+    w7 = (torch.randn((Kp, 32, 64, 3, 3), generator=g) * 0.05).cuda()
+    scale = (0.5 + torch.rand((Kp, 32), generator=g)).cuda()
+    shift = (torch.randn((Kp, 32), generator=g) * 0.2).cuda()
+    w8 = (torch.randn((Kp, 2, 32), generator=g) * 0.2).cuda()
+    b8 = torch.tensor([[0.5, 1.2], [0.4, 1.0], [0.6, 1.4]]).cuda()      # seg around 0.5 (threshold), radius around 1.2 dm
+    mr = torch.full((Kp,), 2.0, dtype=torch.float64, device="cuda")
+    flags = api.RCV_MASK_MAX_RADIUS | api.RCV_MASK_SEM_GT | api.RCV_MASK_RADIUS_POSITIVE
+    fused = ctx.conv7_head_vote_frames(xs, w7, scale, shift, w8, b8, depth, K, max_radii=mr, mask_flags=flags, sem_threshold=0.5, want_radius=True)
+    maps = torch.stack([ctx.conv7_head(xs[k], w7[k], scale[k], shift[k], w8[k], b8[k]) for k in range(Kp)], dim=1)      # (B,Kp,2,H,W)
+    two = ctx.vote_frames(depth, maps[:, :, 1].contiguous(), K, sem=maps[:, :, 0].contiguous(), max_radii=mr, mask_flags=flags, sem_threshold=0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(fused["radius"], maps[:, :, 1])
+    assert int(fused["n_points"].min()) > 100, fused["n_points"]
+    for k in ("centre_mm", "peak", "votes", "n_points", "grid", "status"):
+        assert torch.equal(fused[k], two[k]), k
+
+
+@_pending_gpu
+def test_producer_stage_with_the_fused_tail():
+    """ProducerStage(fuse_tail=True): trunks up to up1, then ONE kernel for conv7 + BN + ReLU + conv8 + mask rule -- against the
+    PyTorch float32 forward of the same trunks (forward_reference) to bf16 accuracy, and through the vote."""
+    from rcvpose_b200 import api, synth
+    ctx = api.VoteContext(0, max_items=16, max_points_total=1 << 22, max_grid=400)
+    torch.manual_seed(9)
+    trunks = [producer.RadiusTrunk() for _ in range(3)]
+    with torch.no_grad():
+        for t in trunks:                                  # non-trivial BatchNorm statistics in conv7
+            t.conv7[1].running_mean.normal_(0.0, 0.1); t.conv7[1].running_var.uniform_(0.5, 1.5); t.conv7[1].weight.uniform_(0.5, 1.5); t.conv7[1].bias.normal_(0.0, 0.1)
+    rgb = torch.rand((1, 3, 96, 128))
+    with torch.no_grad():
+        want = [torch.cat(t.float().cuda().eval().forward_reference(rgb.cuda()), 1) for t in trunks]      # (1,2,H,W) float32 each
+    stage = producer.ProducerStage(trunks, ctx, fuse_tail=True)
+    xs = stage.activations(rgb)
+    assert len(xs) == 3 and xs[0].shape == (1, 64, 96, 128) and xs[0].is_contiguous(memory_format=torch.channels_last)
+    w7, sc, sh, w8, b8 = stage.tail_params
+    for k in range(3):
+        got = ctx.conv7_head(xs[k], w7[k], sc[k], sh[k], w8[k], b8[k])
+        torch.cuda.synchronize()
+        err = (got - want[k]).abs().max().item()
+        assert err <= 0.1 * max(1.0, want[k].abs().max().item()), (k, err)
+    frames = [synth.config3_frame(61)]
+    depth = torch.from_numpy(np.stack([f["depth"] for f in frames]).view(np.int16)).cuda()
+    K = torch.from_numpy(frames[0]["K"]).cuda()
+    mr = torch.full((3,), 1.0e9, dtype=torch.float64, device="cuda")
+    rgb2 = torch.rand((1, 3, 480, 640))
+    out = stage.vote(rgb2, depth, K, mr, mask_flags=api.RCV_MASK_MAX_RADIUS)
+    torch.cuda.synchronize()
+    assert out["centre_mm"].shape == (1, 3, 3) and bool((out["status"] >= 0).all())
+    stage.capture(1, 480, 640)
+    out2 = stage.vote(rgb2, depth, K, mr, mask_flags=api.RCV_MASK_MAX_RADIUS)
+    torch.cuda.synchronize()
+    assert torch.equal(out2["status"], out["status"])
