@@ -30,7 +30,10 @@ def measure(stage, label):
         mark(0)
         up = stage.activations(rgb)
         mark(1)
-        out = ctx.head_vote_frames(up, stage.weight, stage.bias, depth, K, max_radii=max_radii, mask_flags=flags)
+        if stage.fuse_tail:
+            out = ctx.conv7_head_vote_frames(up, *stage.tail_params, depth, K, max_radii=max_radii, mask_flags=flags)
+        else:
+            out = ctx.head_vote_frames(up, stage.weight, stage.bias, depth, K, max_radii=max_radii, mask_flags=flags)
         mark(2)
         RT = ctx.horn_batch(model_mm, out["centre_mm"])
         mark(3)
@@ -62,6 +65,11 @@ del stage
 torch.manual_seed(0)
 stage_cl = producer.ProducerStage([producer.RadiusTrunk() for _ in range(3)], ctx, channels_last=True).capture(B, 480, 640, concurrent=True)
 out, r = measure(stage_cl, "CUDA graph + channels_last trunks")
+rows.append(r)
+del stage_cl
+torch.manual_seed(0)
+stage_ft = producer.ProducerStage([producer.RadiusTrunk() for _ in range(3)], ctx, fuse_tail=True).capture(B, 480, 640, concurrent=True)
+out, r = measure(stage_ft, "CUDA graph + channels_last trunks up to up1 + fused tail kernel (conv7+BN+ReLU+conv8+mask rule)")
 rows.append(r)
 print(json.dumps({"tool": "config2_bench", "workload": "BASELINE configs[1]: RGB -> 3 x FCN-ResNet-152 trunk (bf16, random weights) -> fused head + vote -> Horn",
                   "frames": B, "reps": REPS, "variants": rows, "graph_output_equals_eager": same,
