@@ -57,8 +57,9 @@ struct ItemMeta {
   int D, Dp, zb;  // grid side, padded row stride, zero boundary
   int ni, nj;     // tile shape (slices x rows); every tile spans all k
   int status;
-  int guard;      // glo | ghi << 16: guard cells of a whole-slice tile below 0 / above D - 1 along the in-slice axes (0 for row-band tiles)
-  int clip;       // gen 2: 1 if run boundaries can leave the tile (row bands, or spheres overhang a grid whose guard band was refused)
+  int guard;      // glo | ghi << 16: guard cells below 0 / above D - 1: along both in-slice axes for whole-slice tiles, along C only for row bands (gen 1: none)
+  int clip;       // gen 2: 1 if run boundaries can leave the tile along C (spheres overhang a grid whose guard band was refused)
+  int band;       // 1: row-band tiles (one slice does not fit), 0: whole-slice tiles with guard rows
   double mean[3];
   double rmax;
 };
@@ -665,10 +666,18 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
       const int spare = a.gen >= 2 ? 1 : 0, planes = a.gen >= 2 ? 2 : 1;
       int Dp = row_stride(D + glo + ghi + spare, a.dp_mod, a.gen);
       long long slice = (long long)planes * (D + glo + ghi) * Dp;
-      if (slice > a.tile_words) { glo = 0; ghi = 0; Dp = row_stride(D + spare, a.dp_mod, a.gen); slice = (long long)planes * D * Dp; }   // row-band tiles are not guarded
+      // A slice that does not fit is cut into row bands.  Generation 1 does not guard them; generation 2 keeps the guard cells
+      // along C (z) -- the rows of a band are restricted by the lanes' column ranges, so with the cells guarded no boundary
+      // needs a bounds test and the band runs the same lean column loops as a whole slice.
+      if (slice > a.tile_words) {
+        if (a.gen < 2) { glo = 0; ghi = 0; Dp = row_stride(D + spare, a.dp_mod, a.gen); }
+        slice = (long long)planes * D * Dp;
+        if (a.gen >= 2 && slice <= a.tile_words) slice = a.tile_words + 1;   // (stay in band mode: the guard rows were what did not fit)
+      }
+      m.band = slice > a.tile_words ? 1 : 0;
       m.Dp = Dp;
       m.guard = glo | (ghi << 16);
-      m.clip = (slice > a.tile_words || ((need_lo > 0.0 || need_hi > 0.0) && glo == 0 && ghi == 0)) ? 1 : 0;
+      m.clip = ((a.gen < 2 && slice > a.tile_words) || ((need_lo > 0.0 || need_hi > 0.0) && glo == 0 && ghi == 0)) ? 1 : 0;
       if (slice <= a.tile_words) {
         int ni_max = (int)(a.tile_words / slice);
         if (ni_max > 32) ni_max = 32;   // (gen 1: the polar pass keeps one mask bit per slice of a tile)
@@ -777,7 +786,7 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
   // tile work list
   m = a.meta[item];
   const int glo = m.guard & 0xffff, gspan = (m.guard & 0xffff) + (m.guard >> 16);
-  const bool whole = m.nj >= m.D;   // whole-slice tiles (guarded); otherwise row bands
+  const bool whole = !m.band;       // whole-slice tiles (guard rows inside); otherwise row bands over [0, D)
   const int tj = whole ? 1 : (m.D + m.nj - 1) / m.nj, ti = (m.D + m.ni - 1) / m.ni;
   for (int t = threadIdx.x; t < ti * tj; t += blockDim.x) {
     Unit u;
@@ -1597,9 +1606,9 @@ __device__ __forceinline__ void runs_chunk(const RunPoint& c, const RunLane& L, 
     amax = fmaxf(amax, f2_lo(aa[s]));
   }
   const int Hl = run_half_width(amax);
-  // the lane's own column range [ulo, uhi] (inside the tile's rows when CLIP); empty: ulo > uhi
-  int ulo = -Hl, uhi = Hl;
-  if (CLIP) { ulo = max(ulo, t.j0 - c.ipb); uhi = min(uhi, t.j0 + t.nj - 1 - c.ipb); }
+  // the lane's own column range [ulo, uhi], inside the tile's rows (a no-op for whole-slice tiles, whose guard rows hold every
+  // sphere; the restriction that makes a row band a band); empty: ulo > uhi
+  int ulo = max(-Hl, t.j0 - c.ipb), uhi = min(Hl, t.j0 + t.nj - 1 - c.ipb);
   if (Hl < 0) { ulo = 1; uhi = 0; }
   const bool some = ulo <= uhi;
   int wlo = __reduce_min_sync(0xffffffffu, some ? ulo : 0x7fffffff), whi = __reduce_max_sync(0xffffffffu, some ? uhi : -0x7fffffff);
@@ -1608,7 +1617,7 @@ __device__ __forceinline__ void runs_chunk(const RunPoint& c, const RunLane& L, 
   int mlo = __reduce_max_sync(0xffffffffu, some ? ulo : 0x7fffffff), mhi = __reduce_min_sync(0xffffffffu, some ? uhi : -0x7fffffff);
   mlo = max(mlo, wlo); mhi = min(mhi, whi);
   // a lane without columns parks on a row that is certainly inside the tile
-  const int upark = CLIP ? min(max(0, t.j0 - c.ipb), t.j0 + t.nj - 1 - c.ipb) : 0;
+  const int upark = min(max(0, t.j0 - c.ipb), t.j0 + t.nj - 1 - c.ipb);
   if (!some) { ulo = upark; uhi = upark; }
   // starts go to plane 0, ends to plane 1; a slice of the chunk beyond the tile (its columns are all empty) re-uses the
   // last real slice's cells, where its four marks cancel

@@ -26,7 +26,11 @@ void render_group(const RunPoint* c, const double (*pd)[3], const HTile& t, Stat
   RunLane L[32];
   for (int l = 0; l < 32; ++l) run_lane_setup(c[l], L[l]);
   for (int i0c = t.i0; i0c < t.i0 + t.ni; i0c += NC) {
-    f2 aa[32][NC]; int Hl[32], H = -1;
+    f2 aa[32][NC];
+    // runs_chunk (rcvvote.cu): every lane's own column range [ulo, uhi] restricted to the tile's rows (a no-op for guarded
+    // whole-slice tiles, the band restriction otherwise); a lane without columns parks on a row inside the tile
+    int ulo[32], uhi[32], upark[32]; bool some[32];
+    int wlo = 0x7fffffff, whi = -0x7fffffff;
     for (int l = 0; l < 32; ++l) {
       float amax = -1.f;
       for (int s = 0; s < NC; ++s) {
@@ -34,24 +38,27 @@ void render_group(const RunPoint* c, const double (*pd)[3], const HTile& t, Stat
         aa[l][s] = run_slice_consts(c[l], L[l], i, i < t.i0 + t.ni);
         if (f2_lo(aa[l][s]) > amax) amax = f2_lo(aa[l][s]);
       }
-      Hl[l] = run_half_width(amax);
-      if (Hl[l] > H) H = Hl[l];
+      const int Hl = run_half_width(amax);
+      ulo[l] = -Hl > t.j0 - c[l].ipb ? -Hl : t.j0 - c[l].ipb;
+      uhi[l] = Hl < t.j0 + t.nj - 1 - c[l].ipb ? Hl : t.j0 + t.nj - 1 - c[l].ipb;
+      if (Hl < 0) { ulo[l] = 1; uhi[l] = 0; }
+      some[l] = ulo[l] <= uhi[l];
+      if (some[l]) { if (ulo[l] < wlo) wlo = ulo[l]; if (uhi[l] > whi) whi = uhi[l]; }
+      int up = 0 > t.j0 - c[l].ipb ? 0 : t.j0 - c[l].ipb;
+      if (up > t.j0 + t.nj - 1 - c[l].ipb) up = t.j0 + t.nj - 1 - c[l].ipb;
+      upark[l] = up;
+      if (!some[l]) { ulo[l] = up; uhi[l] = up; }
     }
-    if (H < 0) continue;
-    for (int u0 = -H; u0 <= H; u0 += 32) {
+    if (wlo > whi) continue;
+    for (int u0 = wlo; u0 <= whi; u0 += 32) {
       unsigned flags[32] = {0};
-      for (int jj = 0; jj < 32 && u0 + jj <= H; ++jj) {
+      for (int jj = 0; jj < 32 && u0 + jj <= whi; ++jj) {
         const int u = u0 + jj;
         for (int l = 0; l < 32; ++l) {
-          // the lane's own column range; beyond it the column is empty by construction and is parked on the lane's edge row
-          int uc = Hl[l] < 0 ? 0 : (u < -Hl[l] ? -Hl[l] : (u > Hl[l] ? Hl[l] : u));
-          int row = c[l].ipb + uc;
-          bool skip = false;
-          if (CLIP) {
-            if (row < t.j0) { uc += t.j0 - row; row = t.j0; skip = true; }
-            if (row > t.j0 + t.nj - 1) { uc -= row - (t.j0 + t.nj - 1); row = t.j0 + t.nj - 1; skip = true; }
-            if (uc != u) skip = true;
-          }
+          // beyond its own range the lane parks on its edge row and the column is empty by construction
+          const int uc = u < ulo[l] ? ulo[l] : (u > uhi[l] ? uhi[l] : u);
+          const bool skip = uc != u || !some[l];
+          const int row = c[l].ipb + uc;
           RunCol C;
           run_col_setup(c[l], u, uc, t.Dp, C);
           if (skip) { C.du = f2_dup(1.0e18f); C.ndu = f2_dup(-1.0e18f); }     // g'' = -huge: the column is empty
@@ -83,10 +90,9 @@ void render_group(const RunPoint* c, const double (*pd)[3], const HTile& t, Stat
           if (!((flags[l] >> jj) & 1u)) continue;
           ++st.flagged_cols;
           const int u = u0 + jj;
-          int uc = Hl[l] < 0 ? 0 : (u < -Hl[l] ? -Hl[l] : (u > Hl[l] ? Hl[l] : u));
-          if (uc != u) continue;   // (a parked column is empty and never flagged; CLIP-skipped columns have NaN z)
+          const int uc = u < ulo[l] ? ulo[l] : (u > uhi[l] ? uhi[l] : u);
+          if (uc != u || !some[l]) { ++st.oob; continue; }   // (a parked column is empty and must never be flagged)
           const int row = c[l].ipb + u;
-          if (CLIP && (row < t.j0 || row > t.j0 + t.nj - 1)) continue;
           RunCol C;
           run_col_setup(c[l], u, uc, t.Dp, C);
           const unsigned base = (unsigned)RCV_MAGIC_BITS + (unsigned)(uc * t.Dp);

@@ -118,6 +118,25 @@ def test_row_bands_partition_the_volume(band):
     assert not got[:j0].any() and not got[j0 + nj:].any()
 
 
+@pytest.mark.parametrize("band", [(0, 12), (12, 13), (25, 12), (8, 1), (30, 7), (0, 37)])
+@pytest.mark.parametrize("NC", [1, 2])
+def test_guarded_row_bands_need_no_clipping(band, NC):
+    """Row bands of a large grid keep the guard cells along z: the rows are restricted by the lanes' column ranges, the cells
+    by the guard, so the unclipped column loops draw a band (spheres overhang the grid on both sides here)."""
+    rng = np.random.default_rng(10)
+    D = 37
+    R = rng.integers(2, 14, size=40).astype(np.int32)
+    p = R[:, None] + 1.0 + rng.random((40, 3)) * (D - 3.0 - 2.0 * R[:, None])
+    p[:8] = np.where(rng.random((8, 3)) < 0.5, R[:8, None] - 2.2 + rng.random((8, 3)), D - 1 - R[:8, None] + 2.2 - rng.random((8, 3)))
+    glo, ghi = _guards(p, R, D)
+    assert 0 < glo <= 8 and 0 < ghi <= 8
+    want = oracle.fast_for(p, R, D)
+    j0, nj = band
+    got, _ = hostsim.render_runs(p, R, D, glo=glo, ghi=ghi, band=band, clip=False, slab=1, NC=NC, sqrt_perturb=1)
+    assert np.array_equal(got[j0:j0 + nj], want[j0:j0 + nj])
+    assert not got[:j0].any() and not got[j0 + nj:].any()
+
+
 def test_large_radius_thick_rings():
     rng = np.random.default_rng(21)
     D = 120
