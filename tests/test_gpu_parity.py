@@ -90,6 +90,50 @@ def test_frames_api_vs_reference(ctx, golden):
         assert np.array_equal(h[key], out[key].cpu().numpy()), key
 
 
+def test_host_entry_point_large_batch_equals_device_path():
+    """rcv_vote_frames_host at a batch size that takes every branch of the host side -- helper threads scanning the depth rows
+    ahead of the copies (n_frames >= 64), the ramped first chunks (n_frames >= 4 chunks of >= 128), the strided copy of a
+    frame's keypoint planes, frames with empty / full-height / single-row depth -- against rcv_vote_frames on device-resident
+    copies of the same arrays: every output identical (the row cropping is bit-neutral), and fewer bytes crossed the bus."""
+    from rcvpose_b200 import api
+    B, Kp, H, W = 640, 2, 48, 64
+    rng = np.random.default_rng(17)
+    depth = np.zeros((B, H, W), np.uint16)
+    radius = rng.uniform(0.25, 0.6, size=(B, Kp, H, W)).astype(np.float32)
+    sem = rng.uniform(0.0, 1.0, size=(B, Kp, H, W)).astype(np.float32)
+    for f in range(B):
+        kind = f % 7
+        if kind == 0:
+            continue                                                   # no depth at all: RCV_ST_EMPTY_MASK
+        r0 = int(rng.integers(0, H - 1)); r1 = int(rng.integers(r0 + 1, min(H, r0 + 20) + 1))
+        if kind == 1:
+            r0, r1 = 0, H                                              # full height: nothing to crop
+        if kind == 2:
+            r1 = r0 + 1                                                # a single row
+        c0 = int(rng.integers(0, W - 8)); c1 = int(rng.integers(c0 + 4, min(W, c0 + 24) + 1))
+        depth[f, r0:r1, c0:c1] = rng.integers(700, 1100, size=(r1 - r0, c1 - c0)).astype(np.uint16)
+        if kind == 3:
+            depth[f, r0, c0:c1] = 0                                    # first row of the block empty again
+    K = np.array([[57.3, 0.0, 32.5], [0.0, 57.4, 24.2], [0.0, 0.0, 1.0]])
+    mr = np.full((Kp,), 0.55, np.float64)
+    flags = api.RCV_MASK_MAX_RADIUS | api.RCV_MASK_SEM_GT
+    ctx = api.VoteContext(0, max_items=256 * Kp, max_points_total=1 << 22, max_grid=256, image=(H, W))
+    h = ctx.vote_frames_host(depth, radius, K, sem=sem, max_radii=mr, mask_flags=flags, sem_threshold=0.3, frames_per_chunk=128)
+    sent = ctx.last_h2d_bytes()
+    outs = []
+    for f0 in range(0, B, 256):                                        # the device path, in batches the context holds
+        sl = slice(f0, min(B, f0 + 256))
+        o = ctx.vote_frames(torch.from_numpy(depth[sl].view(np.int16)).cuda(), torch.from_numpy(radius[sl]).cuda(), torch.from_numpy(K).cuda(),
+                            sem=torch.from_numpy(sem[sl]).cuda(), max_radii=torch.from_numpy(mr).cuda(), mask_flags=flags, sem_threshold=0.3)
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy() for k, v in o.items() if k in ("centre_mm", "peak", "votes", "n_points", "grid", "status")})
+    for key in ("centre_mm", "peak", "votes", "n_points", "grid", "status"):
+        want = np.concatenate([o[key] for o in outs])
+        assert np.array_equal(h[key], want), key
+    assert (h["status"][::7] == api.RCV_ST_EMPTY_MASK).all() and (h["status"] == 0).sum() > B * Kp // 2
+    assert 0 < sent < depth.nbytes + radius.nbytes + sem.nbytes, sent
+
+
 def test_mask_rules_and_max_radius(ctx):
     from rcvpose_b200 import api
     fr = synth.config3_frame(11)
