@@ -2016,6 +2016,7 @@ struct rcv_ctx {
   int last_mask_frames, last_mask_kpts, last_mask_words_per_item;   // survival bits left by the most recent frames call (rcv_scene_clouds_last)
   float* head_radius; long long head_radius_cap;   // fused head: radius planes of the items of a call
   double* icp_scratch; long long icp_cap;         // ICP scratch: per-frame state + per-(frame, tile) partial sums
+  void* icp_grid; long long icp_grid_cap;         // ICP uniform grids (bytes): sized by the scene points of a call
   double* add_part; long long add_part_cap;     // ADD metric scratch: per-(frame, tile) partial sums and minima   // K1 scratch: one survival bit per pixel of every item of a call (grown on demand)
   unsigned long long *best, *votes;
   PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
@@ -2063,7 +2064,7 @@ RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri); cudaFree(c->pool.perm); cudaFree(c->pool.rec); cudaFree(c->pool.grp);
   cudaFree(c->meta); cudaFree(c->units); cudaFree(c->counters); cudaFree(c->cnt); cudaFree(c->best); cudaFree(c->votes);
-  cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits); cudaFree(c->add_part); cudaFree(c->icp_scratch); cudaFree(c->head_radius);
+  cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits); cudaFree(c->add_part); cudaFree(c->icp_scratch); cudaFree(c->icp_grid); cudaFree(c->head_radius);
   for (int s = 0; s < 2; ++s) { cudaFree(c->st_depth[s]); cudaFree(c->st_radius[s]); cudaFree(c->st_sem[s]); }
   cudaFree(c->st_K); cudaFree(c->st_maxr); cudaFree(c->st_centre); cudaFree(c->st_peak); cudaFree(c->st_votes);
   cudaFree(c->st_np); cudaFree(c->st_grid); cudaFree(c->st_status); cudaFree(c->st_horn_in);
@@ -2552,7 +2553,9 @@ RCV_EXPORT int rcv_scene_clouds_last(rcv_ctx* c, int n_frames, int n_kpts, const
 extern "C" long long rcv_icp_scratch_doubles(int n_frames, int n_model);
 extern "C" int rcv_icp_launch(const double* model, int n_model, const double* scene, const long long* scene_off, const double* RT_init,
                               const double* max_dist, int n_frames, int max_iter, double rel_fitness, double rel_rmse, double* scratch,
-                              double* RT_out, double* fitness_out, double* rmse_out, int* iters_out, void* stream, long long* launches);
+                              double* RT_out, double* fitness_out, double* rmse_out, int* iters_out, void* stream, long long* launches,
+                              void* grid_scratch, long long n_scene);
+extern "C" long long rcv_icp_grid_bytes(int n_frames, long long n_scene);
 
 RCV_EXPORT int rcv_icp_batch(rcv_ctx* c, const double* model, int n_model, const double* scene, const long long* scene_offsets,
                              const double* RT_init, const double* max_dist, int n_frames, int max_iter, double rel_fitness, double rel_rmse,
@@ -2570,8 +2573,27 @@ RCV_EXPORT int rcv_icp_batch(rcv_ctx* c, const double* model, int n_model, const
     CK(c, cudaMalloc(&c->icp_scratch, (size_t)need * 8));
     c->icp_cap = need;
   }
+  // Uniform grid over each frame's scene (refine.cu): its scratch depends on the number of scene points, which only the device
+  // knows (scene_offsets): one 8-byte read per call.  RCV_ICP_BRUTE=1, or more frames than the grid tables are worth
+  // (2 x 128 KB each), keeps the all-pairs search.
+  const char* brute_env = getenv("RCV_ICP_BRUTE");          // read per call: the parity test switches it
+  const int brute = (brute_env && atoi(brute_env)) ? 1 : 0;
+  void* grid = nullptr;
+  long long n_scene = 0;
+  if (!brute && n_frames <= 2048) {
+    CK(c, cudaMemcpyAsync(&n_scene, scene_offsets + n_frames, 8, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    if (n_scene < 0) FAIL(c, RCV_E_INVALID, "rcv_icp_batch: negative scene offset");
+    const long long gb = rcv_icp_grid_bytes(n_frames, n_scene);
+    if (gb > c->icp_grid_cap) {
+      cudaFree(c->icp_grid); c->icp_grid = nullptr; c->icp_grid_cap = 0;
+      CK(c, cudaMalloc(&c->icp_grid, (size_t)gb));
+      c->icp_grid_cap = gb;
+    }
+    grid = c->icp_grid;
+  }
   CK(c, (cudaError_t)rcv_icp_launch(model, n_model, scene, scene_offsets, RT_init, max_dist, n_frames, max_iter, rel_fitness, rel_rmse,
-                                    c->icp_scratch, RT_out, fitness_out, rmse_out, iters_out, stream, &c->launches));
+                                    c->icp_scratch, RT_out, fitness_out, rmse_out, iters_out, stream, &c->launches, grid, n_scene));
   return RCV_OK;
 }
 

@@ -24,6 +24,13 @@
 // partials in tile order (deterministic), applies the convergence rule and composes the update; the rotation is Horn's
 // quaternion solution (horn_core.h), which equals the SVD solution of umeyama for non-degenerate correspondences.
 // The whole iteration runs stream-ordered with no host round trip: converged frames raise a flag and their CTAs exit.
+//
+// Uniform grid (default; RCV_ICP_BRUTE=1 keeps the all-pairs search).  A correspondence only counts when it is closer than the
+// frame's max_dist, so the scene points of a frame are binned once per call into cells of side h = max(max_dist, extent / 32)
+// (at most 32^3 cells; counting sort: count, scan, fill) and a source point only visits the cells that the cube p +- max_dist
+// touches -- at most 3 per axis.  Candidates are compared with the SAME score and the same "first index wins a tie" rule as the
+// all-pairs search, and every scene point closer than max_dist lies in a visited cell, so the two searches return the same
+// correspondences wherever one is accepted: the results are bit-identical (tests/test_evaluator.py).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -39,6 +46,11 @@ constexpr int kIcpThreads = 128;
 constexpr int kIcpPts = RCV_ICP_PTS;          // source points per thread
 constexpr int kIcpTile = kIcpThreads * kIcpPts; // source points per CTA = scene points per shared-memory tile
 constexpr int kIcpSums = 17;   // n, sum d2, p[3], q[3], pq[9]
+
+// |e|^2 / 2 with a fixed operation order (both searches must score a scene point with the same number)
+__device__ __forceinline__ double half_norm2(double ex, double ey, double ez) {
+  return __dmul_rn(0.5, __fma_rn(ez, ez, __fma_rn(ey, ey, __dmul_rn(ex, ex))));
+}
 
 struct IcpState {     // one per frame, in the context's scratch
   double T[12];       // current transformation (rows 0..2 of the 4x4)
@@ -97,7 +109,7 @@ __global__ void __launch_bounds__(kIcpThreads) k_icp_corr(const double* __restri
       double ex = 0.0, ey = 0.0, ez = 0.0, eh = INFINITY;   // padding never wins the minimum
       if (e < q1) {
         ex = scene[3 * e] - s_T[12]; ey = scene[3 * e + 1] - s_T[13]; ez = scene[3 * e + 2] - s_T[14];
-        eh = 0.5 * (ex * ex + ey * ey + ez * ez);
+        eh = half_norm2(ex, ey, ez);
       }
       s_q[0][si] = ex; s_q[1][si] = ey; s_q[2][si] = ez; s_q[3][si] = eh;
     }
@@ -138,6 +150,194 @@ __global__ void __launch_bounds__(kIcpThreads) k_icp_corr(const double* __restri
     }
   }
   // deterministic tile reduction: warp shuffles in a fixed pattern, then the warp partials in order
+#pragma unroll
+  for (int i = 0; i < kIcpSums; ++i) {
+#pragma unroll
+    for (int m = 16; m; m >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], m);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < kIcpSums; ++i) s_red[i][threadIdx.x >> 5] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < kIcpSums) {
+    double s = 0.0;
+    for (int w = 0; w < kIcpThreads / 32; ++w) s += s_red[threadIdx.x][w];
+    partials[((long long)frame * tiles + tile) * kIcpSums + threadIdx.x] = s;
+  }
+}
+
+// ---- uniform grid over a frame's scene points ----
+constexpr int kGridMax = 32;                            // cells per axis at most
+constexpr int kGridCells = kGridMax * kGridMax * kGridMax;
+struct IcpGrid {          // one per frame
+  double lo[3];           // lower corner of the scene's bounding box
+  double inv_h;           // 1 / cell side
+  int n[3];               // cells per axis
+  int pad;
+};
+struct IcpSorted { double x, y, z, h; };                // coordinates relative to the frame's origin and |.|^2 / 2, in cell order
+
+__device__ __forceinline__ int grid_cell(double v, double lo, double inv_h, int n) {
+  const int c = (int)floor((v - lo) * inv_h);
+  return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+__global__ void __launch_bounds__(256) k_icp_grid_setup(const double* __restrict__ scene, const long long* __restrict__ scene_off,
+                                                        const double* __restrict__ max_dist, IcpGrid* __restrict__ grids, int* __restrict__ cell_cnt) {
+  const int frame = blockIdx.x;
+  const long long q0 = scene_off[frame], q1 = scene_off[frame + 1];
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (long long e = q0 + threadIdx.x; e < q1; e += blockDim.x)
+    for (int a = 0; a < 3; ++a) { const double v = scene[3 * e + a]; lo[a] = fmin(lo[a], v); hi[a] = fmax(hi[a], v); }
+  __shared__ double s_lo[3][8], s_hi[3][8];
+  for (int a = 0; a < 3; ++a) {
+    for (int m = 16; m; m >>= 1) { lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], m)); hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], m)); }
+    if ((threadIdx.x & 31) == 0) { s_lo[a][threadIdx.x >> 5] = lo[a]; s_hi[a][threadIdx.x >> 5] = hi[a]; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    IcpGrid g;
+    double ext = 0.0;
+    for (int a = 0; a < 3; ++a) {
+      for (int w = 1; w < 8; ++w) { s_lo[a][0] = fmin(s_lo[a][0], s_lo[a][w]); s_hi[a][0] = fmax(s_hi[a][0], s_hi[a][w]); }
+      g.lo[a] = q1 > q0 ? s_lo[a][0] : 0.0;
+      ext = fmax(ext, q1 > q0 ? s_hi[a][0] - s_lo[a][0] : 0.0);
+    }
+    double h = fmax(max_dist[frame], ext / (double)kGridMax);
+    if (!(h > 0.0) || !(h < 1.0e300)) h = 1.0;             // (a degenerate threshold: one cell per occupied position, or a single cell)
+    g.inv_h = 1.0 / h;
+    for (int a = 0; a < 3; ++a) {
+      const double span = q1 > q0 ? (s_hi[a][0] - s_lo[a][0]) * g.inv_h : 0.0;
+      int n = span < (double)kGridMax ? (int)floor(span) + 1 : kGridMax;
+      g.n[a] = n < 1 ? 1 : (n > kGridMax ? kGridMax : n);
+    }
+    g.pad = 0;
+    grids[frame] = g;
+  }
+  int* cnt = cell_cnt + (long long)frame * (kGridCells + 1);
+  for (int i = threadIdx.x; i <= kGridCells; i += blockDim.x) cnt[i] = 0;
+}
+
+// pass 0: count the points of every cell; pass 1: place them (cursor = the cell's start, advanced atomically)
+__global__ void __launch_bounds__(256) k_icp_grid_bin(const double* __restrict__ scene, const long long* __restrict__ scene_off,
+                                                      const IcpGrid* __restrict__ grids, const IcpState* __restrict__ st, int* __restrict__ cell_cnt,
+                                                      int* __restrict__ cursor, IcpSorted* __restrict__ sorted, int* __restrict__ sorted_idx, int pass) {
+  const int frame = blockIdx.y;
+  const long long q0 = scene_off[frame], q1 = scene_off[frame + 1];
+  const IcpGrid g = grids[frame];
+  const double ox = st[frame].origin[0], oy = st[frame].origin[1], oz = st[frame].origin[2];
+  for (long long e = q0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < q1; e += (long long)gridDim.x * blockDim.x) {
+    const double x = scene[3 * e], y = scene[3 * e + 1], z = scene[3 * e + 2];
+    const int cell = (grid_cell(z, g.lo[2], g.inv_h, g.n[2]) * g.n[1] + grid_cell(y, g.lo[1], g.inv_h, g.n[1])) * g.n[0] + grid_cell(x, g.lo[0], g.inv_h, g.n[0]);
+    if (pass == 0) {
+      atomicAdd(cell_cnt + (long long)frame * (kGridCells + 1) + cell, 1);
+    } else {
+      const int pos = atomicAdd(cursor + (long long)frame * kGridCells + cell, 1);
+      const double ex = x - ox, ey = y - oy, ez = z - oz;       // the arithmetic of the all-pairs kernel, so that the scores are the same numbers
+      sorted[q0 + pos] = IcpSorted{ex, ey, ez, half_norm2(ex, ey, ez)};
+      sorted_idx[q0 + pos] = (int)(e - q0);
+    }
+  }
+}
+
+// exclusive scan of a frame's cell counts (in place: cell_cnt becomes the cell starts, entry kGridCells the total) + cursor copy
+__global__ void __launch_bounds__(1024) k_icp_grid_scan(int* __restrict__ cell_cnt, int* __restrict__ cursor) {
+  const int frame = blockIdx.x;
+  int* cnt = cell_cnt + (long long)frame * (kGridCells + 1);
+  int* cur = cursor + (long long)frame * kGridCells;
+  constexpr int kPer = kGridCells / 1024;   // 32 consecutive cells per thread
+  __shared__ int s_w[32];
+  int v[kPer], sum = 0;
+  for (int i = 0; i < kPer; ++i) { v[i] = cnt[threadIdx.x * kPer + i]; sum += v[i]; }
+  int inc = sum;
+  for (int m = 1; m < 32; m <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, m); if ((threadIdx.x & 31) >= m) inc += t; }
+  if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = s_w[threadIdx.x];
+    for (int m = 1; m < 32; m <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, m); if (threadIdx.x >= m) w += t; }
+    s_w[threadIdx.x] = w;
+  }
+  __syncthreads();
+  int run = inc - sum + ((threadIdx.x >> 5) ? s_w[(threadIdx.x >> 5) - 1] : 0);
+  for (int i = 0; i < kPer; ++i) { cnt[threadIdx.x * kPer + i] = run; cur[threadIdx.x * kPer + i] = run; run += v[i]; }
+  if (threadIdx.x == 1023) cnt[kGridCells] = run;
+}
+
+// The correspondences of one evaluation through the grid: same outputs as k_icp_corr.
+__global__ void __launch_bounds__(kIcpThreads) k_icp_corr_grid(const double* __restrict__ model, int n_model, const double* __restrict__ scene,
+                                                              const long long* __restrict__ scene_off, const double* __restrict__ max_dist,
+                                                              const IcpState* __restrict__ st, const IcpGrid* __restrict__ grids,
+                                                              const int* __restrict__ cell_start, const IcpSorted* __restrict__ sorted,
+                                                              const int* __restrict__ sorted_idx, double* __restrict__ partials, int tiles) {
+  const int frame = blockIdx.y, tile = blockIdx.x;
+  if (st[frame].done) return;
+  __shared__ double s_T[15];
+  __shared__ double s_red[kIcpSums][kIcpThreads / 32];
+  __shared__ IcpGrid s_g;
+  if (threadIdx.x < 12) s_T[threadIdx.x] = st[frame].T[threadIdx.x];
+  if (threadIdx.x < 3) s_T[12 + threadIdx.x] = st[frame].origin[threadIdx.x];
+  if (threadIdx.x == 0) s_g = grids[frame];
+  __syncthreads();
+  const long long q0 = scene_off[frame];
+  const double md = max_dist[frame];
+  const int* cs = cell_start + (long long)frame * (kGridCells + 1);
+  const IcpSorted* sp0 = sorted + q0;
+  const int* si0 = sorted_idx + q0;
+  double v[kIcpSums];
+#pragma unroll
+  for (int i = 0; i < kIcpSums; ++i) v[i] = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < kIcpPts; ++j) {
+    const int g = tile * kIcpTile + j * kIcpThreads + threadIdx.x;
+    if (g >= n_model) continue;
+    const double x = model[3 * g], y = model[3 * g + 1], z = model[3 * g + 2];
+    const double px = s_T[0] * x + s_T[1] * y + s_T[2] * z + s_T[3];
+    const double py = s_T[4] * x + s_T[5] * y + s_T[6] * z + s_T[7];
+    const double pz = s_T[8] * x + s_T[9] * y + s_T[10] * z + s_T[11];
+    const double rx = px - s_T[12], ry = py - s_T[13], rz = pz - s_T[14];
+    double best = INFINITY; int bi = -1;
+    // cells touched by the cube p +- max_dist (cell indices are monotone in the coordinate, so every point within max_dist is inside)
+    int c0[3], c1[3];
+    const double pp[3] = {px, py, pz};
+    bool any = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double f0 = floor((pp[a] - md - s_g.lo[a]) * s_g.inv_h), f1 = floor((pp[a] + md - s_g.lo[a]) * s_g.inv_h);
+      if (!(f1 >= 0.0) || !(f0 <= (double)(s_g.n[a] - 1))) any = false;
+      c0[a] = f0 < 0.0 ? 0 : (int)fmin(f0, (double)(s_g.n[a] - 1));
+      c1[a] = f1 > (double)(s_g.n[a] - 1) ? s_g.n[a] - 1 : (int)fmax(f1, 0.0);
+    }
+    if (any) {
+      for (int cz = c0[2]; cz <= c1[2]; ++cz)
+        for (int cy = c0[1]; cy <= c1[1]; ++cy) {
+          const int row = (cz * s_g.n[1] + cy) * s_g.n[0];
+          const int e0 = cs[row + c0[0]], e1 = cs[row + c1[0] + 1];      // the cells of a row are consecutive: one range
+          for (int e = e0; e < e1; ++e) {
+            const IcpSorted q = sp0[e];
+            const double sc = fma(-rz, q.z, fma(-ry, q.y, fma(-rx, q.x, q.h)));
+            const int idx = si0[e];
+            if (sc < best || (sc == best && idx < bi)) { best = sc; bi = idx; }     // first nearest point in scene order wins a tie
+          }
+        }
+    }
+    if (bi < 0) continue;
+    const double* sp = scene + 3 * (q0 + bi);
+    const double sx = sp[0], sy = sp[1], sz = sp[2];
+    const double dx = px - sx, dy = py - sy, dz = pz - sz;
+    const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    if (!(d2 < md * md)) continue;     // strict, like SearchHybrid's lower_bound on radius^2
+    const double a3[3] = {rx, ry, rz};
+    const double b3[3] = {sx - s_T[12], sy - s_T[13], sz - s_T[14]};
+    v[0] += 1.0; v[1] += d2;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      v[2 + r] += a3[r]; v[5 + r] += b3[r];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[8 + 3 * r + c] += a3[r] * b3[c];
+    }
+  }
 #pragma unroll
   for (int i = 0; i < kIcpSums; ++i) {
 #pragma unroll
@@ -212,9 +412,16 @@ extern "C" long long rcv_icp_scratch_doubles(int n_frames, int n_model) {
   return (long long)n_frames * ((long long)(sizeof(IcpState) + 7) / 8 + tiles * kIcpSums) + 1;   // + the converged-frames counter
 }
 
+// Bytes of grid scratch for n_frames frames holding n_scene scene points in total (0 frames: no grid).
+extern "C" long long rcv_icp_grid_bytes(int n_frames, long long n_scene) {
+  return (long long)n_frames * ((long long)sizeof(IcpGrid) + (2LL * kGridCells + 1) * 4) + n_scene * ((long long)sizeof(IcpSorted) + 4) + 256;
+}
+
+// grid_scratch: rcv_icp_grid_bytes(n_frames, n_scene) bytes (256-byte aligned), or NULL for the all-pairs search.
 extern "C" int rcv_icp_launch(const double* model, int n_model, const double* scene, const long long* scene_off, const double* RT_init,
                               const double* max_dist, int n_frames, int max_iter, double rel_fitness, double rel_rmse, double* scratch,
-                              double* RT_out, double* fitness_out, double* rmse_out, int* iters_out, void* stream, long long* launches) {
+                              double* RT_out, double* fitness_out, double* rmse_out, int* iters_out, void* stream, long long* launches,
+                              void* grid_scratch, long long n_scene) {
   cudaStream_t s = (cudaStream_t)stream;
   const int tiles = (n_model + kIcpTile - 1) / kIcpTile;
   IcpState* st = reinterpret_cast<IcpState*>(scratch);
@@ -223,8 +430,26 @@ extern "C" int rcv_icp_launch(const double* model, int n_model, const double* sc
   cudaMemsetAsync(n_done, 0, sizeof(int), s);
   k_icp_init<<<(n_frames + 127) / 128, 128, 0, s>>>(RT_init, n_frames, st);
   *launches += 1;
+  IcpGrid* grids = nullptr; int* cell_start = nullptr; int* cursor = nullptr; IcpSorted* sorted = nullptr; int* sorted_idx = nullptr;
+  if (grid_scratch) {
+    char* p = reinterpret_cast<char*>(grid_scratch);
+    sorted = reinterpret_cast<IcpSorted*>(p); p += n_scene * (long long)sizeof(IcpSorted);
+    grids = reinterpret_cast<IcpGrid*>(p); p += (long long)n_frames * sizeof(IcpGrid);
+    cell_start = reinterpret_cast<int*>(p); p += (long long)n_frames * (kGridCells + 1) * 4;
+    cursor = reinterpret_cast<int*>(p); p += (long long)n_frames * kGridCells * 4;
+    sorted_idx = reinterpret_cast<int*>(p);
+    k_icp_grid_setup<<<n_frames, 256, 0, s>>>(scene, scene_off, max_dist, grids, cell_start);
+    k_icp_grid_bin<<<dim3(16, n_frames), 256, 0, s>>>(scene, scene_off, grids, st, cell_start, cursor, sorted, sorted_idx, 0);
+    k_icp_grid_scan<<<n_frames, 1024, 0, s>>>(cell_start, cursor);
+    k_icp_grid_bin<<<dim3(16, n_frames), 256, 0, s>>>(scene, scene_off, grids, st, cell_start, cursor, sorted, sorted_idx, 1);
+    *launches += 4;
+  }
   for (int k = 0; k <= max_iter; ++k) {
-    k_icp_corr<<<dim3(tiles, n_frames), kIcpThreads, 0, s>>>(model, n_model, scene, scene_off, max_dist, st, partials, tiles);
+    if (grid_scratch)
+      k_icp_corr_grid<<<dim3(tiles, n_frames), kIcpThreads, 0, s>>>(model, n_model, scene, scene_off, max_dist, st, grids, cell_start, sorted, sorted_idx,
+                                                                    partials, tiles);
+    else
+      k_icp_corr<<<dim3(tiles, n_frames), kIcpThreads, 0, s>>>(model, n_model, scene, scene_off, max_dist, st, partials, tiles);
     k_icp_update<<<(n_frames + 63) / 64, 64, 0, s>>>(partials, tiles, n_model, n_frames, k, max_iter, rel_fitness, rel_rmse, st, RT_out,
                                                      fitness_out, rmse_out, iters_out, n_done);
     *launches += 2;

@@ -260,6 +260,40 @@ def test_icp_vs_oracle(ctx):
     assert int(reg0["iters"].max()) == 0 and np.allclose(reg0["RT"].cpu().numpy(), np.stack([c[1] for c in cases]), atol=0)
 
 
+@pytest.mark.gpu
+def test_icp_grid_search_equals_all_pairs(ctx, monkeypatch):
+    """The uniform-grid correspondence search (refine.cu, default) against the all-pairs search (RCV_ICP_BRUTE=1): same scores,
+    same tie rule, every scene point within max_dist inside the visited cells -- bit-identical transformations, fitness, rmse
+    and iteration counts, for thresholds from far below the point spacing to larger than the scene."""
+    rng = np.random.default_rng(43)
+    M = 3000
+    u = rng.normal(size=(M, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    model = u * np.array([60.0, 35.0, 80.0])
+    scenes, inits, mds = [], [], []
+    for b, md in enumerate([0.05, 1.0, 4.0, 9.0, 25.0, 120.0, 1.0e4, 6.0, 6.0]):
+        gt = _pose(rng.normal(size=3), rng.uniform(-100, 100, 3) + np.array([0, 0, 900.0]))
+        pts = model @ gt[:3, :3].T + gt[:3, 3]
+        vis = pts[pts[:, 2] < np.median(pts[:, 2])]
+        n = 700 + 130 * b
+        sc = vis[rng.integers(0, len(vis), size=n)] + rng.normal(0, 0.4, size=(n, 3))
+        if b == 7:
+            sc = np.repeat(sc[:300], 3, axis=0)                      # exact duplicates: ties between scene indices
+        if b == 8:
+            sc = sc[:1]                                              # a single scene point: a one-cell grid
+        scenes.append(sc); mds.append(md)
+        inits.append(_pose(rng.normal(size=3) * 0.03, rng.normal(size=3) * 2.0) @ gt)
+    offs = np.cumsum([0] + [len(x) for x in scenes])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    args = (t(model), t(np.concatenate(scenes)), t(offs), t(np.stack(inits)), t(np.array(mds)))
+    monkeypatch.setenv("RCV_ICP_BRUTE", "1")
+    want = {k: v.cpu().numpy() for k, v in ctx.icp(*args, max_iter=30).items()}
+    monkeypatch.setenv("RCV_ICP_BRUTE", "0")
+    got = {k: v.cpu().numpy() for k, v in ctx.icp(*args, max_iter=30).items()}
+    for k in ("RT", "fitness", "rmse", "iters"):
+        assert np.array_equal(got[k], want[k]), k
+    assert got["fitness"][3] > 0.2 and got["fitness"][0] < got["fitness"][3]
+
+
 def _reference_loop(root, class_name, sym, threshold_mm):
     """estimate_6d_pose_lm's per-image loop (AccumulatorSpace.py:553-731, npy branch) on the oracle's functions."""
     from rcvpose_b200 import evaluate
