@@ -119,7 +119,7 @@ def test_host_entry_point_large_batch_equals_device_path():
     flags = api.RCV_MASK_MAX_RADIUS | api.RCV_MASK_SEM_GT
     ctx = api.VoteContext(0, max_items=256 * Kp, max_points_total=1 << 22, max_grid=256, image=(H, W))
     h = ctx.vote_frames_host(depth, radius, K, sem=sem, max_radii=mr, mask_flags=flags, sem_threshold=0.3, frames_per_chunk=128)
-    sent = ctx.last_h2d_bytes()
+    sent = ctx.last_h2d_bytes
     outs = []
     for f0 in range(0, B, 256):                                        # the device path, in batches the context holds
         sl = slice(f0, min(B, f0 + 256))
