@@ -2022,6 +2022,7 @@ struct rcv_ctx {
   float* head_radius; long long head_radius_cap;   // fused head: radius planes of the items of a call
   double* icp_scratch; long long icp_cap;         // ICP scratch: per-frame state + per-(frame, tile) partial sums
   void* icp_grid; long long icp_grid_cap;         // ICP uniform grids (bytes): sized by the scene points of a call
+  void* add_grid; long long add_grid_cap;         // ADD(-S): grid over the CAD model + the estimated points of a call's frames (bytes)
   double* add_part; long long add_part_cap;     // ADD metric scratch: per-(frame, tile) partial sums and minima   // K1 scratch: one survival bit per pixel of every item of a call (grown on demand)
   unsigned long long *best, *votes;
   PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
@@ -2069,7 +2070,7 @@ RCV_EXPORT void rcv_destroy(rcv_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->pool.X); cudaFree(c->pool.Y); cudaFree(c->pool.Z); cudaFree(c->pool.Rd); cudaFree(c->pool.Ri); cudaFree(c->pool.perm); cudaFree(c->pool.rec); cudaFree(c->pool.grp);
   cudaFree(c->meta); cudaFree(c->units); cudaFree(c->counters); cudaFree(c->cnt); cudaFree(c->best); cudaFree(c->votes);
-  cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits); cudaFree(c->add_part); cudaFree(c->icp_scratch); cudaFree(c->icp_grid); cudaFree(c->head_radius);
+  cudaFree(c->leaves); cudaFree(c->leaf_sums); cudaFree(c->mask_bits); cudaFree(c->add_part); cudaFree(c->icp_scratch); cudaFree(c->icp_grid); cudaFree(c->add_grid); cudaFree(c->head_radius);
   for (int s = 0; s < 2; ++s) { cudaFree(c->st_depth[s]); cudaFree(c->st_radius[s]); cudaFree(c->st_sem[s]); }
   cudaFree(c->st_K); cudaFree(c->st_maxr); cudaFree(c->st_centre); cudaFree(c->st_peak); cudaFree(c->st_votes);
   cudaFree(c->st_np); cudaFree(c->st_grid); cudaFree(c->st_status); cudaFree(c->st_horn_in);
@@ -2456,6 +2457,10 @@ RCV_EXPORT int rcv_horn_batch(rcv_ctx* c, const double* model, long long model_s
   return RCV_OK;
 }
 
+extern "C" long long rcv_add_grid_bytes(int n_frames, int n_model);
+extern "C" int rcv_add_grid_launch(const double* model, int n_model, const double* RT_est, const double* RT_gt, int n_frames, double* part_sum,
+                                   double* part_min, int tiles, int threads_per_tile, void* scratch, void* stream, long long* launches);
+
 RCV_EXPORT int rcv_add_metric_batch(rcv_ctx* c, const double* model_mm, int n_model, const double* RT_est, const double* RT_gt, int n_frames,
                                     double* mean_out, double* min_out, void* stream) {
   if (!c) return RCV_E_INVALID;
@@ -2473,9 +2478,24 @@ RCV_EXPORT int rcv_add_metric_batch(rcv_ctx* c, const double* model_mm, int n_mo
   }
   double* ps = c->add_part;
   double* pm = c->add_part + (long long)n_frames * tiles;
-  k_add_nn<<<dim3(tiles, n_frames), kAddThreads, 0, st>>>(model_mm, n_model, RT_est, RT_gt, ps, pm, tiles);
+  // Nearest neighbours through a grid over the CAD model (refine.cu: same distances, same reduction, bit-identical) unless the
+  // model is small or RCV_ADD_BRUTE=1 asks for the all-pairs kernel.
+  const char* brute_env = getenv("RCV_ADD_BRUTE");
+  if (n_model >= 1024 && !(brute_env && atoi(brute_env))) {
+    const long long gb = rcv_add_grid_bytes(n_frames, n_model);
+    if (gb > c->add_grid_cap) {   // first call of this size only
+      CK(c, cudaStreamSynchronize(st));
+      cudaFree(c->add_grid); c->add_grid = nullptr; c->add_grid_cap = 0;
+      CK(c, cudaMalloc(&c->add_grid, (size_t)gb));
+      c->add_grid_cap = gb;
+    }
+    CK(c, (cudaError_t)rcv_add_grid_launch(model_mm, n_model, RT_est, RT_gt, n_frames, ps, pm, tiles, kAddThreads, c->add_grid, stream, &c->launches));
+  } else {
+    k_add_nn<<<dim3(tiles, n_frames), kAddThreads, 0, st>>>(model_mm, n_model, RT_est, RT_gt, ps, pm, tiles);
+    c->launches += 1;
+  }
   k_add_finish<<<(n_frames + 127) / 128, 128, 0, st>>>(ps, pm, tiles, n_model, n_frames, mean_out, min_out);
-  c->launches += 2;
+  c->launches += 1;
   CK(c, cudaGetLastError());
   return RCV_OK;
 }

@@ -404,7 +404,147 @@ __global__ void k_icp_update(const double* __restrict__ partials, int tiles, int
   st[f] = s;
 }
 
+// ---- ADD(-S) through a grid over the CAD model (rcv_add_metric_batch; AccumulatorSpace.py:664-702) ----
+// For every ground-truth point g (the model under RT_gt) the distance to the nearest ESTIMATED point (the model under RT_est).
+// Both clouds are the same model, so ONE grid over the model serves every frame: the estimated points are laid out in the
+// grid's cell order (the same permutation for all frames) and g is looked up at q = R_est^T (g - t_est), its position in the
+// model frame.  Cells are visited in shells of growing Chebyshev radius r around q's cell; every point in a shell beyond r is at
+// least r cell sides away from q, so the search stops as soon as the best distance is below r h (with a 1e-9 margin for the
+// rounding of the frame change).  Candidates are compared by the SAME camera-frame squared distance as the all-pairs kernel
+// (k_add_nn, rcvvote.cu), and the minimum of a set of numbers does not depend on the order: bit-identical results.
+constexpr int kAddThreads = 256;     // = rcvvote.cu's: one CTA per (frame, 256 ground-truth points), same reduction tree
+
+__device__ __forceinline__ void rt_apply_ref(const double* __restrict__ RT, double x, double y, double z, double& ox, double& oy, double& oz) {
+  // np.dot(xyz, R.T) + t (project(), AccumulatorSpace.py:71): row . point, accumulated left to right (as in rcvvote.cu)
+  ox = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, RT[0]), __dmul_rn(y, RT[1])), __dmul_rn(z, RT[2])), RT[3]);
+  oy = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, RT[4]), __dmul_rn(y, RT[5])), __dmul_rn(z, RT[6])), RT[7]);
+  oz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, RT[8]), __dmul_rn(y, RT[9])), __dmul_rn(z, RT[10])), RT[11]);
+}
+
+__global__ void k_add_grid_init(int n_model, long long* __restrict__ off2, double* __restrict__ md1, IcpState* __restrict__ st1) {
+  off2[0] = 0; off2[1] = n_model; md1[0] = 0.0;
+  IcpState s;
+  for (int i = 0; i < 12; ++i) s.T[i] = 0.0;
+  s.origin[0] = s.origin[1] = s.origin[2] = 0.0; s.prev_fitness = s.prev_rmse = 0.0; s.done = 0; s.iters = 0;
+  st1[0] = s;
+}
+
+// est[frame][s] = the model point of grid slot s under RT_est[frame]
+__global__ void __launch_bounds__(256) k_add_est_points(const IcpSorted* __restrict__ sorted, int n_model, const double* __restrict__ RT_est,
+                                                        double* __restrict__ est) {
+  const int frame = blockIdx.y;
+  __shared__ double s_rt[12];
+  if (threadIdx.x < 12) s_rt[threadIdx.x] = RT_est[16LL * frame + threadIdx.x];
+  __syncthreads();
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_model) return;
+  const IcpSorted m = sorted[s];
+  double ex, ey, ez;
+  rt_apply_ref(s_rt, m.x, m.y, m.z, ex, ey, ez);
+  double* o = est + ((long long)frame * n_model + s) * 3;
+  o[0] = ex; o[1] = ey; o[2] = ez;
+}
+
+__global__ void __launch_bounds__(kAddThreads) k_add_nn_grid(const double* __restrict__ model, int n_model, const double* __restrict__ RT_est,
+                                                            const double* __restrict__ RT_gt, const IcpGrid* __restrict__ grid,
+                                                            const int* __restrict__ cell_start, const double* __restrict__ est,
+                                                            double* __restrict__ part_sum, double* __restrict__ part_min, int tiles) {
+  const int frame = blockIdx.y, tile = blockIdx.x;
+  __shared__ double s_rt[2][12];
+  __shared__ double s_red[2][kAddThreads / 32];
+  __shared__ IcpGrid s_g;
+  if (threadIdx.x < 12) { s_rt[0][threadIdx.x] = RT_est[16LL * frame + threadIdx.x]; s_rt[1][threadIdx.x] = RT_gt[16LL * frame + threadIdx.x]; }
+  if (threadIdx.x == 0) s_g = grid[0];
+  __syncthreads();
+  const int g = tile * kAddThreads + threadIdx.x;
+  double best = INFINITY;
+  if (g < n_model) {
+    double gx, gy, gz;
+    rt_apply_ref(s_rt[1], model[3 * g], model[3 * g + 1], model[3 * g + 2], gx, gy, gz);
+    // q = R_est^T (g - t_est): where g sits in the model frame (R_est is a rotation up to rounding)
+    const double ux = gx - s_rt[0][3], uy = gy - s_rt[0][7], uz = gz - s_rt[0][11];
+    const double q[3] = {s_rt[0][0] * ux + s_rt[0][4] * uy + s_rt[0][8] * uz, s_rt[0][1] * ux + s_rt[0][5] * uy + s_rt[0][9] * uz,
+                         s_rt[0][2] * ux + s_rt[0][6] * uy + s_rt[0][10] * uz};
+    int c0[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double f = floor((q[a] - s_g.lo[a]) * s_g.inv_h);
+      c0[a] = !(f >= 0.0) ? 0 : (f > (double)(s_g.n[a] - 1) ? s_g.n[a] - 1 : (int)f);      // (NaN -> 0: the search then visits everything)
+    }
+    const double h = 1.0 / s_g.inv_h;
+    const int rmax = max(max(s_g.n[0], s_g.n[1]), s_g.n[2]);
+    const double* e0 = est + (long long)frame * n_model * 3;
+    for (int r = 0; r <= rmax; ++r) {
+      const int z0 = max(c0[2] - r, 0), z1 = min(c0[2] + r, s_g.n[2] - 1), y0 = max(c0[1] - r, 0), y1 = min(c0[1] + r, s_g.n[1] - 1);
+      for (int cz = z0; cz <= z1; ++cz)
+        for (int cy = y0; cy <= y1; ++cy) {
+          const int row = (cz * s_g.n[1] + cy) * s_g.n[0];
+          const bool face = (cz - c0[2] == r) || (c0[2] - cz == r) || (cy - c0[1] == r) || (c0[1] - cy == r);
+          // a row of the shell's faces: all its cells; an inner row: the two end cells only
+          for (int part = 0; part < (face || r == 0 ? 1 : 2); ++part) {
+            int xa, xb;
+            if (face || r == 0) { xa = max(c0[0] - r, 0); xb = min(c0[0] + r, s_g.n[0] - 1); }
+            else { xa = xb = part == 0 ? c0[0] - r : c0[0] + r; if (xa < 0 || xa > s_g.n[0] - 1) continue; }
+            const int s0 = cell_start[row + xa], s1 = cell_start[row + xb + 1];
+            for (int sidx = s0; sidx < s1; ++sidx) {
+              const double dx = gx - e0[3 * sidx], dy = gy - e0[3 * sidx + 1], dz = gz - e0[3 * sidx + 2];
+              const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+              best = fmin(best, d2);
+            }
+          }
+        }
+      const double reach = (double)r * h * (1.0 - 1.0e-9);
+      if (best <= reach * reach) break;
+    }
+  }
+  double dist = g < n_model ? sqrt(best) : 0.0, dmin = g < n_model ? dist : INFINITY;
+#pragma unroll
+  for (int m = 16; m; m >>= 1) { dist += __shfl_xor_sync(0xffffffffu, dist, m); dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, m)); }
+  if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = dist; s_red[1][threadIdx.x >> 5] = dmin; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0, mn = INFINITY;
+    for (int w = 0; w < kAddThreads / 32; ++w) { s += s_red[0][w]; mn = fmin(mn, s_red[1][w]); }
+    part_sum[(long long)frame * tiles + tile] = s;
+    part_min[(long long)frame * tiles + tile] = mn;
+  }
+}
+
 }  // namespace
+
+// Bytes of scratch for rcv_add_grid_launch.
+extern "C" long long rcv_add_grid_bytes(int n_frames, int n_model) {
+  return (long long)n_model * (long long)sizeof(IcpSorted) + (long long)sizeof(IcpGrid) + (2LL * kGridCells + 1) * 4 + (long long)n_model * 4 +
+         (long long)sizeof(IcpState) + 64 + (long long)n_frames * n_model * 24 + 1024;
+}
+
+// The partial sums / minima of ADD(-S) through the model grid; the caller reduces them (k_add_finish).  threads_per_tile must be
+// the all-pairs kernel's (256): the two reduce alike.
+extern "C" int rcv_add_grid_launch(const double* model, int n_model, const double* RT_est, const double* RT_gt, int n_frames, double* part_sum,
+                                   double* part_min, int tiles, int threads_per_tile, void* scratch, void* stream, long long* launches) {
+  if (threads_per_tile != kAddThreads) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* p = reinterpret_cast<char*>(scratch);
+  auto take = [&](long long bytes) { char* r = p; p += (bytes + 255) / 256 * 256; return r; };
+  IcpSorted* sorted = reinterpret_cast<IcpSorted*>(take((long long)n_model * sizeof(IcpSorted)));
+  IcpGrid* grid = reinterpret_cast<IcpGrid*>(take(sizeof(IcpGrid)));
+  int* cell_start = reinterpret_cast<int*>(take((kGridCells + 1) * 4LL));
+  int* cursor = reinterpret_cast<int*>(take(kGridCells * 4LL));
+  int* sorted_idx = reinterpret_cast<int*>(take((long long)n_model * 4));
+  IcpState* st1 = reinterpret_cast<IcpState*>(take(sizeof(IcpState)));
+  long long* off2 = reinterpret_cast<long long*>(take(16));
+  double* md1 = reinterpret_cast<double*>(take(8));
+  double* est = reinterpret_cast<double*>(take((long long)n_frames * n_model * 24));
+  k_add_grid_init<<<1, 1, 0, s>>>(n_model, off2, md1, st1);
+  k_icp_grid_setup<<<1, 256, 0, s>>>(model, off2, md1, grid, cell_start);
+  k_icp_grid_bin<<<dim3(16, 1), 256, 0, s>>>(model, off2, grid, st1, cell_start, cursor, sorted, sorted_idx, 0);
+  k_icp_grid_scan<<<1, 1024, 0, s>>>(cell_start, cursor);
+  k_icp_grid_bin<<<dim3(16, 1), 256, 0, s>>>(model, off2, grid, st1, cell_start, cursor, sorted, sorted_idx, 1);
+  k_add_est_points<<<dim3((n_model + 255) / 256, n_frames), 256, 0, s>>>(sorted, n_model, RT_est, est);
+  k_add_nn_grid<<<dim3(tiles, n_frames), kAddThreads, 0, s>>>(model, n_model, RT_est, RT_gt, grid, cell_start, est, part_sum, part_min, tiles);
+  *launches += 7;
+  return (int)cudaGetLastError();
+}
 
 // Scratch (in doubles) the launch needs for n_frames frames of an n_model-point source.
 extern "C" long long rcv_icp_scratch_doubles(int n_frames, int n_model) {

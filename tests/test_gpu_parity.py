@@ -385,6 +385,39 @@ def test_add_metric_vs_kdtree(ctx):
     assert float(mean[0]) == 0.0 and float(mean[B - 1]) > float(mean[1]) > 0.0
 
 
+def test_add_metric_model_grid_equals_all_pairs(ctx, monkeypatch):
+    """ADD(-S) through the grid over the CAD model (refine.cu, default for models of 1024 points and more) against the all-pairs
+    kernel (RCV_ADD_BRUTE=1): the same squared distances and the same reduction tree, so mean and minimum are bit-identical --
+    for nearly equal poses (one or two shells of cells), a grossly wrong pose (the search visits the whole grid), a pose that
+    puts the query cloud outside the grid's box, and a flat model (a grid one cell thick)."""
+    rng = np.random.default_rng(33)
+
+    def pose(rv, t):
+        th = np.linalg.norm(rv); k = rv / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        RT = np.eye(4); RT[:3, :3] = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx; RT[:3, 3] = t
+        return RT
+    for M, flat in ((5841, False), (2048, True)):
+        u = rng.normal(size=(M, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+        model = u * np.array([45.0, 30.0, 60.0]) * rng.uniform(0.8, 1.0, size=(M, 1))
+        if flat:
+            model[:, 2] = 0.0
+        B = 7
+        RT_gt = np.stack([pose(rng.normal(size=3), rng.uniform(-200, 200, 3) + np.array([0, 0, 900.0])) for _ in range(B)])
+        RT_est = RT_gt.copy()
+        for b in range(1, B):
+            RT_est[b] = pose(rng.normal(size=3) * 0.01 * b, rng.normal(size=3) * 1.5 * b) @ RT_gt[b]
+        RT_est[5] = pose(rng.normal(size=3) * 2.0, np.array([40.0, -25.0, 30.0])) @ RT_gt[5]          # grossly wrong rotation
+        RT_est[6] = pose(rng.normal(size=3) * 0.01, np.array([500.0, 300.0, -400.0])) @ RT_gt[6]       # half a metre away
+        args = (torch.from_numpy(model).cuda(), torch.from_numpy(RT_est).cuda(), torch.from_numpy(RT_gt).cuda())
+        monkeypatch.setenv("RCV_ADD_BRUTE", "1")
+        want = [t.cpu().numpy() for t in ctx.add_metric(*args)]
+        monkeypatch.setenv("RCV_ADD_BRUTE", "0")
+        got = [t.cpu().numpy() for t in ctx.add_metric(*args)]
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (M, got, want)
+        assert got[0][0] == 0.0 and got[0][6] > 100.0 and np.isfinite(got[0]).all()
+
+
 @pytest.mark.parametrize("shape", [(1, 480, 640), (3, 480, 640), (2, 24, 40), (1, 8, 24)])
 def test_head_1x1_tensor_core_vs_torch(ctx, shape):
     """K5 (conv8 of the producer, models/fcnresnet.py:118,187-189): tcgen05 kernel vs torch's fp32 conv of the same
