@@ -155,7 +155,8 @@ int rcv_horn_batch_host(rcv_ctx* ctx, const double* model, long long model_strid
  * The step right after the path: the CAD points are transformed by the estimated pose and
  * by the ground-truth pose (project(), :64-75: xyz @ R^T + t) and, for every ground-truth point, the distance to the
  * NEAREST estimated point is taken (open3d compute_point_cloud_distance, :688/:692); the reference thresholds the
- * MEAN of these distances, or their MINIMUM for the symmetric classes.  Brute-force float64 nearest neighbour.
+ * MEAN of these distances, or their MINIMUM for the symmetric classes.  Exact float64 nearest neighbour (through a grid over the
+ * model for models of 1,024 points and more; bit-identical to the all-pairs search, RCV_ADD_BRUTE=1).
  *   model_mm [n_model][3] float64 (one CAD model shared by the frames), RT_est / RT_gt [n_frames][4][4] float64
  *   row-major (rows 0..2 used; translations in the unit of model_mm), outputs mean_out / min_out [n_frames] float64. */
 int rcv_add_metric_batch(rcv_ctx* ctx, const double* model_mm, int n_model, const double* RT_est, const double* RT_gt, int n_frames,
@@ -183,13 +184,15 @@ int rcv_scene_clouds_last(rcv_ctx* ctx, int n_frames, int n_kpts, const void* de
  * Replaces open3d 0.14.1 (rcvpose.yml:176; third-party, not in the reference tree)
  *   registration_icp(source = CAD model, target = scene, max_correspondence_distance, init,
  *                    TransformationEstimationPointToPoint(), ICPConvergenceCriteria(relative_fitness, relative_rmse, max_iteration))
- * for n_frames frames at once (see csrc/refine.cu for the restated algorithm).  Exact brute-force float64 nearest neighbour.
+ * for n_frames frames at once (see csrc/refine.cu for the restated algorithm).  Exact float64 nearest neighbour within max_dist
+ * (a uniform grid over each frame's scene, built once per call; bit-identical to the all-pairs search, RCV_ICP_BRUTE=1).
  *   model [n_model][3] float64 (shared by the frames), scene [*][3] float64 with frame f owning
  *   [scene_offsets[f], scene_offsets[f+1]) (the layout rcv_scene_clouds writes), RT_init [n_frames][4][4] row-major,
  *   max_dist [n_frames] (the reference passes the ADD(-S) distance before ICP), defaults of open3d: max_iter 30,
  *   rel_fitness = rel_rmse = 1e-6.  Outputs: RT_out [n_frames][4][4] (reg.transformation), fitness_out / rmse_out
- *   [n_frames] (reg.fitness, reg.inlier_rmse), iters_out [n_frames] (updates applied).  Stream-ordered; for
- *   max_iter > 32 the call looks at a device counter every 32 iterations and stops once every frame has converged. */
+ *   [n_frames] (reg.fitness, reg.inlier_rmse), iters_out [n_frames] (updates applied).  Stream-ordered, except that the call
+ *   reads scene_offsets[n_frames] (8 bytes) to size the grid scratch, and for max_iter > 32 looks at a device counter every 32
+ *   iterations and stops once every frame has converged. */
 int rcv_icp_batch(rcv_ctx* ctx, const double* model, int n_model, const double* scene, const long long* scene_offsets,
                   const double* RT_init, const double* max_dist, int n_frames, int max_iter, double rel_fitness, double rel_rmse,
                   double* RT_out, double* fitness_out, double* rmse_out, int* iters_out, void* stream);
