@@ -512,11 +512,25 @@ __global__ void __launch_bounds__(kAddThreads) k_add_nn_grid(const double* __res
 
 }  // namespace
 
-// Bytes of scratch for rcv_add_grid_launch.
-extern "C" long long rcv_add_grid_bytes(int n_frames, int n_model) {
-  return (long long)n_model * (long long)sizeof(IcpSorted) + (long long)sizeof(IcpGrid) + (2LL * kGridCells + 1) * 4 + (long long)n_model * 4 +
-         (long long)sizeof(IcpState) + 64 + (long long)n_frames * n_model * 24 + 1024;
-}
+// Layout of rcv_add_grid_launch's scratch: every array starts on a 256-byte boundary.
+struct AddGridLayout {
+  long long sorted, grid, cell_start, cursor, sorted_idx, st1, off2, md1, est, total;
+  AddGridLayout(int n_frames, int n_model) {
+    long long p = 0;
+    auto take = [&](long long bytes) { const long long r = p; p += (bytes + 255) / 256 * 256; return r; };
+    sorted = take((long long)n_model * (long long)sizeof(IcpSorted));
+    grid = take((long long)sizeof(IcpGrid));
+    cell_start = take((kGridCells + 1) * 4LL);
+    cursor = take(kGridCells * 4LL);
+    sorted_idx = take((long long)n_model * 4);
+    st1 = take((long long)sizeof(IcpState));
+    off2 = take(16);
+    md1 = take(8);
+    est = take((long long)n_frames * n_model * 24);
+    total = p;
+  }
+};
+extern "C" long long rcv_add_grid_bytes(int n_frames, int n_model) { return AddGridLayout(n_frames, n_model).total; }
 
 // The partial sums / minima of ADD(-S) through the model grid; the caller reduces them (k_add_finish).  threads_per_tile must be
 // the all-pairs kernel's (256): the two reduce alike.
@@ -525,16 +539,16 @@ extern "C" int rcv_add_grid_launch(const double* model, int n_model, const doubl
   if (threads_per_tile != kAddThreads) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
   char* p = reinterpret_cast<char*>(scratch);
-  auto take = [&](long long bytes) { char* r = p; p += (bytes + 255) / 256 * 256; return r; };
-  IcpSorted* sorted = reinterpret_cast<IcpSorted*>(take((long long)n_model * sizeof(IcpSorted)));
-  IcpGrid* grid = reinterpret_cast<IcpGrid*>(take(sizeof(IcpGrid)));
-  int* cell_start = reinterpret_cast<int*>(take((kGridCells + 1) * 4LL));
-  int* cursor = reinterpret_cast<int*>(take(kGridCells * 4LL));
-  int* sorted_idx = reinterpret_cast<int*>(take((long long)n_model * 4));
-  IcpState* st1 = reinterpret_cast<IcpState*>(take(sizeof(IcpState)));
-  long long* off2 = reinterpret_cast<long long*>(take(16));
-  double* md1 = reinterpret_cast<double*>(take(8));
-  double* est = reinterpret_cast<double*>(take((long long)n_frames * n_model * 24));
+  const AddGridLayout L(n_frames, n_model);
+  IcpSorted* sorted = reinterpret_cast<IcpSorted*>(p + L.sorted);
+  IcpGrid* grid = reinterpret_cast<IcpGrid*>(p + L.grid);
+  int* cell_start = reinterpret_cast<int*>(p + L.cell_start);
+  int* cursor = reinterpret_cast<int*>(p + L.cursor);
+  int* sorted_idx = reinterpret_cast<int*>(p + L.sorted_idx);
+  IcpState* st1 = reinterpret_cast<IcpState*>(p + L.st1);
+  long long* off2 = reinterpret_cast<long long*>(p + L.off2);
+  double* md1 = reinterpret_cast<double*>(p + L.md1);
+  double* est = reinterpret_cast<double*>(p + L.est);
   k_add_grid_init<<<1, 1, 0, s>>>(n_model, off2, md1, st1);
   k_icp_grid_setup<<<1, 256, 0, s>>>(model, off2, md1, grid, cell_start);
   k_icp_grid_bin<<<dim3(16, 1), 256, 0, s>>>(model, off2, grid, st1, cell_start, cursor, sorted, sorted_idx, 0);
