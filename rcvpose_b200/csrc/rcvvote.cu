@@ -2340,7 +2340,7 @@ RCV_EXPORT int rcv_vote_frames_host(rcv_ctx* c, int n_frames, int n_kpts, const 
   // seg plane cross the bus; the depth slot is cleared first, and whatever the other planes still hold outside the range sits
   // under zero depth.  Results are bit-identical to copying whole images; a dense depth image costs one row of scanning.
   // The scan reads most of every depth image from host DRAM, so helper threads run ahead of the thread that issues the copies
-  // (frame f belongs to helper f % T; RCV_HOST_THREADS, default 3; small calls scan inline).
+  // (helpers claim frames in order from a shared counter; RCV_HOST_THREADS, default 3; small calls scan inline).
   const long long row_b = (long long)fp->width * dbytes;
   const int height = fp->height;
   auto scan_frame = [depth, px, dbytes, row_b, height](int f, int& r0, int& r1) {
@@ -2352,16 +2352,23 @@ RCV_EXPORT int rcv_vote_frames_host(rcv_ctx* c, int n_frames, int n_kpts, const 
   struct RowRange { int r0, r1; std::atomic<int> ready; };
   int n_helpers = host_helper_threads();
   if (n_frames < 64) n_helpers = 0;
-  std::vector<RowRange> ranges(n_helpers ? (size_t)n_frames : 0);
+  std::vector<RowRange> ranges;
   std::vector<std::thread> helpers;
+  std::atomic<int> next_frame{0};
   struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (auto& h : t) if (h.joinable()) h.join(); } } joiner{helpers};   // also on the error returns below
   if (n_helpers) {
-    for (auto& r : ranges) r.ready.store(0, std::memory_order_relaxed);
-    RowRange* rr = ranges.data();
-    for (int t = 0; t < n_helpers; ++t)
-      helpers.emplace_back([=]() {
-        for (int f = t; f < n_frames; f += n_helpers) { scan_frame(f, rr[f].r0, rr[f].r1); rr[f].ready.store(1, std::memory_order_release); }
-      });
+    try {                                               // no exception may cross the C ABI: without helpers the caller scans
+      ranges = std::vector<RowRange>((size_t)n_frames);
+      for (auto& r : ranges) r.ready.store(0, std::memory_order_relaxed);
+      RowRange* rr = ranges.data();
+      std::atomic<int>* nf = &next_frame;
+      for (int t = 0; t < n_helpers; ++t)
+        helpers.emplace_back([=]() {                    // frames are claimed in order, so any number of helpers (>= 1) finishes them all
+          for (int f = nf->fetch_add(1); f < n_frames; f = nf->fetch_add(1)) { scan_frame(f, rr[f].r0, rr[f].r1); rr[f].ready.store(1, std::memory_order_release); }
+        });
+    } catch (...) {
+      if (helpers.empty()) n_helpers = 0;
+    }
   }
   // The first copy is not hidden behind any voting: the first two chunks are a quarter and a half of the regular size.
   int chunk = 0;
