@@ -2587,7 +2587,7 @@ extern "C" int rcv_icp_launch(const double* model, int n_model, const double* sc
                               const double* max_dist, int n_frames, int max_iter, double rel_fitness, double rel_rmse, double* scratch,
                               double* RT_out, double* fitness_out, double* rmse_out, int* iters_out, void* stream, long long* launches,
                               void* grid_scratch, long long n_scene);
-extern "C" long long rcv_icp_grid_bytes(int n_frames, long long n_scene);
+extern "C" long long rcv_icp_grid_bytes(int n_frames, long long n_scene, int n_model);
 
 RCV_EXPORT int rcv_icp_batch(rcv_ctx* c, const double* model, int n_model, const double* scene, const long long* scene_offsets,
                              const double* RT_init, const double* max_dist, int n_frames, int max_iter, double rel_fitness, double rel_rmse,
@@ -2616,7 +2616,7 @@ RCV_EXPORT int rcv_icp_batch(rcv_ctx* c, const double* model, int n_model, const
     CK(c, cudaMemcpyAsync(&n_scene, scene_offsets + n_frames, 8, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     if (n_scene < 0) FAIL(c, RCV_E_INVALID, "rcv_icp_batch: negative scene offset");
-    const long long gb = rcv_icp_grid_bytes(n_frames, n_scene);
+    const long long gb = rcv_icp_grid_bytes(n_frames, n_scene, n_model);
     if (gb > c->icp_grid_cap) {
       cudaFree(c->icp_grid); c->icp_grid = nullptr; c->icp_grid_cap = 0;
       CK(c, cudaMalloc(&c->icp_grid, (size_t)gb));

@@ -52,6 +52,13 @@ __device__ __forceinline__ double half_norm2(double ex, double ey, double ez) {
   return __dmul_rn(0.5, __fma_rn(ez, ez, __fma_rn(ey, ey, __dmul_rn(ex, ex))));
 }
 
+// p = T m with a fixed operation order: the search kernels and the summing kernel must see the same source point
+__device__ __forceinline__ void icp_transform(const double* __restrict__ T, double x, double y, double z, double& px, double& py, double& pz) {
+  px = __fma_rn(T[0], x, __fma_rn(T[1], y, __fma_rn(T[2], z, T[3])));
+  py = __fma_rn(T[4], x, __fma_rn(T[5], y, __fma_rn(T[6], z, T[7])));
+  pz = __fma_rn(T[8], x, __fma_rn(T[9], y, __fma_rn(T[10], z, T[11])));
+}
+
 struct IcpState {     // one per frame, in the context's scratch
   double T[12];       // current transformation (rows 0..2 of the 4x4)
   double origin[3];   // translation of the initial pose: sums are taken relative to it
@@ -89,9 +96,7 @@ __global__ void __launch_bounds__(kIcpThreads) k_icp_corr(const double* __restri
     px[j] = py[j] = pz[j] = 0.0;
     if (g < n_model) {
       const double x = model[3 * g], y = model[3 * g + 1], z = model[3 * g + 2];
-      px[j] = s_T[0] * x + s_T[1] * y + s_T[2] * z + s_T[3];
-      py[j] = s_T[4] * x + s_T[5] * y + s_T[6] * z + s_T[7];
-      pz[j] = s_T[8] * x + s_T[9] * y + s_T[10] * z + s_T[11];
+      icp_transform(s_T, x, y, z, px[j], py[j], pz[j]);
     }
     // argmin_q |p - q|^2 = argmin_q (|q|^2 / 2 - p . q): three DFMA and one compare per pair instead of seven float64
     // operations (the kernel is bound by the float64 pipe).  Coordinates are taken relative to the frame's origin (|.| ~ the
@@ -265,12 +270,19 @@ __global__ void __launch_bounds__(1024) k_icp_grid_scan(int* __restrict__ cell_c
   if (threadIdx.x == 1023) cnt[kGridCells] = run;
 }
 
-// The correspondences of one evaluation through the grid: same outputs as k_icp_corr.
+// The correspondences of one evaluation through the grid: same outputs as k_icp_corr.  Two launches per evaluation:
+//   MODE 1  search only: thread slot s handles model point model_perm[s] -- the model in the cell order of a grid over the MODEL, so
+//           that the lanes of a warp look up neighbouring source points (the same scene cells: coalesced candidates, equal trip
+//           counts) -- and writes the index of its correspondence (or -1) to corr[frame][point];
+//   MODE 2  sums only, source points in their original order: the partial sums and their reduction tree are those of k_icp_corr.
+// (MODE 0 does both in the original order in one launch.)
+template <int MODE>
 __global__ void __launch_bounds__(kIcpThreads) k_icp_corr_grid(const double* __restrict__ model, int n_model, const double* __restrict__ scene,
                                                               const long long* __restrict__ scene_off, const double* __restrict__ max_dist,
                                                               const IcpState* __restrict__ st, const IcpGrid* __restrict__ grids,
                                                               const int* __restrict__ cell_start, const IcpSorted* __restrict__ sorted,
-                                                              const int* __restrict__ sorted_idx, double* __restrict__ partials, int tiles) {
+                                                              const int* __restrict__ sorted_idx, double* __restrict__ partials, int tiles,
+                                                              const int* __restrict__ model_perm, int* __restrict__ corr) {
   const int frame = blockIdx.y, tile = blockIdx.x;
   if (st[frame].done) return;
   __shared__ double s_T[15];
@@ -290,14 +302,16 @@ __global__ void __launch_bounds__(kIcpThreads) k_icp_corr_grid(const double* __r
   for (int i = 0; i < kIcpSums; ++i) v[i] = 0.0;
 #pragma unroll 1
   for (int j = 0; j < kIcpPts; ++j) {
-    const int g = tile * kIcpTile + j * kIcpThreads + threadIdx.x;
+    int g = tile * kIcpTile + j * kIcpThreads + threadIdx.x;
     if (g >= n_model) continue;
+    if (MODE == 1) g = model_perm[g];
     const double x = model[3 * g], y = model[3 * g + 1], z = model[3 * g + 2];
-    const double px = s_T[0] * x + s_T[1] * y + s_T[2] * z + s_T[3];
-    const double py = s_T[4] * x + s_T[5] * y + s_T[6] * z + s_T[7];
-    const double pz = s_T[8] * x + s_T[9] * y + s_T[10] * z + s_T[11];
+    double px, py, pz;
+    icp_transform(s_T, x, y, z, px, py, pz);
     const double rx = px - s_T[12], ry = py - s_T[13], rz = pz - s_T[14];
     double best = INFINITY; int bi = -1;
+    if (MODE == 2) bi = corr[(long long)frame * n_model + g];
+    if (MODE != 2) {
     // cells touched by the cube p +- max_dist (cell indices are monotone in the coordinate, so every point within max_dist is inside)
     int c0[3], c1[3];
     const double pp[3] = {px, py, pz};
@@ -322,6 +336,8 @@ __global__ void __launch_bounds__(kIcpThreads) k_icp_corr_grid(const double* __r
           }
         }
     }
+    }
+    if (MODE == 1) { corr[(long long)frame * n_model + g] = bi; continue; }
     if (bi < 0) continue;
     const double* sp = scene + 3 * (q0 + bi);
     const double sx = sp[0], sy = sp[1], sz = sp[2];
@@ -338,6 +354,7 @@ __global__ void __launch_bounds__(kIcpThreads) k_icp_corr_grid(const double* __r
       for (int c = 0; c < 3; ++c) v[8 + 3 * r + c] += a3[r] * b3[c];
     }
   }
+  if (MODE == 1) return;
 #pragma unroll
   for (int i = 0; i < kIcpSums; ++i) {
 #pragma unroll
@@ -566,12 +583,15 @@ extern "C" long long rcv_icp_scratch_doubles(int n_frames, int n_model) {
   return (long long)n_frames * ((long long)(sizeof(IcpState) + 7) / 8 + tiles * kIcpSums) + 1;   // + the converged-frames counter
 }
 
-// Bytes of grid scratch for n_frames frames holding n_scene scene points in total (0 frames: no grid).
-extern "C" long long rcv_icp_grid_bytes(int n_frames, long long n_scene) {
-  return (long long)n_frames * ((long long)sizeof(IcpGrid) + (2LL * kGridCells + 1) * 4) + n_scene * ((long long)sizeof(IcpSorted) + 4) + 256;
+// Bytes of grid scratch for n_frames frames holding n_scene scene points in total and an n_model-point source.
+static long long icp_scene_grid_bytes(int n_frames, long long n_scene) {
+  return ((long long)n_frames * ((long long)sizeof(IcpGrid) + (2LL * kGridCells + 1) * 4) + n_scene * ((long long)sizeof(IcpSorted) + 4) + 255) / 256 * 256;
+}
+extern "C" long long rcv_icp_grid_bytes(int n_frames, long long n_scene, int n_model) {
+  return icp_scene_grid_bytes(n_frames, n_scene) + AddGridLayout(0, n_model).total + ((long long)n_frames * n_model * 4 + 255) / 256 * 256;
 }
 
-// grid_scratch: rcv_icp_grid_bytes(n_frames, n_scene) bytes (256-byte aligned), or NULL for the all-pairs search.
+// grid_scratch: rcv_icp_grid_bytes(n_frames, n_scene, n_model) bytes (256-byte aligned), or NULL for the all-pairs search.
 extern "C" int rcv_icp_launch(const double* model, int n_model, const double* scene, const long long* scene_off, const double* RT_init,
                               const double* max_dist, int n_frames, int max_iter, double rel_fitness, double rel_rmse, double* scratch,
                               double* RT_out, double* fitness_out, double* rmse_out, int* iters_out, void* stream, long long* launches,
@@ -585,6 +605,7 @@ extern "C" int rcv_icp_launch(const double* model, int n_model, const double* sc
   k_icp_init<<<(n_frames + 127) / 128, 128, 0, s>>>(RT_init, n_frames, st);
   *launches += 1;
   IcpGrid* grids = nullptr; int* cell_start = nullptr; int* cursor = nullptr; IcpSorted* sorted = nullptr; int* sorted_idx = nullptr;
+  int* model_perm = nullptr; int* corr = nullptr;
   if (grid_scratch) {
     char* p = reinterpret_cast<char*>(grid_scratch);
     sorted = reinterpret_cast<IcpSorted*>(p); p += n_scene * (long long)sizeof(IcpSorted);
@@ -596,13 +617,33 @@ extern "C" int rcv_icp_launch(const double* model, int n_model, const double* sc
     k_icp_grid_bin<<<dim3(16, n_frames), 256, 0, s>>>(scene, scene_off, grids, st, cell_start, cursor, sorted, sorted_idx, 0);
     k_icp_grid_scan<<<n_frames, 1024, 0, s>>>(cell_start, cursor);
     k_icp_grid_bin<<<dim3(16, n_frames), 256, 0, s>>>(scene, scene_off, grids, st, cell_start, cursor, sorted, sorted_idx, 1);
-    *launches += 4;
+    // the source points in the cell order of a grid over the model: model_perm[slot] = model index
+    char* m = reinterpret_cast<char*>(grid_scratch) + icp_scene_grid_bytes(n_frames, n_scene);
+    const AddGridLayout L(0, n_model);
+    IcpSorted* m_sorted = reinterpret_cast<IcpSorted*>(m + L.sorted);
+    IcpGrid* m_grid = reinterpret_cast<IcpGrid*>(m + L.grid);
+    int* m_start = reinterpret_cast<int*>(m + L.cell_start);
+    int* m_cursor = reinterpret_cast<int*>(m + L.cursor);
+    model_perm = reinterpret_cast<int*>(m + L.sorted_idx);
+    IcpState* st1 = reinterpret_cast<IcpState*>(m + L.st1);
+    long long* off2 = reinterpret_cast<long long*>(m + L.off2);
+    double* md1 = reinterpret_cast<double*>(m + L.md1);
+    corr = reinterpret_cast<int*>(m + L.total);
+    k_add_grid_init<<<1, 1, 0, s>>>(n_model, off2, md1, st1);
+    k_icp_grid_setup<<<1, 256, 0, s>>>(model, off2, md1, m_grid, m_start);
+    k_icp_grid_bin<<<dim3(16, 1), 256, 0, s>>>(model, off2, m_grid, st1, m_start, m_cursor, m_sorted, model_perm, 0);
+    k_icp_grid_scan<<<1, 1024, 0, s>>>(m_start, m_cursor);
+    k_icp_grid_bin<<<dim3(16, 1), 256, 0, s>>>(model, off2, m_grid, st1, m_start, m_cursor, m_sorted, model_perm, 1);
+    *launches += 9;
   }
   for (int k = 0; k <= max_iter; ++k) {
-    if (grid_scratch)
-      k_icp_corr_grid<<<dim3(tiles, n_frames), kIcpThreads, 0, s>>>(model, n_model, scene, scene_off, max_dist, st, grids, cell_start, sorted, sorted_idx,
-                                                                    partials, tiles);
-    else
+    if (grid_scratch) {
+      k_icp_corr_grid<1><<<dim3(tiles, n_frames), kIcpThreads, 0, s>>>(model, n_model, scene, scene_off, max_dist, st, grids, cell_start, sorted,
+                                                                       sorted_idx, partials, tiles, model_perm, corr);
+      k_icp_corr_grid<2><<<dim3(tiles, n_frames), kIcpThreads, 0, s>>>(model, n_model, scene, scene_off, max_dist, st, grids, cell_start, sorted,
+                                                                       sorted_idx, partials, tiles, model_perm, corr);
+      *launches += 1;
+    } else
       k_icp_corr<<<dim3(tiles, n_frames), kIcpThreads, 0, s>>>(model, n_model, scene, scene_off, max_dist, st, partials, tiles);
     k_icp_update<<<(n_frames + 63) / 64, 64, 0, s>>>(partials, tiles, n_model, n_frames, k, max_iter, rel_fitness, rel_rmse, st, RT_out,
                                                      fitness_out, rmse_out, iters_out, n_done);

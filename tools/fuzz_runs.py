@@ -37,7 +37,16 @@ while time.time() - t0 < T:
     if clip: glo = ghi = 0
     slab = int(rng.integers(1, 9))
     want = oracle.fast_for(p, R, D, method="scatter" if D > 64 else "brute")
-    got, st = hostsim.render_runs(p, R, D, glo=glo, ghi=ghi, clip=clip, slab=slab, NC=min(slab, int(rng.integers(1, 5))), sqrt_perturb=seed % 2)
+    NC = min(slab, int(rng.integers(1, 5)))
+    if seed % 3 == 0:   # row bands (large-grid tiles): the rows of a band are restricted by the lanes' column ranges, guards along z only
+        nj = int(rng.integers(1, max(2, D // 2)))
+        got = np.zeros((D, D, D), np.int32); st = dict(flagged_cols=0, fixes=0, atomics=0)
+        for j0 in range(0, D, nj):
+            g1, s1 = hostsim.render_runs(p, R, D, glo=glo, ghi=ghi, band=(j0, min(nj, D - j0)), clip=clip, slab=slab, NC=NC, sqrt_perturb=seed % 2)
+            got += g1
+            for k in st: st[k] += s1[k]
+    else:
+        got, st = hostsim.render_runs(p, R, D, glo=glo, ghi=ghi, clip=clip, slab=slab, NC=NC, sqrt_perturb=seed % 2)
     if not np.array_equal(got, want):
         print("MISMATCH seed", seed - 1, "kind", kind, "ndiff", int((got != want).sum())); sys.exit(1)
     cases += 1; votes += int(want.sum()); flagged += st["flagged_cols"]; fixes += st["fixes"]; atomics += st["atomics"]
