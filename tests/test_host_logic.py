@@ -206,3 +206,41 @@ def test_shard_by_cost_balances_contiguous_ranges():
     assert pipeline.shard_by_cost([0.0, 0.0, 0.0, 0.0], 2) == [(0, 2), (2, 4)]
     rg = pipeline.shard_by_cost([5.0], 4)
     assert sum(b - a for a, b in rg) == 1
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """include/rcvvote.h is the boundary a reference-side binding compiles against: it must be valid C99 on its own (no C++-isms,
+    no torch types) and a C program must link against librcvvote.so; without a GPU rcv_create reports RCV_E_NOGPU."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from rcvpose_b200 import _lib
+    _lib.load()
+    src = tmp_path / "c_abi.c"
+    src.write_text('''
+#include "rcvvote.h"
+#include <stdio.h>
+int main(void) {
+  rcv_config cfg = {RCV_ABI_VERSION, 16, 1 << 20, 256, 0, 0, 0, 0};
+  rcv_ctx* ctx = 0;
+  int rc = rcv_create(0, &cfg, &ctx);
+  printf("%d %d %d\\n", rcv_abi_version(), rc, ctx != 0);
+  if (ctx) rcv_destroy(ctx);
+  return 0;
+}
+''')
+    exe = tmp_path / "c_abi"
+    libdir = os.path.join(ROOT, "rcvpose_b200")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src),
+                          "-L", libdir, "-lrcvvote", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    abi, rc, has_ctx = [int(x) for x in out.stdout.split()]
+    assert abi == _lib.RCV_ABI_VERSION
+    import torch
+    if torch.cuda.is_available():
+        assert rc == 0 and has_ctx == 1
+    else:
+        assert rc == -4 and has_ctx == 0          # RCV_E_NOGPU: there is no CPU fallback
