@@ -1414,7 +1414,10 @@ constexpr int kRunsThreads = RCV_RUNS_THREADS;
 constexpr int kRunsWarps = kRunsThreads / 32;
 constexpr int kRunsWorkList = 1024;
 constexpr int kRunsSmemBytes = RCV_RUNS_CTAS == 1 ? kSmemBytes : (228 * 1024 / RCV_RUNS_CTAS - 1024) & ~15;   // 228 KB per SM, 1 KB reserved per CTA
-constexpr int kRunsTileWords = kRunsSmemBytes / 4 - 192 - kRunsWorkList / 2 - 2 * 64 * (RCV_RUNS_THREADS / 32);    // static shared variables: 192 words + the per-warp queues of deferred exact decisions
+#ifndef RCV_RUNS_QUEUE
+#define RCV_RUNS_QUEUE 40             // deferred exact decisions a warp can hold (8 bytes each); drained 32 at a time
+#endif
+constexpr int kRunsTileWords = kRunsSmemBytes / 4 - 192 - kRunsWorkList / 2 - 2 * RCV_RUNS_QUEUE * (RCV_RUNS_THREADS / 32);    // static shared variables: 192 words + the per-warp queues of deferred exact decisions
 // The two planes of a tile sit at a fixed distance (half the tile memory), so the address of an end mark is the start
 // plane's address plus an immediate.
 constexpr int kRunsPlaneWords = (kRunsTileWords / 2) & ~3;
@@ -1464,7 +1467,7 @@ __device__ __noinline__ void runs_slow_column(RunPoint c, int pidx, RunSlowCtx s
 // A flagged (point, column) is not decided where it is found -- one lane would walk the float64 path while 31 wait --
 // but queued per warp; the queue is drained 32 items at a time (every lane takes one) and at the end of the tile.  An item
 // carries what the rare path needs to re-derive the column: the point's index in vote order, the column, the chunk.
-constexpr int kRunsQueue = 64;
+constexpr int kRunsQueue = RCV_RUNS_QUEUE;
 struct RunTile {               // per-tile constants of the rare path
   Tile t;
   unsigned tile_s, slice_bytes;
