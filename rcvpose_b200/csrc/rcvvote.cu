@@ -670,14 +670,16 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
       // gen 2 also keeps TWO planes per slice (run starts, run ends: only `add 1` merges lanes that hit the same address).
       const int spare = a.gen >= 2 ? 1 : 0, planes = a.gen >= 2 ? 2 : 1;
       int Dp = row_stride(D + glo + ghi + spare, a.dp_mod, a.gen);
-      long long slice = (long long)planes * (D + glo + ghi) * Dp;
+      // Generation 2 keeps guard CELLS (along z) only: the rows a lane draws are the intersection of its column range with the tile's
+      // rows, so spheres that overhang the grid along x simply lose those columns and a slice is D rows, not D + guards.
+      const int rows_whole = a.gen >= 2 ? D : D + glo + ghi;
+      long long slice = (long long)planes * rows_whole * Dp;
       // A slice that does not fit is cut into row bands.  Generation 1 does not guard them; generation 2 keeps the guard cells
       // along C (z) -- the rows of a band are restricted by the lanes' column ranges, so with the cells guarded no boundary
       // needs a bounds test and the band runs the same lean column loops as a whole slice.
       if (slice > a.tile_words) {
         if (a.gen < 2) { glo = 0; ghi = 0; Dp = row_stride(D + spare, a.dp_mod, a.gen); }
         slice = (long long)planes * D * Dp;
-        if (a.gen >= 2 && slice <= a.tile_words) slice = a.tile_words + 1;   // (stay in band mode: the guard rows were what did not fit)
       }
       m.band = slice > a.tile_words ? 1 : 0;
       m.Dp = Dp;
@@ -687,8 +689,8 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
         int ni_max = (int)(a.tile_words / slice);
         if (ni_max > 32) ni_max = 32;   // (gen 1: the polar pass keeps one mask bit per slice of a tile)
         if (ni_max > D) ni_max = D;
-        m.ni = ni_max >= D ? D : slab_thickness(ni_max);   // a multiple of 3 or 4: the ring passes walk a slab in chunks
-        m.nj = D + glo + ghi;
+        m.ni = ni_max >= D ? D : (a.gen >= 2 ? ni_max : slab_thickness(ni_max));   // gen 1: a multiple of 3 or 4 (its ring passes walk a slab in whole chunks)
+        m.nj = a.gen >= 2 ? D : D + glo + ghi;
         nunits = (D + m.ni - 1) / m.ni;
       } else {
         const int nj_max = a.tile_words / (planes * Dp);
@@ -790,14 +792,14 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
   }
   // tile work list
   m = a.meta[item];
-  const int glo = m.guard & 0xffff, gspan = (m.guard & 0xffff) + (m.guard >> 16);
+  const int glo = m.guard & 0xffff;
   const bool whole = !m.band;       // whole-slice tiles (guard rows inside); otherwise row bands over [0, D)
   const int tj = whole ? 1 : (m.D + m.nj - 1) / m.nj, ti = (m.D + m.ni - 1) / m.ni;
   for (int t = threadIdx.x; t < ti * tj; t += blockDim.x) {
     Unit u;
     u.item = item;
     u.i0 = (t / tj) * m.ni; u.ni = min(m.ni, m.D - u.i0);
-    if (whole) { u.j0 = -glo; u.nj = m.D + gspan; }
+    if (whole) { u.j0 = m.nj > m.D ? -glo : 0; u.nj = m.nj; }   // gen 1: guard rows inside the tile; gen 2: the grid's rows only
     else { u.j0 = (t % tj) * m.nj; u.nj = min(m.nj, m.D - u.j0); }
     a.units[s_ubase + t] = u;
   }

@@ -77,10 +77,11 @@ def lib_runs():
 
 def render_runs(p, R, D, glo=4, ghi=4, slab=4, NC=None, band=None, clip=False, sqrt_perturb=0):
     """Vote counts (D,D,D) int32 in REFERENCE axis order from the run-length rasteriser, rendered slab by slab like the kernel
-    (slabs of `slab` y-slices; band = (j0, nj) restricts the x rows of every tile and needs clip=True)."""
+    (slabs of `slab` y-slices; band = (j0, nj) = the x rows of every tile: the grid's rows by default, as in the kernel -- a
+    lane only draws the columns of its range that fall on the tile's rows; (-glo, D + glo + ghi) adds guard rows)."""
     p = np.ascontiguousarray(p, dtype=np.float64)
     R = np.ascontiguousarray(R, dtype=np.int32)
-    j0, nj = band if band is not None else (-glo, D + glo + ghi)
+    j0, nj = band if band is not None else (0, D)
     NC = NC or min(slab, 4)
     tot = np.zeros(8, dtype=np.int64)
     vol = np.zeros((D, D, D), dtype=np.int32)     # [x][y][z]

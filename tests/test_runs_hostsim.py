@@ -103,6 +103,9 @@ def test_guard_band_holds_overhanging_spheres():
     glo, ghi = _guards(p, R, D)
     assert 0 < glo <= 8 and 0 < ghi <= 8
     _check(p, R, D, glo=glo, ghi=ghi, slab=4)
+    # guard rows as well as guard cells (what a tile looked like before the rows were restricted to the grid's): same counts
+    got, _ = hostsim.render_runs(p, R, D, glo=glo, ghi=ghi, slab=4, band=(-glo, D + glo + ghi))
+    assert np.array_equal(got, oracle.fast_for(p, R, D))
 
 
 @pytest.mark.parametrize("band", [(0, 37), (0, 12), (12, 13), (25, 12), (8, 1), (30, 7)])
