@@ -57,9 +57,13 @@ struct ItemMeta {
   int D, Dp, zb;  // grid side, padded row stride, zero boundary
   int ni, nj;     // tile shape (slices x rows); every tile spans all k
   int status;
-  int guard;      // glo | ghi << 16: guard cells below 0 / above D - 1: along both in-slice axes for whole-slice tiles, along C only for row bands (gen 1: none)
+  int guard;      // (glo & 0xffff) | ghi << 16, SIGNED 16-bit each.  Gen 2: a tile row holds the cells [-glo, D - 1 + ghi] (+ one spare): guard
+                  // cells where the spheres overhang the grid along C, and NEGATIVE values where they stay inside it (cells no sphere
+                  // reaches are not stored).  Gen 1: unsigned guards along both in-slice axes of whole-slice tiles, none for row bands.
   int clip;       // gen 2: 1 if run boundaries can leave the tile along C (spheres overhang a grid whose guard band was refused)
   int band;       // 1: row-band tiles (one slice does not fit), 0: whole-slice tiles with guard rows
+  int rw0, rwn;   // gen 2: the rows (B = reference x) any sphere of the item can reach: tiles cover [rw0, rw0 + rwn) only
+  int sw0, swn;   // gen 2: likewise the slices (A = reference y); the cells (C = z) window is the signed guard pair below
   double mean[3];
   double rmax;
 };
@@ -541,6 +545,7 @@ __device__ double pw_leaf_sum(const double* __restrict__ a, int n) {
 
 struct PreludeArgs {
   Pool pool; ItemMeta* meta; Unit* units; int* counters; int max_units; int max_grid; int policy; int tile_words; int gen; int dp_mod;
+  int full_window;   // 1: tiles cover the whole grid (RCV_FULL_WINDOW=1: A/B against the windows)
   PwLeaf* leaves; double* leaf_sums; long long leaf_cap;
 };
 
@@ -569,7 +574,7 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
   __shared__ int s_nleaf;
   __shared__ double s_mean[3];
   __shared__ double s_red[3][kPreludeThreads / 32];
-  __shared__ double s_red2[2][kPreludeThreads / 32];
+  __shared__ double s_red2[8][kPreludeThreads / 32];
   __shared__ int s_zb, s_ok, s_ubase;
   if (n <= 0) {
     if (threadIdx.x == 0) { if (!(m.status & RCV_ST_POINT_OVERFLOW)) m.status |= RCV_ST_EMPTY_MASK; a.meta[item] = m; }
@@ -619,6 +624,7 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
   // recentre; global min / max over all three axes; max radius
   double vmin = INFINITY, vmax = -INFINITY, rmax = -INFINITY;
   double elo = INFINITY, ehi = -INFINITY;   // extent of the drawn spheres (coordinate -+ integer radius), for the guard band
+  double axl[3] = {INFINITY, INFINITY, INFINITY}, axh[3] = {-INFINITY, -INFINITY, -INFINITY};   // the same per axis (x, y, z): the tile windows
   for (int q = threadIdx.x; q < n; q += blockDim.x) {
     const double x = __dsub_rn(X[q], mx), y = __dsub_rn(Y[q], my), z = __dsub_rn(Z[q], mz);
     X[q] = x; Y[q] = y; Z[q] = z;
@@ -627,17 +633,27 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
     vmax = fmax(vmax, hi3);
     rmax = fmax(rmax, Rd[q]);
     const int ri = a.pool.Ri[m.off + q];
-    if (ri > 0) { elo = fmin(elo, lo3 - (double)ri); ehi = fmax(ehi, hi3 + (double)ri); }
+    if (ri > 0) {
+      elo = fmin(elo, lo3 - (double)ri); ehi = fmax(ehi, hi3 + (double)ri);
+      axl[0] = fmin(axl[0], x - (double)ri); axh[0] = fmax(axh[0], x + (double)ri);
+      axl[1] = fmin(axl[1], y - (double)ri); axh[1] = fmax(axh[1], y + (double)ri);
+      axl[2] = fmin(axl[2], z - (double)ri); axh[2] = fmax(axh[2], z + (double)ri);
+    }
   }
+  for (int c3 = 0; c3 < 3; ++c3) { axl[c3] = warp_min_f64(axl[c3]); axh[c3] = warp_max_f64(axh[c3]); }
   vmin = warp_min_f64(vmin); vmax = warp_max_f64(vmax); rmax = warp_max_f64(rmax);
   elo = warp_min_f64(elo); ehi = warp_max_f64(ehi);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { s_red[0][warp] = vmin; s_red[1][warp] = vmax; s_red[2][warp] = rmax; s_red2[0][warp] = elo; s_red2[1][warp] = ehi; }
+  if (lane == 0) {
+    s_red[0][warp] = vmin; s_red[1][warp] = vmax; s_red[2][warp] = rmax; s_red2[0][warp] = elo; s_red2[1][warp] = ehi;
+    for (int c3 = 0; c3 < 3; ++c3) { s_red2[2 + c3][warp] = axl[c3]; s_red2[5 + c3][warp] = axh[c3]; }
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < kPreludeThreads / 32; ++w) {
       vmin = fmin(vmin, s_red[0][w]); vmax = fmax(vmax, s_red[1][w]); rmax = fmax(rmax, s_red[2][w]);
       elo = fmin(elo, s_red2[0][w]); ehi = fmax(ehi, s_red2[1][w]);
+      for (int c3 = 0; c3 < 3; ++c3) { axl[c3] = fmin(axl[c3], s_red2[2 + c3][w]); axh[c3] = fmax(axh[c3], s_red2[5 + c3][w]); }
     }
     // zero_boundary = int(xyz_mm_min - radius_max) + 1   (int() truncates toward zero)
     const double zbd = __dsub_rn(vmin, rmax);
@@ -665,38 +681,59 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
       int glo = need_lo > 0.0 ? (need_lo < 1e6 ? (int)ceil(need_lo) : kMaxGuard + 1) : 0;
       int ghi = need_hi > 0.0 ? (need_hi < 1e6 ? (int)ceil(need_hi) : kMaxGuard + 1) : 0;
       if (glo > kMaxGuard || ghi > kMaxGuard) { glo = 0; ghi = 0; }   // YCBGEN-style grids without upper pad: clipped passes
+      const bool clipped = (need_lo > 0.0 || need_hi > 0.0) && glo == 0 && ghi == 0;
+      // Generation 2: windows.  A sphere reaches the voxels within its integer radius of its centre (+ the margin of the guard
+      // rule), so per axis only [min(coord - R) - 2.5, max(coord + R) + 2.5] can hold a mark.  Tiles cover that box only: the rows
+      // [rw0, rw0 + rwn) and slices [sw0, sw0 + swn) inside the grid, and along C the cells [-glo, D - 1 + ghi] with SIGNED glo / ghi --
+      // guard cells where the spheres overhang the grid, fewer cells than D where they do not (the reference sizes the grid by the
+      // widest axis; along the others, typically z for a surface seen by a camera, ~10 % of it is never reached).
+      int rw0 = 0, rwn = D, sw0 = 0, swn = D;
+      if (a.gen >= 2 && !a.full_window && axl[0] <= axh[0]) {
+        auto lo_cell = [&](double v) { const double f = floor(v - shift - 2.5); return f < -1e6 ? -1000000 : (f > 1e6 ? 1000000 : (int)f); };
+        auto hi_cell = [&](double v) { const double f = ceil(v - shift + 2.5); return f < -1e6 ? -1000000 : (f > 1e6 ? 1000000 : (int)f); };
+        const int x0 = max(lo_cell(axl[0]), 0), x1 = min(hi_cell(axh[0]), D - 1), y0 = max(lo_cell(axl[1]), 0), y1 = min(hi_cell(axh[1]), D - 1);
+        if (x0 <= x1) { rw0 = x0; rwn = x1 - x0 + 1; } else { rw0 = 0; rwn = 1; }       // (spheres entirely outside the grid: nothing to draw)
+        if (y0 <= y1) { sw0 = y0; swn = y1 - y0 + 1; } else { sw0 = 0; swn = 1; }
+        if (!clipped) {
+          const int z0 = lo_cell(axl[2]), z1 = hi_cell(axh[2]);
+          int g0 = -z0, g1 = z1 - (D - 1);                       // signed guards of the cell window [z0, z1]
+          if (g0 <= -D) g0 = -(D - 1);                           // (window entirely above / below the grid: keep one cell)
+          if (g1 <= -D) g1 = -(D - 1);
+          if (g0 <= kMaxGuard && g1 <= kMaxGuard && D + g0 + g1 >= 1) { glo = g0; ghi = g1; }
+        }
+      }
       // odd row stride: consecutive rows start in different banks.  The run rasteriser (gen 2) keeps one spare cell above the
       // upper guard: the -1 that closes a run ending at the last cell lands there.
       // gen 2 also keeps TWO planes per slice (run starts, run ends: only `add 1` merges lanes that hit the same address).
       const int spare = a.gen >= 2 ? 1 : 0, planes = a.gen >= 2 ? 2 : 1;
       int Dp = row_stride(D + glo + ghi + spare, a.dp_mod, a.gen);
       // Generation 2 keeps guard CELLS (along z) only: the rows a lane draws are the intersection of its column range with the tile's
-      // rows, so spheres that overhang the grid along x simply lose those columns and a slice is D rows, not D + guards.
-      const int rows_whole = a.gen >= 2 ? D : D + glo + ghi;
+      // rows, so spheres that overhang the grid along x simply lose those columns and a slice is the window's rows, not D + guards.
+      const int rows_whole = a.gen >= 2 ? rwn : D + glo + ghi;
       long long slice = (long long)planes * rows_whole * Dp;
       // A slice that does not fit is cut into row bands.  Generation 1 does not guard them; generation 2 keeps the guard cells
       // along C (z) -- the rows of a band are restricted by the lanes' column ranges, so with the cells guarded no boundary
       // needs a bounds test and the band runs the same lean column loops as a whole slice.
       if (slice > a.tile_words) {
-        if (a.gen < 2) { glo = 0; ghi = 0; Dp = row_stride(D + spare, a.dp_mod, a.gen); }
-        slice = (long long)planes * D * Dp;
+        if (a.gen < 2) { glo = 0; ghi = 0; Dp = row_stride(D + spare, a.dp_mod, a.gen); slice = (long long)planes * D * Dp; }
       }
       m.band = slice > a.tile_words ? 1 : 0;
       m.Dp = Dp;
-      m.guard = glo | (ghi << 16);
-      m.clip = ((a.gen < 2 && slice > a.tile_words) || ((need_lo > 0.0 || need_hi > 0.0) && glo == 0 && ghi == 0)) ? 1 : 0;
+      m.guard = (glo & 0xffff) | (ghi << 16);
+      m.clip = ((a.gen < 2 && slice > a.tile_words) || clipped) ? 1 : 0;
+      m.rw0 = rw0; m.rwn = rwn; m.sw0 = sw0; m.swn = swn;
       if (slice <= a.tile_words) {
         int ni_max = (int)(a.tile_words / slice);
         if (ni_max > 32) ni_max = 32;   // (gen 1: the polar pass keeps one mask bit per slice of a tile)
-        if (ni_max > D) ni_max = D;
-        m.ni = ni_max >= D ? D : (a.gen >= 2 ? ni_max : slab_thickness(ni_max));   // gen 1: a multiple of 3 or 4 (its ring passes walk a slab in whole chunks)
-        m.nj = a.gen >= 2 ? D : D + glo + ghi;
-        nunits = (D + m.ni - 1) / m.ni;
+        if (ni_max > swn) ni_max = swn;
+        m.ni = ni_max >= swn ? swn : (a.gen >= 2 ? ni_max : slab_thickness(ni_max));   // gen 1: a multiple of 3 or 4 (its ring passes walk a slab in whole chunks)
+        m.nj = a.gen >= 2 ? rwn : D + glo + ghi;
+        nunits = (swn + m.ni - 1) / m.ni;
       } else {
         const int nj_max = a.tile_words / (planes * Dp);
-        const int nt = (D + nj_max - 1) / nj_max;
-        m.ni = 1; m.nj = (D + nt - 1) / nt;
-        nunits = D * ((D + m.nj - 1) / m.nj);
+        const int nt = (rwn + nj_max - 1) / nj_max;
+        m.ni = 1; m.nj = (rwn + nt - 1) / nt;
+        nunits = swn * ((rwn + m.nj - 1) / m.nj);
       }
       const int ub = atomicAdd(&a.counters[0], nunits);
       if (ub + nunits > a.max_units) { m.status |= RCV_ST_UNIT_OVERFLOW; ok = 0; atomicSub(&a.counters[0], nunits); }
@@ -768,6 +805,8 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
       if (a.gen >= 2) {   // internal axes (A,B,C) = reference (y,x,z)
         RunPoint rp;
         run_point_setup(rp, Y[q], X[q], Z[q], Ri[q]);
+        // a point that draws nothing (R <= 0) still leaves its four cancelling marks at its own cell: it must be one the rows store
+        if (rp.R <= 0) { const int g0 = (short)(a.meta[item].guard & 0xffff); rp.ipc = g0 < 0 ? -g0 : 0; rp.fc = 0.f; }
         int4* rec = a.pool.rec + 2 * (m.off + pos);
         rec[0] = make_int4(rp.ipa, rp.ipb, rp.ipc, rp.R);
         rec[1] = make_int4(__float_as_int(rp.fa), __float_as_int(rp.fb), __float_as_int(rp.fc), __float_as_int(rp.W));
@@ -792,15 +831,15 @@ __global__ void __launch_bounds__(kPreludeThreads) k_prelude(PreludeArgs a) {
   }
   // tile work list
   m = a.meta[item];
-  const int glo = m.guard & 0xffff;
-  const bool whole = !m.band;       // whole-slice tiles (guard rows inside); otherwise row bands over [0, D)
-  const int tj = whole ? 1 : (m.D + m.nj - 1) / m.nj, ti = (m.D + m.ni - 1) / m.ni;
+  const int glo = (short)(m.guard & 0xffff);
+  const bool whole = !m.band;       // whole-slice tiles; otherwise row bands over the row window
+  const int tj = whole ? 1 : (m.rwn + m.nj - 1) / m.nj, ti = (m.swn + m.ni - 1) / m.ni;
   for (int t = threadIdx.x; t < ti * tj; t += blockDim.x) {
     Unit u;
     u.item = item;
-    u.i0 = (t / tj) * m.ni; u.ni = min(m.ni, m.D - u.i0);
-    if (whole) { u.j0 = m.nj > m.D ? -glo : 0; u.nj = m.nj; }   // gen 1: guard rows inside the tile; gen 2: the grid's rows only
-    else { u.j0 = (t % tj) * m.nj; u.nj = min(m.nj, m.D - u.j0); }
+    u.i0 = m.sw0 + (t / tj) * m.ni; u.ni = min(m.ni, m.sw0 + m.swn - u.i0);
+    if (whole) { u.j0 = m.nj > m.D ? -glo : m.rw0; u.nj = m.nj; }   // gen 1: guard rows inside the tile; gen 2: the row window
+    else { u.j0 = m.rw0 + (t % tj) * m.nj; u.nj = min(m.nj, m.rw0 + m.rwn - u.j0); }
     a.units[s_ubase + t] = u;
   }
 }
@@ -1306,7 +1345,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) k_vote(VoteArgs a) {
     const ItemMeta& m = a.meta[u.item];
     const int D = m.D, Dp = m.Dp, n = m.n;
     const long long off = m.off;
-    const int glo = m.guard & 0xffff, ghi = m.guard >> 16;
+    const int glo = (short)(m.guard & 0xffff), ghi = m.guard >> 16;     // signed: negative where the spheres stay inside the grid along C
     const Tile t{u.i0, u.ni, u.j0, u.nj, D, Dp, glo, ghi};
     // voxel (i, j, k) of the tile sits at word ((i - i0) * nj + (j - j0)) * Dp + k of the pointer shifted by the low guard
     const SmemEmit emit{tile_s + 4u * (unsigned)glo, 4 * (kTileWords + warp * 32 + lane - glo)};
@@ -1668,7 +1707,7 @@ __global__ void __launch_bounds__(kRunsThreads, RCV_RUNS_CTAS) k_vote_runs(VoteA
     const ItemMeta& m = a.meta[u.item];
     const int D = m.D, Dp = m.Dp, n = m.n;
     const long long off = m.off;
-    const int glo = m.guard & 0xffff, ghi = m.guard >> 16;
+    const int glo = (short)(m.guard & 0xffff), ghi = m.guard >> 16;     // signed: negative where the spheres stay inside the grid along C
     const Tile t{u.i0, u.ni, u.j0, u.nj, D, Dp, glo, ghi};
     // whole-slice tiles whose guard band holds every sphere of the item need no clipping (the prelude sized the guards);
     // row bands and unguarded grids (guard = 0 although spheres overhang) take the clipped variant
@@ -1728,7 +1767,7 @@ __global__ void __launch_bounds__(kRunsThreads, RCV_RUNS_CTAS) k_vote_runs(VoteA
       if (lane == 0) k = atomicAdd(&s_next, 1);
       k = __shfl_sync(0xffffffffu, k, 0);
       ch = -1; g = 0;
-      r0 = make_int4(0, 0, 0, 0); r1 = make_int4(0, 0, 0, 0);
+      r0 = make_int4(0, 0, glo < 0 ? -glo : 0, 0); r1 = make_int4(0, 0, 0, 0);     // padding lanes: R = 0, at a cell the rows store
       if (k >= nwork) return;
       if (use_list) { const int e = (int)s_work[k < nbig ? k : kRunsWorkList - 1 - (k - nbig)]; ch = e >> 11; g = e & 2047; }
       else { ch = k / ngroups; g = k - ch * ngroups; }
@@ -1747,7 +1786,8 @@ __global__ void __launch_bounds__(kRunsThreads, RCV_RUNS_CTAS) k_vote_runs(VoteA
       // does any sphere of the group reach the chunk's slices?
       const bool here = c.R > 0 && (c.ipa + c.R + 1 >= i0c) && (c.ipa - c.R - 1 <= i0c + nsl - 1);
       if (!__any_sync(0xffffffffu, here)) continue;
-      if (!here) c.R = 0;
+      if (!here) c.R = 0;     // (a lane that draws nothing leaves cancelling marks at its own cell: inside the window for a real point,
+                              // and the prelude / the padding below give the others a stored cell)
       RunLane L;
       run_lane_setup(c, L);
       const int pidx = cur + lane;
@@ -1773,16 +1813,17 @@ __global__ void __launch_bounds__(kRunsThreads, RCV_RUNS_CTAS) k_vote_runs(VoteA
     const int jr0 = u.j0 < 0 ? 0 : u.j0, njr = min(u.j0 + u.nj, D) - jr0;   // the real rows of a slice (guard rows are not read back)
     const int rows = u.ni * njr;
     const bool dump = a.volume && (long long)D * D * D <= a.volume_cap;
+    const int klo = glo < 0 ? -glo : 0, khi = ghi < 0 ? D - 1 + ghi : D - 1;     // the grid's cells that the tile stores
     for (int r = threadIdx.x; r < rows; r += kRunsThreads) {
       const int sa = r / njr, gb = jr0 + r - sa * njr, ga = u.i0 + sa;
       const unsigned lin0 = ((unsigned)gb * (unsigned)D + (unsigned)ga) * (unsigned)D;
       int* row = tile + (sa * u.nj + (gb - u.j0)) * Dp;
       const int* rowe = row + kRunsPlaneWords;
       int run = 0;
-      for (int k = 0; k < glo; ++k) run += row[k] - rowe[k];
-      int best = -1, bestk = 0;
-      row += glo; rowe += glo;
-      for (int k = 0; k < D; ++k) {
+      for (int k = 0; k < glo; ++k) run += row[k] - rowe[k];     // guard cells below the grid
+      int best = 0, bestk = 0;                                   // (cells outside the window hold no vote: count 0 at k = 0 is the row's floor)
+      row += glo; rowe += glo;                                   // cell k of the row is row[k], for k in [klo, khi]
+      for (int k = klo; k <= khi; ++k) {
         run += row[k] - rowe[k];
         sum += (unsigned)run;
         if (run > best) { best = run; bestk = k; }
@@ -1791,13 +1832,13 @@ __global__ void __launch_bounds__(kRunsThreads, RCV_RUNS_CTAS) k_vote_runs(VoteA
       const unsigned long long kk = pack_peak(best, lin0 + (unsigned)bestk);
       key = kk > key ? kk : key;
     }
-    if (dump) {   // parity / debug: the counts go to HBM, coalesced
+    if (dump) {   // parity / debug: the counts go to HBM, coalesced (the volume was zeroed by the host: cells outside the window stay 0)
       __syncthreads();
       for (int r = warp; r < rows; r += kRunsWarps) {
         const int sa = r / njr, gb = jr0 + r - sa * njr, ga = u.i0 + sa;
         const unsigned lin0 = ((unsigned)gb * (unsigned)D + (unsigned)ga) * (unsigned)D;
         const int* row = tile + glo + (sa * u.nj + (gb - u.j0)) * Dp;
-        for (int k = lane; k < D; k += 32) a.volume[(long long)lin0 + k] = row[k];
+        for (int k = klo + lane; k <= khi; k += 32) a.volume[(long long)lin0 + k] = row[k];
       }
     }
     key = warp_max_u64(key); sum = warp_sum_u64(sum);
@@ -1831,7 +1872,10 @@ __global__ void k_finalize(FinalArgs a) {
   if (st == RCV_ST_OK) {
     const unsigned long long key = a.best[b];
     pk = (int)(key >> 32);
-    const unsigned lin = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+    nv = (long long)a.votes[b];
+    // no vote at all: argwhere(V == 0)[0] is voxel (0, 0, 0), which a tile need not cover (tiles span the box the spheres can reach)
+    const unsigned lin = nv == 0 ? 0u : 0xffffffffu - (unsigned)(key & 0xffffffffu);
+    if (nv == 0) pk = 0;
     const unsigned D = (unsigned)m.D;
     const int idx[3] = {(int)(lin / (D * D)), (int)((lin / D) % D), (int)(lin % D)};
     for (int q = 0; q < 3; ++q) {
@@ -2026,6 +2070,7 @@ struct rcv_ctx {
   int last_mask_frames, last_mask_kpts, last_mask_words_per_item;   // survival bits left by the most recent frames call (rcv_scene_clouds_last)
   float* head_radius; long long head_radius_cap;   // fused head: radius planes of the items of a call
   double* icp_scratch; long long icp_cap;         // ICP scratch: per-frame state + per-(frame, tile) partial sums
+  int full_window;                                // RCV_FULL_WINDOW=1: gen-2 tiles cover the whole grid instead of the reachable box
   void* icp_grid; long long icp_grid_cap;         // ICP uniform grids (bytes): sized by the scene points of a call
   void* add_grid; long long add_grid_cap;         // ADD(-S): grid over the CAD model + the estimated points of a call's frames (bytes)
   double* add_part; long long add_part_cap;     // ADD metric scratch: per-(frame, tile) partial sums and minima   // K1 scratch: one survival bit per pixel of every item of a call (grown on demand)
@@ -2112,6 +2157,7 @@ RCV_EXPORT int rcv_create(int device, const rcv_config* cfg, rcv_ctx** out) {
   c->device = device; c->cfg = *cfg; c->sms = prop.multiProcessorCount;
   { const char* g = getenv("RCV_VOTE_GEN"); c->gen = (g && atoi(g) == 1) ? 1 : 2; }
   { const char* g = getenv("RCV_DP_MOD"); c->dp_mod = g ? atoi(g) : -1; }
+  { const char* g = getenv("RCV_FULL_WINDOW"); c->full_window = (g && atoi(g)) ? 1 : 0; }
   if (c->cfg.max_units <= 0) {
     // worst case per item: D slices x ceil(D / rows-per-tile) tiles
     const long long per_item = (long long)cfg->max_grid * ((cfg->max_grid * (long long)(cfg->max_grid | 1)) / kTileWords + 1);
@@ -2166,7 +2212,8 @@ static int run_items(rcv_ctx* c, int n_items, const rcv_vote_params* vp, double*
   CK(c, cudaMemsetAsync(c->best, 0, 8 * (size_t)n_items, st));
   CK(c, cudaMemsetAsync(c->votes, 0, 8 * (size_t)n_items, st));
   PreludeArgs pa{c->pool, c->meta, c->units, c->counters, c->cfg.max_units, c->cfg.max_grid, vp->grid_policy,
-                 c->gen >= 2 ? 2 * kRunsPlaneWords : kTileWords, c->gen, c->dp_mod, c->leaves, c->leaf_sums, c->leaf_cap};
+                 c->gen >= 2 ? 2 * kRunsPlaneWords : kTileWords, c->gen, c->dp_mod, c->full_window, c->leaves, c->leaf_sums, c->leaf_cap};
+  if (volume) CK(c, cudaMemsetAsync(volume, 0, (size_t)volume_cap * 4, st));   // tiles only cover the box the spheres can reach: the rest of a dumped volume is zero
   k_prelude<<<n_items, kPreludeThreads, 0, st>>>(pa);
   VoteArgs va{c->pool, c->meta, c->units, c->counters, c->best, c->votes, volume, volume_cap};
   const int slot = (int)(c->ev_count % 64);

@@ -22,9 +22,15 @@ struct HTile {
 };
 
 template <int NC, bool CLIP>
-void render_group(const RunPoint* c, const double (*pd)[3], const HTile& t, Stats& st) {
+void render_group(const RunPoint* c_in, const double (*pd)[3], const HTile& t, Stats& st) {
   RunLane L[32];
-  for (int l = 0; l < 32; ++l) run_lane_setup(c[l], L[l]);
+  RunPoint cc[32];
+  for (int l = 0; l < 32; ++l) {
+    cc[l] = c_in[l];
+    if (cc[l].R <= 0) { cc[l].ipc = t.glo < 0 ? -t.glo : 0; cc[l].fc = 0.f; }     // k_vote_runs: a lane that draws nothing marks a cell the row stores
+    run_lane_setup(cc[l], L[l]);
+  }
+  const RunPoint* c = cc;
   for (int i0c = t.i0; i0c < t.i0 + t.ni; i0c += NC) {
     f2 aa[32][NC];
     // runs_chunk (rcvvote.cu): every lane's own column range [ulo, uhi] restricted to the tile's rows (a no-op for guarded

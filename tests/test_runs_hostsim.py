@@ -140,6 +140,29 @@ def test_guarded_row_bands_need_no_clipping(band, NC):
     assert not got[:j0].any() and not got[j0 + nj:].any()
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_tiles_cover_only_the_box_the_spheres_reach(seed):
+    """The prelude's windows: along z a tile stores the cells [min(z - R) - 2.5, max(z + R) + 2.5] only -- SIGNED guards, negative
+    where the spheres stay inside the grid -- and along x the rows the spheres can reach.  The reference sizes the grid by
+    the widest axis, so the other axes have slack (here: a cloud that is flat along z and off-centre along x)."""
+    rng = np.random.default_rng(100 + seed)
+    D = 64
+    n = 80
+    R = rng.integers(1, 12, size=n).astype(np.int32)
+    p = np.stack([rng.uniform(14, 40, n), rng.uniform(13, 51, n), rng.uniform(28, 36, n)], axis=1)
+    if seed % 2:
+        p[:, 2] += 14.0                                    # the window touches / overhangs the top of the grid instead
+    lo = (p - R[:, None]).min(axis=0) - 2.5
+    hi = (p + R[:, None]).max(axis=0) + 2.5
+    glo, ghi = -int(np.floor(lo[2])), int(np.ceil(hi[2])) - (D - 1)
+    assert glo < 0 and (ghi < 0 or seed % 2)
+    x0, x1 = max(0, int(np.floor(lo[0]))), min(D - 1, int(np.ceil(hi[0])))
+    want = oracle.fast_for(p, R, D)
+    for slab, NC in ((3, 3), (5, 2), (4, 4)):
+        got, _ = hostsim.render_runs(p, R, D, glo=glo, ghi=min(ghi, 8), band=(x0, x1 - x0 + 1), slab=slab, NC=NC, sqrt_perturb=seed % 2)
+        assert np.array_equal(got, want), (slab, NC)
+
+
 def test_large_radius_thick_rings():
     rng = np.random.default_rng(21)
     D = 120
