@@ -301,7 +301,7 @@ def run_ours(args):
                "steps": args.e2e_steps, "h2d_bytes_per_step_uncropped": int(h2d_full),
                "h2d_gbs_per_gpu": h2d * args.e2e_steps / float(dt.item()) / 1e9,
                "api": "rcv_vote_frames_host + rcv_horn_batch_host (pinned host buffers, 256-frame chunks, copy/compute overlap; the entry point "
-                      "copies only the rows between the first and last non-zero depth row of each frame, two copy streams)"}
+                      "copies only the rows between the first and last non-zero depth row of each frame, two copy streams; up to 3 helper threads scan the depth rows ahead of the copies)"}
         del hd, hr
 
     # ---- cpu_baseline + live parity spot check (rank 0, single GPU only) ----
